@@ -1,0 +1,235 @@
+/* rcu_b200 — C-ABI of the B200-native stochastic-inference + uncertainty hot path.
+ *
+ * The reference (alainjungo/reliability-challenges-uncertainty) is pure Python and has no FFI; its seams on
+ * this path are Python protocols.  Each entry point below names the reference interface it stands behind
+ * (path:line relative to the reference root).  The Python drop-ins in
+ * reliability-challenges-uncertainty_b200/ bind these symbols with ctypes.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative rcu_status; rcu_last_error() gives the message of
+ *     the calling thread's last failure;
+ *   - all data pointers are DEVICE pointers owned by the caller unless marked "host"; small parameter
+ *     tables (edges, thresholds, break tables) are host pointers read before the call returns;
+ *   - every call is asynchronous and ordered on the given stream (a cudaStream_t passed as void*);
+ *   - no hidden device allocation after rcu_unet_plan(); metric calls use a caller-provided workspace;
+ *   - one rcu_unet handle per (device, weight set); a handle is not thread-safe, distinct handles are.
+ */
+#ifndef RCU_B200_H
+#define RCU_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RCU_ABI_VERSION 1
+
+typedef enum rcu_status {
+  RCU_OK = 0,
+  RCU_EINVAL = -1,   /* bad argument (the Python side turns these into the reference's ValueError) */
+  RCU_ECUDA = -2,    /* CUDA runtime / driver error */
+  RCU_ENOTSUP = -3,  /* configuration outside the supported hot path */
+  RCU_ENOMEM = -4    /* workspace too small */
+} rcu_status;
+
+#define RCU_MAX_BINS 32        /* ECE reliability bins per call */
+#define RCU_MAX_UE_CLASSES 32  /* uncertainty intervals (= thresholds + 1) per call */
+#define RCU_MAX_BREAKS 96      /* float32 break points of the p -> interval table */
+
+int rcu_abi_version(void);
+const char* rcu_last_error(void);
+/* 0 if a usable sm_100 device is present, RCU_ECUDA otherwise (message says why). */
+int rcu_device_check(int device);
+
+/* ------------------------------------------------------------------------------------------------
+ * Calibration / uncertainty-error histograms
+ * ------------------------------------------------------------------------------------------------ */
+
+/* Workspace (bytes) the metric calls below need for `n_subjects` subjects per launch. */
+size_t rcu_metrics_workspace_bytes(int n_subjects);
+/* Must be called once on a fresh workspace (zeroes the per-subject tickets); stream-ordered. */
+int rcu_metrics_workspace_init(void* workspace, size_t workspace_bytes, void* stream);
+
+/* ECE reliability-bin tables.
+ * Stands behind np_fn._binary_calibration (common/evalutation/numpyfunctions.py:51-69), reached from
+ * EceBinaryNumpy.__call__ (common/evalutation/eval.py:129-142) -> ece_binary (:6-23) -> binary_calibration (:26-48).
+ *   p         float32[n_subjects * voxels_per_subject]  foreground probability (prob[..., 1])
+ *   target    uint8  [same]                            ground truth {0,1}
+ *   mask      uint8  [same] or NULL                    voxels with mask==0 are skipped (BraTS T2>0 brain mask)
+ *   edges_f32 host float32[n_bins+1]                   smallest float32 >= each float64 np.linspace(0, 1+1e-8, n_bins+1) edge
+ *   range_lo/hi                                        `threshold_range` (exclusive both sides); pass NaN,NaN for None
+ * Outputs, per subject, n_bins+1 slots each (slot n_bins counts values no bin takes: p<0, p>=last edge, NaN):
+ *   count     uint64[n_subjects][n_bins+1]             == np.bincount(binids)            (bit-exact)
+ *   positives uint64[n_subjects][n_bins+1]             == np.bincount(binids, weights=target) (exact integers)
+ *   conf_sum  float64[n_subjects][n_bins+1]            == np.bincount(binids, weights=p) up to fp64 summation order;
+ *                                                      deterministic run to run (fixed reduction tree)
+ */
+int rcu_calib_hist(const float* p, const uint8_t* target, const uint8_t* mask, int64_t voxels_per_subject,
+                   int n_subjects, const float* edges_f32, int n_bins, float range_lo, float range_hi,
+                   uint64_t* count, uint64_t* positives, double* conf_sum, void* workspace, size_t workspace_bytes,
+                   void* stream);
+
+/* Joint histogram (confusion class x uncertainty interval), all sweep thresholds in one pass.
+ * Stands behind np_fn.uncertainty (common/evalutation/numpyfunctions.py:86-107) as called, once per threshold,
+ * by UncertaintyAndCorrectionEvalNumpy.__call__ (common/evalutation/eval.py:182-226) and
+ * UncertaintyErrorDiceNumpy.__call__ (:156-173) from the CorrectionAction sweep (bin-eval/eval_uncertainty.py:195-202).
+ *
+ * The interval index of a voxel is j = seg_class[#{b : breaks[b] <= v}] (ordinary float comparison) where
+ *   value_kind 0: v is the float32 foreground probability p; the host derives `breaks_f32` (every float32 value
+ *                 at which some predicate u(p) > th_k flips, sorted) and `seg_class` (how many thresholds are
+ *                 exceeded between consecutive breaks) from the reference's own float arithmetic
+ *                 u(p) = H([1-p, p]) / ln 2 (numpyfunctions.py:166-168, analysis.py:201), so counts are bit-exact;
+ *   value_kind 1: v is a float32 uncertainty map, breaks_f32[k] = smallest float32 > th_k, seg_class = identity;
+ *   value_kind 2: v is a float64 uncertainty map (what ToEntropy produces); breaks_f64 = the thresholds and the
+ *                 comparison is strict (b < v), seg_class = identity.
+ * Breaks must be sorted ascending.  Output ue_counts uint64[n_subjects][4][n_classes]: rows tp, tn, fp, fn
+ * (prediction/target as booleans), column j = voxels whose uncertainty exceeds exactly j of the thresholds.
+ * Thresholded counts are suffix sums: tpu(th_k) = sum_{j>k} ue_counts[tp][j]; tp = sum_j ue_counts[tp][j].
+ * `invalid` (uint64[n_subjects], may be NULL) counts values that are negative or NaN (kinds 0 and 1).
+ * `mask` (may be NULL) restricts the voxels (UncertaintyErrorDiceNumpy(with_mask=True): mask = ~target_boarder).
+ */
+int rcu_ue_hist(const void* values, int value_kind, const uint8_t* prediction, const uint8_t* target,
+                const uint8_t* mask, int64_t voxels_per_subject, int n_subjects, const float* breaks_f32,
+                const double* breaks_f64, int n_breaks, const uint8_t* seg_class, int n_classes,
+                uint64_t* ue_counts, uint64_t* invalid, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Both of the above in one pass over (p, prediction, target, mask): 7 bytes per voxel.
+ * `mask` applies to the calibration tables only (as in EceAction, bin-eval/eval_uncertainty.py:151-152 vs
+ * CorrectionAction :195-202 which is unmasked). */
+int rcu_eval_fused(const float* p, const uint8_t* prediction, const uint8_t* target, const uint8_t* mask,
+                   int64_t voxels_per_subject, int n_subjects, const float* edges_f32, int n_bins,
+                   const float* breaks_f32, int n_breaks, const uint8_t* seg_class, int n_classes,
+                   uint64_t* count, uint64_t* positives, double* conf_sum, uint64_t* ue_counts, uint64_t* invalid,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* Confusion counts with pymia 0.2.1 `ConfusionMatrix` semantics (prediction == 1 / == 0 vs label == 1 / == 0), the
+ * arithmetic behind np_fn.dice / confusion_matrx / accuracy (common/evalutation/numpyfunctions.py:128-151).
+ * counts uint64[n_subjects][4] = tp, tn, fp, fn (zeroed by the call). */
+int rcu_confusion(const uint8_t* prediction, const uint8_t* target, int64_t voxels_per_subject, int n_subjects,
+                  uint64_t* counts, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Per-pixel aggregation over samples / ensemble members
+ * ------------------------------------------------------------------------------------------------ */
+
+/* Stands behind MultiPredictionSummary.__call__ (rechun/dl/customsteps.py:50-71) + th.entropy
+ * (common/utils/torchhelper.py:53-54), with the per-sample F.softmax(logits, 1) of McPredictStep
+ * (rechun/dl/customsteps.py:31-36) / EnsemblePredictionStep (bin-dl/brats_test_ensemble.py:85-93) folded in.
+ *   input_kind 0: logits, pixel-interleaved  float32[n_samples][n_images][hw][2]   (what rcu_unet_forward emits)
+ *   input_kind 1: probabilities, planar      float32[n_samples][n_images][2][hw]   (a reference-made
+ *                 `multi_probabilities` tensor; no softmax applied)
+ *   input_kind 2: logits, planar             float32[n_samples][n_images][2][hw]
+ * Outputs (any may be NULL except mean):
+ *   mean       float32[n_images][2][hw]   sum_t p_t / n_samples  (sequential fp32 sum in t, like torch)
+ *   entropy    float32[n_images][hw]      -sum_c where(p>0, p ln p, 0) of the mean
+ *   mutual_info float32[n_images][hw]     entropy - mean_t H(p_t)
+ *   variance   float32[n_images][hw]      mean_c var_t(p_t,c), unbiased
+ *   prediction uint8  [n_images][hw]      argmax_c mean (ties -> class 0, like np.argmax)
+ *   multi_out  float32[n_samples][n_images][2][hw] planar per-sample probabilities (the reference's
+ *              `multi_probabilities`), only written when non-NULL
+ */
+int rcu_aggregate(const float* input, int input_kind, int n_samples, int64_t n_images, int64_t hw, float* mean,
+                  float* entropy, float* mutual_info, float* variance, uint8_t* prediction, float* multi_out,
+                  void* stream);
+
+/* Partial aggregation for sample-sharded runs: writes the raw fp32 sums so ranks can allreduce them.
+ *   sums float32[n_images][K][hw] with K = 2 (sum p0, sum p1) [+1: sum_t H(p_t) if want_mi] [+2: sum p0^2, sum p1^2 if want_var]
+ * and the finisher that turns allreduced sums into the same outputs as rcu_aggregate. */
+int rcu_aggregate_partial(const float* input, int input_kind, int n_samples, int64_t n_images, int64_t hw,
+                          int want_mi, int want_var, float* sums, void* stream);
+int rcu_aggregate_finish(const float* sums, int total_samples, int64_t n_images, int64_t hw, int has_mi, int has_var,
+                         float* mean, float* entropy, float* mutual_info, float* variance, uint8_t* prediction,
+                         void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Philox4x32-10 Dropout2d keep masks
+ * ------------------------------------------------------------------------------------------------ */
+
+/* Materialises the keep-scale table the conv epilogues otherwise generate in registers (same stream):
+ *   scale[(sample * n_slices + slice) * total_channels + site_offset[s] + c]
+ *       = philox4x32_10(ctr=(c/4, s, slice_index0 + slice, sample0 + sample), key=seed)[c%4] >= thr ? 1/(1-p) : 0
+ * Stands behind nn.Dropout2d in train mode inside Conv2dBnRelu (common/model/unet.py:14-15) as toggled by
+ * th.set_dropout_mode (common/utils/torchhelper.py:44-50).  site_channels is a host array.
+ * rcu_philox_masks_host computes the identical table on the host (no GPU needed) for injection into the reference. */
+int rcu_philox_masks(uint64_t seed, float p_drop, const int* site_channels, int n_sites, int64_t slice_index0,
+                     int64_t n_slices, int sample0, int n_samples, float* scale, void* stream);
+int rcu_philox_masks_host(uint64_t seed, float p_drop, const int* site_channels, int n_sites, int64_t slice_index0,
+                          int64_t n_slices, int sample0, int n_samples, float* scale_host);
+
+/* ------------------------------------------------------------------------------------------------
+ * U-Net forward (tcgen05 implicit-GEMM convolutions)
+ * ------------------------------------------------------------------------------------------------ */
+
+typedef struct rcu_unet rcu_unet;
+
+/* One 3x3 'conv -> [Dropout2d] -> BN(eval) -> ReLU' unit (Conv2dBnRelu, common/model/unet.py:8-23), host fp32. */
+typedef struct rcu_conv_unit {
+  const float* weight;       /* [c_out][c_in][3][3] as in nn.Conv2d.weight */
+  const float* bias;         /* [c_out] */
+  const float* bn_weight;    /* [c_out] gamma, or NULL when the unit has no BN (up-path `upconv`, head 1x1) */
+  const float* bn_bias;      /* beta */
+  const float* bn_mean;      /* running_mean */
+  const float* bn_var;       /* running_var */
+  int c_in, c_out;
+  int has_dropout;           /* a Dropout2d sits between conv and BN */
+} rcu_conv_unit;
+
+/* Topology and weights of common/model/unet.py:123-186 UNet(nb_classes=2, in_channels, depth, start_filters,
+ * dropout, dropout_center) with residual=False, sigma_out=False, bn=True.  Arrays are host pointers.
+ *   units   : 2*depth + 2 + 2*depth + 1 Conv2dBnRelu units in forward order (down blocks, bottom, up blocks, conv_cls.0)
+ *   upconvs : depth plain 3x3 convs `up_convs.i.upconv.1` (bias only, applied after nearest x2), bn_* = NULL
+ *   head    : `conv_cls.1`, 1x1, c_in = start_filters, c_out = 2 (weight [2][c_in][1][1])
+ */
+typedef struct rcu_unet_desc {
+  int in_channels, depth, start_filters, nb_classes;
+  float p_drop;              /* Dropout2d p (unused if no unit has_dropout) */
+  float bn_eps;
+  const rcu_conv_unit* units;
+  int n_units;
+  const rcu_conv_unit* upconvs;
+  int n_upconvs;
+  rcu_conv_unit head;
+} rcu_unet_desc;
+
+/* Folds BN into per-channel scale/shift, converts weights to the device layout, uploads them. */
+int rcu_unet_create(const rcu_unet_desc* desc, int device, rcu_unet** out);
+void rcu_unet_destroy(rcu_unet* net);
+
+/* Fixes the spatial size and the number of images (slices x samples) processed per internal chunk and
+ * allocates the activation workspace (the only allocation the handle ever makes).  Returns bytes reserved. */
+int rcu_unet_plan(rcu_unet* net, int height, int width, int max_images_per_chunk, size_t* workspace_bytes);
+
+/* Runs `n_samples` forwards of each of `n_slices` input slices (the samples are folded into the batch, weights
+ * are read once per tile) and writes pixel-interleaved logits float32[n_samples][n_slices][H*W][2].
+ * Stands behind `context.model(images)` = UNet.forward (common/model/unet.py:166-186) as called by
+ * SegmentationPredictStep (common/trainloop/steps.py:84), McPredictStep (rechun/dl/customsteps.py:23,32) and
+ * EnsemblePredictionStep (bin-dl/brats_test_ensemble.py:85,89).
+ *   images        float32[n_slices][in_channels][H][W]   NCHW, as the reference hands them to the model
+ *   dropout_mode  0: every Dropout2d in eval mode (identity) for all samples
+ *                 1: sample index `sample0 + t` draws its masks from Philox(seed) — free-running MC dropout
+ *                 2: masks come from `scale` (float32[n_stochastic_samples][n_slices][total_dropout_channels],
+ *                    values 0 or 1/(1-p); n_stochastic_samples = n_samples - (det_first != 0)), e.g.
+ *                    reference-supplied decisions
+ *   det_first     when non-zero, sample 0 of the folded batch is the deterministic "weight scaling" pass of
+ *                 McPredictStep (customsteps.py:23-25) and the remaining n_samples-1 are stochastic
+ */
+int rcu_unet_forward(rcu_unet* net, const float* images, int64_t n_slices, int n_samples, int dropout_mode,
+                     int det_first, uint64_t seed, int64_t slice_index0, int sample0, const float* scale,
+                     float* logits, void* stream);
+
+/* Introspection used by tests and the benchmark. */
+int rcu_unet_total_dropout_channels(const rcu_unet* net);
+/* Copies a named internal activation of the LAST chunk of the last forward to `out` as fp32 NHWC (debug/parity). */
+int rcu_unet_debug_activation(rcu_unet* net, int index, float* out, size_t out_elems, void* stream);
+/* Selects the convolution implementation: 0 = tcgen05/TMEM/TMA implicit GEMM (default, the product path),
+ * 1 = straightforward CUDA-core fp32-accumulate kernel over the same bf16 data (on-device cross-check only). */
+int rcu_unet_set_conv_impl(rcu_unet* net, int impl);
+/* Number of kernel launches issued by the last rcu_unet_forward on this handle. */
+int64_t rcu_unet_last_launch_count(const rcu_unet* net);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RCU_B200_H */

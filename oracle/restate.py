@@ -1,0 +1,514 @@
+"""TEST INFRASTRUCTURE ONLY — CPU restatement of the reference's stochastic-inference + uncertainty path.
+
+The reference is pure Python; its arithmetic on this path is torch (CPU) and numpy.  This module restates
+that arithmetic with the same library primitives, independent of the reference tree, so it can travel to
+the GPU box (where /root/reference does not exist).  It is *pinned*: tests/test_oracle_golden.py checks
+every function here against fixtures under tests/golden/ that tests/golden/make_golden.py produced by
+running the unmodified reference (through oracle/ref_shim.py) in the authoring container.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this
+module, and only as the checker / the CPU baseline.  The product package never imports it.
+
+Reference citations (path:line relative to the reference root):
+  U-Net forward ............ common/model/unet.py:8-23,26-39,63-82,85-120,123-186; common/model/helpers.py:5-16
+  MC / ensemble steps ...... rechun/dl/customsteps.py:16-39; bin-dl/brats_test_ensemble.py:78-94
+  deterministic step ....... common/trainloop/steps.py:69-90
+  summary .................. rechun/dl/customsteps.py:50-71; common/utils/torchhelper.py:53-54
+  ECE ...................... common/evalutation/numpyfunctions.py:6-23,26-48,51-69,72-83
+  U-E counts / ratios ...... common/evalutation/numpyfunctions.py:86-125; common/evalutation/eval.py:145-226
+  Dice / accuracy / cm ..... common/evalutation/numpyfunctions.py:128-151 (+ pymia 0.2.1 metric classes, restated)
+  eval-side preparation .... rechun/eval/helper.py:25-47; rechun/eval/analysis.py:147-151,189-203
+  threshold sweep / table .. bin-eval/eval_uncertainty.py:176-202,239; bin-analysis/table_ece_ue_bnf_dice.py:56-59
+"""
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+BN_EPS = 1e-5  # nn.BatchNorm2d default, common/model/unet.py:17
+SWEEP_THRESHOLDS = (0.05, 0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9, 0.95)  # bin-eval/eval_uncertainty.py:239
+
+
+# ------------------------------------------------------------------------------------------------
+# U-Net topology (common/model/unet.py:128-164)
+# ------------------------------------------------------------------------------------------------
+class UNetConfig:
+    """Constructor arguments of the reference UNet that the hot path supports."""
+
+    def __init__(self, nb_classes=2, in_channels=4, depth=4, start_filters=32, dropout=0.05, dropout_center=None):
+        self.nb_classes = nb_classes
+        self.in_channels = in_channels
+        self.depth = depth
+        self.start_filters = start_filters
+        self.dropout = dropout
+        self.dropout_center = dropout_center
+
+
+def _block_dropout_flags(cfg, level, is_down):
+    """Which of the two convs of the block at `level` carry a Dropout2d (unet.py:63-82)."""
+    if cfg.dropout is None:
+        return (False, False)
+    if cfg.dropout_center is None:
+        return (True, True)
+    if level == cfg.depth:
+        return (False, False)
+    if level + cfg.dropout_center >= cfg.depth:
+        return (False, True) if is_down else (True, False)
+    return (False, False)
+
+
+def conv_sites(cfg):
+    """Ordered list of every 3x3 'conv [-> dropout] -> bn -> relu' unit, in forward order.
+
+    Each entry: (state_dict prefix, c_in, c_out, has_dropout).  The order is the order in which the
+    reference's forward visits them, which is also the order dropout sites are numbered in.
+    """
+    sites = []
+    c_in, c_out = cfg.in_channels, cfg.start_filters
+    for lvl in range(cfg.depth):
+        flags = _block_dropout_flags(cfg, lvl, True)
+        for rep in range(2):
+            sites.append(('down_convs.%d.block.block.%d.conv2d_batch_relu' % (lvl, rep),
+                          c_in if rep == 0 else c_out, c_out, flags[rep]))
+        c_in, c_out = c_out, c_out * 2
+    flags = _block_dropout_flags(cfg, cfg.depth, True)
+    for rep in range(2):
+        sites.append(('bottom_convs.block.%d.conv2d_batch_relu' % rep, c_in if rep == 0 else c_out, c_out, flags[rep]))
+    for j, lvl in enumerate(range(cfg.depth - 1, -1, -1)):
+        c_in, c_out = c_out, c_out // 2
+        flags = _block_dropout_flags(cfg, lvl, False)
+        for rep in range(2):
+            sites.append(('up_convs.%d.block.block.%d.conv2d_batch_relu' % (j, rep),
+                          2 * c_out if rep == 0 else c_out, c_out, flags[rep]))
+    sites.append(('conv_cls.0.conv2d_batch_relu', c_out, c_out, cfg.dropout is not None))
+    return sites
+
+
+def dropout_sites(cfg):
+    """[(prefix, channels)] of the units that own a Dropout2d, in forward order."""
+    return [(p, co) for (p, ci, co, d) in conv_sites(cfg) if d]
+
+
+def init_state_dict(cfg, seed):
+    """Reproduce `torch.manual_seed(seed); UNet(**cfg).state_dict()` without the reference tree.
+
+    Parameter creation order follows the reference constructor (unet.py:134-164): for every block the conv
+    (kaiming-uniform weight, then uniform bias — torch's nn.Conv2d.reset_parameters) then the BN (no RNG);
+    in each UpConv the block is built *before* the upconv conv (unet.py:155-157: the block is an argument
+    expression evaluated before UpConv.__init__ creates `upconv`); finally conv_cls.0 then conv_cls.1.
+    Pinned bit-for-bit against the reference by tests/golden (same torch version on both boxes).
+    """
+    gen_state = torch.random.get_rng_state()
+    torch.manual_seed(seed)
+    sd = OrderedDict()
+
+    def conv(prefix_w, c_out, c_in, k):
+        w = torch.empty(c_out, c_in, k, k)
+        torch.nn.init.kaiming_uniform_(w, a=math.sqrt(5))
+        bound = 1 / math.sqrt(c_in * k * k)
+        b = torch.empty(c_out)
+        torch.nn.init.uniform_(b, -bound, bound)
+        sd[prefix_w + '.weight'] = w
+        sd[prefix_w + '.bias'] = b
+
+    def unit(prefix, c_in, c_out):
+        conv(prefix + '.conv', c_out, c_in, 3)
+        sd[prefix + '.bn.weight'] = torch.ones(c_out)
+        sd[prefix + '.bn.bias'] = torch.zeros(c_out)
+        sd[prefix + '.bn.running_mean'] = torch.zeros(c_out)
+        sd[prefix + '.bn.running_var'] = torch.ones(c_out)
+        sd[prefix + '.bn.num_batches_tracked'] = torch.tensor(0, dtype=torch.long)
+
+    sites = conv_sites(cfg)
+    n_down = 2 * cfg.depth + 2
+    for (p, ci, co, _) in sites[:n_down]:
+        unit(p, ci, co)
+    k = n_down
+    for j in range(cfg.depth):
+        (p0, ci0, co0, _), (p1, ci1, co1, _) = sites[k], sites[k + 1]
+        unit(p0, ci0, co0)
+        unit(p1, ci1, co1)
+        conv('up_convs.%d.upconv.1' % j, co0, 2 * co0, 3)
+        k += 2
+    p, ci, co, _ = sites[k]
+    unit(p, ci, co)
+    conv('conv_cls.1', cfg.nb_classes, co, 1)
+    torch.random.set_rng_state(gen_state)
+
+    # state_dict order of the reference module tree: inside UpConv, `block` is registered before `upconv`
+    return sd
+
+
+def randomize_statistics(sd, seed, logit_gain=24.0):
+    """Give a random-init net non-degenerate behaviour (random-init probabilities sit at ~0.49 everywhere).
+
+    BN affine/running stats are drawn from a seeded generator and the 1x1 head is scaled so logits spread
+    over several units.  Pure test-data synthesis (no reference counterpart).
+    """
+    g = torch.Generator().manual_seed(seed)
+    out = OrderedDict()
+    for k, v in sd.items():
+        if k.endswith('bn.weight'):
+            out[k] = 0.75 + 0.5 * torch.rand(v.shape, generator=g)
+        elif k.endswith('bn.bias'):
+            out[k] = 0.1 * torch.randn(v.shape, generator=g)
+        elif k.endswith('bn.running_mean'):
+            out[k] = 0.1 * torch.randn(v.shape, generator=g)
+        elif k.endswith('bn.running_var'):
+            out[k] = 0.5 + torch.rand(v.shape, generator=g)
+        elif k.startswith('conv_cls.1.weight'):
+            out[k] = v * logit_gain
+        else:
+            out[k] = v.clone()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# U-Net forward (common/model/unet.py:166-186) with optional injected Dropout2d keep-masks
+# ------------------------------------------------------------------------------------------------
+def _unit(x, sd, prefix, p_drop, keep):
+    y = F.conv2d(x, sd[prefix + '.conv.weight'], sd[prefix + '.conv.bias'], padding=1)
+    if keep is not None:
+        # nn.Dropout2d in train mode: per-(n, c) Bernoulli(1-p) noise divided by (1-p), multiplied in.
+        noise = keep.to(y.dtype) / (1.0 - p_drop)
+        y = y * noise[:, :, None, None]
+    y = F.batch_norm(y, sd[prefix + '.bn.running_mean'], sd[prefix + '.bn.running_var'],
+                     sd[prefix + '.bn.weight'], sd[prefix + '.bn.bias'], False, 0.0, BN_EPS)
+    return F.relu(y)
+
+
+def unet_forward(sd, x, cfg, keep_masks=None):
+    """Logits (N, nb_classes, H, W) of the reference UNet in eval mode.
+
+    keep_masks: None (all Dropout2d in eval mode = identity) or a list, one entry per dropout site in
+    forward order, of (N, C) {0,1} tensors = the Bernoulli keep decisions of Dropout2d in train mode.
+    """
+    sites = conv_sites(cfg)
+    masks = iter(keep_masks) if keep_masks is not None else None
+
+    def run(x, idx):
+        prefix, _, _, has_do = sites[idx]
+        keep = next(masks) if (masks is not None and has_do) else None
+        return _unit(x, sd, prefix, cfg.dropout, keep)
+
+    skips = []
+    idx = 0
+    for _ in range(cfg.depth):
+        x = run(x, idx)
+        x = run(x, idx + 1)
+        idx += 2
+        skips.append(x)
+        x = F.max_pool2d(x, 2)
+    x = run(x, idx)
+    x = run(x, idx + 1)
+    idx += 2
+    for j in range(cfg.depth):
+        skip = skips[-(j + 1)]
+        up = F.interpolate(x, scale_factor=2, mode='nearest')
+        up = F.conv2d(up, sd['up_convs.%d.upconv.1.weight' % j], sd['up_convs.%d.upconv.1.bias' % j], padding=1)
+        if up.shape[-2:] != skip.shape[-2:]:
+            dy = skip.shape[-2] - up.shape[-2]
+            dx = skip.shape[-1] - up.shape[-1]
+            up = F.pad(up, (dx // 2, dx // 2 + dx % 2, dy // 2, dy // 2 + dy % 2))
+        x = torch.cat((up, skip), 1)
+        x = run(x, idx)
+        x = run(x, idx + 1)
+        idx += 2
+    x = run(x, idx)
+    return F.conv2d(x, sd['conv_cls.1.weight'], sd['conv_cls.1.bias'])
+
+
+def predict_deterministic(sd, images, cfg):
+    """SegmentationPredictStep(do_probs=True) (common/trainloop/steps.py:69-90)."""
+    logits = unet_forward(sd, images.float(), cfg)
+    return {'logits': logits, 'probabilities': F.softmax(logits, 1)}
+
+
+def predict_mc(sd, images, cfg, mc_steps, keep_masks_per_step):
+    """McPredictStep (rechun/dl/customsteps.py:16-39) with the dropout decisions supplied by the caller.
+
+    keep_masks_per_step[t] is the per-site mask list of sample t (see unet_forward).
+    """
+    images = images.float()
+    out = {'ws_probabilities': F.softmax(unet_forward(sd, images, cfg), 1)}
+    probs = []
+    for t in range(mc_steps):
+        probs.append(F.softmax(unet_forward(sd, images, cfg, keep_masks_per_step[t]), 1))
+    out['multi_probabilities'] = torch.stack(probs)
+    return out
+
+
+def predict_ensemble(state_dicts, images, cfg):
+    """EnsemblePredictionStep (bin-dl/brats_test_ensemble.py:78-94)."""
+    images = images.float()
+    return {'multi_probabilities': torch.stack([F.softmax(unet_forward(sd, images, cfg), 1) for sd in state_dicts])}
+
+
+def torch_entropy(p, dim=-1, keepdim=False):
+    """th.entropy (common/utils/torchhelper.py:53-54): natural log, 0·log0 := 0."""
+    return -torch.where(p > 0, p * p.log(), torch.zeros((), dtype=p.dtype)).sum(dim=dim, keepdim=keepdim)
+
+
+def summarize(multi_probabilities, do_mi=False, do_var=False):
+    """MultiPredictionSummary (rechun/dl/customsteps.py:50-71)."""
+    out = {}
+    probabilities = multi_probabilities.mean(dim=0)
+    out['probabilities'] = probabilities
+    entropy = torch_entropy(probabilities, dim=1, keepdim=True)
+    out['entropy'] = entropy
+    if do_mi:
+        out['mutual_info'] = entropy - torch_entropy(multi_probabilities, dim=2, keepdim=True).mean(dim=0)
+    if do_var:
+        out['variance'] = multi_probabilities.var(dim=0).mean(dim=1, keepdim=True)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Philox4x32-10 keep-mask stream (new in the build; host restatement of csrc/philox.cuh)
+# ------------------------------------------------------------------------------------------------
+_PHILOX_M0 = np.uint64(0xD2511F53)
+_PHILOX_M1 = np.uint64(0xCD9E8D57)
+_PHILOX_W0 = 0x9E3779B9
+_PHILOX_W1 = 0xBB67AE85
+_MASK32 = np.uint64(0xFFFFFFFF)
+
+
+def philox4x32_10(counter, key):
+    """Vectorised Philox4x32-10.  counter: (..., 4) uint32, key: (2,) ints.  Returns (..., 4) uint32."""
+    c = [np.asarray(counter[..., i], dtype=np.uint64) for i in range(4)]
+    k0, k1 = int(key[0]) & 0xFFFFFFFF, int(key[1]) & 0xFFFFFFFF
+    for _ in range(10):
+        p0 = _PHILOX_M0 * c[0]
+        p1 = _PHILOX_M1 * c[2]
+        hi0, lo0 = p0 >> np.uint64(32), p0 & _MASK32
+        hi1, lo1 = p1 >> np.uint64(32), p1 & _MASK32
+        c = [hi1 ^ c[1] ^ np.uint64(k0), lo1, hi0 ^ c[3] ^ np.uint64(k1), lo0]
+        k0 = (k0 + _PHILOX_W0) & 0xFFFFFFFF
+        k1 = (k1 + _PHILOX_W1) & 0xFFFFFFFF
+    return np.stack(c, axis=-1).astype(np.uint32)
+
+
+def dropout_threshold(p):
+    """keep  <=>  u32 >= ceil(p * 2**32)   (u32 uniform on [0, 2**32))."""
+    return min(0xFFFFFFFF, int(math.ceil(p * 4294967296.0)))
+
+
+def philox_keep_masks(cfg, seed, sample, slice_index0, n_slices):
+    """Keep decisions of MC sample `sample` for slices [slice_index0, slice_index0+n_slices).
+
+    Stream definition (must match csrc/philox.cuh): for dropout site s, slice g (a run-global index so the
+    stream is independent of batching and of the GPU a slice lands on), sample t and channel c:
+        r = philox4x32_10(counter=(c // 4, s, g, t), key=(seed_lo, seed_hi));  keep = r[c % 4] >= thr(p)
+    Returns a list (one per site) of (n_slices, C) uint8 tensors.
+    """
+    thr = dropout_threshold(cfg.dropout)
+    key = (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    masks = []
+    for s, (_, ch) in enumerate(dropout_sites(cfg)):
+        groups = (ch + 3) // 4
+        ctr = np.zeros((n_slices, groups, 4), dtype=np.uint32)
+        ctr[..., 0] = np.arange(groups, dtype=np.uint32)[None, :]
+        ctr[..., 1] = s
+        ctr[..., 2] = (slice_index0 + np.arange(n_slices, dtype=np.uint32))[:, None]
+        ctr[..., 3] = sample
+        r = philox4x32_10(ctr, key).reshape(n_slices, groups * 4)[:, :ch]
+        masks.append(torch.from_numpy((r >= np.uint32(thr)).astype(np.uint8)))
+    return masks
+
+
+# ------------------------------------------------------------------------------------------------
+# Calibration: ECE reliability bins (common/evalutation/numpyfunctions.py:6-83)
+# ------------------------------------------------------------------------------------------------
+def calibration_edges(n_bins=10):
+    return np.linspace(0., 1. + 1e-8, n_bins + 1)  # numpyfunctions.py:53 (float64)
+
+
+def calibration_tables(probabilities, target, n_bins=10, threshold_range=None, mask=None):
+    """Un-compacted per-bin tables: (count int64[n], positives float64[n], confidence_sum float64[n]).
+
+    Follows binary_calibration/_binary_calibration (numpyfunctions.py:26-69) up to the three bincounts.
+    Values outside [0, 1+1e-8) make np.bincount return more than n_bins entries in the reference; the
+    tables returned here then have that longer length too (callers decide the policy).
+    """
+    if probabilities.ndim > target.ndim:
+        if probabilities.shape[-1] > 2:
+            raise ValueError('can only evaluate the calibration for binary classification')
+        elif probabilities.shape[-1] == 2:
+            probabilities = probabilities[..., 1]
+        else:
+            probabilities = np.squeeze(probabilities, axis=-1)
+    if mask is not None:
+        probabilities, target = probabilities[mask], target[mask]
+    if threshold_range is not None:
+        lo, hi = threshold_range
+        keep = np.logical_and(probabilities < hi, probabilities > lo)
+        probabilities, target = probabilities[keep], target[keep]
+    p = probabilities.flatten()
+    t = target.flatten()
+    ids = np.digitize(p, calibration_edges(n_bins)) - 1
+    conf_sum = np.bincount(ids, weights=p, minlength=n_bins)
+    positives = np.bincount(ids, weights=t, minlength=n_bins)
+    count = np.bincount(ids, minlength=n_bins)
+    return count, positives, conf_sum
+
+
+def ece_from_tables(count, positives, conf_sum, bin_weighting='proportion', n_dim=3):
+    """ECE and the compacted bin arrays from the three tables (numpyfunctions.py:6-23,65-83)."""
+    non_zero = count != 0
+    pos_frac = positives[non_zero] / count[non_zero]
+    mean_conf = conf_sum[non_zero] / count[non_zero]
+    cnt = count[non_zero]
+    if bin_weighting == 'proportion':
+        w = cnt / cnt.sum()
+    elif bin_weighting == 'log_proportion':
+        w = np.log(cnt) / np.log(cnt).sum()
+    elif bin_weighting == 'power_proportion':
+        w = cnt ** (1 / n_dim) / (cnt ** (1 / n_dim)).sum()
+    elif bin_weighting == 'mean_proportion':
+        w = 1 / non_zero.sum()
+    else:
+        raise ValueError('unknown bin weighting "{}"'.format(bin_weighting))
+    ece = (np.abs(mean_conf - pos_frac) * w).sum()
+    return ece, {'bins_count': cnt, 'bins_avg_confidence': mean_conf, 'bins_positive_fraction': pos_frac,
+                 'bins_non_zero': non_zero}
+
+
+def ece_binary(probabilities, target, n_bins=10, threshold_range=None, mask=None, bin_weighting='proportion'):
+    count, positives, conf_sum = calibration_tables(probabilities, target, n_bins, threshold_range, mask)
+    return ece_from_tables(count, positives, conf_sum, bin_weighting, target.ndim)
+
+
+# ------------------------------------------------------------------------------------------------
+# Eval-side preparation (rechun/eval/helper.py:25-47, rechun/eval/analysis.py:147-151,189-203)
+# ------------------------------------------------------------------------------------------------
+def add_background_probability(p_foreground):
+    if p_foreground.max() > 1:
+        raise ValueError('Found value larger than 1: "{}"'.format(p_foreground.max()))
+    if p_foreground.min() < 0:
+        raise ValueError('Found value smaller than 0: "{}"'.format(p_foreground.min()))
+    return np.stack([1 - p_foreground, p_foreground], axis=-1)
+
+
+def numpy_entropy(p, axis=-1):
+    # numpyfunctions.py:166-168 — the float list literal makes np.where promote to float64 before the sum
+    return -np.where(p > 0, p * np.log(p), [0.0]).sum(axis=axis)
+
+
+def normalized_entropy(prob_2class):
+    """ToEntropy (analysis.py:189-203): H(prob)/ln 2, float64."""
+    return numpy_entropy(prob_2class) / np.log(2)
+
+
+# ------------------------------------------------------------------------------------------------
+# Confusion / Dice / accuracy (numpyfunctions.py:128-151 via pymia 0.2.1 metric classes)
+# ------------------------------------------------------------------------------------------------
+def confusion(prediction, target):
+    tp = np.sum(np.logical_and(prediction == 1, target == 1))
+    tn = np.sum(np.logical_and(prediction == 0, target == 0))
+    fp = np.sum(np.logical_and(prediction == 1, target == 0))
+    fn = np.sum(np.logical_and(prediction == 0, target == 1))
+    return tp, tn, fp, fn, prediction.size
+
+
+def dice_from_counts(tp, fp, fn):
+    if tp == 0 and (tp + fp + fn) == 0:
+        return 1.
+    return 2 * tp / (2 * tp + fp + fn)
+
+
+def accuracy_from_counts(tp, tn, fp, fn):
+    s = tp + tn + fp + fn
+    return (tp + tn) / s if s != 0 else 0
+
+
+def dice(prediction, target):
+    tp, tn, fp, fn, _ = confusion(prediction, target)
+    return dice_from_counts(tp, fp, fn)
+
+
+def accuracy(prediction, target):
+    tp, tn, fp, fn, _ = confusion(prediction, target)
+    return accuracy_from_counts(tp, tn, fp, fn)
+
+
+# ------------------------------------------------------------------------------------------------
+# Uncertainty-error overlap (numpyfunctions.py:86-125, eval.py:145-226)
+# ------------------------------------------------------------------------------------------------
+def uncertainty_counts(prediction, target, thresholded_uncertainty, mask=None):
+    """tp, tn, fp, fn and their intersections with the thresholded-uncertainty map (numpyfunctions.py:86-107)."""
+    if mask is not None:
+        prediction, target, thresholded_uncertainty = prediction[mask], target[mask], thresholded_uncertainty[mask]
+    classes = (np.logical_and(target, prediction), np.logical_and(~target, ~prediction),
+               np.logical_and(~target, prediction), np.logical_and(target, ~prediction))
+    with_u = tuple(np.logical_and(c, thresholded_uncertainty).sum() for c in classes)
+    plain = tuple(c.sum() for c in classes)
+    return plain + with_u  # tp, tn, fp, fn, tpu, tnu, fpu, fnu
+
+
+def error_dice(fp, fn, tpu, tnu, fpu, fnu):
+    if (fnu + fpu) == 0 and (fn + fp + fnu + fpu + tnu + tpu) == 0:
+        return 1.
+    return (2 * (fnu + fpu)) / (fn + fp + fnu + fpu + tnu + tpu)
+
+
+def error_recall(fp, fn, fpu, fnu):
+    if (fnu + fpu) == 0 and (fn + fp) == 0:
+        return 1.
+    return (fnu + fpu) / (fn + fp)
+
+
+def error_precision(tpu, tnu, fpu, fnu):
+    if (fnu + fpu) == 0 and (fnu + fpu + tpu + tnu) == 0:
+        return 1.
+    return (fnu + fpu) / (fnu + fpu + tpu + tnu)
+
+
+def uncertainty_error_dice(prediction, target, uncertainty, threshold, prefix='', target_boarder=None):
+    """UncertaintyErrorDiceNumpy.__call__ (eval.py:156-173)."""
+    target = target.astype(bool)
+    prediction = prediction.astype(bool)
+    mask = None if target_boarder is None else ~target_boarder
+    tp, tn, fp, fn, tpu, tnu, fpu, fnu = uncertainty_counts(prediction, target, uncertainty > threshold, mask)
+    return {prefix + 'precision': error_precision(tpu, tnu, fpu, fnu), prefix + 'recall': error_recall(fp, fn, fpu, fnu),
+            prefix + 'dice': error_dice(fp, fn, tpu, tnu, fpu, fnu)}
+
+
+def uncertainty_and_correction(prediction, target, uncertainty, threshold):
+    """UncertaintyAndCorrectionEvalNumpy.__call__ (eval.py:182-226), materialising the corrected maps."""
+    target = target.astype(bool)
+    prediction = prediction.astype(bool)
+    thr_u = uncertainty > threshold
+    tp, tn, fp, fn, tpu, tnu, fpu, fnu = uncertainty_counts(prediction, target, thr_u)
+    r = {'tpu': tpu, 'tnu': tnu, 'fpu': fpu, 'fnu': fnu, 'tp': tp, 'tn': tn, 'fp': fp, 'fn': fn}
+    with np.errstate(divide='ignore', invalid='ignore'):
+        ratio = r['tpu'] / r['fpu']
+        jaccard = r['tp'] / (r['tp'] + r['fp'] + r['fn'])
+    r['dice_benefit'] = ratio < jaccard
+    r['accuracy_benefit'] = ratio < 1
+    r['dice'] = dice(prediction, target)
+    r['accuracy'] = accuracy(prediction, target)
+    corrected = prediction.copy()
+    corrected[thr_u] = 0
+    r['corrected_dice'] = dice(corrected, target)
+    r['corrected_accuracy'] = accuracy(corrected, target)
+    r['dice_benefit_correct'] = (r['corrected_dice'] > r['dice']) == r['dice_benefit']
+    r['accuracy_benefit_correct'] = (r['corrected_accuracy'] > r['accuracy']) == r['accuracy_benefit']
+    corrected = prediction.copy()
+    corrected[thr_u] = 1
+    r['corrected_add_dice'] = dice(corrected, target)
+    r['corrected_add_accuracy'] = accuracy(corrected, target)
+    return r
+
+
+def sweep(prediction, target, uncertainty, thresholds=SWEEP_THRESHOLDS):
+    """CorrectionAction (bin-eval/eval_uncertainty.py:195-202): one result dict per threshold."""
+    return [uncertainty_and_correction(prediction, target, uncertainty, th) for th in thresholds]
+
+
+def ue_table_row(r):
+    """bin-analysis/table_ece_ue_bnf_dice.py:56-59 per-subject derived columns."""
+    denom = r['fn'] + r['fp'] + r['fnu'] + r['fpu'] + r['tnu'] + r['tpu']
+    return {'benefit': r['corrected_dice'] > r['dice'],
+            'ue': (2 * (r['fnu'] + r['fpu'])) / denom if denom else float('nan')}

@@ -1,0 +1,249 @@
+// Per-pixel aggregation over MC samples / ensemble members: softmax, running mean, predictive entropy,
+// mutual information, variance, argmax — one pass over the per-sample logits (HBM-bound: 8*T+12 B/voxel).
+//
+// Reference arithmetic (citations relative to the reference root):
+//   rechun/dl/customsteps.py:31-36   probs_t = F.softmax(logits_t, 1); torch.stack
+//   rechun/dl/customsteps.py:57-71   mean(dim=0); entropy; mutual_info = H(mean) - mean_t H(p_t);
+//                                    variance = var(dim=0, unbiased).mean(dim=1)
+//   common/utils/torchhelper.py:53-54 entropy = -sum_c where(p > 0, p * log p, 0)
+//   bin-dl/brats_test_default.py:97  prediction = np.argmax(probabilities, -1)   (ties -> class 0)
+#include "common.cuh"
+
+namespace rcu {
+
+constexpr int kAggThreads = 256;
+
+__device__ __forceinline__ void softmax2(float l0, float l1, float& p0, float& p1) {
+  // same formulation as torch: exp(l - max) / sum
+  const float m = fmaxf(l0, l1);
+  const float e0 = expf(l0 - m), e1 = expf(l1 - m);
+  const float s = e0 + e1;
+  p0 = __fdiv_rn(e0, s);
+  p1 = __fdiv_rn(e1, s);
+}
+
+__device__ __forceinline__ float plogp(float p) { return p > 0.0f ? p * logf(p) : 0.0f; }
+
+struct AggAcc {
+  float s0, s1;      // sum_t p
+  float h;           // sum_t H(p_t)
+  float m0, m1;      // running mean (Welford) for the unbiased variance
+  float q0, q1;      // sum of squared deviations
+};
+
+// One thread = 2 adjacent pixels (float4 of interleaved logits, or two float2 of planar values).
+// KIND 0: interleaved logits [t][n][hw][2];  1: planar probabilities [t][n][2][hw];  2: planar logits.
+template <int KIND, bool MI, bool VAR, bool PARTIAL>
+__global__ void __launch_bounds__(kAggThreads)
+aggregate_kernel(const float* __restrict__ in, int n_samples, long long n_images, long long hw, float inv_or_scale,
+                 float* __restrict__ mean, float* __restrict__ entropy, float* __restrict__ mutual_info,
+                 float* __restrict__ variance, unsigned char* __restrict__ prediction, float* __restrict__ multi_out,
+                 float* __restrict__ sums) {
+  const long long pairs_per_image = hw >> 1;  // hw is even (checked on the host)
+  const long long total_pairs = n_images * pairs_per_image;
+  const long long sample_stride = n_images * hw * 2;
+  for (long long pair = (long long)blockIdx.x * kAggThreads + threadIdx.x; pair < total_pairs;
+       pair += (long long)gridDim.x * kAggThreads) {
+    const long long img = pair / pairs_per_image;
+    const long long px = (pair - img * pairs_per_image) * 2;
+    const float* src = in + img * hw * 2 + (KIND == 0 ? px * 2 : px);
+    AggAcc a[2] = {};
+    for (int t = 0; t < n_samples; ++t) {
+      float v00, v01, v10, v11;  // [pixel][class]
+      if (KIND == 0) {
+        const float4 v = ld_stream_f4(src + (long long)t * sample_stride);
+        v00 = v.x; v01 = v.y; v10 = v.z; v11 = v.w;
+      } else {
+        const float2 c0 = ld_stream_f2(src + (long long)t * sample_stride);
+        const float2 c1 = ld_stream_f2(src + (long long)t * sample_stride + hw);
+        v00 = c0.x; v10 = c0.y; v01 = c1.x; v11 = c1.y;
+      }
+      float p[2][2];
+      if (KIND == 1) {
+        p[0][0] = v00; p[0][1] = v01; p[1][0] = v10; p[1][1] = v11;
+      } else {
+        softmax2(v00, v01, p[0][0], p[0][1]);
+        softmax2(v10, v11, p[1][0], p[1][1]);
+      }
+      if (multi_out != nullptr) {
+        float* dst = multi_out + (long long)t * sample_stride + img * hw * 2 + px;
+        *reinterpret_cast<float2*>(dst) = make_float2(p[0][0], p[1][0]);
+        *reinterpret_cast<float2*>(dst + hw) = make_float2(p[0][1], p[1][1]);
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        a[k].s0 += p[k][0];
+        a[k].s1 += p[k][1];
+        if (MI) a[k].h += -(plogp(p[k][0]) + plogp(p[k][1]));
+        if (VAR) {
+          if (PARTIAL) {  // raw second moments, combined across ranks later
+            a[k].q0 += p[k][0] * p[k][0];
+            a[k].q1 += p[k][1] * p[k][1];
+          } else {
+            const float inv = 1.0f / (float)(t + 1);
+            const float d0 = p[k][0] - a[k].m0, d1 = p[k][1] - a[k].m1;
+            a[k].m0 += d0 * inv;
+            a[k].m1 += d1 * inv;
+            a[k].q0 += d0 * (p[k][0] - a[k].m0);
+            a[k].q1 += d1 * (p[k][1] - a[k].m1);
+          }
+        }
+      }
+    }
+    if (PARTIAL) {
+      const int planes = 2 + (MI ? 1 : 0) + (VAR ? 2 : 0);
+      float* dst = sums + img * planes * hw + px;
+      *reinterpret_cast<float2*>(dst) = make_float2(a[0].s0, a[1].s0);
+      *reinterpret_cast<float2*>(dst + hw) = make_float2(a[0].s1, a[1].s1);
+      int pl = 2;
+      if (MI) { *reinterpret_cast<float2*>(dst + pl * hw) = make_float2(a[0].h, a[1].h); ++pl; }
+      if (VAR) {
+        *reinterpret_cast<float2*>(dst + pl * hw) = make_float2(a[0].q0, a[1].q0);
+        *reinterpret_cast<float2*>(dst + (pl + 1) * hw) = make_float2(a[0].q1, a[1].q1);
+      }
+    }
+    if (!PARTIAL) {
+    float m0[2], m1[2], ent[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      // torch: sum then divide by T
+      m0[k] = __fdiv_rn(a[k].s0, inv_or_scale);
+      m1[k] = __fdiv_rn(a[k].s1, inv_or_scale);
+      ent[k] = -(plogp(m0[k]) + plogp(m1[k]));
+    }
+    float* mdst = mean + img * hw * 2 + px;
+    *reinterpret_cast<float2*>(mdst) = make_float2(m0[0], m0[1]);
+    *reinterpret_cast<float2*>(mdst + hw) = make_float2(m1[0], m1[1]);
+    const long long o = img * hw + px;
+    if (entropy) *reinterpret_cast<float2*>(entropy + o) = make_float2(ent[0], ent[1]);
+    if (MI) *reinterpret_cast<float2*>(mutual_info + o) =
+        make_float2(ent[0] - __fdiv_rn(a[0].h, inv_or_scale), ent[1] - __fdiv_rn(a[1].h, inv_or_scale));
+    if (VAR) {
+      const float dn = (float)(n_samples - 1);
+      *reinterpret_cast<float2*>(variance + o) =
+          make_float2(0.5f * (a[0].q0 / dn + a[0].q1 / dn), 0.5f * (a[1].q0 / dn + a[1].q1 / dn));
+    }
+    if (prediction) {
+      uchar2 pr;
+      pr.x = m1[0] > m0[0] ? 1 : 0;
+      pr.y = m1[1] > m0[1] ? 1 : 0;
+      *reinterpret_cast<uchar2*>(prediction + o) = pr;
+    }
+    }  // !PARTIAL
+  }
+}
+
+// sums [n][K][hw] (allreduced across ranks) -> same outputs as the one-pass kernel
+__global__ void __launch_bounds__(kAggThreads)
+aggregate_finish_kernel(const float* __restrict__ sums, float total_samples, long long n_images, long long hw, int has_mi,
+                        int has_var, float* __restrict__ mean, float* __restrict__ entropy, float* __restrict__ mutual_info,
+                        float* __restrict__ variance, unsigned char* __restrict__ prediction) {
+  const int planes = 2 + (has_mi ? 1 : 0) + (has_var ? 2 : 0);
+  const long long total = n_images * hw;
+  for (long long i = (long long)blockIdx.x * kAggThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kAggThreads) {
+    const long long img = i / hw, px = i - img * hw;
+    const float* s = sums + img * planes * hw + px;
+    const float s0 = s[0], s1 = s[hw];
+    const float m0 = __fdiv_rn(s0, total_samples), m1 = __fdiv_rn(s1, total_samples);
+    const float ent = -(plogp(m0) + plogp(m1));
+    mean[img * 2 * hw + px] = m0;
+    mean[img * 2 * hw + hw + px] = m1;
+    if (entropy) entropy[i] = ent;
+    int pl = 2;
+    if (has_mi) {
+      if (mutual_info) mutual_info[i] = ent - __fdiv_rn(s[pl * hw], total_samples);
+      ++pl;
+    }
+    if (has_var && variance) {
+      // unbiased variance from raw moments: (sum p^2 - T * mean^2) / (T - 1), averaged over the two classes
+      const float q0 = s[pl * hw], q1 = s[(pl + 1) * hw];
+      const float dn = total_samples - 1.0f;
+      variance[i] = 0.5f * ((q0 - total_samples * m0 * m0) / dn + (q1 - total_samples * m1 * m1) / dn);
+    }
+    if (prediction) prediction[i] = m1 > m0 ? 1 : 0;
+  }
+}
+
+template <int KIND, bool PARTIAL>
+static int launch_aggregate(bool mi, bool var, const float* in, int n_samples, int64_t n_images, int64_t hw, float denom,
+                            float* mean, float* entropy, float* mutual_info, float* variance, uint8_t* prediction,
+                            float* multi_out, float* sums, cudaStream_t st) {
+  const long long total_pairs = n_images * (hw / 2);
+  if (total_pairs == 0) return RCU_OK;
+  long long blocks = (total_pairs + kAggThreads - 1) / kAggThreads;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+#define RCU_AGG_LAUNCH(MI_, VAR_)                                                                                    \
+  aggregate_kernel<KIND, MI_, VAR_, PARTIAL><<<(unsigned)blocks, kAggThreads, 0, st>>>(                               \
+      in, n_samples, (long long)n_images, (long long)hw, denom, mean, entropy, mutual_info, variance, prediction,     \
+      multi_out, sums)
+  if (mi && var) RCU_AGG_LAUNCH(true, true);
+  else if (mi) RCU_AGG_LAUNCH(true, false);
+  else if (var) RCU_AGG_LAUNCH(false, true);
+  else RCU_AGG_LAUNCH(false, false);
+#undef RCU_AGG_LAUNCH
+  RCU_LAUNCH_CHECK();
+  return RCU_OK;
+}
+
+static int check_agg_common(const float* input, int input_kind, int n_samples, int64_t n_images, int64_t hw) {
+  RCU_CHECK_ARG(input != nullptr, "input is NULL");
+  RCU_CHECK_ARG(input_kind >= 0 && input_kind <= 2, "input_kind must be 0, 1 or 2");
+  RCU_CHECK_ARG(n_samples >= 1 && n_images >= 0 && hw >= 0, "bad sizes: n_samples=%d n_images=%lld hw=%lld", n_samples,
+                (long long)n_images, (long long)hw);
+  RCU_CHECK_ARG(hw % 2 == 0, "hw=%lld must be even (pixel pairs are processed together)", (long long)hw);
+  RCU_CHECK_ARG(reinterpret_cast<uintptr_t>(input) % 16 == 0, "input must be 16-byte aligned");
+  return RCU_OK;
+}
+
+}  // namespace rcu
+
+using namespace rcu;
+
+extern "C" int rcu_aggregate(const float* input, int input_kind, int n_samples, int64_t n_images, int64_t hw, float* mean,
+                             float* entropy, float* mutual_info, float* variance, uint8_t* prediction, float* multi_out,
+                             void* stream) {
+  int rc = check_agg_common(input, input_kind, n_samples, n_images, hw);
+  if (rc) return rc;
+  RCU_CHECK_ARG(mean != nullptr, "mean output is NULL");
+  RCU_CHECK_ARG(variance == nullptr || n_samples >= 2, "variance needs at least two samples");
+  const bool mi = mutual_info != nullptr, var = variance != nullptr;
+  cudaStream_t st = (cudaStream_t)stream;
+  const float denom = (float)n_samples;
+  switch (input_kind) {
+    case 0: return launch_aggregate<0, false>(mi, var, input, n_samples, n_images, hw, denom, mean, entropy, mutual_info, variance, prediction, multi_out, nullptr, st);
+    case 1: return launch_aggregate<1, false>(mi, var, input, n_samples, n_images, hw, denom, mean, entropy, mutual_info, variance, prediction, multi_out, nullptr, st);
+    default: return launch_aggregate<2, false>(mi, var, input, n_samples, n_images, hw, denom, mean, entropy, mutual_info, variance, prediction, multi_out, nullptr, st);
+  }
+}
+
+extern "C" int rcu_aggregate_partial(const float* input, int input_kind, int n_samples, int64_t n_images, int64_t hw,
+                                     int want_mi, int want_var, float* sums, void* stream) {
+  int rc = check_agg_common(input, input_kind, n_samples, n_images, hw);
+  if (rc) return rc;
+  RCU_CHECK_ARG(sums != nullptr, "sums output is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (input_kind) {
+    case 0: return launch_aggregate<0, true>(want_mi != 0, want_var != 0, input, n_samples, n_images, hw, 1.f, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, sums, st);
+    case 1: return launch_aggregate<1, true>(want_mi != 0, want_var != 0, input, n_samples, n_images, hw, 1.f, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, sums, st);
+    default: return launch_aggregate<2, true>(want_mi != 0, want_var != 0, input, n_samples, n_images, hw, 1.f, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, sums, st);
+  }
+}
+
+extern "C" int rcu_aggregate_finish(const float* sums, int total_samples, int64_t n_images, int64_t hw, int has_mi, int has_var,
+                                    float* mean, float* entropy, float* mutual_info, float* variance, uint8_t* prediction,
+                                    void* stream) {
+  RCU_CHECK_ARG(sums != nullptr && mean != nullptr, "NULL pointer argument");
+  RCU_CHECK_ARG(total_samples >= 1 && n_images >= 0 && hw >= 0, "bad sizes");
+  RCU_CHECK_ARG(!(has_var && variance) || total_samples >= 2, "variance needs at least two samples");
+  const long long total = n_images * hw;
+  if (total == 0) return RCU_OK;
+  long long blocks = (total + kAggThreads - 1) / kAggThreads;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  aggregate_finish_kernel<<<(unsigned)blocks, kAggThreads, 0, (cudaStream_t)stream>>>(
+      sums, (float)total_samples, (long long)n_images, (long long)hw, has_mi, has_var, mean, entropy, mutual_info, variance,
+      prediction);
+  RCU_LAUNCH_CHECK();
+  return RCU_OK;
+}

@@ -1,0 +1,518 @@
+// Calibration (ECE reliability bins) and uncertainty-error joint histograms — HBM-bound streaming kernels.
+//
+// Reference arithmetic restated on device (citations relative to the reference root):
+//   common/evalutation/numpyfunctions.py:51-69   _binary_calibration: np.digitize against float64
+//                                                np.linspace(0, 1+1e-8, n+1) edges + three np.bincount
+//   common/evalutation/numpyfunctions.py:86-107  uncertainty(): tp/tn/fp/fn and their intersection with (u > th)
+//   bin-eval/eval_uncertainty.py:195-202,239     the 11-threshold sweep (11 passes in the reference, one here)
+//
+// Design: one pass, 6-7 bytes per voxel (float4 + packed-byte loads, L1 no-allocate).  Every thread owns a
+// private column of shared-memory counters (no atomics, no bank conflicts: bank == lane), blocks reduce their
+// columns in a fixed order and the last block of each subject (ticket) folds the per-block partials in a fixed
+// order, so the float64 confidence sums are deterministic run to run.  Integer tables are exact.
+#include "common.cuh"
+
+namespace rcu {
+
+constexpr int kHistThreads = 256;
+constexpr int kMaxBlocksPerSubject = 1024;
+constexpr int kPartialSlots = 3 * (RCU_MAX_BINS + 1) + 4 * RCU_MAX_UE_CLASSES + 1;
+constexpr int kMaxVoxelsPerThread = 60000;  // 16-bit private counters must not wrap
+constexpr int kBreakPad = 128;              // break table padded with +inf to a power of two
+
+struct CalibParams {
+  float edges[RCU_MAX_BINS + 1];
+  int n_bins;
+  float range_lo, range_hi;
+  int has_range;
+};
+
+struct UeParams {
+  float breaks32[RCU_MAX_BREAKS];
+  double breaks64[RCU_MAX_UE_CLASSES];
+  unsigned char seg_class[RCU_MAX_BREAKS + 1];
+  int n_breaks;
+  int n_classes;
+  int search_top;   // first step of the branch-free search (power of two)
+  int check_range;  // count values outside [0, 1] (value_kind 0: p must be a probability)
+};
+
+struct HistOut {
+  unsigned long long* count;
+  unsigned long long* positives;
+  double* conf_sum;
+  unsigned long long* ue_counts;
+  unsigned long long* invalid;
+};
+
+__device__ __forceinline__ int calib_bin(float p, const float* s_edges, int n_bins, float n_bins_f) {
+  // k = floor(p * n) is right up to +-1 (fp32 rounding of the product, and the 1e-8 stretch of the edges);
+  // the comparison against the exact float32-rounded-up edges settles it.  NaN / negative / >= last edge -> n_bins.
+  if (!(p >= 0.0f) || !(p < s_edges[n_bins])) return n_bins;
+  int k = min((int)(p * n_bins_f), n_bins - 1);
+  k += (p >= s_edges[k + 1]) ? 1 : 0;
+  k -= (p < s_edges[k]) ? 1 : 0;
+  return k;
+}
+
+template <typename T, bool STRICT>
+__device__ __forceinline__ int count_breaks(T x, const T* s_breaks, int top) {
+  // number of (sorted, +inf padded) breaks b with b <= x (or b < x when STRICT); NaN compares false -> 0
+  int lo = 0;
+  for (int step = top; step >= 1; step >>= 1) {
+    const T b = s_breaks[lo + step - 1];
+    const bool take = STRICT ? (b < x) : (b <= x);
+    lo += take ? step : 0;
+  }
+  return lo;
+}
+
+// VK: 0 = float32 p (or float32 uncertainty, same search), 2 = float64 uncertainty; -1 = no U-E part.
+template <bool CALIB, int VK, bool HAS_MASK>
+__global__ void __launch_bounds__(kHistThreads)
+eval_hist_kernel(const float* __restrict__ p, const double* __restrict__ u64v, const unsigned char* __restrict__ pred,
+                 const unsigned char* __restrict__ target, const unsigned char* __restrict__ mask,
+                 long long voxels_per_subject, int blocks_per_subject, const __grid_constant__ CalibParams cp,
+                 const __grid_constant__ UeParams up, HistOut out, unsigned int* __restrict__ tickets,
+                 unsigned long long* __restrict__ partials, int vec_ok) {
+  constexpr bool UE = VK >= 0;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x;
+  const int nb1 = CALIB ? cp.n_bins + 1 : 0;
+  const int ncls = UE ? up.n_classes : 0;
+
+  // shared layout: conf (double) | cntpos (u32) | ue (u16) | edges (float) | breaks (float/double) | seg (u8)
+  double* s_conf = reinterpret_cast<double*>(smem_raw);
+  unsigned int* s_cntpos = reinterpret_cast<unsigned int*>(s_conf + nb1 * kHistThreads);
+  unsigned short* s_ue = reinterpret_cast<unsigned short*>(s_cntpos + nb1 * kHistThreads);
+  unsigned char* tail = reinterpret_cast<unsigned char*>(s_ue + 4 * ncls * kHistThreads);
+  tail = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tail) + 15) & ~uintptr_t(15));
+  double* s_breaks_d = reinterpret_cast<double*>(tail);
+  float* s_breaks_f = reinterpret_cast<float*>(s_breaks_d + (VK == 2 ? RCU_MAX_UE_CLASSES : 0));
+  float* s_edges = s_breaks_f + (VK == 0 ? kBreakPad : 0);
+  unsigned char* s_seg = reinterpret_cast<unsigned char*>(s_edges + (CALIB ? RCU_MAX_BINS + 1 : 0));
+  __shared__ int s_is_last;
+
+  for (int i = tid; i < nb1 * kHistThreads; i += kHistThreads) {
+    s_conf[i] = 0.0;
+    s_cntpos[i] = 0u;
+  }
+  for (int i = tid; i < 4 * ncls * kHistThreads; i += kHistThreads) s_ue[i] = 0;
+  if (CALIB)
+    for (int i = tid; i <= cp.n_bins; i += kHistThreads) s_edges[i] = cp.edges[i];
+  if (VK == 0)
+    for (int i = tid; i < kBreakPad; i += kHistThreads) s_breaks_f[i] = i < up.n_breaks ? up.breaks32[i] : __int_as_float(0x7f800000);
+  if (VK == 2)
+    for (int i = tid; i < RCU_MAX_UE_CLASSES; i += kHistThreads) s_breaks_d[i] = i < up.n_breaks ? up.breaks64[i] : __longlong_as_double(0x7ff0000000000000LL);
+  if (UE)
+    for (int i = tid; i <= up.n_breaks; i += kHistThreads) s_seg[i] = up.seg_class[i];
+  __syncthreads();
+
+  const int subject = blockIdx.y;
+  const long long base = (long long)subject * voxels_per_subject;
+  // contiguous chunk of this block, in units of 4 voxels
+  const long long groups = (voxels_per_subject + 3) >> 2;
+  const long long gpb = (groups + blocks_per_subject - 1) / blocks_per_subject;
+  const long long g0 = (long long)blockIdx.x * gpb;
+  const long long g1 = min(groups, g0 + gpb);
+  const float n_bins_f = (float)cp.n_bins;
+  unsigned int n_invalid = 0;
+
+  auto one = [&](float pv, double uv, unsigned int t, unsigned int d, unsigned int m) {
+    if (CALIB) {
+      bool use = HAS_MASK ? (m != 0) : true;
+      if (cp.has_range) use = use && (pv < cp.range_hi) && (pv > cp.range_lo);
+      if (use) {
+        const int k = calib_bin(pv, s_edges, cp.n_bins, n_bins_f);
+        s_cntpos[k * kHistThreads + tid] += 1u + ((t != 0) ? 65536u : 0u);
+        s_conf[k * kHistThreads + tid] += (double)pv;
+      }
+    }
+    if (UE) {
+      // U-E tables are unmasked in the fused kernel (mask belongs to the calibration part); in the
+      // U-E-only kernel HAS_MASK applies to them (UncertaintyErrorDiceNumpy(with_mask=True)).
+      const bool use = (HAS_MASK && !CALIB) ? (m != 0) : true;
+      if (use) {
+        int idx;
+        if (VK == 2) {
+          idx = count_breaks<double, true>(uv, s_breaks_d, up.search_top);
+        } else {
+          idx = count_breaks<float, false>(pv, s_breaks_f, up.search_top);
+          n_invalid += up.check_range ? (!(pv >= 0.0f && pv <= 1.0f) ? 1u : 0u) : (!(pv == pv) ? 1u : 0u);
+        }
+        const int j = s_seg[idx];
+        const int row = (t != 0) ? ((d != 0) ? 0 : 3) : ((d != 0) ? 2 : 1);  // tp, tn, fp, fn
+        s_ue[(row * ncls + j) * kHistThreads + tid] += 1;
+      }
+    }
+  };
+
+  if (vec_ok) {
+    constexpr int U = 4;
+    for (long long g = g0 + tid; g < g1; g += (long long)kHistThreads * U) {
+      float4 pv[U];
+      double2 uv[U][2];
+      unsigned int tv[U], dv[U], mv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long gg = g + (long long)u * kHistThreads;
+        const bool in = gg < g1 && (gg * 4 + 3 < voxels_per_subject);
+        pv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        tv[u] = dv[u] = 0u;
+        mv[u] = 0u;
+        if (in) {
+          const long long v = base + gg * 4;
+          if (VK != 2) pv[u] = ld_stream_f4(p + v);
+          if (VK == 2) {
+            uv[u][0] = *reinterpret_cast<const double2*>(u64v + v);
+            uv[u][1] = *reinterpret_cast<const double2*>(u64v + v + 2);
+          }
+          tv[u] = ld_stream_u32(target + v);
+          if (UE) dv[u] = ld_stream_u32(pred + v);
+          if (HAS_MASK) mv[u] = ld_stream_u32(mask + v);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long gg = g + (long long)u * kHistThreads;
+        if (gg >= g1) break;
+        if (gg * 4 + 3 < voxels_per_subject) {
+          const float pe[4] = {pv[u].x, pv[u].y, pv[u].z, pv[u].w};
+          double ue[4] = {0., 0., 0., 0.};
+          if (VK == 2) { ue[0] = uv[u][0].x; ue[1] = uv[u][0].y; ue[2] = uv[u][1].x; ue[3] = uv[u][1].y; }
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            one(pe[e], ue[e], (tv[u] >> (8 * e)) & 0xffu, (dv[u] >> (8 * e)) & 0xffu, (mv[u] >> (8 * e)) & 0xffu);
+        } else {  // ragged last group of the subject
+          for (long long v = gg * 4; v < voxels_per_subject; ++v) {
+            const long long a = base + v;
+            one(VK != 2 ? p[a] : 0.f, VK == 2 ? u64v[a] : 0., target[a], UE ? pred[a] : 0, HAS_MASK ? mask[a] : 1);
+          }
+        }
+      }
+    }
+  } else {
+    for (long long g = g0 + tid; g < g1; g += kHistThreads) {
+      const long long vend = min(voxels_per_subject, g * 4 + 4);
+      for (long long v = g * 4; v < vend; ++v) {
+        const long long a = base + v;
+        one(VK != 2 ? p[a] : 0.f, VK == 2 ? u64v[a] : 0., target[a], UE ? pred[a] : 0, HAS_MASK ? mask[a] : 1);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- block reduction of the private columns, fixed order ----
+  const int warp = tid >> 5, lane = tid & 31;
+  const int n_slots = 3 * nb1 + 4 * ncls + 1;
+  unsigned long long* my_partial = partials + ((long long)subject * blocks_per_subject + blockIdx.x) * kPartialSlots;
+  for (int s = warp; s < n_slots - 1; s += kHistThreads / 32) {
+    if (s >= 2 * nb1 && s < 3 * nb1) {
+      const double* col = s_conf + (s - 2 * nb1) * kHistThreads;
+      double acc = 0.0;
+#pragma unroll
+      for (int i = 0; i < kHistThreads / 32; ++i) acc += col[lane + 32 * i];
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+      if (lane == 0) my_partial[s] = (unsigned long long)__double_as_longlong(acc);
+    } else {
+      unsigned long long acc = 0;
+      if (s < 2 * nb1) {
+        const unsigned int* col = s_cntpos + (s < nb1 ? s : s - nb1) * kHistThreads;
+        const int sh = s < nb1 ? 0 : 16;
+#pragma unroll
+        for (int i = 0; i < kHistThreads / 32; ++i) acc += (col[lane + 32 * i] >> sh) & 0xffffu;
+      } else {
+        const unsigned short* col = s_ue + (s - 3 * nb1) * kHistThreads;
+#pragma unroll
+        for (int i = 0; i < kHistThreads / 32; ++i) acc += col[lane + 32 * i];
+      }
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+      if (lane == 0) my_partial[s] = acc;
+    }
+  }
+  // invalid-key count lives in registers: block-wide sum through a scratch word per warp (the columns are dead now)
+  __syncthreads();
+  unsigned int* s_scratch = reinterpret_cast<unsigned int*>(smem_raw);
+  {
+    unsigned int v = n_invalid;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) s_scratch[warp] = v;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long tot = 0;
+    for (int w = 0; w < kHistThreads / 32; ++w) tot += s_scratch[w];
+    my_partial[n_slots - 1] = tot;
+  }
+
+  // ---- last block of the subject folds the partials in block order ----
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int t = atomicAdd(&tickets[subject], 1u);
+    s_is_last = (t == (unsigned int)blocks_per_subject - 1u);
+  }
+  __syncthreads();
+  if (!s_is_last) return;
+  __threadfence();
+  const unsigned long long* sp = partials + (long long)subject * blocks_per_subject * kPartialSlots;
+  for (int s = warp; s < n_slots; s += kHistThreads / 32) {
+    const bool is_conf = (s >= 2 * nb1 && s < 3 * nb1);
+    unsigned long long iacc = 0;
+    double dacc = 0.0;
+    for (int b = lane; b < blocks_per_subject; b += 32) {
+      const unsigned long long v = __ldcg(sp + (long long)b * kPartialSlots + s);
+      if (is_conf) dacc += __longlong_as_double((long long)v);
+      else iacc += v;
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      iacc += __shfl_down_sync(0xffffffffu, iacc, o);
+      dacc += __shfl_down_sync(0xffffffffu, dacc, o);
+    }
+    if (lane == 0) {
+      if (s < nb1) out.count[(long long)subject * nb1 + s] = iacc;
+      else if (s < 2 * nb1) out.positives[(long long)subject * nb1 + (s - nb1)] = iacc;
+      else if (s < 3 * nb1) out.conf_sum[(long long)subject * nb1 + (s - 2 * nb1)] = dacc;
+      else if (s < n_slots - 1) out.ue_counts[(long long)subject * 4 * ncls + (s - 3 * nb1)] = iacc;
+      else if (out.invalid) out.invalid[subject] = iacc;
+    }
+  }
+  if (tid == 0) tickets[subject] = 0u;  // workspace is reusable by the next stream-ordered call
+}
+
+
+// Confusion matrix with pymia 0.2.1 semantics (ConfusionMatrix: prediction == 1 / == 0 against label == 1 / == 0),
+// reached from np_fn.dice / confusion_matrx / accuracy (common/evalutation/numpyfunctions.py:128-151).  2 B/voxel.
+__global__ void __launch_bounds__(256)
+confusion_kernel(const unsigned char* __restrict__ pred, const unsigned char* __restrict__ target, long long vps,
+                 unsigned long long* __restrict__ out /* [S][4] tp tn fp fn */, int vec_ok) {
+  const int subject = blockIdx.y;
+  const long long base = (long long)subject * vps;
+  unsigned int c[4] = {0u, 0u, 0u, 0u};
+  auto one = [&](unsigned int d, unsigned int t) {
+    c[0] += (d == 1u && t == 1u);
+    c[1] += (d == 0u && t == 0u);
+    c[2] += (d == 1u && t == 0u);
+    c[3] += (d == 0u && t == 1u);
+  };
+  const long long groups = (vps + 15) >> 4;
+  for (long long g = (long long)blockIdx.x * 256 + threadIdx.x; g < groups; g += (long long)gridDim.x * 256) {
+    const long long v = g * 16;
+    if (vec_ok && v + 15 < vps) {
+      const uint4 dv = ld_stream_u4(pred + base + v), tv = ld_stream_u4(target + base + v);
+      const unsigned int dw[4] = {dv.x, dv.y, dv.z, dv.w}, tw[4] = {tv.x, tv.y, tv.z, tv.w};
+#pragma unroll
+      for (int w = 0; w < 4; ++w)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) one((dw[w] >> (8 * e)) & 0xffu, (tw[w] >> (8 * e)) & 0xffu);
+    } else {
+      for (long long a = v; a < min(vps, v + 16); ++a) one(pred[base + a], target[base + a]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    unsigned int v = c[k];
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(out + subject * 4 + k, (unsigned long long)v);
+  }
+}
+
+static size_t tickets_bytes(int n_subjects) { return ((size_t)n_subjects * sizeof(unsigned int) + 255) & ~size_t(255); }
+static long long partial_blocks_cap(int n_subjects) { return n_subjects > 2048 ? n_subjects : 2048; }
+
+static size_t hist_smem_bytes(bool calib, int vk, int n_bins, int n_classes) {
+  const int nb1 = calib ? n_bins + 1 : 0;
+  const int ncls = vk >= 0 ? n_classes : 0;
+  size_t b = (size_t)nb1 * kHistThreads * (sizeof(double) + sizeof(unsigned int)) + (size_t)4 * ncls * kHistThreads * sizeof(unsigned short);
+  b = (b + 15) & ~size_t(15);
+  b += (vk == 2 ? RCU_MAX_UE_CLASSES * sizeof(double) : 0) + (vk == 0 ? kBreakPad * sizeof(float) : 0) +
+       (calib ? (RCU_MAX_BINS + 1) * sizeof(float) : 0) + (RCU_MAX_BREAKS + 1) + 64;
+  return b < 64 ? 64 : b;
+}
+
+template <bool CALIB, int VK, bool HAS_MASK>
+static int launch_hist(const float* p, const double* u64v, const uint8_t* pred, const uint8_t* target, const uint8_t* mask,
+                       int64_t vps, int n_subjects, const CalibParams& cp, const UeParams& up, HistOut out, void* workspace,
+                       size_t workspace_bytes, cudaStream_t stream) {
+  RCU_CHECK_ARG(workspace_bytes >= rcu_metrics_workspace_bytes(n_subjects), "metrics workspace too small: %zu < %zu",
+                workspace_bytes, rcu_metrics_workspace_bytes(n_subjects));
+  const int sms = sm_count();
+  long long bps = ((long long)sms * 6 + n_subjects - 1) / n_subjects;  // ~2 waves at 3 resident blocks / SM
+  const long long groups = (vps + 3) / 4;
+  const long long min_groups_per_block = 256;  // do not shred small subjects into blocks with < 1 group / thread
+  if (bps * min_groups_per_block > groups) bps = groups / min_groups_per_block;
+  if (bps < 1) bps = 1;
+  if (bps > kMaxBlocksPerSubject) bps = kMaxBlocksPerSubject;
+  if (bps * n_subjects > partial_blocks_cap(n_subjects)) bps = partial_blocks_cap(n_subjects) / n_subjects;
+  if (bps < 1) bps = 1;
+  const long long per_thread = ((groups + bps - 1) / bps + kHistThreads - 1) / kHistThreads * 4;
+  RCU_CHECK_ARG(per_thread <= kMaxVoxelsPerThread, "subject of %lld voxels is too large for one launch (split it)", (long long)vps);
+  RCU_CHECK_ARG(n_subjects <= 65535, "n_subjects %d exceeds grid.y limit", n_subjects);
+
+  const bool aligned = ((VK == 2 ? (reinterpret_cast<uintptr_t>(u64v) % 16 == 0) : (reinterpret_cast<uintptr_t>(p) % 16 == 0)) &&
+                        reinterpret_cast<uintptr_t>(target) % 4 == 0 && (pred == nullptr || reinterpret_cast<uintptr_t>(pred) % 4 == 0) &&
+                        (mask == nullptr || reinterpret_cast<uintptr_t>(mask) % 4 == 0));
+  const int vec_ok = aligned && (n_subjects == 1 || vps % 4 == 0);
+
+  auto kern = eval_hist_kernel<CALIB, VK, HAS_MASK>;
+  const size_t smem = hist_smem_bytes(CALIB, VK, cp.n_bins, up.n_classes);
+  RCU_CHECK_ARG(smem <= 227 * 1024, "bin/class configuration needs %zu bytes of shared memory", smem);
+  static size_t configured[64] = {0};
+  int dev = 0;
+  RCU_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || smem > configured[dev]) {
+    RCU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (dev >= 0 && dev < 64) configured[dev] = smem;
+  }
+  unsigned int* tickets = reinterpret_cast<unsigned int*>(workspace);
+  unsigned long long* partials = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(workspace) + tickets_bytes(n_subjects));
+  dim3 grid((unsigned)bps, (unsigned)n_subjects);
+  kern<<<grid, kHistThreads, smem, stream>>>(p, u64v, pred, target, mask, (long long)vps, (int)bps, cp, up, out, tickets, partials, vec_ok);
+  RCU_LAUNCH_CHECK();
+  return RCU_OK;
+}
+
+static int fill_calib(CalibParams& cp, const float* edges, int n_bins, float lo, float hi) {
+  RCU_CHECK_ARG(n_bins >= 1 && n_bins <= RCU_MAX_BINS, "n_bins must be in [1, %d], got %d", RCU_MAX_BINS, n_bins);
+  RCU_CHECK_ARG(edges != nullptr, "edges_f32 is NULL");
+  for (int i = 0; i <= n_bins; ++i) {
+    cp.edges[i] = edges[i];
+    RCU_CHECK_ARG(i == 0 || edges[i] > edges[i - 1], "edges must be strictly increasing");
+  }
+  cp.n_bins = n_bins;
+  cp.has_range = !(lo != lo) && !(hi != hi);
+  cp.range_lo = lo;
+  cp.range_hi = hi;
+  return RCU_OK;
+}
+
+static int fill_ue(UeParams& up, int value_kind, const float* b32, const double* b64, int n_breaks, const uint8_t* seg, int n_classes) {
+  RCU_CHECK_ARG(n_classes >= 1 && n_classes <= RCU_MAX_UE_CLASSES, "n_classes must be in [1, %d], got %d", RCU_MAX_UE_CLASSES, n_classes);
+  RCU_CHECK_ARG(seg != nullptr, "seg_class is NULL");
+  if (value_kind == 2) {
+    RCU_CHECK_ARG(n_breaks >= 0 && n_breaks < RCU_MAX_UE_CLASSES, "float64 mode takes at most %d thresholds", RCU_MAX_UE_CLASSES - 1);
+    RCU_CHECK_ARG(b64 != nullptr || n_breaks == 0, "breaks_f64 is NULL");
+    for (int i = 0; i < n_breaks; ++i) {
+      up.breaks64[i] = b64[i];
+      RCU_CHECK_ARG(i == 0 || b64[i] >= b64[i - 1], "thresholds must be sorted ascending");
+    }
+  } else {
+    RCU_CHECK_ARG(n_breaks >= 0 && n_breaks <= RCU_MAX_BREAKS, "at most %d break points", RCU_MAX_BREAKS);
+    RCU_CHECK_ARG(b32 != nullptr || n_breaks == 0, "breaks_f32 is NULL");
+    for (int i = 0; i < n_breaks; ++i) {
+      up.breaks32[i] = b32[i];
+      RCU_CHECK_ARG(i == 0 || b32[i] >= b32[i - 1], "break points must be sorted ascending");
+    }
+  }
+  for (int i = 0; i <= n_breaks; ++i) {
+    RCU_CHECK_ARG(seg[i] < n_classes, "seg_class[%d]=%d is not below n_classes=%d", i, (int)seg[i], n_classes);
+    up.seg_class[i] = seg[i];
+  }
+  up.n_breaks = n_breaks;
+  up.n_classes = n_classes;
+  // branch-free search: steps top, top/2, ..., 1 reach counts up to 2*top-1 and read indices <= 2*top-2,
+  // which stay inside the +inf padded tables (128 float / 32 double entries).
+  int top = 1;
+  while (2 * top - 1 < n_breaks) top *= 2;
+  up.search_top = top;
+  up.check_range = value_kind == 0 ? 1 : 0;
+  return RCU_OK;
+}
+
+}  // namespace rcu
+
+using namespace rcu;
+
+extern "C" size_t rcu_metrics_workspace_bytes(int n_subjects) {
+  if (n_subjects < 1) n_subjects = 1;
+  return tickets_bytes(n_subjects) + (size_t)partial_blocks_cap(n_subjects) * kPartialSlots * sizeof(unsigned long long);
+}
+
+extern "C" int rcu_metrics_workspace_init(void* workspace, size_t workspace_bytes, void* stream) {
+  RCU_CHECK_ARG(workspace != nullptr, "workspace is NULL");
+  RCU_CHECK_ARG(workspace_bytes >= rcu_metrics_workspace_bytes(1), "workspace too small");
+  RCU_CUDA(cudaMemsetAsync(workspace, 0, workspace_bytes, (cudaStream_t)stream));
+  return RCU_OK;
+}
+
+extern "C" int rcu_calib_hist(const float* p, const uint8_t* target, const uint8_t* mask, int64_t vps, int n_subjects,
+                              const float* edges_f32, int n_bins, float range_lo, float range_hi, uint64_t* count,
+                              uint64_t* positives, double* conf_sum, void* workspace, size_t workspace_bytes, void* stream) {
+  RCU_CHECK_ARG(p && target && count && positives && conf_sum && workspace, "NULL pointer argument");
+  RCU_CHECK_ARG(vps >= 0 && n_subjects >= 1, "bad sizes: voxels_per_subject=%lld n_subjects=%d", (long long)vps, n_subjects);
+  CalibParams cp;
+  UeParams up = {};
+  int rc = fill_calib(cp, edges_f32, n_bins, range_lo, range_hi);
+  if (rc) return rc;
+  HistOut out = {reinterpret_cast<unsigned long long*>(count), reinterpret_cast<unsigned long long*>(positives), conf_sum, nullptr, nullptr};
+  if (mask) return launch_hist<true, -1, true>(p, nullptr, nullptr, target, mask, vps, n_subjects, cp, up, out, workspace, workspace_bytes, (cudaStream_t)stream);
+  return launch_hist<true, -1, false>(p, nullptr, nullptr, target, nullptr, vps, n_subjects, cp, up, out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int rcu_ue_hist(const void* values, int value_kind, const uint8_t* prediction, const uint8_t* target,
+                           const uint8_t* mask, int64_t vps, int n_subjects, const float* breaks_f32,
+                           const double* breaks_f64, int n_breaks, const uint8_t* seg_class, int n_classes,
+                           uint64_t* ue_counts, uint64_t* invalid, void* workspace, size_t workspace_bytes, void* stream) {
+  RCU_CHECK_ARG(values && prediction && target && ue_counts && workspace, "NULL pointer argument");
+  RCU_CHECK_ARG(vps >= 0 && n_subjects >= 1, "bad sizes: voxels_per_subject=%lld n_subjects=%d", (long long)vps, n_subjects);
+  RCU_CHECK_ARG(value_kind >= 0 && value_kind <= 2, "value_kind must be 0, 1 or 2");
+  CalibParams cp = {};
+  UeParams up;
+  int rc = fill_ue(up, value_kind, breaks_f32, breaks_f64, n_breaks, seg_class, n_classes);
+  if (rc) return rc;
+  HistOut out = {nullptr, nullptr, nullptr, reinterpret_cast<unsigned long long*>(ue_counts), reinterpret_cast<unsigned long long*>(invalid)};
+  cudaStream_t st = (cudaStream_t)stream;
+  if (value_kind == 2) {
+    const double* u = reinterpret_cast<const double*>(values);
+    if (mask) return launch_hist<false, 2, true>(nullptr, u, prediction, target, mask, vps, n_subjects, cp, up, out, workspace, workspace_bytes, st);
+    return launch_hist<false, 2, false>(nullptr, u, prediction, target, nullptr, vps, n_subjects, cp, up, out, workspace, workspace_bytes, st);
+  }
+  const float* pf = reinterpret_cast<const float*>(values);
+  if (mask) return launch_hist<false, 0, true>(pf, nullptr, prediction, target, mask, vps, n_subjects, cp, up, out, workspace, workspace_bytes, st);
+  return launch_hist<false, 0, false>(pf, nullptr, prediction, target, nullptr, vps, n_subjects, cp, up, out, workspace, workspace_bytes, st);
+}
+
+extern "C" int rcu_eval_fused(const float* p, const uint8_t* prediction, const uint8_t* target, const uint8_t* mask,
+                              int64_t vps, int n_subjects, const float* edges_f32, int n_bins, const float* breaks_f32,
+                              int n_breaks, const uint8_t* seg_class, int n_classes, uint64_t* count, uint64_t* positives,
+                              double* conf_sum, uint64_t* ue_counts, uint64_t* invalid, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+  RCU_CHECK_ARG(p && prediction && target && count && positives && conf_sum && ue_counts && workspace, "NULL pointer argument");
+  RCU_CHECK_ARG(vps >= 0 && n_subjects >= 1, "bad sizes: voxels_per_subject=%lld n_subjects=%d", (long long)vps, n_subjects);
+  CalibParams cp;
+  UeParams up;
+  int rc = fill_calib(cp, edges_f32, n_bins, nanf(""), nanf(""));
+  if (rc) return rc;
+  rc = fill_ue(up, 0, breaks_f32, nullptr, n_breaks, seg_class, n_classes);
+  if (rc) return rc;
+  HistOut out = {reinterpret_cast<unsigned long long*>(count), reinterpret_cast<unsigned long long*>(positives), conf_sum,
+                 reinterpret_cast<unsigned long long*>(ue_counts), reinterpret_cast<unsigned long long*>(invalid)};
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mask) return launch_hist<true, 0, true>(p, nullptr, prediction, target, mask, vps, n_subjects, cp, up, out, workspace, workspace_bytes, st);
+  return launch_hist<true, 0, false>(p, nullptr, prediction, target, nullptr, vps, n_subjects, cp, up, out, workspace, workspace_bytes, st);
+}
+
+extern "C" int rcu_confusion(const uint8_t* prediction, const uint8_t* target, int64_t vps, int n_subjects, uint64_t* counts,
+                             void* stream) {
+  RCU_CHECK_ARG(prediction && target && counts, "NULL pointer argument");
+  RCU_CHECK_ARG(vps >= 0 && n_subjects >= 1 && n_subjects <= 65535, "bad sizes: voxels_per_subject=%lld n_subjects=%d", (long long)vps, n_subjects);
+  cudaStream_t st = (cudaStream_t)stream;
+  RCU_CUDA(cudaMemsetAsync(counts, 0, sizeof(uint64_t) * 4 * n_subjects, st));
+  if (vps == 0) return RCU_OK;
+  // a thread's 32-bit partial counters see at most 16 * ceil(groups / (grid*256)) voxels
+  const long long groups = (vps + 15) / 16;
+  long long bx = ((long long)sm_count() * 8 + n_subjects - 1) / n_subjects;
+  if (bx > (groups + 255) / 256) bx = (groups + 255) / 256;
+  if (bx < 1) bx = 1;
+  const int vec_ok = reinterpret_cast<uintptr_t>(prediction) % 16 == 0 && reinterpret_cast<uintptr_t>(target) % 16 == 0 &&
+                     (n_subjects == 1 || vps % 16 == 0);
+  dim3 grid((unsigned)bx, (unsigned)n_subjects);
+  confusion_kernel<<<grid, 256, 0, st>>>(prediction, target, (long long)vps, reinterpret_cast<unsigned long long*>(counts), vec_ok);
+  RCU_LAUNCH_CHECK();
+  return RCU_OK;
+}

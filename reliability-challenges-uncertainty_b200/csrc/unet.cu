@@ -1,0 +1,620 @@
+// U-Net forward engine behind rcu_unet_* (include/rcu_b200.h).
+//
+// Restates UNet.forward (common/model/unet.py:166-186) for residual=False, sigma_out=False, bn=True,
+// transpose=False (the only configuration the reference ships, unet.py:157) as a fixed schedule of kernels over
+// bf16 NHWC activations with the MC samples folded into the batch ([sample][slice] image order inside a chunk).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "conv_tc.cuh"
+#include "philox.cuh"
+#include "unet_kernels.cuh"
+
+namespace rcu {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+enum OpKind { OP_FIRST = 0, OP_CONV = 1, OP_POOL = 2 };
+
+struct ConvLayer {
+  int c0 = 0, c1 = 0, c_out = 0;
+  int n_taps = 9, n_phases = 1, out_mul = 1, relu = 1;
+  signed char dy[kMaxPhases][kMaxTaps];
+  signed char dx[kMaxPhases][kMaxTaps];
+  __nv_bfloat16* d_weights = nullptr;  // [n_phases * n_taps][c_out][c0 + c1]
+  int coef_off = 0;
+  int block_n = 0, kc = 0;
+  bool head = false;
+  // plan-time
+  int in_h = 0, in_w = 0;
+  const __nv_bfloat16* src0 = nullptr;
+  const __nv_bfloat16* src1 = nullptr;
+  __nv_bfloat16* dst = nullptr;
+  CUtensorMap map_a0, map_a1, map_w;
+};
+
+struct Op {
+  OpKind kind;
+  int conv = -1;                         // index into convs for OP_CONV
+  const __nv_bfloat16* in = nullptr;     // OP_POOL
+  __nv_bfloat16* out = nullptr;          // output buffer (debug view)
+  int h = 0, w = 0, c = 0;               // output dims (for POOL: input dims in in_h/in_w)
+  int in_h = 0, in_w = 0;
+};
+
+}  // namespace rcu
+
+using namespace rcu;
+
+struct rcu_unet {
+  int device = 0;
+  int in_channels = 0, depth = 0, start_filters = 0;
+  float p_drop = 0.f;
+  int n_sites = 0, total_dropout_channels = 0;
+  std::vector<int> site_channels;
+  // device constants
+  float* d_first_w = nullptr;            // [c_in*9][sf]
+  int first_coef_off = 0;
+  float* d_head = nullptr;               // [2][sf] + [2]
+  std::vector<ConvLayer> convs;          // execution order
+  CoefColumns cols{};
+  std::vector<void*> owned;              // device allocations freed in destroy
+  int n_cols = 0;
+  // plan
+  int H = 0, W = 0, max_images = 0;
+  void* arena = nullptr;
+  size_t arena_bytes = 0;
+  float2* d_coef = nullptr;
+  __nv_bfloat16* first_out = nullptr;
+  __nv_bfloat16* head_feat = nullptr;    // features of conv_cls.0 for the cross-check path
+  std::vector<Op> ops;
+  int conv_impl = 0;
+  long long last_launches = 0;
+  int last_n_img = 0;
+};
+
+namespace rcu {
+
+template <typename T>
+static int dev_upload(rcu_unet* net, const std::vector<T>& host, T** out) {
+  void* d = nullptr;
+  RCU_CUDA(cudaMalloc(&d, host.size() * sizeof(T) + 16));
+  net->owned.push_back(d);
+  RCU_CUDA(cudaMemcpy(d, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *out = reinterpret_cast<T*>(d);
+  return RCU_OK;
+}
+
+static inline uint16_t f32_to_bf16_rn(float f) {
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40u);  // NaN
+  const uint32_t lsb = (u >> 16) & 1u;
+  u += 0x7fffu + lsb;
+  return (uint16_t)(u >> 16);
+}
+
+static void fold_unit(const rcu_conv_unit& u, float eps, std::vector<float>& fa, std::vector<float>& fba, std::vector<float>& fd) {
+  for (int c = 0; c < u.c_out; ++c) {
+    if (u.bn_weight) {
+      const float a = u.bn_weight[c] / std::sqrt(u.bn_var[c] + eps);
+      fa.push_back(a);
+      fba.push_back(u.bias[c] * a);
+      fd.push_back(u.bn_bias[c] - a * u.bn_mean[c]);
+    } else {
+      fa.push_back(1.0f);
+      fba.push_back(u.bias[c]);
+      fd.push_back(0.0f);
+    }
+  }
+}
+
+static int pick_tiles(int c_src_min, int c_out, int* block_n, int* kc) {
+  *kc = (c_src_min % 64 == 0) ? 64 : 32;
+  *block_n = c_out >= 256 ? 256 : c_out;
+  if (c_src_min % 32 != 0 || (*block_n != 32 && *block_n != 64 && *block_n != 128 && *block_n != 256) || c_out % *block_n != 0) {
+    set_error("channel configuration (c_in multiple of %d, c_out=%d) is outside the tcgen05 tile set", c_src_min, c_out);
+    return RCU_ENOTSUP;
+  }
+  return RCU_OK;
+}
+
+// weights [c_out][c_in][3][3] fp32 -> bf16 [tap][c_out][c_in]
+static std::vector<uint16_t> pack_conv3x3(const rcu_conv_unit& u) {
+  std::vector<uint16_t> w((size_t)9 * u.c_out * u.c_in);
+  for (int tap = 0; tap < 9; ++tap)
+    for (int co = 0; co < u.c_out; ++co)
+      for (int ci = 0; ci < u.c_in; ++ci)
+        w[((size_t)tap * u.c_out + co) * u.c_in + ci] = f32_to_bf16_rn(u.weight[((size_t)co * u.c_in + ci) * 9 + tap]);
+  return w;
+}
+
+// nearest-x2 followed by conv3x3(pad 1) == four 2x2-tap convolutions on the low-res input, one per output parity
+// (a, b): rows {2y+a-1, 2y+a, 2y+a+1} of the upsampled image collapse onto low-res rows
+//   a = 0: {y-1 | y, y}    -> taps i=0: dy=-1, ky {0};   i=1: dy=0,  ky {1,2}
+//   a = 1: {y, y | y+1}    -> taps i=0: dy=0,  ky {0,1}; i=1: dy=+1, ky {2}
+// (same along x).  Zero padding of the upsampled image coincides with zero OOB fill of the low-res image.
+static std::vector<uint16_t> pack_upconv_phases(const rcu_conv_unit& u, ConvLayer& L) {
+  std::vector<uint16_t> w((size_t)16 * u.c_out * u.c_in);
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b) {
+      const int ph = a * 2 + b;
+      for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j) {
+          const int tap = i * 2 + j;
+          L.dy[ph][tap] = (signed char)(a == 0 ? i - 1 : i);
+          L.dx[ph][tap] = (signed char)(b == 0 ? j - 1 : j);
+          int ky0, ky1, kx0, kx1;
+          if (a == 0) { ky0 = i == 0 ? 0 : 1; ky1 = i == 0 ? 0 : 2; } else { ky0 = i == 0 ? 0 : 2; ky1 = i == 0 ? 1 : 2; }
+          if (b == 0) { kx0 = j == 0 ? 0 : 1; kx1 = j == 0 ? 0 : 2; } else { kx0 = j == 0 ? 0 : 2; kx1 = j == 0 ? 1 : 2; }
+          for (int co = 0; co < u.c_out; ++co)
+            for (int ci = 0; ci < u.c_in; ++ci) {
+              float s = 0.0f;
+              for (int ky = ky0; ky <= ky1; ++ky)
+                for (int kx = kx0; kx <= kx1; ++kx) s += u.weight[((size_t)co * u.c_in + ci) * 9 + ky * 3 + kx];
+              w[((size_t)(ph * 4 + tap) * u.c_out + co) * u.c_in + ci] = f32_to_bf16_rn(s);
+            }
+        }
+    }
+  return w;
+}
+
+static int make_act_map(CUtensorMap* map, const void* base, int c, int w, int h, int n, int kc) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available (driver too old?)"); return RCU_ECUDA; }
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
+  cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)kTileW, (cuuint32_t)kTileH, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUtensorMapSwizzle sw = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activation c=%d w=%d h=%d n=%d kc=%d) failed: %d", c, w, h, n, kc, (int)r); return RCU_ECUDA; }
+  return RCU_OK;
+}
+
+static int make_weight_map(CUtensorMap* map, const void* base, int c_in, int c_out, int taps, int kc, int block_n) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available (driver too old?)"); return RCU_ECUDA; }
+  cuuint64_t dims[3] = {(cuuint64_t)c_in, (cuuint64_t)c_out, (cuuint64_t)taps};
+  cuuint64_t strides[2] = {(cuuint64_t)c_in * 2, (cuuint64_t)c_out * c_in * 2};
+  cuuint32_t box[3] = {(cuuint32_t)kc, (cuuint32_t)block_n, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const CUtensorMapSwizzle sw = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights c_in=%d c_out=%d taps=%d) failed: %d", c_in, c_out, taps, (int)r); return RCU_ECUDA; }
+  return RCU_OK;
+}
+
+template <int BLOCK_N, int KC>
+static int launch_conv_tc(const ConvLayer& L, const ConvParams& prm, cudaStream_t st) {
+  using S = ConvSmem<BLOCK_N, KC>;
+  auto kern = conv_tc_kernel<BLOCK_N, KC>;
+  static int ctas_per_sm[64] = {0};
+  int dev = 0;
+  RCU_CUDA(cudaGetDevice(&dev));
+  dev = dev < 0 || dev >= 64 ? 0 : dev;
+  if (ctas_per_sm[dev] == 0) {
+    RCU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    int occ = 0;
+    RCU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kConvThreads, S::kTotal));
+    // TMEM: 512 columns per SM shared by the resident CTAs
+    const int tmem_limit = 512 / S::kTmemCols;
+    if (occ > tmem_limit) occ = tmem_limit;
+    if (occ > 2) occ = 2;
+    if (occ < 1) { set_error("conv_tc_kernel<%d,%d> does not fit on an SM", BLOCK_N, KC); return RCU_ECUDA; }
+    ctas_per_sm[dev] = occ;
+  }
+  const long long total_tiles = (long long)prm.n_img * prm.n_phases * prm.tiles_y * prm.tiles_x * prm.n_tiles_n;
+  long long grid = (long long)sm_count() * ctas_per_sm[dev];
+  if (grid > total_tiles) grid = total_tiles;
+  if (grid < 1) return RCU_OK;
+  kern<<<(unsigned)grid, kConvThreads, S::kTotal, st>>>(L.map_a0, L.map_a1, L.map_w, prm);
+  RCU_LAUNCH_CHECK();
+  return RCU_OK;
+}
+
+static int dispatch_conv_tc(const ConvLayer& L, const ConvParams& prm, cudaStream_t st) {
+  if (L.kc == 32) {
+    if (L.block_n == 32) return launch_conv_tc<32, 32>(L, prm, st);
+    if (L.block_n == 64) return launch_conv_tc<64, 32>(L, prm, st);
+  } else {
+    if (L.block_n == 32) return launch_conv_tc<32, 64>(L, prm, st);
+    if (L.block_n == 64) return launch_conv_tc<64, 64>(L, prm, st);
+    if (L.block_n == 128) return launch_conv_tc<128, 64>(L, prm, st);
+    if (L.block_n == 256) return launch_conv_tc<256, 64>(L, prm, st);
+  }
+  set_error("no tcgen05 conv instantiation for BLOCK_N=%d KC=%d", L.block_n, L.kc);
+  return RCU_ENOTSUP;
+}
+
+}  // namespace rcu
+
+extern "C" int rcu_unet_create(const rcu_unet_desc* d, int device, rcu_unet** out) {
+  RCU_CHECK_ARG(d != nullptr && out != nullptr, "NULL argument");
+  *out = nullptr;
+  int rc = rcu_device_check(device);
+  if (rc) return rc;
+  if (d->nb_classes != 2) { set_error("nb_classes=%d: the hot path is binary (2 classes)", d->nb_classes); return RCU_ENOTSUP; }
+  RCU_CHECK_ARG(d->depth >= 1 && d->depth <= 6, "depth %d out of range", d->depth);
+  RCU_CHECK_ARG(d->n_units == 4 * d->depth + 3, "expected %d conv units for depth %d, got %d", 4 * d->depth + 3, d->depth, d->n_units);
+  RCU_CHECK_ARG(d->n_upconvs == d->depth, "expected %d upconvs, got %d", d->depth, d->n_upconvs);
+  RCU_CHECK_ARG(d->in_channels >= 1 && d->in_channels <= 8, "in_channels %d out of range [1, 8]", d->in_channels);
+  if (d->start_filters != 32 && d->start_filters != 64) { set_error("start_filters=%d: supported 32 or 64", d->start_filters); return RCU_ENOTSUP; }
+  RCU_CHECK_ARG(d->p_drop >= 0.f && d->p_drop < 1.f, "dropout p out of range");
+  RCU_CUDA(cudaSetDevice(device));
+
+  rcu_unet* net = new rcu_unet();
+  net->device = device;
+  net->in_channels = d->in_channels;
+  net->depth = d->depth;
+  net->start_filters = d->start_filters;
+  net->p_drop = d->p_drop;
+  const int sf = d->start_filters;
+
+  // ---- column tables (units first, then upconvs) ----
+  std::vector<float> fa, fba, fd;
+  std::vector<int> site, chin, scol;
+  std::vector<int> unit_off(d->n_units), up_off(d->n_upconvs);
+  int n_sites = 0, drop_cols = 0;
+  for (int u = 0; u < d->n_units; ++u) {
+    const rcu_conv_unit& cu = d->units[u];
+    if (!(cu.weight && cu.bias && cu.bn_weight && cu.bn_bias && cu.bn_mean && cu.bn_var)) {
+      set_error("unit %d: NULL weight/bn pointer (bn=False nets are outside the hot path)", u);
+      rcu_unet_destroy(net);
+      return RCU_EINVAL;
+    }
+    unit_off[u] = (int)fa.size();
+    fold_unit(cu, d->bn_eps, fa, fba, fd);
+    for (int c = 0; c < cu.c_out; ++c) {
+      site.push_back(cu.has_dropout ? n_sites : -1);
+      chin.push_back(c);
+      scol.push_back(cu.has_dropout ? drop_cols + c : 0);
+    }
+    if (cu.has_dropout) {
+      net->site_channels.push_back(cu.c_out);
+      ++n_sites;
+      drop_cols += cu.c_out;
+    }
+  }
+  for (int u = 0; u < d->n_upconvs; ++u) {
+    up_off[u] = (int)fa.size();
+    fold_unit(d->upconvs[u], d->bn_eps, fa, fba, fd);
+    for (int c = 0; c < d->upconvs[u].c_out; ++c) { site.push_back(-1); chin.push_back(c); scol.push_back(0); }
+  }
+  net->n_sites = n_sites;
+  net->total_dropout_channels = drop_cols;
+  net->n_cols = (int)fa.size();
+
+#define RCU_TRY(expr) do { int rc__ = (expr); if (rc__) { rcu_unet_destroy(net); return rc__; } } while (0)
+  float *dfa, *dfba, *dfd; int *dsite, *dchin, *dscol;
+  RCU_TRY(dev_upload(net, fa, &dfa)); RCU_TRY(dev_upload(net, fba, &dfba)); RCU_TRY(dev_upload(net, fd, &dfd));
+  RCU_TRY(dev_upload(net, site, &dsite)); RCU_TRY(dev_upload(net, chin, &dchin)); RCU_TRY(dev_upload(net, scol, &dscol));
+  net->cols = CoefColumns{dfa, dfba, dfd, dsite, dchin, dscol, net->n_cols};
+
+  // ---- first conv: fp32 [c_in*9][sf] ----
+  {
+    const rcu_conv_unit& u0 = d->units[0];
+    if (u0.c_in != d->in_channels || u0.c_out != sf) { set_error("unit 0 must map in_channels -> start_filters"); rcu_unet_destroy(net); return RCU_EINVAL; }
+    std::vector<float> w((size_t)u0.c_in * 9 * sf);
+    for (int co = 0; co < sf; ++co)
+      for (int ci = 0; ci < u0.c_in; ++ci)
+        for (int k = 0; k < 9; ++k) w[((size_t)ci * 9 + k) * sf + co] = u0.weight[((size_t)co * u0.c_in + ci) * 9 + k];
+    RCU_TRY(dev_upload(net, w, &net->d_first_w));
+    net->first_coef_off = unit_off[0];
+  }
+  // ---- head ----
+  {
+    const rcu_conv_unit& h = d->head;
+    if (!(h.weight && h.bias) || h.c_in != sf || h.c_out != 2) { set_error("head must be a 1x1 conv start_filters -> 2"); rcu_unet_destroy(net); return RCU_EINVAL; }
+    std::vector<float> hw((size_t)2 * sf + 2);
+    for (int i = 0; i < 2 * sf; ++i) hw[i] = h.weight[i];
+    hw[2 * sf] = h.bias[0];
+    hw[2 * sf + 1] = h.bias[1];
+    RCU_TRY(dev_upload(net, hw, &net->d_head));
+  }
+  // ---- tensor-core conv layers in execution order ----
+  auto add_unit = [&](int u, int c0, int c1, bool head) -> int {
+    const rcu_conv_unit& cu = d->units[u];
+    if (cu.c_in != c0 + c1) { set_error("unit %d: c_in=%d does not match the topology (%d)", u, cu.c_in, c0 + c1); return RCU_EINVAL; }
+    ConvLayer L;
+    L.c0 = c0; L.c1 = c1; L.c_out = cu.c_out; L.n_taps = 9; L.n_phases = 1; L.out_mul = 1; L.relu = 1; L.head = head;
+    for (int t = 0; t < 9; ++t) { L.dy[0][t] = (signed char)(t / 3 - 1); L.dx[0][t] = (signed char)(t % 3 - 1); }
+    L.coef_off = unit_off[u];
+    int rc2 = pick_tiles(c1 > 0 ? (c0 < c1 ? c0 : c1) : c0, cu.c_out, &L.block_n, &L.kc);
+    if (rc2) return rc2;
+    if (head && (L.block_n != 32 || cu.c_out != 32)) { set_error("fused head needs start_filters == 32"); return RCU_ENOTSUP; }
+    std::vector<uint16_t> w = pack_conv3x3(cu);
+    uint16_t* dw;
+    rc2 = dev_upload(net, w, &dw);
+    if (rc2) return rc2;
+    L.d_weights = reinterpret_cast<__nv_bfloat16*>(dw);
+    net->convs.push_back(L);
+    return RCU_OK;
+  };
+  auto add_upconv = [&](int j, int c_in, int c_out) -> int {
+    const rcu_conv_unit& cu = d->upconvs[j];
+    if (cu.c_in != c_in || cu.c_out != c_out || !cu.weight || !cu.bias) { set_error("upconv %d: shape mismatch", j); return RCU_EINVAL; }
+    ConvLayer L;
+    L.c0 = c_in; L.c1 = 0; L.c_out = c_out; L.n_taps = 4; L.n_phases = 4; L.out_mul = 2; L.relu = 0;
+    L.coef_off = up_off[j];
+    int rc2 = pick_tiles(c_in, c_out, &L.block_n, &L.kc);
+    if (rc2) return rc2;
+    std::vector<uint16_t> w = pack_upconv_phases(cu, L);
+    uint16_t* dw;
+    rc2 = dev_upload(net, w, &dw);
+    if (rc2) return rc2;
+    L.d_weights = reinterpret_cast<__nv_bfloat16*>(dw);
+    net->convs.push_back(L);
+    return RCU_OK;
+  };
+  {
+    int u = 1;  // unit 0 is the first conv
+    int c = sf;
+    RCU_TRY(add_unit(u++, c, 0, false));                 // down 0, second conv
+    for (int l = 1; l < d->depth; ++l) {
+      RCU_TRY(add_unit(u++, c, 0, false));               // c -> 2c
+      c *= 2;
+      RCU_TRY(add_unit(u++, c, 0, false));
+    }
+    RCU_TRY(add_unit(u++, c, 0, false));                 // bottom
+    c *= 2;
+    RCU_TRY(add_unit(u++, c, 0, false));
+    for (int j = 0; j < d->depth; ++j) {
+      RCU_TRY(add_upconv(j, c, c / 2));
+      c /= 2;
+      RCU_TRY(add_unit(u++, c, c, false));               // cat((up, skip), 1)
+      RCU_TRY(add_unit(u++, c, 0, false));
+    }
+    const bool fuse_head = (sf == 32);
+    RCU_TRY(add_unit(u++, c, 0, fuse_head));             // conv_cls.0
+  }
+#undef RCU_TRY
+  *out = net;
+  return RCU_OK;
+}
+
+extern "C" void rcu_unet_destroy(rcu_unet* net) {
+  if (!net) return;
+  cudaSetDevice(net->device);
+  for (void* p : net->owned) cudaFree(p);
+  if (net->arena) cudaFree(net->arena);
+  delete net;
+}
+
+extern "C" int rcu_unet_total_dropout_channels(const rcu_unet* net) { return net ? net->total_dropout_channels : 0; }
+extern "C" int64_t rcu_unet_last_launch_count(const rcu_unet* net) { return net ? net->last_launches : 0; }
+extern "C" int rcu_unet_set_conv_impl(rcu_unet* net, int impl) {
+  RCU_CHECK_ARG(net != nullptr, "NULL handle");
+  RCU_CHECK_ARG(impl == 0 || impl == 1, "conv impl must be 0 (tcgen05) or 1 (cross-check)");
+  net->conv_impl = impl;
+  return RCU_OK;
+}
+
+extern "C" int rcu_unet_plan(rcu_unet* net, int height, int width, int max_images_per_chunk, size_t* workspace_bytes) {
+  RCU_CHECK_ARG(net != nullptr, "NULL handle");
+  const int div = 1 << net->depth;
+  if (height % div != 0 || width % div != 0 || height < div || width < div) {
+    set_error("spatial size %dx%d must be a multiple of 2^depth = %d (the reference's F.pad branch is not on the hot path)", height, width, div);
+    return RCU_ENOTSUP;
+  }
+  RCU_CHECK_ARG(max_images_per_chunk >= 1, "max_images_per_chunk must be >= 1");
+  RCU_CUDA(cudaSetDevice(net->device));
+  if (net->arena) { RCU_CUDA(cudaFree(net->arena)); net->arena = nullptr; }
+  net->ops.clear();
+  net->H = height; net->W = width; net->max_images = max_images_per_chunk;
+  const long long N = max_images_per_chunk;
+  const int sf = net->start_filters, depth = net->depth;
+
+  // ---- carve the arena: per level l: A (conv0 out / block conv0 out), SKIP, U (upconv out / block conv1 out), POOL ----
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 1023) & ~size_t(1023); return o; };
+  std::vector<size_t> oA(depth + 1), oS(depth + 1), oU(depth + 1), oP(depth + 1);
+  for (int l = 0; l <= depth; ++l) {
+    const size_t px = (size_t)(height >> l) * (width >> l) * N;
+    const size_t c = (size_t)sf << l;
+    oA[l] = carve(px * c * 2);
+    oS[l] = carve(px * c * 2);
+    if (l < depth) {
+      oU[l] = carve(px * c * 2);
+      oP[l] = carve(px / 4 * c * 2);
+    }
+  }
+  const size_t o_feat = carve((size_t)height * width * N * sf * 2);
+  const size_t o_coef = carve((size_t)N * net->n_cols * sizeof(float2));
+  RCU_CUDA(cudaMalloc(&net->arena, off));
+  net->arena_bytes = off;
+  uint8_t* base = reinterpret_cast<uint8_t*>(net->arena);
+  auto B = [&](size_t o) { return reinterpret_cast<__nv_bfloat16*>(base + o); };
+  net->d_coef = reinterpret_cast<float2*>(base + o_coef);
+  net->head_feat = B(o_feat);
+  net->first_out = B(oA[0]);
+
+  // ---- schedule ----
+  int ci = 0;
+  auto push_conv = [&](const __nv_bfloat16* s0, const __nv_bfloat16* s1, __nv_bfloat16* dst, int in_h, int in_w) -> int {
+    ConvLayer& L = net->convs[ci];
+    L.src0 = s0; L.src1 = s1; L.dst = dst; L.in_h = in_h; L.in_w = in_w;
+    int rc = make_act_map(&L.map_a0, s0, L.c0, in_w, in_h, (int)N, L.kc);
+    if (rc) return rc;
+    rc = make_act_map(&L.map_a1, s1 ? s1 : s0, s1 ? L.c1 : L.c0, in_w, in_h, (int)N, L.kc);
+    if (rc) return rc;
+    rc = make_weight_map(&L.map_w, L.d_weights, L.c0 + L.c1, L.c_out, L.n_taps * L.n_phases, L.kc, L.block_n);
+    if (rc) return rc;
+    Op op;
+    op.kind = OP_CONV; op.conv = ci; op.out = L.head ? net->head_feat : dst;
+    op.h = in_h * L.out_mul; op.w = in_w * L.out_mul; op.c = L.c_out;
+    net->ops.push_back(op);
+    ++ci;
+    return RCU_OK;
+  };
+  auto push_pool = [&](const __nv_bfloat16* in, __nv_bfloat16* out, int in_h, int in_w, int c) {
+    Op op;
+    op.kind = OP_POOL; op.in = in; op.out = out; op.in_h = in_h; op.in_w = in_w; op.h = in_h / 2; op.w = in_w / 2; op.c = c;
+    net->ops.push_back(op);
+  };
+  {
+    Op first;
+    first.kind = OP_FIRST; first.out = B(oA[0]); first.h = height; first.w = width; first.c = sf;
+    net->ops.push_back(first);
+  }
+  int rc = push_conv(B(oA[0]), nullptr, B(oS[0]), height, width);
+  if (rc) return rc;
+  for (int l = 1; l <= depth; ++l) {
+    const int h = height >> l, w = width >> l;
+    push_pool(B(oS[l - 1]), B(oP[l - 1]), h * 2, w * 2, sf << (l - 1));
+    if ((rc = push_conv(B(oP[l - 1]), nullptr, B(oA[l]), h, w))) return rc;
+    if ((rc = push_conv(B(oA[l]), nullptr, B(oS[l]), h, w))) return rc;
+  }
+  const __nv_bfloat16* cur = B(oS[depth]);
+  for (int l = depth - 1; l >= 0; --l) {
+    const int h = height >> l, w = width >> l;
+    if ((rc = push_conv(cur, nullptr, B(oU[l]), h / 2, w / 2))) return rc;       // upconv phases: low-res in, high-res out
+    if ((rc = push_conv(B(oU[l]), B(oS[l]), B(oA[l]), h, w))) return rc;         // cat((up, skip)) conv
+    if ((rc = push_conv(B(oA[l]), nullptr, B(oU[l]), h, w))) return rc;
+    cur = B(oU[l]);
+  }
+  if ((rc = push_conv(cur, nullptr, B(oA[0]), height, width))) return rc;        // conv_cls.0 (+ fused head)
+  if (workspace_bytes) *workspace_bytes = off;
+  return RCU_OK;
+}
+
+extern "C" int rcu_unet_forward(rcu_unet* net, const float* images, int64_t n_slices, int n_samples, int dropout_mode,
+                                int det_first, uint64_t seed, int64_t slice_index0, int sample0, const float* scale,
+                                float* logits, void* stream) {
+  RCU_CHECK_ARG(net != nullptr && images != nullptr && logits != nullptr, "NULL argument");
+  RCU_CHECK_ARG(!net->ops.empty(), "rcu_unet_plan has not been called");
+  RCU_CHECK_ARG(n_slices >= 0 && n_samples >= 1, "bad sizes: n_slices=%lld n_samples=%d", (long long)n_slices, n_samples);
+  RCU_CHECK_ARG(dropout_mode >= 0 && dropout_mode <= 2, "dropout_mode must be 0, 1 or 2");
+  RCU_CHECK_ARG(dropout_mode != 2 || scale != nullptr || net->total_dropout_channels == 0, "dropout_mode 2 needs a scale table");
+  RCU_CHECK_ARG(n_samples <= net->max_images, "n_samples=%d exceeds the planned chunk of %d images", n_samples, net->max_images);
+  cudaStream_t st = (cudaStream_t)stream;
+  RCU_CUDA(cudaSetDevice(net->device));
+  const int H = net->H, W = net->W, sf = net->start_filters;
+  const int chunk_slices_max = net->max_images / n_samples;
+  const uint32_t thr = dropout_threshold_u32(net->p_drop);
+  const float inv_keep = 1.0f / (1.0f - net->p_drop);
+  long long launches = 0;
+
+  for (int64_t s0 = 0; s0 < n_slices; s0 += chunk_slices_max) {
+    const int cs = (int)((n_slices - s0) < chunk_slices_max ? (n_slices - s0) : chunk_slices_max);
+    const int n_img = cs * n_samples;
+    net->last_n_img = n_img;
+    {
+      const long long total = (long long)n_img * net->n_cols;
+      long long blocks = (total + 255) / 256;
+      if (blocks > (long long)sm_count() * 8) blocks = (long long)sm_count() * 8;
+      coef_kernel<<<(unsigned)blocks, 256, 0, st>>>(net->cols, net->d_coef, n_img, cs, (long long)s0, (long long)n_slices, dropout_mode,
+                                                    det_first, (uint32_t)seed, (uint32_t)(seed >> 32), thr, inv_keep,
+                                                    (long long)slice_index0, sample0, scale, net->total_dropout_channels);
+      RCU_LAUNCH_CHECK();
+      ++launches;
+    }
+    for (const Op& op : net->ops) {
+      if (op.kind == OP_FIRST) {
+        const int tiles = ((H + kFirstTile - 1) / kFirstTile) * ((W + kFirstTile - 1) / kFirstTile);
+        const size_t smem = ((size_t)net->in_channels * 9 * sf + (size_t)net->in_channels * 324) * sizeof(float);
+        dim3 grid((unsigned)tiles, (unsigned)cs);
+        if (sf == 32)
+          first_conv_kernel<32><<<grid, 256, smem, st>>>(images, net->in_channels, H, W, (long long)s0, cs, n_samples, net->d_first_w,
+                                                         net->d_coef, net->n_cols, net->first_coef_off, net->first_out);
+        else
+          first_conv_kernel<64><<<grid, 256, smem, st>>>(images, net->in_channels, H, W, (long long)s0, cs, n_samples, net->d_first_w,
+                                                         net->d_coef, net->n_cols, net->first_coef_off, net->first_out);
+        RCU_LAUNCH_CHECK();
+        ++launches;
+      } else if (op.kind == OP_POOL) {
+        const long long total = (long long)n_img * op.h * op.w * (op.c / 8);
+        long long blocks = (total + 255) / 256;
+        if (blocks > (long long)sm_count() * 16) blocks = (long long)sm_count() * 16;
+        maxpool2_kernel<<<(unsigned)blocks, 256, 0, st>>>(op.in, op.out, n_img, op.in_h, op.in_w, op.c);
+        RCU_LAUNCH_CHECK();
+        ++launches;
+      } else {
+        const ConvLayer& L = net->convs[op.conv];
+        ConvParams prm;
+        std::memset(&prm, 0, sizeof(prm));
+        prm.n_img = n_img;
+        prm.in_h = L.in_h; prm.in_w = L.in_w;
+        prm.tiles_x = (L.in_w + kTileW - 1) / kTileW;
+        prm.tiles_y = (L.in_h + kTileH - 1) / kTileH;
+        prm.n_tiles_n = L.c_out / L.block_n;
+        prm.kc0 = L.c0 / L.kc; prm.kc1 = L.c1 / L.kc;
+        prm.n_taps = L.n_taps; prm.n_phases = L.n_phases;
+        std::memcpy(prm.dy, L.dy, sizeof(prm.dy));
+        std::memcpy(prm.dx, L.dx, sizeof(prm.dx));
+        prm.out_mul = L.out_mul;
+        prm.out_h = L.in_h * L.out_mul; prm.out_w = L.in_w * L.out_mul; prm.out_c = L.c_out;
+        prm.out = L.dst;
+        prm.coef = net->d_coef; prm.coef_stride = net->n_cols; prm.coef_off = L.coef_off;
+        prm.relu = L.relu;
+        prm.head = nullptr; prm.logits = logits;
+        prm.chunk_slices = cs; prm.slice0 = s0; prm.n_slices_total = n_slices;
+        if (net->conv_impl == 0) {
+          if (L.head) prm.head = net->d_head;
+          int rc = dispatch_conv_tc(L, prm, st);
+          if (rc) return rc;
+          ++launches;
+        } else {
+          if (L.head) prm.out = net->head_feat;
+          const long long total = (long long)n_img * L.n_phases * L.in_h * L.in_w * L.c_out;
+          long long blocks = (total + 255) / 256;
+          if (blocks > (long long)sm_count() * 32) blocks = (long long)sm_count() * 32;
+          conv_check_kernel<<<(unsigned)blocks, 256, 0, st>>>(L.src0, L.src1, L.c0, L.c1, L.d_weights, L.c_out, prm);
+          RCU_LAUNCH_CHECK();
+          ++launches;
+          if (L.head) {
+            const long long px = (long long)n_img * H * W;
+            long long hb = (px + 255) / 256;
+            if (hb > (long long)sm_count() * 32) hb = (long long)sm_count() * 32;
+            head_check_kernel<<<(unsigned)hb, 256, 0, st>>>(net->head_feat, net->d_head, logits, n_img, H, W, sf, cs, (long long)s0, (long long)n_slices);
+            RCU_LAUNCH_CHECK();
+            ++launches;
+          }
+        }
+      }
+    }
+  }
+  net->last_launches = launches;
+  return RCU_OK;
+}
+
+extern "C" int rcu_unet_debug_activation(rcu_unet* net, int index, float* out, size_t out_elems, void* stream) {
+  RCU_CHECK_ARG(net != nullptr && out != nullptr, "NULL argument");
+  RCU_CHECK_ARG(index >= 0 && index < (int)net->ops.size(), "activation index %d out of range [0, %d)", index, (int)net->ops.size());
+  const Op& op = net->ops[index];
+  if (op.kind == OP_CONV && net->convs[op.conv].head && net->conv_impl == 0) {
+    set_error("activation %d is fused away (conv_cls.0 feeds the head in registers on the tcgen05 path)", index);
+    return RCU_ENOTSUP;
+  }
+  const long long n = (long long)net->last_n_img * op.h * op.w * op.c;
+  RCU_CHECK_ARG((long long)out_elems >= n, "output holds %zu elements, activation has %lld", out_elems, n);
+  if (n == 0) return RCU_OK;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 4096) blocks = 4096;
+  bf16_to_f32_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(op.out, out, n);
+  RCU_LAUNCH_CHECK();
+  return RCU_OK;
+}

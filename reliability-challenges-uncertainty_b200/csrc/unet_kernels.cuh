@@ -1,0 +1,215 @@
+// Non-GEMM kernels of the U-Net forward: first conv (tiny K, fp32 NCHW input), 2x2 max-pool, the per-(image,
+// channel) epilogue-coefficient table (BN fold x Dropout2d keep-scale, Philox generated), and a plain CUDA-core
+// convolution over the same bf16 data that exists only as an on-device cross-check of the tcgen05 path.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "conv_tc.cuh"
+#include "philox.cuh"
+
+namespace rcu {
+
+// ---------------------------------------------------------------------------------------------------------
+// Epilogue coefficient table.  For unit u, channel c, image i (= sample t, slice g):
+//     s = 1 (Dropout2d in eval mode)  or  keep(t, g, site(u), c) / (1 - p)        (common/model/unet.py:14-15)
+//     y = relu( (conv + bias) * s * a + d ),  a = gamma / sqrt(var + eps),  d = beta - a * mean   (unet.py:16-19)
+//       = relu( conv * (a*s) + (bias*a*s + d) )            -> coef = (a*s, bias*a*s + d)
+// Units without BN (up-path `upconv`, unet.py:105): coef = (1, bias).
+// ---------------------------------------------------------------------------------------------------------
+struct CoefColumns {            // device arrays, one entry per column of the table
+  const float* fold_a;          // a        (1 for no-BN units)
+  const float* fold_ba;         // bias * a (bias for no-BN units)
+  const float* fold_d;          // d        (0 for no-BN units)
+  const int* site;              // dropout site index or -1
+  const int* ch_in_site;        // channel index inside the site
+  const int* scale_col;         // column inside a caller-supplied scale row (mode 2)
+  int n_cols;
+};
+
+__global__ void coef_kernel(CoefColumns cols, float2* __restrict__ coef, int n_img, int chunk_slices, long long slice0,
+                            long long n_slices_total, int dropout_mode, int det_first, uint32_t seed_lo, uint32_t seed_hi,
+                            uint32_t thr, float inv_keep, long long slice_index0, int sample0, const float* __restrict__ scale,
+                            int scale_cols) {
+  const long long total = (long long)n_img * cols.n_cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(i % cols.n_cols);
+    const int img = (int)(i / cols.n_cols);
+    const int t = img / chunk_slices, sl = img - t * chunk_slices;
+    const long long g = slice0 + sl;  // slice index inside this forward call
+    float s = 1.0f;
+    const int site = cols.site[col];
+    const bool stochastic = dropout_mode != 0 && site >= 0 && !(det_first && t == 0);
+    if (stochastic) {
+      const int ts = t - (det_first ? 1 : 0);
+      if (dropout_mode == 1)
+        s = dropout_scale(seed_lo, seed_hi, thr, inv_keep, (uint32_t)site, (uint32_t)(slice_index0 + g), (uint32_t)(sample0 + ts),
+                          (uint32_t)cols.ch_in_site[col]);
+      else
+        s = scale[((long long)ts * n_slices_total + g) * scale_cols + cols.scale_col[col]];
+    }
+    const float as = cols.fold_a[col] * s;
+    coef[i] = make_float2(as, fmaf(cols.fold_ba[col], s, cols.fold_d[col]));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// First conv: fp32 NCHW slices (C_in = 3 or 4) -> bf16 NHWC, 32*k output channels.  K = 9*C_in <= 36 is too
+// thin for a tensor-core tile; the convolution itself does not depend on the MC sample (dropout acts after it),
+// so each thread convolves its pixel ONCE and then only re-applies the per-sample coefficients: the layer is
+// store-bound (64 B per pixel-sample).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kFirstTile = 16;  // 16x16 pixels per block, 256 threads
+
+template <int C_OUT>
+__global__ void __launch_bounds__(256)
+first_conv_kernel(const float* __restrict__ images, int c_in, int h, int w, long long slice0, int chunk_slices, int n_samples,
+                  const float* __restrict__ weight /* [c_in*9][C_OUT] */, const float2* __restrict__ coef, long long coef_stride,
+                  int coef_off, __nv_bfloat16* __restrict__ out) {
+  extern __shared__ float s_first[];
+  float* s_w = s_first;                                  // [c_in*9][C_OUT]
+  float* s_in = s_first + c_in * 9 * C_OUT;              // [c_in][18][18]
+  const int tiles_x = (w + kFirstTile - 1) / kFirstTile;
+  const int tile = blockIdx.x;
+  const int sl = blockIdx.y;
+  const int ty0 = (tile / tiles_x) * kFirstTile, tx0 = (tile % tiles_x) * kFirstTile;
+  const float* img = images + (slice0 + sl) * (long long)c_in * h * w;
+  for (int i = threadIdx.x; i < c_in * 9 * C_OUT; i += 256) s_w[i] = weight[i];
+  for (int i = threadIdx.x; i < c_in * 18 * 18; i += 256) {
+    const int c = i / 324, r = i - c * 324;
+    const int yy = ty0 + r / 18 - 1, xx = tx0 + r % 18 - 1;
+    s_in[i] = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? img[((long long)c * h + yy) * w + xx] : 0.0f;
+  }
+  __syncthreads();
+  const int ly = threadIdx.x >> 4, lx = threadIdx.x & 15;
+  const int y = ty0 + ly, x = tx0 + lx;
+  float acc[C_OUT];
+#pragma unroll
+  for (int c = 0; c < C_OUT; ++c) acc[c] = 0.0f;
+  for (int ci = 0; ci < c_in; ++ci)
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const float v = s_in[ci * 324 + (ly + k / 3) * 18 + lx + k % 3];
+      const float4* wr = reinterpret_cast<const float4*>(s_w + (ci * 9 + k) * C_OUT);
+#pragma unroll
+      for (int c4 = 0; c4 < C_OUT / 4; ++c4) {
+        const float4 wv = wr[c4];
+        acc[4 * c4 + 0] = fmaf(v, wv.x, acc[4 * c4 + 0]);
+        acc[4 * c4 + 1] = fmaf(v, wv.y, acc[4 * c4 + 1]);
+        acc[4 * c4 + 2] = fmaf(v, wv.z, acc[4 * c4 + 2]);
+        acc[4 * c4 + 3] = fmaf(v, wv.w, acc[4 * c4 + 3]);
+      }
+    }
+  if (y >= h || x >= w) return;
+  for (int t = 0; t < n_samples; ++t) {
+    const int im = t * chunk_slices + sl;
+    const float2* cf = coef + (long long)im * coef_stride + coef_off;
+    uint4* dst = reinterpret_cast<uint4*>(out + (((long long)im * h + y) * w + x) * C_OUT);
+#pragma unroll
+    for (int c8 = 0; c8 < C_OUT / 8; ++c8) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 c0 = __ldg(cf + 8 * c8 + 2 * j), c1 = __ldg(cf + 8 * c8 + 2 * j + 1);
+        const float a0 = fmaxf(fmaf(acc[8 * c8 + 2 * j], c0.x, c0.y), 0.0f);
+        const float a1 = fmaxf(fmaf(acc[8 * c8 + 2 * j + 1], c1.x, c1.y), 0.0f);
+        __nv_bfloat162 b = __floats2bfloat162_rn(a0, a1);
+        pk[j] = *reinterpret_cast<uint32_t*>(&b);
+      }
+      dst[c8] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// 2x2 max-pool, bf16 NHWC (nn.MaxPool2d(2), common/model/unet.py:90).  One thread = 8 channels of one output pixel.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 bf16x8_max(uint4 a, uint4 b) {
+  uint4 r;
+  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+  __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) pr[i] = __hmax2(pa[i], pb[i]);
+  return r;
+}
+
+__global__ void __launch_bounds__(256)
+maxpool2_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n_img, int h, int w, int c) {
+  const int oh = h >> 1, ow = w >> 1, c8 = c >> 3;
+  const long long total = n_img * oh * ow * c8;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int cc = (int)(i % c8);
+    long long r = i / c8;
+    const int ox = (int)(r % ow); r /= ow;
+    const int oy = (int)(r % oh);
+    const long long im = r / oh;
+    const uint4* p = reinterpret_cast<const uint4*>(in + ((im * h + 2 * oy) * w + 2 * ox) * c) + cc;
+    const long long row = (long long)w * c8, px = c8;
+    const uint4 m = bf16x8_max(bf16x8_max(__ldg(p), __ldg(p + px)), bf16x8_max(__ldg(p + row), __ldg(p + row + px)));
+    reinterpret_cast<uint4*>(out)[i] = m;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Cross-check convolution (CUDA cores, fp32 accumulate) with exactly the tcgen05 kernel's contract.
+// One thread = one output pixel x one output channel.  Debug only: rcu_unet_set_conv_impl(net, 1).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+conv_check_kernel(const __nv_bfloat16* __restrict__ src0, const __nv_bfloat16* __restrict__ src1, int c0, int c1,
+                  const __nv_bfloat16* __restrict__ weights, int c_out, const ConvParams prm) {
+  const int c_in = c0 + c1;
+  const long long total = (long long)prm.n_img * prm.n_phases * prm.in_h * prm.in_w * c_out;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    long long r = i;
+    const int co = (int)(r % c_out); r /= c_out;
+    const int x = (int)(r % prm.in_w); r /= prm.in_w;
+    const int y = (int)(r % prm.in_h); r /= prm.in_h;
+    const int ph = (int)(r % prm.n_phases);
+    const int img = (int)(r / prm.n_phases);
+    float acc = 0.0f;
+    for (int tap = 0; tap < prm.n_taps; ++tap) {
+      const int yy = y + prm.dy[ph][tap], xx = x + prm.dx[ph][tap];
+      if (yy < 0 || yy >= prm.in_h || xx < 0 || xx >= prm.in_w) continue;
+      const __nv_bfloat16* wrow = weights + ((long long)(ph * prm.n_taps + tap) * c_out + co) * c_in;
+      const __nv_bfloat16* a0 = src0 + (((long long)img * prm.in_h + yy) * prm.in_w + xx) * c0;
+      for (int k = 0; k < c0; ++k) acc = fmaf(__bfloat162float(a0[k]), __bfloat162float(wrow[k]), acc);
+      if (c1 > 0) {
+        const __nv_bfloat16* a1 = src1 + (((long long)img * prm.in_h + yy) * prm.in_w + xx) * c1;
+        for (int k = 0; k < c1; ++k) acc = fmaf(__bfloat162float(a1[k]), __bfloat162float(wrow[c0 + k]), acc);
+      }
+    }
+    const float2 cf = prm.coef[(long long)img * prm.coef_stride + prm.coef_off + co];
+    float v = fmaf(acc, cf.x, cf.y);
+    if (prm.relu) v = fmaxf(v, 0.0f);
+    const int oy = prm.out_mul * y + (ph >> 1), ox = prm.out_mul * x + (ph & 1);
+    prm.out[(((long long)img * prm.out_h + oy) * prm.out_w + ox) * prm.out_c + co] = __float2bfloat16_rn(v);
+  }
+}
+
+// 1x1 head for the cross-check path: bf16 features [img][h][w][32] -> logits (the tcgen05 path fuses this).
+__global__ void __launch_bounds__(256)
+head_check_kernel(const __nv_bfloat16* __restrict__ feat, const float* __restrict__ head, float* __restrict__ logits, int n_img,
+                  int h, int w, int c, int chunk_slices, long long slice0, long long n_slices_total) {
+  const long long total = (long long)n_img * h * w;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const long long img = i / ((long long)h * w), px = i - img * h * w;
+    float l0 = head[2 * c], l1 = head[2 * c + 1];
+    for (int k = 0; k < c; ++k) {
+      const float a = __bfloat162float(feat[i * c + k]);
+      l0 = fmaf(a, head[k], l0);
+      l1 = fmaf(a, head[c + k], l1);
+    }
+    const int t = (int)(img / chunk_slices), sl = (int)(img - (long long)t * chunk_slices);
+    const long long gimg = (long long)t * n_slices_total + slice0 + sl;
+    reinterpret_cast<float2*>(logits)[gimg * h * w + px] = make_float2(l0, l1);
+  }
+}
+
+// NHWC bf16 -> fp32 copy used by rcu_unet_debug_activation.
+__global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = __bfloat162float(in[i]);
+}
+
+}  // namespace rcu

@@ -1,0 +1,216 @@
+"""Device entry points of the calibration / uncertainty-error metrics (thin wrappers over the C-ABI).
+
+Inputs may be numpy arrays (the reference's EvaluationStrategy protocol hands numpy around) or CUDA tensors
+(the in-memory pipeline: probabilities never leave HBM).  numpy inputs are copied to the current CUDA device;
+results come back as small numpy integer / float64 tables.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import tables
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise _lib.RcuError('rcu_b200 metrics need a CUDA device (there is no CPU fallback)')
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def _to_device(x, dtype, name):
+    """Flat contiguous CUDA tensor of `dtype` for a numpy array / torch tensor (bool -> uint8)."""
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        if x.dtype == np.bool_:
+            x = x.view(np.uint8)
+        t = torch.from_numpy(np.ascontiguousarray(x))
+    elif torch.is_tensor(x):
+        t = x
+        if t.dtype == torch.bool:
+            t = t.to(torch.uint8)
+    else:
+        raise ValueError("object of type '{}' must be '{}'".format(type(x).__name__, np.ndarray.__name__))
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    t = t.to(_device(), non_blocking=True).contiguous().view(-1)
+    return t
+
+
+class _Workspace:
+    """Per-device scratch for the deterministic two-stage reductions (allocated once, reused)."""
+    _cache = {}
+
+    @classmethod
+    def get(cls, n_subjects):
+        dev = torch.cuda.current_device()
+        need = int(_lib.lib().rcu_metrics_workspace_bytes(int(n_subjects)))
+        buf = cls._cache.get(dev)
+        if buf is None or buf.numel() < need:
+            buf = torch.empty(need, dtype=torch.uint8, device=_device())
+            _lib.check(_lib.lib().rcu_metrics_workspace_init(_lib.ptr(buf), buf.numel(), _lib.current_stream()))
+            cls._cache[dev] = buf
+        return buf
+
+
+def _f32_array(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a, a.ctypes.data_as(_lib.c_float_p)
+
+
+def _check_lengths(n, vps, n_subjects, **arrays):
+    for k, v in arrays.items():
+        if v is not None and v.numel() != n:
+            raise ValueError('"{}" has {} elements, expected {}'.format(k, v.numel(), n))
+    if vps * n_subjects != n:
+        raise ValueError('{} elements do not split into {} subjects'.format(n, n_subjects))
+
+
+def calibration_tables(p, target, mask=None, n_bins=10, threshold_range=None, n_subjects=1, sync=True):
+    """ECE reliability tables of `n_subjects` equally sized subjects laid out back to back.
+
+    Returns (count int64[S, n_bins+1], positives int64[S, n_bins+1], conf_sum float64[S, n_bins+1]); the last
+    slot counts values outside every bin (p < 0, p >= 1+1e-8, NaN).  With sync=False CUDA tensors are returned.
+    """
+    p_d = _to_device(p, torch.float32, 'probabilities')
+    t_d = _to_device(target, torch.uint8, 'target')
+    m_d = _to_device(mask, torch.uint8, 'mask')
+    n = p_d.numel()
+    vps = n // max(n_subjects, 1)
+    _check_lengths(n, vps, n_subjects, target=t_d, mask=m_d)
+    dev = p_d.device
+    count = torch.zeros((n_subjects, n_bins + 1), dtype=torch.int64, device=dev)
+    positives = torch.zeros_like(count)
+    conf = torch.zeros((n_subjects, n_bins + 1), dtype=torch.float64, device=dev)
+    if n > 0:
+        edges, edges_p = _f32_array(tables.calibration_edges_f32(n_bins))
+        lo, hi = (float('nan'), float('nan')) if threshold_range is None else (float(threshold_range[0]), float(threshold_range[1]))
+        ws = _Workspace.get(n_subjects)
+        _lib.check(_lib.lib().rcu_calib_hist(_lib.ptr(p_d), _lib.ptr(t_d), _lib.ptr(m_d), vps, n_subjects, edges_p, n_bins, lo, hi,
+                                             _lib.ptr(count), _lib.ptr(positives), _lib.ptr(conf), _lib.ptr(ws), ws.numel(),
+                                             _lib.current_stream()))
+    if not sync:
+        return count, positives, conf
+    return count.cpu().numpy(), positives.cpu().numpy(), conf.cpu().numpy()
+
+
+def _ue_tables_for(kind, thresholds):
+    if kind == 'p':
+        return tables.uncertainty_break_table(thresholds)
+    if kind == 'u32':
+        return tables.threshold_breaks_f32(thresholds)
+    ths = np.asarray(thresholds, dtype=np.float64)
+    order = np.argsort(ths, kind='stable')
+    return ths[order], np.arange(len(ths) + 1, dtype=np.uint8), order
+
+
+def ue_tables(values, prediction, target, thresholds=tables.SWEEP_THRESHOLDS, mask=None, kind='p', n_subjects=1, sync=True,
+              break_table=None):
+    """Joint (confusion class x thresholds-exceeded) histogram for all thresholds in one pass.
+
+    kind 'p'   : `values` is the float32 foreground probability; uncertainty = H([1-p, p]) / ln 2 in the
+                 reference's arithmetic (ToEntropy after AddBackgroundProbabilities), classified through an exact
+                 float32 break table.
+    kind 'u32' : `values` is a float32 uncertainty map;  kind 'u64': a float64 uncertainty map (ToEntropy output).
+    Returns (table int64[S, 4, K+1] rows tp, tn, fp, fn; invalid int64[S]; order) — `order` maps the k-th smallest
+    threshold back to the caller's index.
+    """
+    if kind not in ('p', 'u32', 'u64'):
+        raise ValueError('unknown kind "{}"'.format(kind))
+    breaks, seg, order = break_table if break_table is not None else _ue_tables_for(kind, thresholds)
+    n_classes = len(order) + 1
+    v_d = _to_device(values, torch.float64 if kind == 'u64' else torch.float32, 'values')
+    d_d = _to_device(prediction, torch.uint8, 'prediction')
+    t_d = _to_device(target, torch.uint8, 'target')
+    m_d = _to_device(mask, torch.uint8, 'mask')
+    n = v_d.numel()
+    vps = n // max(n_subjects, 1)
+    _check_lengths(n, vps, n_subjects, prediction=d_d, target=t_d, mask=m_d)
+    dev = v_d.device
+    table = torch.zeros((n_subjects, 4, n_classes), dtype=torch.int64, device=dev)
+    invalid = torch.zeros((n_subjects,), dtype=torch.int64, device=dev)
+    if n > 0:
+        seg = np.ascontiguousarray(seg, dtype=np.uint8)
+        seg_p = seg.ctypes.data_as(_lib.c_uint8_p)
+        ws = _Workspace.get(n_subjects)
+        if kind == 'u64':
+            b64 = np.ascontiguousarray(breaks, dtype=np.float64)
+            b32_p, b64_p = None, b64.ctypes.data_as(_lib.c_double_p)
+            vk = 2
+        else:
+            b32, b32_p = _f32_array(breaks)
+            b64_p = None
+            vk = 0 if kind == 'p' else 1
+        _lib.check(_lib.lib().rcu_ue_hist(_lib.ptr(v_d), vk, _lib.ptr(d_d), _lib.ptr(t_d), _lib.ptr(m_d), vps, n_subjects, b32_p, b64_p,
+                                          len(breaks), seg_p, n_classes, _lib.ptr(table), _lib.ptr(invalid), _lib.ptr(ws), ws.numel(),
+                                          _lib.current_stream()))
+    if not sync:
+        return table, invalid, order
+    return table.cpu().numpy(), invalid.cpu().numpy(), order
+
+
+def eval_fused(p, prediction, target, mask=None, n_bins=10, thresholds=tables.SWEEP_THRESHOLDS, n_subjects=1, sync=True,
+               break_table=None):
+    """ECE tables (masked) and the U-E joint table (unmasked) in ONE pass over (p, prediction, target, mask).
+
+    Returns (count, positives, conf_sum, ue_table, invalid, order) as in calibration_tables / ue_tables.
+    """
+    breaks, seg, order = break_table if break_table is not None else tables.uncertainty_break_table(thresholds)
+    n_classes = len(order) + 1
+    p_d = _to_device(p, torch.float32, 'probabilities')
+    d_d = _to_device(prediction, torch.uint8, 'prediction')
+    t_d = _to_device(target, torch.uint8, 'target')
+    m_d = _to_device(mask, torch.uint8, 'mask')
+    n = p_d.numel()
+    vps = n // max(n_subjects, 1)
+    _check_lengths(n, vps, n_subjects, prediction=d_d, target=t_d, mask=m_d)
+    dev = p_d.device
+    count = torch.zeros((n_subjects, n_bins + 1), dtype=torch.int64, device=dev)
+    positives = torch.zeros_like(count)
+    conf = torch.zeros((n_subjects, n_bins + 1), dtype=torch.float64, device=dev)
+    table = torch.zeros((n_subjects, 4, n_classes), dtype=torch.int64, device=dev)
+    invalid = torch.zeros((n_subjects,), dtype=torch.int64, device=dev)
+    if n > 0:
+        edges, edges_p = _f32_array(tables.calibration_edges_f32(n_bins))
+        b32, b32_p = _f32_array(breaks)
+        seg = np.ascontiguousarray(seg, dtype=np.uint8)
+        ws = _Workspace.get(n_subjects)
+        _lib.check(_lib.lib().rcu_eval_fused(_lib.ptr(p_d), _lib.ptr(d_d), _lib.ptr(t_d), _lib.ptr(m_d), vps, n_subjects, edges_p, n_bins,
+                                             b32_p, len(breaks), seg.ctypes.data_as(_lib.c_uint8_p), n_classes, _lib.ptr(count),
+                                             _lib.ptr(positives), _lib.ptr(conf), _lib.ptr(table), _lib.ptr(invalid), _lib.ptr(ws),
+                                             ws.numel(), _lib.current_stream()))
+    if not sync:
+        return count, positives, conf, table, invalid, order
+    return (count.cpu().numpy(), positives.cpu().numpy(), conf.cpu().numpy(), table.cpu().numpy(), invalid.cpu().numpy(), order)
+
+
+def philox_keep_scale_host(seed, p_drop, site_channels, slice_index0, n_slices, sample0, n_samples):
+    """Host copy of the engine's Dropout2d keep-scale stream (no GPU needed): float32[n_samples, n_slices, sum(C)]."""
+    sc = (ctypes.c_int * len(site_channels))(*[int(c) for c in site_channels])
+    out = np.zeros((n_samples, n_slices, int(sum(site_channels))), dtype=np.float32)
+    _lib.check(_lib.lib().rcu_philox_masks_host(int(seed), float(p_drop), sc, len(site_channels), int(slice_index0), int(n_slices),
+                                                int(sample0), int(n_samples), out.ctypes.data_as(_lib.c_float_p)))
+    return out
+
+
+def philox_keep_scale(seed, p_drop, site_channels, slice_index0, n_slices, sample0, n_samples):
+    """Device version of philox_keep_scale_host (same stream, CUDA tensor)."""
+    sc = (ctypes.c_int * len(site_channels))(*[int(c) for c in site_channels])
+    out = torch.empty((n_samples, n_slices, int(sum(site_channels))), dtype=torch.float32, device=_device())
+    _lib.check(_lib.lib().rcu_philox_masks(int(seed), float(p_drop), sc, len(site_channels), int(slice_index0), int(n_slices),
+                                           int(sample0), int(n_samples), _lib.ptr(out), _lib.current_stream()))
+    return out
+
+
+def confusion_counts(prediction, target, n_subjects=1, sync=True):
+    """tp, tn, fp, fn per subject with pymia's ConfusionMatrix semantics (== 1 / == 0 comparisons)."""
+    d_d = _to_device(prediction, torch.uint8, 'prediction')
+    t_d = _to_device(target, torch.uint8, 'target')
+    n = d_d.numel()
+    vps = n // max(n_subjects, 1)
+    _check_lengths(n, vps, n_subjects, target=t_d)
+    out = torch.zeros((n_subjects, 4), dtype=torch.int64, device=d_d.device)
+    _lib.check(_lib.lib().rcu_confusion(_lib.ptr(d_d), _lib.ptr(t_d), vps, n_subjects, _lib.ptr(out), _lib.current_stream()))
+    return out.cpu().numpy() if sync else out

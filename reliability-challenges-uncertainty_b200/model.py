@@ -1,0 +1,262 @@
+"""B200UNet — drop-in for the reference's `context.model` on the inference path.
+
+`B200UNet.from_reference(module)` consumes a loaded reference `UNet` (common/model/unet.py:123-186: its
+state_dict and the placement of its Dropout2d modules) and runs the forward through rcu_unet_* (tcgen05
+implicit-GEMM convolutions, BN folded, ReLU + Dropout2d keep-scale in the epilogue, MC samples folded into the
+batch).  It honours the reference's MC-dropout switch: `th.set_dropout_mode(model, True)`
+(common/utils/torchhelper.py:44-50) flips every nn.Dropout2d submodule to train mode — this module owns one such
+submodule as its switch, so the unmodified `McPredictStep` loop drives it correctly (each stochastic call is the
+next Philox sample).  The fused steps in steps.py use `forward_samples` instead and get all T+1 passes in one go.
+"""
+import ctypes
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+BN_EPS = 1e-5  # nn.BatchNorm2d default (common/model/unet.py:17)
+
+
+def block_dropout_flags(dropout, dropout_center, level, depth, is_down):
+    """(first conv, second conv) of the block at `level` carry a Dropout2d — the placement rule of
+    common/model/unet.py:63-82 (_get_dropout / _get_dropout_mode)."""
+    if dropout is None:
+        return (False, False)
+    if dropout_center is None:
+        return (True, True)
+    if level == depth:
+        return (False, False)
+    if level + dropout_center >= depth:
+        return (False, True) if is_down else (True, False)
+    return (False, False)
+
+
+def unit_layout(in_channels, depth, start_filters, dropout, dropout_center):
+    """[(state_dict prefix, c_in, c_out, has_dropout)] for every Conv2dBnRelu in forward order, and
+    [(prefix, c_in, c_out)] for the up-path `upconv` convolutions."""
+    units, upconvs = [], []
+    c_in, c_out = in_channels, start_filters
+    for lvl in range(depth):
+        flags = block_dropout_flags(dropout, dropout_center, lvl, depth, True)
+        units.append(('down_convs.%d.block.block.0.conv2d_batch_relu' % lvl, c_in, c_out, flags[0]))
+        units.append(('down_convs.%d.block.block.1.conv2d_batch_relu' % lvl, c_out, c_out, flags[1]))
+        c_in, c_out = c_out, 2 * c_out
+    flags = block_dropout_flags(dropout, dropout_center, depth, depth, True)
+    units.append(('bottom_convs.block.0.conv2d_batch_relu', c_in, c_out, flags[0]))
+    units.append(('bottom_convs.block.1.conv2d_batch_relu', c_out, c_out, flags[1]))
+    for j in range(depth):
+        lvl = depth - 1 - j
+        c_in, c_out = c_out, c_out // 2
+        upconvs.append(('up_convs.%d.upconv.1' % j, c_in, c_out))
+        flags = block_dropout_flags(dropout, dropout_center, lvl, depth, False)
+        units.append(('up_convs.%d.block.block.0.conv2d_batch_relu' % j, 2 * c_out, c_out, flags[0]))
+        units.append(('up_convs.%d.block.block.1.conv2d_batch_relu' % j, c_out, c_out, flags[1]))
+    units.append(('conv_cls.0.conv2d_batch_relu', c_out, c_out, dropout is not None))
+    return units, upconvs
+
+
+def _f32(t):
+    return np.ascontiguousarray(t.detach().to('cpu', torch.float32).numpy())
+
+
+class B200UNet(nn.Module):
+    """See module docstring.  Not trainable: there are no parameters, only a device handle."""
+
+    DEFAULT_CHUNK_IMAGES = int(os.environ.get('RCU_B200_CHUNK_IMAGES', '168'))
+
+    def __init__(self, state_dict, nb_classes=2, in_channels=4, depth=4, start_filters=32, dropout=0.05,
+                 dropout_center=None, device=None, seed=20, chunk_images=None):
+        super().__init__()
+        if nb_classes != 2:
+            raise NotImplementedError('the B200 hot path is binary (nb_classes == 2)')
+        state_dict = {(k[len('module.'):] if k.startswith('module.') else k): v for k, v in state_dict.items()}
+        for bad, why in (('conv_sigma', 'sigma_out=True'), ('.residual.', 'residual=True')):
+            if any(bad in k for k in state_dict):
+                raise NotImplementedError('{} nets are outside the B200 hot path'.format(why))
+        self.nb_classes, self.in_channels, self.depth, self.start_filters = nb_classes, in_channels, depth, start_filters
+        self.dropout, self.dropout_center = dropout, dropout_center
+        self.seed = int(seed)
+        self.chunk_images = int(chunk_images or self.DEFAULT_CHUNK_IMAGES)
+        # the reference toggles MC dropout by flipping nn.Dropout2d modules (torchhelper.py:44-50); this is ours
+        self.mc_dropout_switch = nn.Dropout2d(p=dropout if dropout is not None else 0.0)
+        self.provide_features = False
+        self.features = None
+        self._next_sample = 0      # Philox sample index of the next free-running stochastic forward() call
+        self._next_slice = 0       # run-global slice counter for forward() calls
+        self._handle = None
+        self._plan = None
+        self._device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
+        units, upconvs = unit_layout(in_channels, depth, start_filters, dropout, dropout_center)
+        self.site_channels = [co for (_, _, co, d) in units if d]
+        self._create(state_dict, units, upconvs)
+
+    # ------------------------------------------------------------------ construction
+    @classmethod
+    def from_reference(cls, module, device=None, seed=20, chunk_images=None):
+        """Build from a loaded reference `common.model.unet.UNet` (any object with its attribute layout)."""
+        if isinstance(module, nn.DataParallel):
+            module = module.module
+        if getattr(module, 'conv_sigma', None) is not None:
+            raise NotImplementedError('sigma_out=True nets are outside the B200 hot path')
+        sd = module.state_dict()
+        depth = len(module.down_convs)
+        w0 = sd['down_convs.0.block.block.0.conv2d_batch_relu.conv.weight']
+        start_filters, in_channels = int(w0.shape[0]), int(w0.shape[1])
+        nb_classes = int(sd['conv_cls.1.weight'].shape[0])
+        if not any(k.endswith('.bn.weight') for k in sd):
+            raise NotImplementedError('bn=False nets are outside the B200 hot path')
+        for up in module.up_convs:
+            if isinstance(up.upconv, nn.ConvTranspose2d):
+                raise NotImplementedError('transpose=True up-convolutions are outside the B200 hot path')
+        # dropout placement is read off the module tree, not guessed from constructor arguments
+        drop_ps, has_drop = [], {}
+        for name, m in module.named_modules():
+            if isinstance(m, nn.Dropout2d):
+                drop_ps.append(m.p)
+                has_drop[name.rsplit('.', 1)[0]] = True
+        dropout = drop_ps[0] if drop_ps else None
+        if any(abs(p - dropout) > 0 for p in drop_ps):
+            raise NotImplementedError('per-layer dropout probabilities differ')
+        # recover dropout_center by matching the observed placement
+        for center in [None] + list(range(0, depth + 1)):
+            units, _ = unit_layout(in_channels, depth, start_filters, dropout, center)
+            if all(bool(has_drop.get(p, False)) == d for (p, _, _, d) in units):
+                dropout_center = center
+                break
+        else:
+            raise NotImplementedError('unrecognised Dropout2d placement')
+        if device is None:
+            p0 = next(module.parameters())
+            device = p0.device if p0.is_cuda else None
+        net = cls(sd, nb_classes, in_channels, depth, start_filters, dropout, dropout_center, device, seed, chunk_images)
+        net.provide_features = bool(getattr(module, 'provide_features', False))
+        if net.provide_features:
+            raise NotImplementedError('provide_features=True (auxiliary feature nets) is outside the B200 hot path')
+        return net
+
+    def _create(self, sd, units, upconvs):
+        keep = []  # numpy arrays referenced by the ctypes structs
+
+        def arr(key):
+            if key not in sd:
+                raise ValueError('state_dict is missing "{}"'.format(key))
+            a = _f32(sd[key])
+            keep.append(a)
+            return a.ctypes.data_as(_lib.c_float_p)
+
+        def unit_struct(prefix, c_in, c_out, has_dropout, bn=True, conv_key='.conv'):
+            u = _lib.RcuConvUnit()
+            u.weight = arr(prefix + conv_key + '.weight')
+            u.bias = arr(prefix + conv_key + '.bias')
+            if bn:
+                u.bn_weight = arr(prefix + '.bn.weight')
+                u.bn_bias = arr(prefix + '.bn.bias')
+                u.bn_mean = arr(prefix + '.bn.running_mean')
+                u.bn_var = arr(prefix + '.bn.running_var')
+            w = sd[prefix + conv_key + '.weight']
+            if tuple(w.shape[:2]) != (c_out, c_in):
+                raise ValueError('{}: weight shape {} does not match the topology ({}, {})'.format(prefix, tuple(w.shape), c_out, c_in))
+            u.c_in, u.c_out, u.has_dropout = c_in, c_out, int(bool(has_dropout))
+            return u
+
+        unit_arr = (_lib.RcuConvUnit * len(units))(*[unit_struct(p, ci, co, d) for (p, ci, co, d) in units])
+        up_arr = (_lib.RcuConvUnit * len(upconvs))(*[unit_struct(p, ci, co, False, bn=False, conv_key='') for (p, ci, co) in upconvs])
+        desc = _lib.RcuUnetDesc()
+        desc.in_channels, desc.depth, desc.start_filters, desc.nb_classes = self.in_channels, self.depth, self.start_filters, self.nb_classes
+        desc.p_drop = float(self.dropout) if self.dropout is not None else 0.0
+        desc.bn_eps = BN_EPS
+        desc.units, desc.n_units = unit_arr, len(units)
+        desc.upconvs, desc.n_upconvs = up_arr, len(upconvs)
+        desc.head = unit_struct('conv_cls.1', self.start_filters, self.nb_classes, False, bn=False, conv_key='')
+        handle = ctypes.c_void_p()
+        dev_index = self._device.index if self._device.index is not None else torch.cuda.current_device()
+        _lib.check(_lib.lib().rcu_unet_create(ctypes.byref(desc), int(dev_index), ctypes.byref(handle)))
+        self._handle = handle
+        del keep
+
+    def __del__(self):
+        h = getattr(self, '_handle', None)
+        if h:
+            try:
+                _lib.lib().rcu_unet_destroy(h)
+            except Exception:  # interpreter shutdown
+                pass
+            self._handle = None
+
+    # ------------------------------------------------------------------ nn.Module surface
+    def to(self, *args, **kwargs):  # weights already live on the device chosen at construction
+        return self
+
+    @property
+    def device(self):
+        return self._device
+
+    @property
+    def total_dropout_channels(self):
+        return int(sum(self.site_channels))
+
+    def set_conv_impl(self, impl):
+        """0 = tcgen05 (product path), 1 = CUDA-core cross-check kernels (tests only)."""
+        _lib.check(_lib.lib().rcu_unet_set_conv_impl(self._handle, int(impl)))
+
+    def last_launch_count(self):
+        return int(_lib.lib().rcu_unet_last_launch_count(self._handle))
+
+    def reset_stream(self, seed=None, slice_index=0, sample=0):
+        """Rewind the free-running Philox position used by forward() in MC mode."""
+        if seed is not None:
+            self.seed = int(seed)
+        self._next_slice, self._next_sample = int(slice_index), int(sample)
+
+    def _ensure_plan(self, h, w, n_samples):
+        need = max(self.chunk_images, n_samples)
+        if self._plan is None or self._plan[:2] != (h, w) or self._plan[2] < need:
+            ws = ctypes.c_size_t()
+            _lib.check(_lib.lib().rcu_unet_plan(self._handle, int(h), int(w), int(need), ctypes.byref(ws)))
+            self._plan = (h, w, need, int(ws.value))
+
+    def forward_samples(self, images, n_samples=1, dropout_mode=0, det_first=False, seed=None, slice_index0=0, sample0=0,
+                        scale=None):
+        """All samples of all slices in one call.
+
+        images: (N, C, H, W) tensor (moved to the device as float32).  Returns pixel-interleaved logits
+        float32 (n_samples, N, H, W, 2).  dropout_mode: 0 eval, 1 Philox MC dropout (sample ids sample0...),
+        2 caller-supplied keep-scale table `scale` float32 (n_stochastic, N, total_dropout_channels)."""
+        if images.dim() != 4 or images.shape[1] != self.in_channels:
+            raise ValueError('expected images of shape (N, {}, H, W), got {}'.format(self.in_channels, tuple(images.shape)))
+        x = images.to(self._device, torch.float32).contiguous()
+        n, _, h, w = x.shape
+        self._ensure_plan(h, w, n_samples)
+        logits = torch.empty((n_samples, n, h, w, 2), dtype=torch.float32, device=self._device)
+        scale_d = None
+        if dropout_mode == 2:
+            n_stoch = n_samples - (1 if det_first else 0)
+            scale_d = torch.as_tensor(scale, dtype=torch.float32).to(self._device).contiguous()
+            if tuple(scale_d.shape) != (n_stoch, n, self.total_dropout_channels):
+                raise ValueError('scale must have shape {}, got {}'.format((n_stoch, n, self.total_dropout_channels), tuple(scale_d.shape)))
+        with torch.cuda.device(self._device):
+            _lib.check(_lib.lib().rcu_unet_forward(self._handle, _lib.ptr(x), n, int(n_samples), int(dropout_mode), int(bool(det_first)),
+                                                   int(self.seed if seed is None else seed), int(slice_index0), int(sample0),
+                                                   _lib.ptr(scale_d), _lib.ptr(logits), _lib.current_stream()))
+        return logits
+
+    def forward(self, x):
+        """`model(images)` of the reference: logits (N, 2, H, W) float32 (a channels-last strided view).
+
+        Deterministic while the Dropout2d switch is in eval mode; in train mode (th.set_dropout_mode(model, True))
+        every call is the next MC sample of the Philox stream for these slices."""
+        if self.mc_dropout_switch.training and self.dropout:
+            logits = self.forward_samples(x, 1, dropout_mode=1, slice_index0=self._next_slice, sample0=self._next_sample)
+            self._next_sample += 1
+        else:
+            logits = self.forward_samples(x, 1, dropout_mode=0)
+        return logits[0].permute(0, 3, 1, 2)
+
+    def debug_activation(self, index, shape):
+        """fp32 copy of the index-th internal activation (NHWC) of the last chunk of the last forward."""
+        out = torch.empty(shape, dtype=torch.float32, device=self._device)
+        _lib.check(_lib.lib().rcu_unet_debug_activation(self._handle, int(index), _lib.ptr(out), out.numel(), _lib.current_stream()))
+        return out

@@ -1,0 +1,223 @@
+"""Drop-in BatchSteps for the reference's test loop (common/trainloop/loops.py:204-223).
+
+Same names, constructor arguments, call protocol `(batch_context, task_context, context)`, output keys, shapes,
+dtypes and device placement as
+  SegmentationPredictStep   common/trainloop/steps.py:69-90
+  McPredictStep             rechun/dl/customsteps.py:10-39
+  MultiPredictionSummary    rechun/dl/customsteps.py:42-71
+  EnsemblePredictionStep    bin-dl/brats_test_ensemble.py:72-94 (ISIC twin bin-dl/isic_test_ensemble.py:73-95)
+but the T+1 (or M) forwards run folded into one batch on the tcgen05 engine and softmax / mean / entropy are one
+fused pass over the logits.  `batch_context.output['multi_probabilities']` is a LazyMultiProbabilities: the fused
+summary consumes the logits behind it directly; anything else that touches it gets the real (T, N, C, H, W) tensor.
+"""
+import abc
+
+import torch
+
+from . import _lib
+from .model import B200UNet
+
+try:  # inside the reference tree the real protocol classes are used, so isinstance checks keep working
+    import common.trainloop.steps as _ref_steps
+    import common.trainloop.context as _ref_ctx
+    _BatchStepBase = _ref_steps.BatchStep
+    _CONTEXT_TYPES = (_ref_ctx.TorchTrainContext, _ref_ctx.TorchTestContext)
+except Exception:  # standalone use: duck-typed contexts
+    _ref_ctx = None
+    _CONTEXT_TYPES = None
+
+    class _BatchStepBase(abc.ABC):
+        @abc.abstractmethod
+        def __call__(self, batch_context, task_context, context) -> None:
+            pass
+
+
+def _type_error_msg(obj, expected_cls):
+    # common/utils/messages.py:4-10
+    exp = '({})'.format(','.join(e.__name__ for e in expected_cls)) if len(expected_cls) > 1 else expected_cls[0].__name__
+    return 'expected type is "{}" but object is of type "{}"'.format(exp, obj.__class__.__name__)
+
+
+def _check_context(context):
+    if _CONTEXT_TYPES is not None:
+        if not isinstance(context, _CONTEXT_TYPES):
+            raise ValueError(_type_error_msg(context, _CONTEXT_TYPES))
+    elif not (hasattr(context, 'model') and hasattr(context, 'device')):
+        raise ValueError('expected type is "(TorchTrainContext,TorchTestContext)" but object is of type "{}"'.format(
+            context.__class__.__name__))
+
+
+_ENGINES = {}
+
+
+def engine_for(model, device=None, seed=None):
+    """The B200UNet behind a model: the model itself, or a cached conversion of a reference UNet."""
+    if isinstance(model, B200UNet):
+        return model
+    key = id(model)
+    eng = _ENGINES.get(key)
+    if eng is None or eng[0] is not model:
+        kw = {} if seed is None else {'seed': seed}
+        eng = (model, B200UNet.from_reference(model, device=device, **kw))
+        _ENGINES[key] = eng
+    return eng[1]
+
+
+def softmax_planar(logits_interleaved):
+    """(N, H, W, 2) interleaved logits -> (N, 2, H, W) probabilities through the aggregation kernel (1 sample)."""
+    n, h, w, _ = logits_interleaved.shape
+    out = torch.empty((n, 2, h, w), dtype=torch.float32, device=logits_interleaved.device)
+    _lib.check(_lib.lib().rcu_aggregate(_lib.ptr(logits_interleaved), 0, 1, n, h * w, _lib.ptr(out), None, None, None, None, None,
+                                        _lib.current_stream()))
+    return out
+
+
+class LazyMultiProbabilities:
+    """Stands in for the stacked per-sample probabilities (T, N, 2, H, W) without materialising them."""
+
+    def __init__(self, logits):
+        self.logits = logits  # (T, N, H, W, 2) interleaved, float32
+        self._tensor = None
+
+    @property
+    def shape(self):
+        t, n, h, w, c = self.logits.shape
+        return torch.Size((t, n, c, h, w))
+
+    def materialize(self):
+        if self._tensor is None:
+            t, n, h, w, _ = self.logits.shape
+            mean = torch.empty((n, 2, h, w), dtype=torch.float32, device=self.logits.device)
+            multi = torch.empty((t, n, 2, h, w), dtype=torch.float32, device=self.logits.device)
+            _lib.check(_lib.lib().rcu_aggregate(_lib.ptr(self.logits), 0, t, n, h * w, _lib.ptr(mean), None, None, None, None,
+                                                _lib.ptr(multi), _lib.current_stream()))
+            self._tensor = multi
+        return self._tensor
+
+    def __torch_function__(self, func, types, args=(), kwargs=None):
+        kwargs = kwargs or {}
+        args = tuple(a.materialize() if isinstance(a, LazyMultiProbabilities) else a for a in args)
+        return func(*args, **kwargs)
+
+    def __getattr__(self, name):  # anything tensor-like falls through to the real tensor
+        if name.startswith('__'):
+            raise AttributeError(name)
+        return getattr(self.materialize(), name)
+
+
+class SegmentationPredictStep(_BatchStepBase):
+
+    def __init__(self, has_labels=False, do_probs=False) -> None:
+        super().__init__()
+        self.has_labels = has_labels
+        self.do_probs = do_probs
+
+    def __call__(self, batch_context, task_context, context) -> None:
+        _check_context(context)
+        batch_context.input['images'] = batch_context.input['images'].float().to(context.device)
+        if self.has_labels:
+            batch_context.input['labels'] = batch_context.input['labels'].long().to(context.device)
+        engine = engine_for(context.model, context.device)
+        logits = engine.forward_samples(batch_context.input['images'], 1, dropout_mode=0)[0]
+        batch_context.output['logits'] = logits.permute(0, 3, 1, 2)
+        if self.do_probs:
+            batch_context.output['probabilities'] = softmax_planar(logits)
+
+
+class McPredictStep(_BatchStepBase):
+    """T stochastic forwards + the deterministic weight-scaling forward, as ONE folded batch of (T+1)·N images."""
+
+    def __init__(self, mc_steps) -> None:
+        super().__init__()
+        self.mc_steps = mc_steps
+        self.slices_seen = 0  # run-global slice index: the Philox stream does not depend on batching
+
+    def __call__(self, batch_context, task_context, context) -> None:
+        _check_context(context)
+        batch_context.input['images'] = batch_context.input['images'].float().to(context.device)
+        images = batch_context.input['images']
+        engine = engine_for(context.model, context.device, _context_seed(context))
+        mode = 1 if engine.dropout else 0
+        logits = engine.forward_samples(images, self.mc_steps + 1, dropout_mode=mode, det_first=True,
+                                        slice_index0=self.slices_seen, sample0=0)
+        self.slices_seen += images.shape[0]
+        batch_context.output['ws_probabilities'] = softmax_planar(logits[0])
+        batch_context.output['multi_probabilities'] = LazyMultiProbabilities(logits[1:])
+
+
+class EnsemblePredictionStep(_BatchStepBase):
+
+    def __init__(self, additional_models) -> None:
+        super().__init__()
+        self.additional_models = additional_models
+
+    def __call__(self, batch_context, task_context, context) -> None:
+        _check_context(context)
+        batch_context.input['images'] = batch_context.input['images'].float().to(context.device)
+        images = batch_context.input['images']
+        members = [context.model] + list(self.additional_models)
+        n, _, h, w = images.shape
+        logits = torch.empty((len(members), n, h, w, 2), dtype=torch.float32, device=images.device)
+        for m, member in enumerate(members):
+            logits[m] = engine_for(member, context.device).forward_samples(images, 1, dropout_mode=0)[0]
+        batch_context.output['multi_probabilities'] = LazyMultiProbabilities(logits)
+
+
+class MultiPredictionSummary(_BatchStepBase):
+
+    def __init__(self, do_mi=False, do_var=False, remove_multi_probs=True, emit_prediction=False) -> None:
+        super().__init__()
+        self.do_mi = do_mi
+        self.do_var = do_var
+        self.remove_multi_probs = remove_multi_probs
+        self.emit_prediction = emit_prediction  # extra 'prediction' (N, H, W) uint8 output for the in-memory metric path
+
+    def __call__(self, batch_context, task_context, context) -> None:
+        if self.remove_multi_probs:
+            multi = batch_context.output.pop('multi_probabilities')
+        else:
+            multi = batch_context.output['multi_probabilities']
+        out = summarize(multi, self.do_mi, self.do_var, self.emit_prediction)
+        if not self.remove_multi_probs and isinstance(multi, LazyMultiProbabilities):
+            batch_context.output['multi_probabilities'] = multi.materialize()
+        batch_context.output.update(out)
+
+
+def summarize(multi, do_mi=False, do_var=False, emit_prediction=False):
+    """mean / entropy / [mutual_info] / [variance] / [prediction] of a LazyMultiProbabilities or a real
+    (T, N, 2, H, W) probability tensor — one fused pass (rechun/dl/customsteps.py:57-71)."""
+    if isinstance(multi, LazyMultiProbabilities):
+        src, kind = multi.logits, 0
+        t, n, h, w, c = src.shape
+    else:
+        if multi.dim() != 5 or multi.shape[2] != 2:
+            raise ValueError('multi_probabilities must have shape (T, N, 2, H, W), got {}'.format(tuple(multi.shape)))
+        src, kind = multi.float().contiguous(), 1
+        t, n, c, h, w = src.shape
+        if not src.is_cuda:
+            raise _lib.RcuError('multi_probabilities must live on the GPU (there is no CPU fallback)')
+    dev = src.device
+    mean = torch.empty((n, 2, h, w), dtype=torch.float32, device=dev)
+    entropy = torch.empty((n, 1, h, w), dtype=torch.float32, device=dev)
+    mi = torch.empty((n, 1, h, w), dtype=torch.float32, device=dev) if do_mi else None
+    var = torch.empty((n, 1, h, w), dtype=torch.float32, device=dev) if do_var else None
+    pred = torch.empty((n, h, w), dtype=torch.uint8, device=dev) if emit_prediction else None
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().rcu_aggregate(_lib.ptr(src), kind, t, n, h * w, _lib.ptr(mean), _lib.ptr(entropy), _lib.ptr(mi),
+                                            _lib.ptr(var), _lib.ptr(pred), None, _lib.current_stream()))
+    out = {'probabilities': mean, 'entropy': entropy}
+    if do_mi:
+        out['mutual_info'] = mi
+    if do_var:
+        out['variance'] = var
+    if emit_prediction:
+        out['prediction'] = pred
+    return out
+
+
+def _context_seed(context):
+    try:
+        seed = context.get_seed()
+    except Exception:
+        seed = None
+    return seed
