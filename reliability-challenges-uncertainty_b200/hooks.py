@@ -1,0 +1,67 @@
+"""DeviceMetricsHook — evaluates each finished subject on the GPU inside the test loop, so the calibration and
+uncertainty-error tables no longer need the NIfTI round trip through bin-eval/eval_uncertainty.py.
+
+It follows the TestLoopHook callback protocol of common/trainloop/hooks.py:67-98 (only the callbacks it needs do
+anything) and can be composed with the reference's hooks through ReducedComposeTestLoopHook (hooks.py:116-151).
+Rows carry the entries the `ece_dice`, `calib` and `bnf_ue` actions write (bin-eval/eval_uncertainty.py:112-202).
+"""
+import numpy as np
+
+from . import metrics
+from . import tables
+
+
+class DeviceMetricsHook:
+
+    def __init__(self, thresholds=tables.SWEEP_THRESHOLDS, n_bins=10, mask_entry=None, label_entry='labels',
+                 probability_entry='probabilities') -> None:
+        self.thresholds = tuple(thresholds)
+        self.n_bins = n_bins
+        self.mask_entry = mask_entry
+        self.label_entry = label_entry
+        self.probability_entry = probability_entry
+        self.break_table = tables.uncertainty_break_table(self.thresholds)
+        self.rows = []
+
+    # ---- callbacks that do nothing (protocol completeness) ----
+    def on_startup(self): pass
+    def end_startup(self, context): pass
+    def on_termination(self, context): pass
+    def on_test_start(self, task_context, context): pass
+    def on_test_end(self, task_context, context): pass
+    def on_test_batch_start(self, batch_context, task_context, context): pass
+    def on_test_batch_end(self, batch_context, task_context, context): pass
+    def on_test_subject_start(self, subject_context, task_context, context): pass
+
+    def on_test_subject_end(self, subject_context, task_context, context):
+        data = subject_context.subject_data
+        prob = data[self.probability_entry]
+        # what WriteHook saves and the eval script reloads (bin-dl/brats_test_default.py:96-98): argmax + foreground p
+        if prob.shape[-1] == 2:
+            prediction = (prob[..., 1] > prob[..., 0]).astype(np.uint8)
+            p = np.ascontiguousarray(prob[..., 1], dtype=np.float32)
+        else:
+            p = np.ascontiguousarray(prob, dtype=np.float32)
+            prediction = np.asarray(data['prediction'], dtype=np.uint8)
+        target = (np.asarray(data[self.label_entry]) != 0).astype(np.uint8)
+        mask = None if self.mask_entry is None else np.asarray(data[self.mask_entry]).astype(bool)
+        self.rows.append(self.evaluate(subject_context.subject_index, p, prediction, target, mask))
+
+    def evaluate(self, subject, p, prediction, target, mask=None):
+        count, positives, conf, ue, invalid, order = metrics.eval_fused(p, prediction, target, mask, self.n_bins, self.thresholds,
+                                                                        break_table=self.break_table)
+        if invalid[0] or count[0, self.n_bins]:
+            raise ValueError('subject {}: probabilities outside [0, 1]'.format(subject))
+        row = {'subject': subject}
+        bins = {}
+        row['ece'] = tables.ece_from_tables(count[0, :self.n_bins], positives[0, :self.n_bins], conf[0, :self.n_bins],
+                                            n_dim=np.ndim(target), out_bins=bins)
+        row.update(bins)
+        tp, tn, fp, fn = (ue[0, i].sum() for i in range(4))
+        row.update(tp=tp, tn=tn, fp=fp, fn=fn, n=int(np.size(target)), dice=tables.dice_from_counts(tp, fp, fn))
+        row['sweep'] = {}
+        for k_sorted, idx in enumerate(order):
+            r = tables.correction_results(*tables.counts_at_threshold(ue[0], k_sorted))
+            r.update(tables.ue_table_columns(r))
+            row['sweep'][self.thresholds[idx]] = r
+        return row

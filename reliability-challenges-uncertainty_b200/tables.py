@@ -145,14 +145,13 @@ def uncertainty_break_table(thresholds=SWEEP_THRESHOLDS, rel_eps=4e-6, max_zone=
 
 
 def threshold_breaks_f32(thresholds):
-    """For a float32 uncertainty map: u > th  <=>  u >= (smallest float32 > th).  Returns (breaks, identity, order)."""
+    """For a float32 uncertainty map numpy evaluates `u > th` in float32 (the Python-float threshold is cast to the
+    array's dtype, under value-based casting as well as NEP 50):  u > fl32(th)  <=>  u >= nextafter(fl32(th), +inf).
+    Returns (breaks, identity seg_class, order)."""
     ths = np.asarray(thresholds, dtype=np.float64)
     order = np.argsort(ths, kind='stable')
-    s = ths[order]
-    b = s.astype(np.float32)
-    le = b.astype(np.float64) <= s
-    b[le] = np.nextafter(b[le], np.float32(np.inf))
-    return b, np.arange(len(s) + 1, dtype=np.uint8), order
+    b = np.nextafter(ths[order].astype(np.float32), np.float32(np.inf))
+    return b, np.arange(len(ths) + 1, dtype=np.uint8), order
 
 
 # --------------------------------------------------------------------------------------------------

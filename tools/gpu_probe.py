@@ -33,6 +33,7 @@ def synth_maps(n, seed=20):
     br, _, _ = tables.uncertainty_break_table()
     adv = np.concatenate([adv, br, np.nextafter(br, np.float32(0)), np.nextafter(br, np.float32(2))])
     adv = adv[(adv >= 0) & (adv <= 1)]
+    adv = adv[:n]
     p[:len(adv)] = adv
     target = (rng.random(n) < p).astype(np.uint8)
     mask = (rng.random(n) < 0.25)
