@@ -226,6 +226,16 @@ int rcu_unet_debug_activation(rcu_unet* net, int index, float* out, size_t out_e
 /* Selects the convolution implementation: 0 = tcgen05/TMEM/TMA implicit GEMM (default, the product path),
  * 1 = straightforward CUDA-core fp32-accumulate kernel over the same bf16 data (on-device cross-check only). */
 int rcu_unet_set_conv_impl(rcu_unet* net, int impl);
+/* Optional per-op device timing: when enabled, every kernel launch of rcu_unet_forward is bracketed by CUDA events
+ * on the launch stream.  rcu_unet_read_timing synchronises those events and returns, per op of the schedule (see
+ * rcu_unet_op_info), the accumulated milliseconds and launch count since the last read.  ms/launches hold n_ops
+ * entries; entry n_ops-1 is the per-chunk coefficient-table kernel. */
+int rcu_unet_enable_timing(rcu_unet* net, int enable);
+int rcu_unet_num_ops(const rcu_unet* net);
+/* kind: 0 first conv (CUDA cores), 1 tcgen05 conv, 2 max-pool, 3 coefficient table.  macs_per_image: algorithmic
+ * multiply-accumulates of the reference layer this op computes (0 for non-conv ops). */
+int rcu_unet_op_info(const rcu_unet* net, int op, int* kind, int64_t* macs_per_image, int* c_in, int* c_out, int* h, int* w);
+int rcu_unet_read_timing(rcu_unet* net, float* ms, int64_t* launches, int n_ops);
 /* Number of kernel launches issued by the last rcu_unet_forward on this handle. */
 int64_t rcu_unet_last_launch_count(const rcu_unet* net);
 

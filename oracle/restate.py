@@ -393,7 +393,8 @@ def add_background_probability(p_foreground):
 
 def numpy_entropy(p, axis=-1):
     # numpyfunctions.py:166-168 — the float list literal makes np.where promote to float64 before the sum
-    return -np.where(p > 0, p * np.log(p), [0.0]).sum(axis=axis)
+    with np.errstate(divide='ignore', invalid='ignore'):  # log(0) and 0*inf of the discarded where-branch
+        return -np.where(p > 0, p * np.log(p), [0.0]).sum(axis=axis)
 
 
 def normalized_entropy(prob_2class):

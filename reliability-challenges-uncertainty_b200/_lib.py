@@ -62,6 +62,10 @@ PROTOTYPES = {
     'rcu_unet_debug_activation': (c_int, [c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     'rcu_unet_set_conv_impl': (c_int, [c_void_p, c_int]),
     'rcu_unet_last_launch_count': (c_int64, [c_void_p]),
+    'rcu_unet_enable_timing': (c_int, [c_void_p, c_int]),
+    'rcu_unet_num_ops': (c_int, [c_void_p]),
+    'rcu_unet_op_info': (c_int, [c_void_p, c_int, c_int_p, ctypes.POINTER(c_int64), c_int_p, c_int_p, c_int_p, c_int_p]),
+    'rcu_unet_read_timing': (c_int, [c_void_p, c_float_p, ctypes.POINTER(c_int64), c_int]),
 }
 
 _lib = None

@@ -92,7 +92,30 @@ struct rcu_unet {
   int conv_impl = 0;
   long long last_launches = 0;
   int last_n_img = 0;
+  // optional per-op timing
+  bool timing = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+  std::vector<int> ev_op;      // op index of every recorded pair since the last read
+  size_t ev_used = 0;
 };
+
+namespace rcu {
+struct OpTimer {  // brackets one launch with events when timing is on
+  rcu_unet* net; cudaStream_t st; int slot = -1;
+  OpTimer(rcu_unet* n, int op, cudaStream_t s) : net(n), st(s) {
+    if (!net->timing) return;
+    if (net->ev_used == net->ev_pool.size()) {
+      cudaEvent_t a, b;
+      if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) { cudaGetLastError(); return; }
+      net->ev_pool.push_back({a, b});
+    }
+    slot = (int)net->ev_used++;
+    net->ev_op.push_back(op);
+    cudaEventRecord(net->ev_pool[slot].first, st);
+  }
+  ~OpTimer() { if (slot >= 0) cudaEventRecord(net->ev_pool[slot].second, st); }
+};
+}  // namespace rcu
 
 namespace rcu {
 
@@ -399,6 +422,7 @@ extern "C" int rcu_unet_create(const rcu_unet_desc* d, int device, rcu_unet** ou
 extern "C" void rcu_unet_destroy(rcu_unet* net) {
   if (!net) return;
   cudaSetDevice(net->device);
+  for (auto& e : net->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   for (void* p : net->owned) cudaFree(p);
   if (net->arena) cudaFree(net->arena);
   delete net;
@@ -526,13 +550,16 @@ extern "C" int rcu_unet_forward(rcu_unet* net, const float* images, int64_t n_sl
       const long long total = (long long)n_img * net->n_cols;
       long long blocks = (total + 255) / 256;
       if (blocks > (long long)sm_count() * 8) blocks = (long long)sm_count() * 8;
+      OpTimer timer(net, (int)net->ops.size(), st);
       coef_kernel<<<(unsigned)blocks, 256, 0, st>>>(net->cols, net->d_coef, n_img, cs, (long long)s0, (long long)n_slices, dropout_mode,
                                                     det_first, (uint32_t)seed, (uint32_t)(seed >> 32), thr, inv_keep,
                                                     (long long)slice_index0, sample0, scale, net->total_dropout_channels);
       RCU_LAUNCH_CHECK();
       ++launches;
     }
-    for (const Op& op : net->ops) {
+    for (size_t op_index = 0; op_index < net->ops.size(); ++op_index) {
+      const Op& op = net->ops[op_index];
+      OpTimer timer(net, (int)op_index, st);
       if (op.kind == OP_FIRST) {
         const int tiles = ((H + kFirstTile - 1) / kFirstTile) * ((W + kFirstTile - 1) / kFirstTile);
         const size_t smem = ((size_t)net->in_channels * 9 * sf + (size_t)net->in_channels * 324) * sizeof(float);
@@ -616,5 +643,61 @@ extern "C" int rcu_unet_debug_activation(rcu_unet* net, int index, float* out, s
   if (blocks > 4096) blocks = 4096;
   bf16_to_f32_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(op.out, out, n);
   RCU_LAUNCH_CHECK();
+  return RCU_OK;
+}
+
+extern "C" int rcu_unet_enable_timing(rcu_unet* net, int enable) {
+  RCU_CHECK_ARG(net != nullptr, "NULL handle");
+  net->timing = enable != 0;
+  net->ev_used = 0;
+  net->ev_op.clear();
+  return RCU_OK;
+}
+
+extern "C" int rcu_unet_num_ops(const rcu_unet* net) { return net ? (int)net->ops.size() + 1 : 0; }
+
+extern "C" int rcu_unet_op_info(const rcu_unet* net, int op, int* kind, int64_t* macs_per_image, int* c_in, int* c_out, int* h, int* w) {
+  RCU_CHECK_ARG(net != nullptr, "NULL handle");
+  RCU_CHECK_ARG(op >= 0 && op <= (int)net->ops.size(), "op index %d out of range", op);
+  int k = 3, ci = 0, co = 0, hh = 0, ww = 0;
+  int64_t macs = 0;
+  if (op < (int)net->ops.size()) {
+    const Op& o = net->ops[op];
+    hh = o.h; ww = o.w; co = o.c;
+    if (o.kind == OP_FIRST) {
+      k = 0; ci = net->in_channels;
+      macs = (int64_t)net->H * net->W * 9 * net->in_channels * net->start_filters;
+    } else if (o.kind == OP_POOL) {
+      k = 2; ci = o.c;
+    } else {
+      const ConvLayer& L = net->convs[o.conv];
+      k = 1; ci = L.c0 + L.c1;
+      // algorithmic MACs of the reference layer: a 3x3 conv at the OUTPUT resolution (for the up-path conv that is
+      // the conv after nearest-x2, common/model/unet.py:105), plus the fused 1x1 head
+      macs = (int64_t)o.h * o.w * 9 * ci * L.c_out + (L.head ? (int64_t)o.h * o.w * L.c_out * 2 : 0);
+    }
+  }
+  if (kind) *kind = k;
+  if (macs_per_image) *macs_per_image = macs;
+  if (c_in) *c_in = ci;
+  if (c_out) *c_out = co;
+  if (h) *h = hh;
+  if (w) *w = ww;
+  return RCU_OK;
+}
+
+extern "C" int rcu_unet_read_timing(rcu_unet* net, float* ms, int64_t* launches, int n_ops) {
+  RCU_CHECK_ARG(net != nullptr && ms != nullptr && launches != nullptr, "NULL argument");
+  RCU_CHECK_ARG(n_ops == (int)net->ops.size() + 1, "expected %d ops", (int)net->ops.size() + 1);
+  for (int i = 0; i < n_ops; ++i) { ms[i] = 0.f; launches[i] = 0; }
+  for (size_t i = 0; i < net->ev_used; ++i) {
+    RCU_CUDA(cudaEventSynchronize(net->ev_pool[i].second));
+    float t = 0.f;
+    RCU_CUDA(cudaEventElapsedTime(&t, net->ev_pool[i].first, net->ev_pool[i].second));
+    ms[net->ev_op[i]] += t;
+    launches[net->ev_op[i]] += 1;
+  }
+  net->ev_used = 0;
+  net->ev_op.clear();
   return RCU_OK;
 }

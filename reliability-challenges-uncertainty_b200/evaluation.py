@@ -181,30 +181,36 @@ class EceBinaryNumpy(NumpyEvaluationStrategy):
                                                 self.threshold_range, mask, out_bins, self.bin_weighting)
 
 
-def _sweep_table(to_evaluate, threshold, mask, mask_tag):
-    """Joint table for `threshold`, shared between strategies evaluated on the same `to_evaluate` dict.
-
-    The uncertainty entry decides the route: float64 numpy (what ToEntropy produces) -> exact float64 comparison on
-    the device; float32 -> float32 break points.  Thresholds of the standard sweep are evaluated together."""
-    unc = to_evaluate['uncertainty']
-    _check_ndarray(unc)
-    is64 = (unc.dtype == np.float64) if isinstance(unc, np.ndarray) else (unc.dtype == torch.float64)
-    kind = 'u64' if is64 else 'u32'
-    group = tables.SWEEP_THRESHOLDS if threshold in tables.SWEEP_THRESHOLDS else (threshold,)
-    cache = to_evaluate.setdefault(_CACHE_KEY, {})
-    key = (kind, group, mask_tag, id(unc), id(to_evaluate['prediction']), id(to_evaluate['target']))
-    if key not in cache:
-        table, _, order = metrics.ue_tables(unc, to_evaluate['prediction'], to_evaluate['target'], group, mask, kind=kind)
-        cache[key] = (table[0], list(np.asarray(group)[order]))
-    table, sorted_ths = cache[key]
-    return table, sorted_ths.index(threshold)
-
-
 def _as_bool_u8(x):
     # `.astype(np.bool)` of the reference (eval.py:159-160,184-185): any non-zero value is True
     if torch.is_tensor(x):
         return (x != 0).to(torch.uint8)
     return (np.asarray(x) != 0).view(np.uint8)
+
+
+def _sweep_table(to_evaluate, threshold, mask, mask_tag):
+    """Joint table for `threshold`, shared between strategies evaluated on the same `to_evaluate` dict.
+
+    The uncertainty entry decides the route: float64 numpy (what ToEntropy produces) -> exact float64 comparison on
+    the device; float32 -> float32 break points.  Thresholds of the standard sweep are evaluated together and the
+    table is memoised in the dict, so the eleven CorrectionAction strategies cost one kernel pass."""
+    unc, prediction, target = to_evaluate['uncertainty'], to_evaluate['prediction'], to_evaluate['target']
+    _check_ndarray(unc)
+    _check_ndarray(prediction)
+    _check_ndarray(target)
+    is64 = (unc.dtype == np.float64) if isinstance(unc, np.ndarray) else (unc.dtype == torch.float64)
+    kind = 'u64' if is64 else 'u32'
+    group = tables.SWEEP_THRESHOLDS if threshold in tables.SWEEP_THRESHOLDS else (threshold,)
+    cache = to_evaluate.setdefault(_CACHE_KEY, {})
+    key = (kind, group, mask_tag, id(unc), id(prediction), id(target))
+    if key not in cache:
+        bkey = ('bool', id(prediction), id(target))
+        if bkey not in cache:
+            cache[bkey] = (_as_bool_u8(prediction), _as_bool_u8(target))
+        table, _, order = metrics.ue_tables(unc, cache[bkey][0], cache[bkey][1], group, mask, kind=kind)
+        cache[key] = (table[0], list(np.asarray(group)[order]))
+    table, sorted_ths = cache[key]
+    return table, sorted_ths.index(threshold)
 
 
 class UncertaintyErrorDiceNumpy(NumpyEvaluationStrategy):
@@ -220,9 +226,7 @@ class UncertaintyErrorDiceNumpy(NumpyEvaluationStrategy):
         if self.with_mask:
             boarder = to_evaluate['target_boarder']
             mask = (~boarder) if torch.is_tensor(boarder) else ~np.asarray(boarder, dtype=bool)
-        view = dict(to_evaluate)
-        view['prediction'], view['target'] = _as_bool_u8(to_evaluate['prediction']), _as_bool_u8(to_evaluate['target'])
-        table, k = _sweep_table(view, self.uncertainty_threshold, mask, 'boarder' if self.with_mask else None)
+        table, k = _sweep_table(to_evaluate, self.uncertainty_threshold, mask, 'boarder' if self.with_mask else None)
         tp, tn, fp, fn, tpu, tnu, fpu, fnu = tables.counts_at_threshold(table, k)
         results['{}precision'.format(self.prefix)] = tables.error_precision(tpu, tnu, fpu, fnu)
         results['{}recall'.format(self.prefix)] = tables.error_recall(fp, fn, fpu, fnu)
@@ -236,13 +240,7 @@ class UncertaintyAndCorrectionEvalNumpy(NumpyEvaluationStrategy):
         self.uncertainty_threshold = uncertainty_threshold
 
     def __call__(self, to_evaluate: dict, results: dict) -> None:
-        cache = to_evaluate.setdefault(_CACHE_KEY, {})
-        bkey = ('bool', id(to_evaluate['prediction']), id(to_evaluate['target']))
-        if bkey not in cache:
-            cache[bkey] = (_as_bool_u8(to_evaluate['prediction']), _as_bool_u8(to_evaluate['target']))
-        view = {'uncertainty': to_evaluate['uncertainty'], 'prediction': cache[bkey][0], 'target': cache[bkey][1],
-                _CACHE_KEY: cache}
-        table, k = _sweep_table(view, self.uncertainty_threshold, None, None)
+        table, k = _sweep_table(to_evaluate, self.uncertainty_threshold, None, None)
         tables.correction_results(*tables.counts_at_threshold(table, k), results=results)
 
 

@@ -92,6 +92,7 @@ class B200UNet(nn.Module):
         units, upconvs = unit_layout(in_channels, depth, start_filters, dropout, dropout_center)
         self.site_channels = [co for (_, _, co, d) in units if d]
         self._create(state_dict, units, upconvs)
+        self.eval()  # inference engine: the Dropout2d switch starts in eval mode, like load_from_checkpoint leaves the model (context.py:321)
 
     # ------------------------------------------------------------------ construction
     @classmethod
@@ -132,6 +133,7 @@ class B200UNet(nn.Module):
             p0 = next(module.parameters())
             device = p0.device if p0.is_cuda else None
         net = cls(sd, nb_classes, in_channels, depth, start_filters, dropout, dropout_center, device, seed, chunk_images)
+        net.mc_dropout_switch.train(any(m.training for m in module.modules() if isinstance(m, nn.Dropout2d)))
         net.provide_features = bool(getattr(module, 'provide_features', False))
         if net.provide_features:
             raise NotImplementedError('provide_features=True (auxiliary feature nets) is outside the B200 hot path')
@@ -254,6 +256,32 @@ class B200UNet(nn.Module):
         else:
             logits = self.forward_samples(x, 1, dropout_mode=0)
         return logits[0].permute(0, 3, 1, 2)
+
+    def enable_timing(self, enable=True):
+        """Bracket every kernel launch of the forward with CUDA events (read them with read_timing)."""
+        _lib.check(_lib.lib().rcu_unet_enable_timing(self._handle, int(bool(enable))))
+
+    def op_table(self):
+        """[{kind, macs_per_image, c_in, c_out, h, w}] for every op of the planned schedule (last = coefficient table)."""
+        n = int(_lib.lib().rcu_unet_num_ops(self._handle))
+        out = []
+        for i in range(n):
+            kind, ci, co, h, w = (ctypes.c_int() for _ in range(5))
+            macs = ctypes.c_int64()
+            _lib.check(_lib.lib().rcu_unet_op_info(self._handle, i, ctypes.byref(kind), ctypes.byref(macs), ctypes.byref(ci),
+                                                   ctypes.byref(co), ctypes.byref(h), ctypes.byref(w)))
+            out.append({'kind': ('first_conv', 'conv_tc', 'maxpool', 'coef')[kind.value], 'macs_per_image': int(macs.value),
+                        'c_in': ci.value, 'c_out': co.value, 'h': h.value, 'w': w.value})
+        return out
+
+    def read_timing(self):
+        """(ms float32[n_ops], launches int64[n_ops]) accumulated since the last read; synchronises the events."""
+        n = int(_lib.lib().rcu_unet_num_ops(self._handle))
+        ms = np.zeros(n, dtype=np.float32)
+        launches = np.zeros(n, dtype=np.int64)
+        _lib.check(_lib.lib().rcu_unet_read_timing(self._handle, ms.ctypes.data_as(_lib.c_float_p),
+                                                   launches.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), n))
+        return ms, launches
 
     def debug_activation(self, index, shape):
         """fp32 copy of the index-th internal activation (NHWC) of the last chunk of the last forward."""

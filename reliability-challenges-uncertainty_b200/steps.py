@@ -94,7 +94,8 @@ class LazyMultiProbabilities:
             self._tensor = multi
         return self._tensor
 
-    def __torch_function__(self, func, types, args=(), kwargs=None):
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
         kwargs = kwargs or {}
         args = tuple(a.materialize() if isinstance(a, LazyMultiProbabilities) else a for a in args)
         return func(*args, **kwargs)

@@ -78,6 +78,7 @@ def _check_ue(values, kind, pred, target, unc_ref, ths=SWEEP, mask=None, n_subje
         m = None if mask is None else mask[sl]
         assert tab[j].sum() == (vps if m is None else m.sum())
         for k, th in enumerate(sorted_ths):
+            th = float(th)  # the reference compares against a Python float (weak scalar: float32 maps compare in float32)
             exp = R.uncertainty_counts(pred[sl].astype(bool), target[sl].astype(bool), unc_ref[sl] > th, m)
             assert tuple(int(v) for v in tables.counts_at_threshold(tab[j], k)) == tuple(int(v) for v in exp), (kind, j, th)
 
@@ -133,8 +134,11 @@ def test_fifty_subjects_in_one_launch_match_per_subject_calls():
     for j in (0, 17, 49):
         sl = slice(j * vps, (j + 1) * vps)
         single = metrics.eval_fused(p[sl], pred[sl], target[sl], mask[sl])
-        for a, b in zip(batched[:5], single[:5]):
-            assert np.array_equal(a[j], b[0])
+        for i, (a, b) in enumerate(zip(batched[:5], single[:5])):
+            if i == 2:  # float64 confidence sums: a different block partition changes the summation order only
+                assert np.allclose(a[j], b[0], rtol=CONF_RTOL, atol=0)
+            else:
+                assert np.array_equal(a[j], b[0])
 
 
 # ---------------------------------------------------------------------------------------------- drop-in strategies
@@ -175,7 +179,7 @@ def test_sweep_strategies_match_reference_golden(golden_metrics):
         for k in ('precision', 'recall', 'dice'):
             results_equal(res[k], golden_metrics['uedice/%s/%s' % (th, k)], k)
     # the eleven sweep strategies shared one kernel pass
-    assert sum(1 for k in to_eval['_rcu_b200'] if k[0] == 'u64') == 1
+    assert sum(1 for k in to_eval['_rcu_b200'] if k[0] == 'u64') == 2   # one unmasked pass, one with the border mask
     res = {}
     ev.UncertaintySweepFromProbabilities()(to_eval, res)
     for th in SWEEP:
