@@ -127,12 +127,14 @@ int rcu_confusion(const uint8_t* prediction, const uint8_t* target, int64_t voxe
  *   mutual_info float32[n_images][hw]     entropy - mean_t H(p_t)
  *   variance   float32[n_images][hw]      mean_c var_t(p_t,c), unbiased
  *   prediction uint8  [n_images][hw]      argmax_c mean (ties -> class 0, like np.argmax)
+ *   foreground float32[n_images][hw]      mean[:, 1] as a dense map — what WriteHook saves as `*_probabilities.nii.gz`
+ *              (bin-dl/brats_test_default.py:98) and the metric kernels read
  *   multi_out  float32[n_samples][n_images][2][hw] planar per-sample probabilities (the reference's
  *              `multi_probabilities`), only written when non-NULL
  */
 int rcu_aggregate(const float* input, int input_kind, int n_samples, int64_t n_images, int64_t hw, float* mean,
-                  float* entropy, float* mutual_info, float* variance, uint8_t* prediction, float* multi_out,
-                  void* stream);
+                  float* entropy, float* mutual_info, float* variance, uint8_t* prediction, float* foreground,
+                  float* multi_out, void* stream);
 
 /* Partial aggregation for sample-sharded runs: writes the raw fp32 sums so ranks can allreduce them.
  *   sums float32[n_images][K][hw] with K = 2 (sum p0, sum p1) [+1: sum_t H(p_t) if want_mi] [+2: sum p0^2, sum p1^2 if want_var]
@@ -141,7 +143,7 @@ int rcu_aggregate_partial(const float* input, int input_kind, int n_samples, int
                           int want_mi, int want_var, float* sums, void* stream);
 int rcu_aggregate_finish(const float* sums, int total_samples, int64_t n_images, int64_t hw, int has_mi, int has_var,
                          float* mean, float* entropy, float* mutual_info, float* variance, uint8_t* prediction,
-                         void* stream);
+                         float* foreground, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Philox4x32-10 Dropout2d keep masks

@@ -47,10 +47,10 @@ PROTOTYPES = {
                                c_void_p]),
     'rcu_confusion': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     'rcu_aggregate': (c_int, [c_void_p, c_int, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                              c_void_p, c_void_p]),
+                              c_void_p, c_void_p, c_void_p]),
     'rcu_aggregate_partial': (c_int, [c_void_p, c_int, c_int, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p]),
     'rcu_aggregate_finish': (c_int, [c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
-                                     c_void_p, c_void_p]),
+                                     c_void_p, c_void_p, c_void_p]),
     'rcu_philox_masks': (c_int, [c_uint64, c_float, c_int_p, c_int, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p]),
     'rcu_philox_masks_host': (c_int, [c_uint64, c_float, c_int_p, c_int, c_int64, c_int64, c_int, c_int, c_float_p]),
     'rcu_unet_create': (c_int, [ctypes.POINTER(RcuUnetDesc), c_int, ctypes.POINTER(c_void_p)]),

@@ -37,8 +37,8 @@ template <int KIND, bool MI, bool VAR, bool PARTIAL>
 __global__ void __launch_bounds__(kAggThreads)
 aggregate_kernel(const float* __restrict__ in, int n_samples, long long n_images, long long hw, float inv_or_scale,
                  float* __restrict__ mean, float* __restrict__ entropy, float* __restrict__ mutual_info,
-                 float* __restrict__ variance, unsigned char* __restrict__ prediction, float* __restrict__ multi_out,
-                 float* __restrict__ sums) {
+                 float* __restrict__ variance, unsigned char* __restrict__ prediction, float* __restrict__ foreground,
+                 float* __restrict__ multi_out, float* __restrict__ sums) {
   const long long pairs_per_image = hw >> 1;  // hw is even (checked on the host)
   const long long total_pairs = n_images * pairs_per_image;
   const long long sample_stride = n_images * hw * 2;
@@ -129,6 +129,7 @@ aggregate_kernel(const float* __restrict__ in, int n_samples, long long n_images
       pr.y = m1[1] > m0[1] ? 1 : 0;
       *reinterpret_cast<uchar2*>(prediction + o) = pr;
     }
+    if (foreground) *reinterpret_cast<float2*>(foreground + o) = make_float2(m1[0], m1[1]);
     }  // !PARTIAL
   }
 }
@@ -137,7 +138,7 @@ aggregate_kernel(const float* __restrict__ in, int n_samples, long long n_images
 __global__ void __launch_bounds__(kAggThreads)
 aggregate_finish_kernel(const float* __restrict__ sums, float total_samples, long long n_images, long long hw, int has_mi,
                         int has_var, float* __restrict__ mean, float* __restrict__ entropy, float* __restrict__ mutual_info,
-                        float* __restrict__ variance, unsigned char* __restrict__ prediction) {
+                        float* __restrict__ variance, unsigned char* __restrict__ prediction, float* __restrict__ foreground) {
   const int planes = 2 + (has_mi ? 1 : 0) + (has_var ? 2 : 0);
   const long long total = n_images * hw;
   for (long long i = (long long)blockIdx.x * kAggThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kAggThreads) {
@@ -161,13 +162,14 @@ aggregate_finish_kernel(const float* __restrict__ sums, float total_samples, lon
       variance[i] = 0.5f * ((q0 - total_samples * m0 * m0) / dn + (q1 - total_samples * m1 * m1) / dn);
     }
     if (prediction) prediction[i] = m1 > m0 ? 1 : 0;
+    if (foreground) foreground[i] = m1;
   }
 }
 
 template <int KIND, bool PARTIAL>
 static int launch_aggregate(bool mi, bool var, const float* in, int n_samples, int64_t n_images, int64_t hw, float denom,
                             float* mean, float* entropy, float* mutual_info, float* variance, uint8_t* prediction,
-                            float* multi_out, float* sums, cudaStream_t st) {
+                            float* foreground, float* multi_out, float* sums, cudaStream_t st) {
   const long long total_pairs = n_images * (hw / 2);
   if (total_pairs == 0) return RCU_OK;
   long long blocks = (total_pairs + kAggThreads - 1) / kAggThreads;
@@ -176,7 +178,7 @@ static int launch_aggregate(bool mi, bool var, const float* in, int n_samples, i
 #define RCU_AGG_LAUNCH(MI_, VAR_)                                                                                    \
   aggregate_kernel<KIND, MI_, VAR_, PARTIAL><<<(unsigned)blocks, kAggThreads, 0, st>>>(                               \
       in, n_samples, (long long)n_images, (long long)hw, denom, mean, entropy, mutual_info, variance, prediction,     \
-      multi_out, sums)
+      foreground, multi_out, sums)
   if (mi && var) RCU_AGG_LAUNCH(true, true);
   else if (mi) RCU_AGG_LAUNCH(true, false);
   else if (var) RCU_AGG_LAUNCH(false, true);
@@ -201,8 +203,8 @@ static int check_agg_common(const float* input, int input_kind, int n_samples, i
 using namespace rcu;
 
 extern "C" int rcu_aggregate(const float* input, int input_kind, int n_samples, int64_t n_images, int64_t hw, float* mean,
-                             float* entropy, float* mutual_info, float* variance, uint8_t* prediction, float* multi_out,
-                             void* stream) {
+                             float* entropy, float* mutual_info, float* variance, uint8_t* prediction, float* foreground,
+                             float* multi_out, void* stream) {
   int rc = check_agg_common(input, input_kind, n_samples, n_images, hw);
   if (rc) return rc;
   RCU_CHECK_ARG(mean != nullptr, "mean output is NULL");
@@ -211,9 +213,9 @@ extern "C" int rcu_aggregate(const float* input, int input_kind, int n_samples, 
   cudaStream_t st = (cudaStream_t)stream;
   const float denom = (float)n_samples;
   switch (input_kind) {
-    case 0: return launch_aggregate<0, false>(mi, var, input, n_samples, n_images, hw, denom, mean, entropy, mutual_info, variance, prediction, multi_out, nullptr, st);
-    case 1: return launch_aggregate<1, false>(mi, var, input, n_samples, n_images, hw, denom, mean, entropy, mutual_info, variance, prediction, multi_out, nullptr, st);
-    default: return launch_aggregate<2, false>(mi, var, input, n_samples, n_images, hw, denom, mean, entropy, mutual_info, variance, prediction, multi_out, nullptr, st);
+    case 0: return launch_aggregate<0, false>(mi, var, input, n_samples, n_images, hw, denom, mean, entropy, mutual_info, variance, prediction, foreground, multi_out, nullptr, st);
+    case 1: return launch_aggregate<1, false>(mi, var, input, n_samples, n_images, hw, denom, mean, entropy, mutual_info, variance, prediction, foreground, multi_out, nullptr, st);
+    default: return launch_aggregate<2, false>(mi, var, input, n_samples, n_images, hw, denom, mean, entropy, mutual_info, variance, prediction, foreground, multi_out, nullptr, st);
   }
 }
 
@@ -224,15 +226,15 @@ extern "C" int rcu_aggregate_partial(const float* input, int input_kind, int n_s
   RCU_CHECK_ARG(sums != nullptr, "sums output is NULL");
   cudaStream_t st = (cudaStream_t)stream;
   switch (input_kind) {
-    case 0: return launch_aggregate<0, true>(want_mi != 0, want_var != 0, input, n_samples, n_images, hw, 1.f, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, sums, st);
-    case 1: return launch_aggregate<1, true>(want_mi != 0, want_var != 0, input, n_samples, n_images, hw, 1.f, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, sums, st);
-    default: return launch_aggregate<2, true>(want_mi != 0, want_var != 0, input, n_samples, n_images, hw, 1.f, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, sums, st);
+    case 0: return launch_aggregate<0, true>(want_mi != 0, want_var != 0, input, n_samples, n_images, hw, 1.f, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, sums, st);
+    case 1: return launch_aggregate<1, true>(want_mi != 0, want_var != 0, input, n_samples, n_images, hw, 1.f, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, sums, st);
+    default: return launch_aggregate<2, true>(want_mi != 0, want_var != 0, input, n_samples, n_images, hw, 1.f, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, sums, st);
   }
 }
 
 extern "C" int rcu_aggregate_finish(const float* sums, int total_samples, int64_t n_images, int64_t hw, int has_mi, int has_var,
                                     float* mean, float* entropy, float* mutual_info, float* variance, uint8_t* prediction,
-                                    void* stream) {
+                                    float* foreground, void* stream) {
   RCU_CHECK_ARG(sums != nullptr && mean != nullptr, "NULL pointer argument");
   RCU_CHECK_ARG(total_samples >= 1 && n_images >= 0 && hw >= 0, "bad sizes");
   RCU_CHECK_ARG(!(has_var && variance) || total_samples >= 2, "variance needs at least two samples");
@@ -243,7 +245,7 @@ extern "C" int rcu_aggregate_finish(const float* sums, int total_samples, int64_
   if (blocks > cap) blocks = cap;
   aggregate_finish_kernel<<<(unsigned)blocks, kAggThreads, 0, (cudaStream_t)stream>>>(
       sums, (float)total_samples, (long long)n_images, (long long)hw, has_mi, has_var, mean, entropy, mutual_info, variance,
-      prediction);
+      prediction, foreground);
   RCU_LAUNCH_CHECK();
   return RCU_OK;
 }

@@ -101,7 +101,7 @@ def aggregate_finish(sums, total_samples, has_mi=False, has_var=False, emit_pred
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().rcu_aggregate_finish(_lib.ptr(sums), int(total_samples), n, h * w, int(has_mi), int(has_var),
                                                    _lib.ptr(out['probabilities']), _lib.ptr(out['entropy']), _lib.ptr(out.get('mutual_info')),
-                                                   _lib.ptr(out.get('variance')), _lib.ptr(out.get('prediction')), _lib.current_stream()))
+                                                   _lib.ptr(out.get('variance')), _lib.ptr(out.get('prediction')), None, _lib.current_stream()))
     return out
 
 

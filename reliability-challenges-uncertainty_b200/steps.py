@@ -67,7 +67,7 @@ def softmax_planar(logits_interleaved):
     """(N, H, W, 2) interleaved logits -> (N, 2, H, W) probabilities through the aggregation kernel (1 sample)."""
     n, h, w, _ = logits_interleaved.shape
     out = torch.empty((n, 2, h, w), dtype=torch.float32, device=logits_interleaved.device)
-    _lib.check(_lib.lib().rcu_aggregate(_lib.ptr(logits_interleaved), 0, 1, n, h * w, _lib.ptr(out), None, None, None, None, None,
+    _lib.check(_lib.lib().rcu_aggregate(_lib.ptr(logits_interleaved), 0, 1, n, h * w, _lib.ptr(out), None, None, None, None, None, None,
                                         _lib.current_stream()))
     return out
 
@@ -90,7 +90,7 @@ class LazyMultiProbabilities:
             mean = torch.empty((n, 2, h, w), dtype=torch.float32, device=self.logits.device)
             multi = torch.empty((t, n, 2, h, w), dtype=torch.float32, device=self.logits.device)
             _lib.check(_lib.lib().rcu_aggregate(_lib.ptr(self.logits), 0, t, n, h * w, _lib.ptr(mean), None, None, None, None,
-                                                _lib.ptr(multi), _lib.current_stream()))
+                                                None, _lib.ptr(multi), _lib.current_stream()))
             self._tensor = multi
         return self._tensor
 
@@ -166,26 +166,27 @@ class EnsemblePredictionStep(_BatchStepBase):
 
 class MultiPredictionSummary(_BatchStepBase):
 
-    def __init__(self, do_mi=False, do_var=False, remove_multi_probs=True, emit_prediction=False) -> None:
+    def __init__(self, do_mi=False, do_var=False, remove_multi_probs=True, emit_prediction=False, emit_foreground=False) -> None:
         super().__init__()
         self.do_mi = do_mi
         self.do_var = do_var
         self.remove_multi_probs = remove_multi_probs
         self.emit_prediction = emit_prediction  # extra 'prediction' (N, H, W) uint8 output for the in-memory metric path
+        self.emit_foreground = emit_foreground  # extra 'foreground' (N, H, W) float32 = probabilities[:, 1], dense
 
     def __call__(self, batch_context, task_context, context) -> None:
         if self.remove_multi_probs:
             multi = batch_context.output.pop('multi_probabilities')
         else:
             multi = batch_context.output['multi_probabilities']
-        out = summarize(multi, self.do_mi, self.do_var, self.emit_prediction)
+        out = summarize(multi, self.do_mi, self.do_var, self.emit_prediction, self.emit_foreground)
         if not self.remove_multi_probs and isinstance(multi, LazyMultiProbabilities):
             batch_context.output['multi_probabilities'] = multi.materialize()
         batch_context.output.update(out)
 
 
-def summarize(multi, do_mi=False, do_var=False, emit_prediction=False):
-    """mean / entropy / [mutual_info] / [variance] / [prediction] of a LazyMultiProbabilities or a real
+def summarize(multi, do_mi=False, do_var=False, emit_prediction=False, emit_foreground=False):
+    """mean / entropy / [mutual_info] / [variance] / [prediction] / [foreground = mean[:, 1], dense] of a LazyMultiProbabilities or a real
     (T, N, 2, H, W) probability tensor — one fused pass (rechun/dl/customsteps.py:57-71)."""
     if isinstance(multi, LazyMultiProbabilities):
         src, kind = multi.logits, 0
@@ -203,9 +204,10 @@ def summarize(multi, do_mi=False, do_var=False, emit_prediction=False):
     mi = torch.empty((n, 1, h, w), dtype=torch.float32, device=dev) if do_mi else None
     var = torch.empty((n, 1, h, w), dtype=torch.float32, device=dev) if do_var else None
     pred = torch.empty((n, h, w), dtype=torch.uint8, device=dev) if emit_prediction else None
+    fg = torch.empty((n, h, w), dtype=torch.float32, device=dev) if emit_foreground else None
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().rcu_aggregate(_lib.ptr(src), kind, t, n, h * w, _lib.ptr(mean), _lib.ptr(entropy), _lib.ptr(mi),
-                                            _lib.ptr(var), _lib.ptr(pred), None, _lib.current_stream()))
+                                            _lib.ptr(var), _lib.ptr(pred), _lib.ptr(fg), None, _lib.current_stream()))
     out = {'probabilities': mean, 'entropy': entropy}
     if do_mi:
         out['mutual_info'] = mi
@@ -213,6 +215,8 @@ def summarize(multi, do_mi=False, do_var=False, emit_prediction=False):
         out['variance'] = var
     if emit_prediction:
         out['prediction'] = pred
+    if emit_foreground:
+        out['foreground'] = fg
     return out
 
 

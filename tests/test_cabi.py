@@ -54,8 +54,8 @@ def test_argument_validation_without_gpu():
     assert lib.rcu_ue_hist(one, 0, one, one, None, 10, 1, br, None, 2, seg, 3, one, None, one, 1 << 22, None) == _lib.RCU_EINVAL
     assert 'seg_class' in _lib.last_error()
     assert lib.rcu_ue_hist(one, 7, one, one, None, 10, 1, br, None, 2, seg, 3, one, None, one, 1 << 22, None) == _lib.RCU_EINVAL
-    assert lib.rcu_aggregate(one, 0, 3, 2, 15, one, None, None, None, None, None, None) == _lib.RCU_EINVAL  # odd hw
-    assert lib.rcu_aggregate(one, 9, 3, 2, 16, one, None, None, None, None, None, None) == _lib.RCU_EINVAL
+    assert lib.rcu_aggregate(one, 0, 3, 2, 15, one, None, None, None, None, None, None, None) == _lib.RCU_EINVAL  # odd hw
+    assert lib.rcu_aggregate(one, 9, 3, 2, 16, one, None, None, None, None, None, None, None) == _lib.RCU_EINVAL
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-GPU failure mode')

@@ -1,0 +1,65 @@
+"""Summarise an .ncu-rep (raw page, base units) into a compact per-launch CSV + markdown table for profiles/.
+
+    python tools/ncu_summary.py gpurun_out/prof_conv.ncu-rep profiles/r01_conv_tc_ncu
+"""
+import csv
+import io
+import subprocess
+import sys
+
+COLS = [
+    ('gpu__time_duration.sum', 'dur_us', 1e-3),
+    ('sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed', 'tensor_pipe_pct', 1),
+    ('sm__throughput.avg.pct_of_peak_sustained_elapsed', 'sm_pct', 1),
+    ('dram__bytes_read.sum', 'dram_rd_MB', 1e-6),
+    ('dram__bytes_write.sum', 'dram_wr_MB', 1e-6),
+    ('dram__throughput.avg.pct_of_peak_sustained_elapsed', 'dram_pct', 1),
+    ('l1tex__m_xbar2l1tex_read_bytes.sum', 'l2_to_sm_MB', 1e-6),
+    ('l1tex__m_xbar2l1tex_read_bytes.sum.pct_of_peak_sustained_elapsed', 'l2_to_sm_pct', 1),
+    ('lts__throughput.avg.pct_of_peak_sustained_elapsed', 'lts_pct', 1),
+    ('launch__registers_per_thread', 'regs', 1),
+    ('sm__warps_active.avg.pct_of_peak_sustained_active', 'warps_active_pct', 1),
+]
+
+
+def main():
+    rep, out = sys.argv[1], sys.argv[2]
+    raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv', '--print-units', 'base'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr = rows[0]
+    idx = {}
+    for name, short, _ in COLS:
+        for i, h in enumerate(hdr):
+            if h == name or h.endswith('.' + name):
+                idx[short] = i
+                break
+    k_name, k_grid, k_block = hdr.index('Kernel Name'), hdr.index('Grid Size'), hdr.index('Block Size')
+    table = []
+    for r in rows[2:]:
+        if len(r) < len(hdr):
+            continue
+        name = r[k_name]
+        name = name.split('(')[0].replace('void ', '').replace('rcu::', '')
+        rec = {'kernel': name, 'grid': r[k_grid].replace(' ', ''), 'block': r[k_block].replace(' ', '')}
+        for mname, short, scale in COLS:
+            if short in idx:
+                try:
+                    rec[short] = round(float(r[idx[short]].replace(',', '')) * scale, 3)
+                except ValueError:
+                    rec[short] = None
+        table.append(rec)
+    keys = ['kernel', 'grid', 'block'] + [s for _, s, _ in COLS if s in idx]
+    with open(out + '.csv', 'w', newline='') as f:
+        w = csv.DictWriter(f, fieldnames=keys)
+        w.writeheader()
+        for rec in table:
+            w.writerow(rec)
+    with open(out + '.md', 'w') as f:
+        f.write('| # | ' + ' | '.join(keys) + ' |\n|' + '---|' * (len(keys) + 1) + '\n')
+        for i, rec in enumerate(table):
+            f.write('| %d | ' % i + ' | '.join(str(rec.get(k, '')) for k in keys) + ' |\n')
+    print('wrote', out + '.csv', out + '.md', len(table), 'launches')
+
+
+if __name__ == '__main__':
+    main()

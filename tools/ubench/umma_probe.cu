@@ -1,0 +1,305 @@
+// Micro-probes that decide the conv kernel design (run on the GPU box, results kept under profiles/):
+//   1. shifted-window A operands from ONE halo tile in shared memory, SWIZZLE_NONE K-major layout
+//      ([channel-group][y][x][8 ch]): does tcgen05.mma accept 16-byte-granular start addresses?
+//   2. the same with SWIZZLE_128B rows (one pixel = one 128-byte row) and the descriptor's base_offset field
+//   3. tcgen05.mma issue rate vs N for shared-memory operands (is N=32/64 shared-memory-read bound?)
+//   4. L2 -> shared memory bandwidth per SM with cp.async (16 B per thread) and with bulk copies
+//
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I reliability-challenges-uncertainty_b200/csrc \
+//        tools/ubench/umma_probe.cu -o tools/ubench/umma_probe
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "conv_tc.cuh"
+
+using namespace rcu;
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout, uint32_t base_off) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+         (uint64_t(1) << 46) | ((uint64_t)base_off << 49) | ((uint64_t)layout << 61);
+}
+
+// ------------------------------------------------------------------------------------------------ 1 + 2: correctness
+// mode 0: SWIZZLE_NONE planes, C = 32, halo 18 x 10, N = 32
+// mode 1: SWIZZLE_128B rows, C = 64, halo 18 x 16 (pitch 16), N = 32, base_offset = (start >> 7) & 7
+// mode 2: as 1 with base_offset = 0
+__global__ void __launch_bounds__(128, 1) shift_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                                                       float* __restrict__ out, int mode) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sp = smem_raw + (base - smem_u32(smem_raw));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t s_tmem;
+  const int C = mode == 0 ? 32 : 64;
+  const int P = mode == 0 ? 10 : 16;
+  const int N = 32;
+  const uint32_t a_bytes = mode == 0 ? 4 * 18 * 10 * 16 : 18 * 16 * 128;
+  const uint32_t sA = base, sB = (base + a_bytes + 1023u) & ~1023u;
+  uint8_t* pA = sp;
+  uint8_t* pB = sp + (sB - base);
+  // ---- fill A
+  for (int i = threadIdx.x; i < 18 * 10 * (C / 8); i += blockDim.x) {
+    const int g = i % (C / 8), px = (i / (C / 8)) % 10, py = i / (C / 8) / 10;
+    const uint4 v = *reinterpret_cast<const uint4*>(x + ((size_t)(py * 10 + px) * C + g * 8));
+    uint32_t off;
+    if (mode == 0) off = (uint32_t)g * (18 * 10 * 16) + (uint32_t)(py * P + px) * 16;
+    else off = (uint32_t)(py * P + px) * 128 + (uint32_t)((g ^ (px & 7)) * 16);
+    *reinterpret_cast<uint4*>(pA + off) = v;
+  }
+  // ---- fill B: w[tap][n][ci]
+  for (int i = threadIdx.x; i < 9 * N * (C / 8); i += blockDim.x) {
+    const int g = i % (C / 8), n = (i / (C / 8)) % N, tap = i / (C / 8) / N;
+    const uint4 v = *reinterpret_cast<const uint4*>(w + ((size_t)(tap * N + n) * C + g * 8));
+    uint32_t off;
+    if (mode == 0) off = (uint32_t)(tap * (C / 8) + g) * (N * 16) + (uint32_t)n * 16;
+    else off = (uint32_t)tap * (N * 128) + (uint32_t)n * 128 + (uint32_t)((g ^ (n & 7)) * 16);
+    *reinterpret_cast<uint4*>(pB + off) = v;
+  }
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+  if (threadIdx.x < 32) { tmem_alloc(smem_u32(&s_tmem), 32); tmem_relinquish(); }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(N >> 3) << 17) | (uint32_t(128 >> 4) << 24);
+    int first = 1;
+    for (int tap = 0; tap < 9; ++tap) {
+      const int ty = tap / 3, tx = tap % 3;
+      for (int ks = 0; ks < C / 16; ++ks) {
+        uint64_t da, db;
+        if (mode == 0) {
+          da = make_desc(sA + (uint32_t)(2 * ks) * (18 * 10 * 16) + (uint32_t)(ty * P + tx) * 16, 18 * 10 * 16, P * 16, 0, 0);
+          db = make_desc(sB + (uint32_t)(tap * (C / 8) + 2 * ks) * (N * 16), N * 16, 128, 0, 0);
+        } else {
+          const uint32_t start = sA + (uint32_t)(ty * P + tx) * 128 + (uint32_t)ks * 32;
+          da = make_desc(start, 16, P * 128, 2, mode == 1 ? ((start >> 7) & 7u) : 0u);
+          db = make_desc(sB + (uint32_t)tap * (N * 128) + (uint32_t)ks * 32, 16, 1024, 2, 0);
+        }
+        umma_bf16(tmem, da, db, idesc, first ? 0u : 1u);
+        first = 0;
+      }
+    }
+    umma_commit(smem_u32(&bar));
+  }
+  mbar_wait(smem_u32(&bar), 0);
+  tc_fence_after();
+  uint32_t v[32];
+  const int warp = threadIdx.x >> 5;
+  tmem_ld_32x32b_x32(tmem + ((uint32_t)(warp * 32) << 16), v);
+  tmem_ld_wait();
+  for (int c = 0; c < 32; ++c) out[threadIdx.x * 32 + c] = __uint_as_float(v[c]);
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc(tmem, 32);
+}
+
+static void run_shift(int mode) {
+  const int C = mode == 0 ? 32 : 64, N = 32;
+  std::vector<__nv_bfloat16> hx(18 * 10 * C), hw(9 * N * C);
+  std::vector<float> fx(hx.size()), fw(hw.size());
+  srand(1234 + mode);
+  for (size_t i = 0; i < hx.size(); ++i) { fx[i] = (float)(rand() % 5 - 2); hx[i] = __float2bfloat16(fx[i]); }
+  for (size_t i = 0; i < hw.size(); ++i) { fw[i] = (float)(rand() % 5 - 2); hw[i] = __float2bfloat16(fw[i]); }
+  __nv_bfloat16 *dx, *dw;
+  float* dout;
+  CK(cudaMalloc(&dx, hx.size() * 2)); CK(cudaMalloc(&dw, hw.size() * 2)); CK(cudaMalloc(&dout, 128 * 32 * 4));
+  CK(cudaMemcpy(dx, hx.data(), hx.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dw, hw.data(), hw.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dout, 0, 128 * 32 * 4));
+  const int smem = 110 * 1024;
+  CK(cudaFuncSetAttribute(shift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  shift_kernel<<<1, 128, smem>>>(dx, dw, dout, mode);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("SHIFT mode %d: kernel failed: %s\n", mode, cudaGetErrorString(e)); exit(2); }
+  std::vector<float> got(128 * 32);
+  CK(cudaMemcpy(got.data(), dout, got.size() * 4, cudaMemcpyDeviceToHost));
+  int bad = 0;
+  double maxd = 0;
+  for (int r = 0; r < 128; ++r) {
+    const int y = r / 8, xq = r % 8;
+    for (int n = 0; n < N; ++n) {
+      float acc = 0;
+      for (int tap = 0; tap < 9; ++tap) {
+        const int ty = tap / 3, tx = tap % 3;
+        for (int ci = 0; ci < C; ++ci) acc += fx[((y + ty) * 10 + xq + tx) * C + ci] * fw[(tap * N + n) * C + ci];
+      }
+      const double d = fabs((double)acc - got[r * 32 + n]);
+      if (d > maxd) maxd = d;
+      if (d > 1e-3) ++bad;
+    }
+  }
+  printf("SHIFT mode %d (%s): mismatches %d / %d, max |diff| %.3f -> %s\n", mode,
+         mode == 0 ? "SWIZZLE_NONE planes, 16B-granular start" : (mode == 1 ? "SWIZZLE_128B rows, base_offset=(addr>>7)&7" : "SWIZZLE_128B rows, base_offset=0"),
+         bad, 128 * N, maxd, bad == 0 ? "OK" : "WRONG");
+  cudaFree(dx); cudaFree(dw); cudaFree(dout);
+}
+
+// ------------------------------------------------------------------------------------------------ 3: MMA issue rate
+// layout 0: SWIZZLE_NONE (A planes with pitch 10, shifted starts), 2: SWIZZLE_128B (aligned tiles)
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int N, int layout, int iters, long long* cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t s_tmem;
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+  if (threadIdx.x < 32) { tmem_alloc(smem_u32(&s_tmem), 512); tmem_relinquish(); }
+  for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem_raw + (base - smem_u32(smem_raw)))[i] = 0;
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(N >> 3) << 17) | (uint32_t(128 >> 4) << 24);
+    const uint32_t sA = base, sB = base + 64 * 1024;
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const int tap = it % 9, ks = it & 3;
+      uint64_t da, db;
+      if (layout == 0) {
+        da = make_desc(sA + (uint32_t)(2 * ks) * (18 * 10 * 16) + (uint32_t)((tap / 3) * 10 + tap % 3) * 16, 18 * 10 * 16, 160, 0, 0);
+        db = make_desc(sB + (uint32_t)(2 * ks) * (N * 16), N * 16, 128, 0, 0);
+      } else {
+        da = make_desc(sA + (uint32_t)ks * 32 + (uint32_t)(tap & 1) * 16384, 16, 1024, 2, 0);
+        db = make_desc(sB + (uint32_t)ks * 32, 16, 1024, 2, 0);
+      }
+      umma_bf16(tmem + (uint32_t)((it & 1) * 256), da, db, idesc, 1u);
+    }
+    umma_commit(smem_u32(&bar));
+    mbar_wait(smem_u32(&bar), 0);
+    const long long t1 = clock64();
+    cycles[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc(tmem, 512);
+}
+
+static void run_mma_rate(int sms) {
+  long long* dcyc;
+  CK(cudaMalloc(&dcyc, sms * sizeof(long long)));
+  const int smem = 200 * 1024;
+  CK(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int iters = 4096;
+  for (int layout = 0; layout <= 2; layout += 2)
+    for (int N = 32; N <= 256; N *= 2) {
+      mma_rate_kernel<<<sms, 128, smem>>>(N, layout, iters, dcyc);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("MMA rate N=%d layout=%d failed: %s\n", N, layout, cudaGetErrorString(e)); exit(3); }
+      std::vector<long long> h(sms);
+      CK(cudaMemcpy(h.data(), dcyc, sms * sizeof(long long), cudaMemcpyDeviceToHost));
+      long long mx = 0;
+      for (long long c : h) mx = c > mx ? c : mx;
+      const double cyc = (double)mx / iters;
+      printf("MMA_RATE layout=%s M=128 N=%3d K=16: %.1f clk/MMA -> %.0f MAC/clk/SM (floor %d clk), smem operand bytes/MMA %d -> %.0f B/clk\n",
+             layout == 0 ? "NONE  " : "SW128 ", N, cyc, 128.0 * N * 16 / cyc, 128 * N / 256, 4096 + N * 32, (4096 + N * 32) / cyc);
+    }
+  cudaFree(dcyc);
+}
+
+// ------------------------------------------------------------------------------------------------ 4: L2 -> smem bandwidth
+__global__ void __launch_bounds__(256, 1) cpasync_bw_kernel(const uint8_t* __restrict__ src, size_t bytes_per_cta, int rounds, long long* cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint8_t* my = src + (size_t)blockIdx.x * bytes_per_cta;
+  const uint32_t s0 = smem_u32(smem_raw);
+  const int chunk = 256 * 16;  // bytes per block-wide cp.async
+  const int per_round = (int)(bytes_per_cta / chunk);
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int r = 0; r < rounds; ++r) {
+    for (int i = 0; i < per_round; ++i) {
+      const uint32_t dst = s0 + (uint32_t)((i & 15) * chunk) + threadIdx.x * 16;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(my + (size_t)i * chunk + threadIdx.x * 16) : "memory");
+      if ((i & 3) == 3) asm volatile("cp.async.commit_group;" ::: "memory");
+      if ((i & 3) == 3) asm volatile("cp.async.wait_group 3;" ::: "memory");
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  const long long t1 = clock64();
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+__global__ void __launch_bounds__(32, 1) bulk_bw_kernel(const uint8_t* __restrict__ src, size_t bytes_per_cta, int rounds, int piece, long long* cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bars[8];
+  const uint8_t* my = src + (size_t)blockIdx.x * bytes_per_cta;
+  const uint32_t s0 = (smem_u32(smem_raw) + 127u) & ~127u;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 8; ++i) mbar_init(smem_u32(&bars[i]), 1);
+    fence_barrier_init();
+    const int per_round = (int)(bytes_per_cta / piece);
+    const long long t0 = clock64();
+    long long n = 0;
+    for (int r = 0; r < rounds; ++r)
+      for (int i = 0; i < per_round; ++i, ++n) {
+        const int slot = (int)(n & 7);
+        if (n >= 8) mbar_wait(smem_u32(&bars[slot]), (uint32_t)(((n >> 3) - 1) & 1));
+        mbar_expect_tx(smem_u32(&bars[slot]), (uint32_t)piece);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s0 + (uint32_t)(slot * piece)),
+                     "l"(my + (size_t)i * piece), "r"(piece), "r"(smem_u32(&bars[slot]))
+                     : "memory");
+      }
+    for (long long k = (n >= 8 ? n - 8 : 0); k < n; ++k) mbar_wait(smem_u32(&bars[k & 7]), (uint32_t)((k >> 3) & 1));
+    const long long t1 = clock64();
+    cycles[blockIdx.x] = t1 - t0;
+  }
+}
+
+static void run_bw(int sms) {
+  const size_t per_cta = 192 * 1024;           // 148 * 192 KB = 28 MB, L2 resident after the first round
+  uint8_t* src;
+  long long* dcyc;
+  CK(cudaMalloc(&src, per_cta * sms));
+  CK(cudaMemset(src, 1, per_cta * sms));
+  CK(cudaMalloc(&dcyc, sms * sizeof(long long)));
+  CK(cudaFuncSetAttribute(cpasync_bw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  CK(cudaFuncSetAttribute(bulk_bw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 16384 + 256));
+  std::vector<long long> h(sms);
+  for (int rep = 0; rep < 2; ++rep) {
+    const int rounds = 20;
+    cpasync_bw_kernel<<<sms, 256, 64 * 1024>>>(src, per_cta, rounds, dcyc);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(h.data(), dcyc, sms * sizeof(long long), cudaMemcpyDeviceToHost));
+    long long mx = 0;
+    for (long long c : h) mx = c > mx ? c : mx;
+    if (rep) printf("L2_BW cp.async 16B x 256 thr, %d SMs: %.1f B/clk/SM (slowest SM), chip %.0f B/clk\n", sms, (double)per_cta * rounds / mx, (double)per_cta * rounds / mx * sms);
+  }
+  for (int piece = 2048; piece <= 16384; piece *= 2) {
+    const int rounds = 20;
+    for (int rep = 0; rep < 2; ++rep) {
+      bulk_bw_kernel<<<sms, 32, 8 * 16384 + 256>>>(src, per_cta, rounds, piece, dcyc);
+      CK(cudaDeviceSynchronize());
+    }
+    CK(cudaMemcpy(h.data(), dcyc, sms * sizeof(long long), cudaMemcpyDeviceToHost));
+    long long mx = 0;
+    for (long long c : h) mx = c > mx ? c : mx;
+    printf("L2_BW cp.async.bulk %5d B pieces, 8 in flight, %d SMs: %.1f B/clk/SM, chip %.0f B/clk\n", piece, sms, (double)per_cta * rounds / mx, (double)per_cta * rounds / mx * sms);
+  }
+  cudaFree(src); cudaFree(dcyc);
+}
+
+int main(int argc, char** argv) {
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, 0));
+  printf("device %s, %d SMs, cc %d.%d\n", prop.name, prop.multiProcessorCount, prop.major, prop.minor);
+  const char* what = argc > 1 ? argv[1] : "all";
+  const bool all = std::string(what) == "all";
+  if (all || std::string(what) == "shift0") run_shift(0);
+  if (all || std::string(what) == "shift1") run_shift(1);
+  if (all || std::string(what) == "shift2") run_shift(2);
+  if (all || std::string(what) == "rate") run_mma_rate(prop.multiProcessorCount);
+  if (all || std::string(what) == "bw") run_bw(prop.multiProcessorCount);
+  return 0;
+}
