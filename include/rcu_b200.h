@@ -225,9 +225,13 @@ int rcu_unet_forward(rcu_unet* net, const float* images, int64_t n_slices, int n
 int rcu_unet_total_dropout_channels(const rcu_unet* net);
 /* Copies a named internal activation of the LAST chunk of the last forward to `out` as fp32 NHWC (debug/parity). */
 int rcu_unet_debug_activation(rcu_unet* net, int index, float* out, size_t out_elems, void* stream);
-/* Selects the convolution implementation: 0 = tcgen05/TMEM/TMA implicit GEMM (default, the product path),
- * 1 = straightforward CUDA-core fp32-accumulate kernel over the same bf16 data (on-device cross-check only). */
+/* Selects the convolution implementation: 0 = tcgen05/TMEM/TMA implicit GEMM (default, the product path: halo-tile
+ * kernel for the thin high-resolution layers, per-tap kernel for the rest), 1 = straightforward CUDA-core
+ * fp32-accumulate kernel over the same bf16 data (on-device cross-check only), 2 = tcgen05 per-tap kernel everywhere. */
 int rcu_unet_set_conv_impl(rcu_unet* net, int impl);
+/* Debug: bit i of `mask` lets conv i (execution order, the first conv excluded) use the halo-tile kernel when it is
+ * eligible; cleared bits fall back to the per-tap kernel.  Default: all ones. */
+int rcu_unet_set_halo_mask(rcu_unet* net, uint64_t mask);
 /* Optional per-op device timing: when enabled, every kernel launch of rcu_unet_forward is bracketed by CUDA events
  * on the launch stream.  rcu_unet_read_timing synchronises those events and returns, per op of the schedule (see
  * rcu_unet_op_info), the accumulated milliseconds and launch count since the last read.  ms/launches hold n_ops

@@ -1,0 +1,301 @@
+// Halo-tile implicit-GEMM convolution for the high-resolution, thin layers (c_out = 32 / 64, the 240^2 and 120^2
+// levels of the BraTS net, where the per-tap kernel in conv_tc.cuh is bound by L2 -> shared-memory traffic).
+//
+//   * one TMA box per (tile, 64-channel chunk) brings the (16+2) x (8+2) pixel halo window into shared memory ONCE;
+//     the 9 taps (4 for an up-path phase) are shifted VIEWS of that window: the tcgen05 shared-memory descriptor of
+//     tap (dy, dx) is the window's descriptor with the start address advanced by ((dy+1) * 10 + (dx+1)) rows.
+//     SWIZZLE_128B is a function of the absolute shared-memory address, so a row-shifted start is still a valid
+//     K-major operand (checked on B200 by tools/ubench/umma_probe.cu, results in profiles/r01_umma_probe.log);
+//   * GEMM row r of a tile is pixel (y, x) = (r / 8, r % 8): every 8-row core-matrix group is 8 x-adjacent pixels,
+//     i.e. 8 consecutive 128-byte rows of the window, and consecutive groups are one window row (10 pixels) apart —
+//     a uniform stride-byte-offset;
+//   * 32-channel sources (64-byte pixel rows) use the same SWIZZLE_128B map with a 32-channel box: TMA then still
+//     gives every pixel its own 128-byte swizzled row and fills its first 64 logical bytes (measured, probe `tma5d`),
+//     so the descriptors are unchanged and a tap is two K = 16 steps instead of four — full-rate operand reads,
+//     where SWIZZLE_64B rows would read at half rate (2-way bank conflicts, probe `rate`);
+//   * the layer's weights (<= 144 KB as pre-swizzled [c_out][64] tiles) are copied into shared memory once per CTA
+//     and stay resident while the CTA walks its tiles (persistent kernel, one CTA per SM);
+//   * the MMA warp runs warp-uniform control flow and predicates only the tcgen05.mma on elect.sync, so descriptors
+//     live in uniform registers and MMAs issue back to back (N = 32/64 tiles are 40/48-clock MMAs, bound by the
+//     128 B/clk shared-memory operand read — see the probe).
+//
+// Epilogue contract is that of conv_tc.cuh (folded Dropout2d x BN coefficients + ReLU, bf16 NHWC store with a
+// channel offset / pixel stride so producers write straight into the concat buffer, or the fused 1x1 head).
+#pragma once
+#include "conv_tc.cuh"
+
+namespace rcu {
+
+constexpr int kHaloTileH = 16;
+constexpr int kHaloTileW = 8;
+constexpr int kHaloPitch = kHaloTileW + 2;   // window pixels per row
+constexpr int kHaloRows = kHaloTileH + 2;    // window rows
+constexpr int kHaloMaxEntries = 20;
+constexpr int kHaloThreads = 192;
+constexpr int kHaloSmemBudget = 225 * 1024;
+
+struct HaloEntry {
+  uint32_t a_off16;   // offset of the A view inside a stage slot, 16-byte units
+  uint32_t b_off16;   // offset of the weight tile inside the weight image, 16-byte units
+  int n_k16;          // K = 16 steps to issue (4 = a full 128-byte row, 2 = half)
+  int pad;
+};
+
+struct HaloParams {
+  int n_img, in_h, in_w, tiles_x, tiles_y;
+  int n_chunks;              // TMA boxes (pipeline slots) per tile: c_in / 64, or 1 for a 32-channel source
+  int pair;                  // 32-channel source (informational: the entries carry n_k16 = 2)
+  uint32_t chunk_bytes;      // bytes one box delivers
+  uint32_t chunk_stride;     // slot size (multiple of 1024)
+  int n_stages;
+  int e_split;               // entries [0, e_split) read chunk 0, [e_split, n_entries) chunk 1
+  int n_entries;
+  HaloEntry entries[kHaloMaxEntries];
+  const void* w_image;       // pre-swizzled weight tiles in global memory
+  uint32_t w_bytes;
+  // output addressing: pixel (y, x) lands at (out_mul*y + out_dy, out_mul*x + out_dx)
+  int out_mul, out_dy, out_dx, out_h, out_w;
+  int out_c;                 // pixel stride in elements (the channel offset is folded into `out`)
+  long long out_img_stride;  // elements between images
+  __nv_bfloat16* out;
+  const float2* coef;
+  long long coef_stride;
+  int coef_off;
+  int relu;
+  const float* head;
+  float* logits;
+  int chunk_slices;
+  long long slice0, n_slices_total;
+};
+
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred;
+}
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+__device__ __forceinline__ uint64_t desc_from(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+
+template <int N>
+struct HaloSmem {
+  static constexpr int kCoefBytes = 2 * N * (int)sizeof(float2);
+  static constexpr int kHeadBytes = 2 * 32 * 4 + 16;
+  static constexpr int kMaxStages = 8;
+  static constexpr int kBarBytes = (2 * kMaxStages + 5) * 8 + 16;
+  static constexpr int kFixed = 1024 + kCoefBytes + kHeadBytes + kBarBytes;
+  static constexpr int kTmemCols = 2 * N < 32 ? 32 : 2 * N;
+};
+
+template <int N>
+__global__ void __launch_bounds__(kHaloThreads, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ HaloParams prm) {
+  using S = HaloSmem<N>;
+  static_assert(N == 32 || N == 64, "halo kernel serves c_out = 32 / 64");
+  extern __shared__ uint8_t smem_dyn[];
+  const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_dyn + (base - smem_u32(smem_dyn));
+  const uint32_t w_span = (prm.w_bytes + 1023u) & ~1023u;
+  const uint32_t smem_w = base;
+  const uint32_t smem_a = base + w_span;
+  const uint32_t tail = w_span + (uint32_t)prm.n_stages * prm.chunk_stride;
+  float2* s_coef = reinterpret_cast<float2*>(base_ptr + tail);
+  float* s_head = reinterpret_cast<float*>(base_ptr + tail + S::kCoefBytes);
+  uint8_t* bar_ptr = base_ptr + tail + S::kCoefBytes + S::kHeadBytes;
+  const uint32_t bar_full = smem_u32(bar_ptr);                      // [kMaxStages]
+  const uint32_t bar_empty = bar_full + S::kMaxStages * 8;          // [kMaxStages]
+  const uint32_t bar_tfull = bar_empty + S::kMaxStages * 8;         // [2]
+  const uint32_t bar_tempty = bar_tfull + 16;                       // [2]
+  const uint32_t bar_w = bar_tempty + 16;                           // [1]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_ptr + (2 * S::kMaxStages + 5) * 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    for (int s = 0; s < S::kMaxStages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_tfull + 8 * s, 1);
+      mbar_init(bar_tempty + 8 * s, 128);
+    }
+    mbar_init(bar_w, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(s_tmem), S::kTmemCols);
+    tmem_relinquish();
+  }
+  if (prm.head != nullptr && threadIdx.x >= 64 && threadIdx.x < 64 + 66) s_head[threadIdx.x - 64] = prm.head[threadIdx.x - 64];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  const long long tiles_per_img = (long long)prm.tiles_y * prm.tiles_x;
+  const long long total_tiles = (long long)prm.n_img * tiles_per_img;
+
+  if (warp == 0) {
+    // ===================== producer: weights once, then one halo box per (tile, chunk) =====================
+    if (lane == 0) {
+      mbar_expect_tx(bar_w, prm.w_bytes);
+      for (uint32_t off = 0; off < prm.w_bytes; off += 32768u) {
+        const uint32_t n = prm.w_bytes - off < 32768u ? prm.w_bytes - off : 32768u;
+        bulk_load(smem_w + off, reinterpret_cast<const uint8_t*>(prm.w_image) + off, n, bar_w);
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        long long r = tile;
+        const int tx = (int)(r % prm.tiles_x); r /= prm.tiles_x;
+        const int ty = (int)(r % prm.tiles_y);
+        const int img = (int)(r / prm.tiles_y);
+        const int x0 = tx * kHaloTileW - 1, y0 = ty * kHaloTileH;
+        for (int j = 0; j < prm.n_chunks; ++j) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+          mbar_expect_tx(bar_full + 8 * stage, prm.chunk_bytes);
+          const uint32_t dst = smem_a + (uint32_t)stage * prm.chunk_stride;
+          tma_load_4d(dst, &map_a, bar_full + 8 * stage, j * 64, x0, y0 - 1, img);
+          if (++stage == prm.n_stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: warp-uniform flow, elect.sync-predicated tcgen05.mma =====================
+    const bool leader = elect_one() != 0;
+    constexpr uint32_t idesc = make_idesc<N>();
+    // descriptor halves: [0,14) addr>>4, [16,30) LBO>>4 (=1, unused), hi: [0,14) SBO>>4, [14,16) version 1, [29,32) SWIZZLE_128B
+    constexpr uint32_t hi_a = (uint32_t)((kHaloPitch * 128) >> 4) | (1u << 14) | (2u << 29);
+    constexpr uint32_t hi_b = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t lo_b0 = ((smem_w & 0x3FFFFu) >> 4) | (1u << 16);
+    mbar_wait(bar_w, 0);
+    tc_fence_after();
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * N);
+      uint32_t accumulate = 0;
+      for (int j = 0; j < prm.n_chunks; ++j) {
+        mbar_wait(bar_full + 8 * stage, phase);
+        tc_fence_after();
+        const uint32_t lo_a0 = (((smem_a + (uint32_t)stage * prm.chunk_stride) & 0x3FFFFu) >> 4) | (1u << 16);
+        const int e0 = j == 0 ? 0 : prm.e_split, e1 = j == 0 ? prm.e_split : prm.n_entries;
+        for (int e = e0; e < e1; ++e) {
+          const uint32_t la = lo_a0 + prm.entries[e].a_off16, lb = lo_b0 + prm.entries[e].b_off16;
+          if (leader) {
+            umma_bf16(tmem_d, desc_from(la, hi_a), desc_from(lb, hi_b), idesc, accumulate);
+            umma_bf16(tmem_d, desc_from(la + 2, hi_a), desc_from(lb + 2, hi_b), idesc, 1u);
+          }
+          accumulate = 1u;
+          if (prm.entries[e].n_k16 == 4) {
+            if (leader) {
+              umma_bf16(tmem_d, desc_from(la + 4, hi_a), desc_from(lb + 4, hi_b), idesc, 1u);
+              umma_bf16(tmem_d, desc_from(la + 6, hi_a), desc_from(lb + 6, hi_b), idesc, 1u);
+            }
+          }
+        }
+        if (leader) umma_commit(bar_empty + 8 * stage);
+        if (++stage == prm.n_stages) { stage = 0; phase ^= 1u; }
+      }
+      if (leader) umma_commit(bar_tfull + 8 * acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int et = threadIdx.x - 64;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      long long r = tile;
+      const int tx = (int)(r % prm.tiles_x); r /= prm.tiles_x;
+      const int ty = (int)(r % prm.tiles_y);
+      const int img = (int)(r / prm.tiles_y);
+
+      float2* coef = s_coef + acc * N;
+      if (et < N) coef[et] = __ldg(prm.coef + (long long)img * prm.coef_stride + prm.coef_off + et);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+
+      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      tc_fence_after();
+
+      const int y = ty * kHaloTileH + (row >> 3), x = tx * kHaloTileW + (row & 7);
+      const bool valid = (y < prm.in_h) && (x < prm.in_w);
+      const int oy = prm.out_mul * y + prm.out_dy, ox = prm.out_mul * x + prm.out_dx;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * N);
+
+      if (prm.head != nullptr) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr, v);
+        tmem_ld_wait();
+        float l0 = s_head[64], l1 = s_head[65];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const float2 cf = coef[c];
+          float a = fmaf(__uint_as_float(v[c]), cf.x, cf.y);
+          a = prm.relu ? fmaxf(a, 0.0f) : a;
+          l0 = fmaf(a, s_head[c], l0);
+          l1 = fmaf(a, s_head[32 + c], l1);
+        }
+        if (valid) {
+          const int t = img / prm.chunk_slices, sl = img - t * prm.chunk_slices;
+          const long long gimg = (long long)t * prm.n_slices_total + prm.slice0 + sl;
+          float2* dst = reinterpret_cast<float2*>(prm.logits) + (gimg * prm.out_h + oy) * prm.out_w + ox;
+          *dst = make_float2(l0, l1);
+        }
+      } else {
+        __nv_bfloat16* dst = prm.out + (long long)img * prm.out_img_stride + ((long long)oy * prm.out_w + ox) * prm.out_c;
+#pragma unroll 1
+        for (int cb = 0; cb < N; cb += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(taddr + (uint32_t)cb, v);
+          tmem_ld_wait();
+          uint32_t packed[16];
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            const float2 c0 = coef[cb + c], c1 = coef[cb + c + 1];
+            float a0 = fmaf(__uint_as_float(v[c]), c0.x, c0.y);
+            float a1 = fmaf(__uint_as_float(v[c + 1]), c1.x, c1.y);
+            if (prm.relu) { a0 = fmaxf(a0, 0.0f); a1 = fmaxf(a1, 0.0f); }
+            __nv_bfloat162 b = __floats2bfloat162_rn(a0, a1);
+            packed[c >> 1] = *reinterpret_cast<uint32_t*>(&b);
+          }
+          if (valid) {
+            uint4* d4 = reinterpret_cast<uint4*>(dst + cb);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) d4[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_tempty + 8 * acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, S::kTmemCols);
+}
+
+}  // namespace rcu

@@ -41,7 +41,9 @@ struct ConvParams {
   signed char dx[kMaxPhases][kMaxTaps];
   // output addressing: pixel (y, x) of phase (a, b) lands at (out_mul*y + a, out_mul*x + b)
   int out_mul;
-  int out_h, out_w, out_c;
+  int out_h, out_w;
+  int out_c;                 // pixel stride of the output tensor in elements (a channel offset is folded into `out`)
+  long long out_img_stride;  // elements between images (padded tensors carry one extra row per image)
   __nv_bfloat16* out;
   // folded epilogue coefficients: float2 (scale, shift) per (image, channel)
   const float2* coef;
@@ -336,7 +338,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           *dst = make_float2(l0, l1);
         }
       } else {
-        __nv_bfloat16* dst = prm.out + (((long long)img * prm.out_h + oy) * prm.out_w + ox) * prm.out_c + nt * BLOCK_N;
+        __nv_bfloat16* dst = prm.out + (long long)img * prm.out_img_stride + ((long long)oy * prm.out_w + ox) * prm.out_c + nt * BLOCK_N;
 #pragma unroll 1
         for (int cb = 0; cb < BLOCK_N; cb += 32) {
           uint32_t v[32];

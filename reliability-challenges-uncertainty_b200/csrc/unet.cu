@@ -13,6 +13,7 @@
 
 #include "common.cuh"
 #include "conv_tc.cuh"
+#include "conv_halo.cuh"
 #include "philox.cuh"
 #include "unet_kernels.cuh"
 
@@ -37,8 +38,31 @@ static EncodeTiledFn get_encode_fn() {
 
 enum OpKind { OP_FIRST = 0, OP_CONV = 1, OP_POOL = 2 };
 
+// A channel slice of a bf16 NHWC tensor inside the arena.  Producers write slices of the concat buffers directly
+// (torch.cat((up, skip), 1), common/model/unet.py:118, is never materialised by a copy).  `padded` tensors carry one
+// zero row above every image (unused at present: every Act is dense).
+struct Act {
+  __nv_bfloat16* base = nullptr;   // element (image 0, y 0, x 0, first channel of the slice)
+  int c = 0;                       // channels of the slice
+  int c_total = 0;                 // pixel stride in elements
+  int h = 0, w = 0;
+  long long img_stride = 0;        // elements between images
+  bool padded = false;
+};
+
+struct HaloPack {                  // create-time description of a layer the halo kernel can run
+  bool ok = false;
+  bool pair = false;               // 32-channel source: 64-byte pixel rows, two K = 16 steps per tap
+  int n_chunks = 0;
+  int n_phases = 1;
+  int n_entries = 0, e_split = 0;
+  HaloEntry entries[kMaxPhases][kHaloMaxEntries];
+  uint8_t* d_wimg[kMaxPhases] = {nullptr, nullptr, nullptr, nullptr};
+  uint32_t w_bytes = 0;
+};
+
 struct ConvLayer {
-  int c0 = 0, c1 = 0, c_out = 0;
+  int c0 = 0, c1 = 0, c_out = 0;        // c1 is always 0 now (concat buffers), kept for the kernel's two-map interface
   int n_taps = 9, n_phases = 1, out_mul = 1, relu = 1;
   signed char dy[kMaxPhases][kMaxTaps];
   signed char dx[kMaxPhases][kMaxTaps];
@@ -46,19 +70,19 @@ struct ConvLayer {
   int coef_off = 0;
   int block_n = 0, kc = 0;
   bool head = false;
+  HaloPack halo;
   // plan-time
   int in_h = 0, in_w = 0;
-  const __nv_bfloat16* src0 = nullptr;
-  const __nv_bfloat16* src1 = nullptr;
-  __nv_bfloat16* dst = nullptr;
-  CUtensorMap map_a0, map_a1, map_w;
+  Act src, dst;
+  CUtensorMap map_a0, map_a1, map_w, map_halo;
+  int halo_stages = 0;
 };
 
 struct Op {
   OpKind kind;
   int conv = -1;                         // index into convs for OP_CONV
-  const __nv_bfloat16* in = nullptr;     // OP_POOL
-  __nv_bfloat16* out = nullptr;          // output buffer (debug view)
+  Act in;                                // OP_POOL input
+  Act out;                               // output (debug view)
   int h = 0, w = 0, c = 0;               // output dims (for POOL: input dims in in_h/in_w)
   int in_h = 0, in_w = 0;
 };
@@ -86,10 +110,11 @@ struct rcu_unet {
   void* arena = nullptr;
   size_t arena_bytes = 0;
   float2* d_coef = nullptr;
-  __nv_bfloat16* first_out = nullptr;
-  __nv_bfloat16* head_feat = nullptr;    // features of conv_cls.0 for the cross-check path
+  Act first_out;
+  Act head_feat;                         // features of conv_cls.0 for the cross-check path
   std::vector<Op> ops;
   int conv_impl = 0;
+  unsigned long long halo_mask = ~0ull;  // debug: bit i enables the halo kernel for conv i (execution order)
   long long last_launches = 0;
   int last_n_img = 0;
   // optional per-op timing
@@ -203,17 +228,34 @@ static std::vector<uint16_t> pack_upconv_phases(const rcu_conv_unit& u, ConvLaye
   return w;
 }
 
-static int make_act_map(CUtensorMap* map, const void* base, int c, int w, int h, int n, int kc) {
+static int make_act_map(CUtensorMap* map, const Act& a, int n, int kc) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available (driver too old?)"); return RCU_ECUDA; }
-  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
-  cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
+  cuuint64_t dims[4] = {(cuuint64_t)a.c, (cuuint64_t)a.w, (cuuint64_t)a.h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)a.c_total * 2, (cuuint64_t)a.w * a.c_total * 2, (cuuint64_t)a.img_stride * 2};
   cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)kTileW, (cuuint32_t)kTileH, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   const CUtensorMapSwizzle sw = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a.base, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activation c=%d w=%d h=%d n=%d kc=%d) failed: %d", c, w, h, n, kc, (int)r); return RCU_ECUDA; }
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activation c=%d w=%d h=%d n=%d kc=%d) failed: %d", a.c, a.w, a.h, n, kc, (int)r); return RCU_ECUDA; }
+  return RCU_OK;
+}
+
+// Halo window of the halo kernel: (16+2) x (8+2) pixels x box_c channels, SWIZZLE_128B, zero fill outside the image.
+// box_c = 64 fills whole 128-byte rows.  box_c = 32 (32-channel sources): TMA still gives every pixel its own
+// 128-byte swizzled row and fills the first 64 logical bytes (measured: tools/ubench/umma_probe.cu `tma5d`), so the
+// same SWIZZLE_128B descriptors read it at full rate with two K = 16 steps per tap instead of four.
+static int make_halo_map(CUtensorMap* map, const Act& a, int n, int box_c) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available (driver too old?)"); return RCU_ECUDA; }
+  cuuint64_t dims[4] = {(cuuint64_t)a.c, (cuuint64_t)a.w, (cuuint64_t)a.h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)a.c_total * 2, (cuuint64_t)a.w * a.c_total * 2, (cuuint64_t)a.img_stride * 2};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)kHaloPitch, (cuuint32_t)kHaloRows, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a.base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(halo c=%d w=%d h=%d n=%d) failed: %d", a.c, a.w, a.h, n, (int)r); return RCU_ECUDA; }
   return RCU_OK;
 }
 
@@ -271,6 +313,138 @@ static int dispatch_conv_tc(const ConvLayer& L, const ConvParams& prm, cudaStrea
   }
   set_error("no tcgen05 conv instantiation for BLOCK_N=%d KC=%d", L.block_n, L.kc);
   return RCU_ENOTSUP;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Halo-kernel weight images: a sequence of [c_out][64] bf16 tiles in the SWIZZLE_128B K-major shared-memory layout
+// (16-byte chunk index XOR (row & 7)), one tile per HaloEntry, copied verbatim into shared memory by the kernel.
+// ---------------------------------------------------------------------------------------------------------
+static inline size_t sw128_index(int n, int k) {  // element index inside a tile
+  return (size_t)n * 64 + (size_t)((((k >> 3) ^ (n & 7)) << 3) + (k & 7));
+}
+
+static inline uint32_t halo_a_off16(int row, int col, int byte_in_row) { return (uint32_t)(((row * kHaloPitch + col) * 128 + byte_in_row) >> 4); }
+
+constexpr uint32_t kHaloMaxWeightBytes = 150 * 1024;
+
+// plain 3x3 conv: c_in == 32 (pair source) or c_in in {64, 128}
+static int pack_halo_conv3x3(rcu_unet* net, const rcu_conv_unit& u, HaloPack& hp) {
+  const int N = u.c_out;
+  if (!(N == 32 || N == 64)) return RCU_OK;
+  std::vector<uint16_t> img;
+  int n_tiles = 0;
+  auto new_tile = [&]() { img.resize((size_t)(n_tiles + 1) * N * 64, 0); return n_tiles++; };
+  if (u.c_in == 32) {
+    // 64-byte pixel rows: two taps share one [c_out][64] weight tile (k < 32: even tap, k >= 32: odd tap)
+    hp.pair = true; hp.n_chunks = 1;
+    for (int tap = 0; tap < 9; ++tap) {
+      if ((tap & 1) == 0) new_tile();
+      const int t = n_tiles - 1;
+      for (int n = 0; n < N; ++n)
+        for (int k = 0; k < 32; ++k)
+          img[(size_t)t * N * 64 + sw128_index(n, (tap & 1) * 32 + k)] = f32_to_bf16_rn(u.weight[((size_t)n * 32 + k) * 9 + tap]);
+      hp.entries[0][hp.n_entries++] = HaloEntry{halo_a_off16(tap / 3, tap % 3, 0), (uint32_t)(((size_t)t * N * 128 + (tap & 1) * 64) >> 4), 2, 0};
+    }
+    hp.e_split = hp.n_entries;
+  } else if (u.c_in == 64 || u.c_in == 128) {
+    hp.pair = false; hp.n_chunks = u.c_in / 64;
+    for (int j = 0; j < hp.n_chunks; ++j) {
+      for (int tap = 0; tap < 9; ++tap) {
+        const int t = new_tile();
+        for (int n = 0; n < N; ++n)
+          for (int k = 0; k < 64; ++k)
+            img[(size_t)t * N * 64 + sw128_index(n, k)] = f32_to_bf16_rn(u.weight[((size_t)n * u.c_in + j * 64 + k) * 9 + tap]);
+        hp.entries[0][hp.n_entries++] = HaloEntry{halo_a_off16(tap / 3, tap % 3, 0), (uint32_t)((size_t)t * N * 128 >> 4), 4, 0};
+      }
+      if (j == 0) hp.e_split = hp.n_entries;
+    }
+  } else {
+    return RCU_OK;
+  }
+  hp.w_bytes = (uint32_t)(img.size() * 2);
+  if (hp.w_bytes > kHaloMaxWeightBytes) return RCU_OK;
+  uint16_t* d;
+  int rc = dev_upload(net, img, &d);
+  if (rc) return rc;
+  hp.d_wimg[0] = reinterpret_cast<uint8_t*>(d);
+  hp.n_phases = 1;
+  hp.ok = true;
+  return RCU_OK;
+}
+
+// nearest-x2 + conv3x3 as four 2x2-tap phase convolutions (see pack_upconv_phases): one weight image per phase
+static int pack_halo_upconv(rcu_unet* net, const rcu_conv_unit& u, HaloPack& hp) {
+  const int N = u.c_out;
+  if (!(N == 32 || N == 64) || !(u.c_in == 64 || u.c_in == 128)) return RCU_OK;
+  hp.pair = false; hp.n_chunks = u.c_in / 64; hp.n_phases = 4;
+  hp.w_bytes = (uint32_t)(hp.n_chunks * 4 * N * 128);
+  if (hp.w_bytes > kHaloMaxWeightBytes) return RCU_OK;
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b) {
+      const int ph = a * 2 + b;
+      std::vector<uint16_t> img((size_t)hp.n_chunks * 4 * N * 64, 0);
+      int t = 0, ne = 0;
+      for (int j = 0; j < hp.n_chunks; ++j) {
+        for (int i2 = 0; i2 < 2; ++i2)
+          for (int j2 = 0; j2 < 2; ++j2) {
+            const int dy = a == 0 ? i2 - 1 : i2, dx = b == 0 ? j2 - 1 : j2;
+            int ky0, ky1, kx0, kx1;
+            if (a == 0) { ky0 = i2 == 0 ? 0 : 1; ky1 = i2 == 0 ? 0 : 2; } else { ky0 = i2 == 0 ? 0 : 2; ky1 = i2 == 0 ? 1 : 2; }
+            if (b == 0) { kx0 = j2 == 0 ? 0 : 1; kx1 = j2 == 0 ? 0 : 2; } else { kx0 = j2 == 0 ? 0 : 2; kx1 = j2 == 0 ? 1 : 2; }
+            for (int n = 0; n < N; ++n)
+              for (int k = 0; k < 64; ++k) {
+                float sum = 0.0f;
+                for (int ky = ky0; ky <= ky1; ++ky)
+                  for (int kx = kx0; kx <= kx1; ++kx) sum += u.weight[((size_t)n * u.c_in + j * 64 + k) * 9 + ky * 3 + kx];
+                img[(size_t)t * N * 64 + sw128_index(n, k)] = f32_to_bf16_rn(sum);
+              }
+            hp.entries[ph][ne++] = HaloEntry{halo_a_off16(dy + 1, dx + 1, 0), (uint32_t)((size_t)t * N * 128 >> 4), 4, 0};
+            ++t;
+          }
+        if (j == 0) hp.e_split = ne;
+      }
+      hp.n_entries = ne;
+      uint16_t* d;
+      int rc = dev_upload(net, img, &d);
+      if (rc) return rc;
+      hp.d_wimg[ph] = reinterpret_cast<uint8_t*>(d);
+    }
+  hp.ok = true;
+  return RCU_OK;
+}
+
+static uint32_t halo_chunk_stride(bool /*half_rows*/) {
+  const uint32_t bytes = (uint32_t)(kHaloRows * kHaloPitch * 128);   // footprint: 128-byte rows even when only 64 are filled
+  return (bytes + 1023u) & ~1023u;
+}
+
+template <int N>
+static int halo_stage_count(uint32_t w_bytes, bool pair) {
+  const int64_t room = (int64_t)kHaloSmemBudget - HaloSmem<N>::kFixed - (int64_t)((w_bytes + 1023u) & ~1023u);
+  int64_t st = room / halo_chunk_stride(pair);
+  if (st > HaloSmem<N>::kMaxStages) st = HaloSmem<N>::kMaxStages;
+  return (int)st;
+}
+
+template <int N>
+static int launch_conv_halo(const ConvLayer& L, const HaloParams& prm, cudaStream_t st) {
+  auto kern = conv_halo_kernel<N>;
+  static bool configured[64] = {false};
+  int dev = 0;
+  RCU_CUDA(cudaGetDevice(&dev));
+  dev = dev < 0 || dev >= 64 ? 0 : dev;
+  if (!configured[dev]) {
+    RCU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmemBudget));
+    configured[dev] = true;
+  }
+  const size_t smem = (size_t)HaloSmem<N>::kFixed + ((prm.w_bytes + 1023u) & ~1023u) + (size_t)prm.n_stages * prm.chunk_stride;
+  const long long total_tiles = (long long)prm.n_img * prm.tiles_y * prm.tiles_x;
+  long long grid = sm_count();
+  if (grid > total_tiles) grid = total_tiles;
+  if (grid < 1) return RCU_OK;
+  kern<<<(unsigned)grid, kHaloThreads, smem, st>>>(L.map_halo, prm);
+  RCU_LAUNCH_CHECK();
+  return RCU_OK;
 }
 
 }  // namespace rcu
@@ -374,6 +548,8 @@ extern "C" int rcu_unet_create(const rcu_unet_desc* d, int device, rcu_unet** ou
     rc2 = dev_upload(net, w, &dw);
     if (rc2) return rc2;
     L.d_weights = reinterpret_cast<__nv_bfloat16*>(dw);
+    rc2 = pack_halo_conv3x3(net, cu, L.halo);
+    if (rc2) return rc2;
     net->convs.push_back(L);
     return RCU_OK;
   };
@@ -390,6 +566,8 @@ extern "C" int rcu_unet_create(const rcu_unet_desc* d, int device, rcu_unet** ou
     rc2 = dev_upload(net, w, &dw);
     if (rc2) return rc2;
     L.d_weights = reinterpret_cast<__nv_bfloat16*>(dw);
+    rc2 = pack_halo_upconv(net, cu, L.halo);
+    if (rc2) return rc2;
     net->convs.push_back(L);
     return RCU_OK;
   };
@@ -408,7 +586,7 @@ extern "C" int rcu_unet_create(const rcu_unet_desc* d, int device, rcu_unet** ou
     for (int j = 0; j < d->depth; ++j) {
       RCU_TRY(add_upconv(j, c, c / 2));
       c /= 2;
-      RCU_TRY(add_unit(u++, c, c, false));               // cat((up, skip), 1)
+      RCU_TRY(add_unit(u++, 2 * c, 0, false));           // cat((up, skip), 1): one 2c-channel concat buffer
       RCU_TRY(add_unit(u++, c, 0, false));
     }
     const bool fuse_head = (sf == 32);
@@ -432,8 +610,14 @@ extern "C" int rcu_unet_total_dropout_channels(const rcu_unet* net) { return net
 extern "C" int64_t rcu_unet_last_launch_count(const rcu_unet* net) { return net ? net->last_launches : 0; }
 extern "C" int rcu_unet_set_conv_impl(rcu_unet* net, int impl) {
   RCU_CHECK_ARG(net != nullptr, "NULL handle");
-  RCU_CHECK_ARG(impl == 0 || impl == 1, "conv impl must be 0 (tcgen05) or 1 (cross-check)");
+  RCU_CHECK_ARG(impl >= 0 && impl <= 2, "conv impl must be 0 (tcgen05), 1 (cross-check) or 2 (tcgen05, per-tap kernel only)");
   net->conv_impl = impl;
+  return RCU_OK;
+}
+
+extern "C" int rcu_unet_set_halo_mask(rcu_unet* net, uint64_t mask) {
+  RCU_CHECK_ARG(net != nullptr, "NULL handle");
+  net->halo_mask = mask;
   return RCU_OK;
 }
 
@@ -452,78 +636,161 @@ extern "C" int rcu_unet_plan(rcu_unet* net, int height, int width, int max_image
   const long long N = max_images_per_chunk;
   const int sf = net->start_filters, depth = net->depth;
 
-  // ---- carve the arena: per level l: A (conv0 out / block conv0 out), SKIP, U (upconv out / block conv1 out), POOL ----
+  // ---- tensors.  Two passes over the same code: pass 0 sizes the arena, pass 1 hands out pointers.
+  // Level l (resolution H>>l, C_l = sf<<l channels):  E[l] first conv of the encoder block, CAT[l] = [up | skip]
+  // (2*C_l channels; the encoder's second conv writes the skip half, the decoder's upconv the up half), P[l] pooled
+  // skip (input of level l+1), DA/DB[l] the decoder block's two convs.
+  std::vector<Act> E(depth + 1), CAT(depth), P(depth), DA(depth), DB(depth);
+  Act SB, HF;
   size_t off = 0;
-  auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 1023) & ~size_t(1023); return o; };
-  std::vector<size_t> oA(depth + 1), oS(depth + 1), oU(depth + 1), oP(depth + 1);
-  for (int l = 0; l <= depth; ++l) {
-    const size_t px = (size_t)(height >> l) * (width >> l) * N;
-    const size_t c = (size_t)sf << l;
-    oA[l] = carve(px * c * 2);
-    oS[l] = carve(px * c * 2);
-    if (l < depth) {
-      oU[l] = carve(px * c * 2);
-      oP[l] = carve(px / 4 * c * 2);
+  uint8_t* base = nullptr;
+  auto tensor = [&](int c_total, int h, int w) {
+    Act a;
+    a.c = a.c_total = c_total; a.h = h; a.w = w;
+    a.padded = false;
+    const long long rows = a.padded ? h + 1 : h;
+    a.img_stride = rows * w * c_total;
+    const size_t lead = a.padded ? (size_t)w * c_total * 2 : 0;   // the zero row above image 0
+    const size_t bytes = lead + (size_t)N * a.img_stride * 2;
+    if (base) a.base = reinterpret_cast<__nv_bfloat16*>(base + off + lead);
+    off += (bytes + 1023) & ~size_t(1023);
+    return a;
+  };
+  auto slice = [](const Act& t, int ch_off, int c) {
+    Act a = t;
+    a.base = t.base ? t.base + ch_off : nullptr;
+    a.c = c;
+    return a;
+  };
+  size_t o_coef = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    off = 0;
+    for (int l = 0; l <= depth; ++l) {
+      const int h = height >> l, w = width >> l, c = sf << l;
+      E[l] = tensor(c, h, w);
+      if (l < depth) {
+        CAT[l] = tensor(2 * c, h, w);
+        P[l] = tensor(c, h / 2, w / 2);
+        DA[l] = tensor(c, h, w);
+        DB[l] = tensor(c, h, w);
+      } else {
+        SB = tensor(c, h, w);
+      }
+    }
+    HF = tensor(sf, height, width);   // conv_cls.0 features (cross-check path only; the tcgen05 paths fuse the head)
+    o_coef = off;
+    off += ((size_t)N * net->n_cols * sizeof(float2) + 1023) & ~size_t(1023);
+    if (pass == 0) {
+      RCU_CUDA(cudaMalloc(&net->arena, off));
+      RCU_CUDA(cudaMemset(net->arena, 0, off));   // zero rows of the padded tensors are never written again
+      net->arena_bytes = off;
+      base = reinterpret_cast<uint8_t*>(net->arena);
     }
   }
-  const size_t o_feat = carve((size_t)height * width * N * sf * 2);
-  const size_t o_coef = carve((size_t)N * net->n_cols * sizeof(float2));
-  RCU_CUDA(cudaMalloc(&net->arena, off));
-  net->arena_bytes = off;
-  uint8_t* base = reinterpret_cast<uint8_t*>(net->arena);
-  auto B = [&](size_t o) { return reinterpret_cast<__nv_bfloat16*>(base + o); };
   net->d_coef = reinterpret_cast<float2*>(base + o_coef);
-  net->head_feat = B(o_feat);
-  net->first_out = B(oA[0]);
+  net->first_out = E[0];
+  net->head_feat = HF;
 
   // ---- schedule ----
   int ci = 0;
-  auto push_conv = [&](const __nv_bfloat16* s0, const __nv_bfloat16* s1, __nv_bfloat16* dst, int in_h, int in_w) -> int {
+  auto push_conv = [&](const Act& src, const Act& dst) -> int {
     ConvLayer& L = net->convs[ci];
-    L.src0 = s0; L.src1 = s1; L.dst = dst; L.in_h = in_h; L.in_w = in_w;
-    int rc = make_act_map(&L.map_a0, s0, L.c0, in_w, in_h, (int)N, L.kc);
+    if (src.c != L.c0) { set_error("conv %d: source has %d channels, layer expects %d", ci, src.c, L.c0); return RCU_EINVAL; }
+    L.src = src; L.dst = dst; L.in_h = src.h; L.in_w = src.w;
+    int rc = make_act_map(&L.map_a0, src, (int)N, L.kc);
     if (rc) return rc;
-    rc = make_act_map(&L.map_a1, s1 ? s1 : s0, s1 ? L.c1 : L.c0, in_w, in_h, (int)N, L.kc);
-    if (rc) return rc;
+    L.map_a1 = L.map_a0;
     rc = make_weight_map(&L.map_w, L.d_weights, L.c0 + L.c1, L.c_out, L.n_taps * L.n_phases, L.kc, L.block_n);
     if (rc) return rc;
+    if (L.halo.ok) {
+      L.halo_stages = L.c_out == 32 ? halo_stage_count<32>(L.halo.w_bytes, L.halo.pair) : halo_stage_count<64>(L.halo.w_bytes, L.halo.pair);
+      if (L.halo_stages < 2) {
+        L.halo.ok = false;
+      } else {
+        rc = make_halo_map(&L.map_halo, src, (int)N, L.halo.pair ? 32 : 64);
+        if (rc) return rc;
+      }
+    }
     Op op;
     op.kind = OP_CONV; op.conv = ci; op.out = L.head ? net->head_feat : dst;
-    op.h = in_h * L.out_mul; op.w = in_w * L.out_mul; op.c = L.c_out;
+    op.h = src.h * L.out_mul; op.w = src.w * L.out_mul; op.c = L.c_out;
     net->ops.push_back(op);
     ++ci;
     return RCU_OK;
   };
-  auto push_pool = [&](const __nv_bfloat16* in, __nv_bfloat16* out, int in_h, int in_w, int c) {
+  auto push_pool = [&](const Act& in, const Act& out) {
     Op op;
-    op.kind = OP_POOL; op.in = in; op.out = out; op.in_h = in_h; op.in_w = in_w; op.h = in_h / 2; op.w = in_w / 2; op.c = c;
+    op.kind = OP_POOL; op.in = in; op.out = out; op.in_h = in.h; op.in_w = in.w; op.h = in.h / 2; op.w = in.w / 2; op.c = in.c;
     net->ops.push_back(op);
   };
   {
     Op first;
-    first.kind = OP_FIRST; first.out = B(oA[0]); first.h = height; first.w = width; first.c = sf;
+    first.kind = OP_FIRST; first.out = E[0]; first.h = height; first.w = width; first.c = sf;
     net->ops.push_back(first);
   }
-  int rc = push_conv(B(oA[0]), nullptr, B(oS[0]), height, width);
+  int rc = push_conv(E[0], slice(CAT[0], sf, sf));
   if (rc) return rc;
   for (int l = 1; l <= depth; ++l) {
-    const int h = height >> l, w = width >> l;
-    push_pool(B(oS[l - 1]), B(oP[l - 1]), h * 2, w * 2, sf << (l - 1));
-    if ((rc = push_conv(B(oP[l - 1]), nullptr, B(oA[l]), h, w))) return rc;
-    if ((rc = push_conv(B(oA[l]), nullptr, B(oS[l]), h, w))) return rc;
+    const int cp = sf << (l - 1), c = sf << l;
+    push_pool(slice(CAT[l - 1], cp, cp), P[l - 1]);
+    if ((rc = push_conv(P[l - 1], E[l]))) return rc;
+    if ((rc = push_conv(E[l], l < depth ? slice(CAT[l], c, c) : SB))) return rc;
   }
-  const __nv_bfloat16* cur = B(oS[depth]);
+  Act cur = SB;
   for (int l = depth - 1; l >= 0; --l) {
-    const int h = height >> l, w = width >> l;
-    if ((rc = push_conv(cur, nullptr, B(oU[l]), h / 2, w / 2))) return rc;       // upconv phases: low-res in, high-res out
-    if ((rc = push_conv(B(oU[l]), B(oS[l]), B(oA[l]), h, w))) return rc;         // cat((up, skip)) conv
-    if ((rc = push_conv(B(oA[l]), nullptr, B(oU[l]), h, w))) return rc;
-    cur = B(oU[l]);
+    const int c = sf << l;
+    if ((rc = push_conv(cur, slice(CAT[l], 0, c)))) return rc;     // upconv phases: low-res in, high-res up half of the concat
+    if ((rc = push_conv(CAT[l], DA[l]))) return rc;                 // conv over cat((up, skip), 1)
+    if ((rc = push_conv(DA[l], DB[l]))) return rc;
+    cur = DB[l];
   }
-  if ((rc = push_conv(cur, nullptr, B(oA[0]), height, width))) return rc;        // conv_cls.0 (+ fused head)
+  if ((rc = push_conv(cur, net->head_feat))) return rc;             // conv_cls.0 (+ fused head)
   if (workspace_bytes) *workspace_bytes = off;
   return RCU_OK;
 }
+
+namespace rcu {
+
+static int run_conv_halo(rcu_unet* net, const ConvLayer& L, int n_img, int cs, long long s0, long long n_slices, float* logits,
+                         cudaStream_t st, long long* launches) {
+  const HaloPack& hp = L.halo;
+  for (int ph = 0; ph < hp.n_phases; ++ph) {
+    HaloParams prm;
+    std::memset(&prm, 0, sizeof(prm));
+    prm.n_img = n_img;
+    prm.in_h = L.in_h; prm.in_w = L.in_w;
+    prm.tiles_x = (L.in_w + kHaloTileW - 1) / kHaloTileW;
+    prm.tiles_y = (L.in_h + kHaloTileH - 1) / kHaloTileH;
+    prm.n_chunks = hp.n_chunks;
+    prm.pair = hp.pair ? 1 : 0;
+    prm.chunk_bytes = (uint32_t)(kHaloRows * kHaloPitch * (hp.pair ? 64 : 128));   // bytes TMA delivers (complete_tx counts data bytes)
+    prm.chunk_stride = halo_chunk_stride(hp.pair);
+    prm.n_stages = L.halo_stages;
+    prm.e_split = hp.e_split;
+    prm.n_entries = hp.n_entries;
+    std::memcpy(prm.entries, hp.entries[ph], sizeof(HaloEntry) * hp.n_entries);
+    prm.w_image = hp.d_wimg[ph];
+    prm.w_bytes = hp.w_bytes;
+    prm.out_mul = L.out_mul;
+    prm.out_dy = hp.n_phases == 4 ? (ph >> 1) : 0;
+    prm.out_dx = hp.n_phases == 4 ? (ph & 1) : 0;
+    prm.out_h = L.in_h * L.out_mul; prm.out_w = L.in_w * L.out_mul;
+    prm.out_c = L.dst.c_total;
+    prm.out_img_stride = L.dst.img_stride;
+    prm.out = L.dst.base;
+    prm.coef = net->d_coef; prm.coef_stride = net->n_cols; prm.coef_off = L.coef_off;
+    prm.relu = L.relu;
+    prm.head = L.head ? net->d_head : nullptr;
+    prm.logits = logits;
+    prm.chunk_slices = cs; prm.slice0 = s0; prm.n_slices_total = n_slices;
+    int rc = L.c_out == 32 ? launch_conv_halo<32>(L, prm, st) : launch_conv_halo<64>(L, prm, st);
+    if (rc) return rc;
+    ++*launches;
+  }
+  return RCU_OK;
+}
+
+}  // namespace rcu
 
 extern "C" int rcu_unet_forward(rcu_unet* net, const float* images, int64_t n_slices, int n_samples, int dropout_mode,
                                 int det_first, uint64_t seed, int64_t slice_index0, int sample0, const float* scale,
@@ -566,21 +833,29 @@ extern "C" int rcu_unet_forward(rcu_unet* net, const float* images, int64_t n_sl
         dim3 grid((unsigned)tiles, (unsigned)cs);
         if (sf == 32)
           first_conv_kernel<32><<<grid, 256, smem, st>>>(images, net->in_channels, H, W, (long long)s0, cs, n_samples, net->d_first_w,
-                                                         net->d_coef, net->n_cols, net->first_coef_off, net->first_out);
+                                                         net->d_coef, net->n_cols, net->first_coef_off, net->first_out.base,
+                                                         net->first_out.img_stride);
         else
           first_conv_kernel<64><<<grid, 256, smem, st>>>(images, net->in_channels, H, W, (long long)s0, cs, n_samples, net->d_first_w,
-                                                         net->d_coef, net->n_cols, net->first_coef_off, net->first_out);
+                                                         net->d_coef, net->n_cols, net->first_coef_off, net->first_out.base,
+                                                         net->first_out.img_stride);
         RCU_LAUNCH_CHECK();
         ++launches;
       } else if (op.kind == OP_POOL) {
         const long long total = (long long)n_img * op.h * op.w * (op.c / 8);
         long long blocks = (total + 255) / 256;
         if (blocks > (long long)sm_count() * 16) blocks = (long long)sm_count() * 16;
-        maxpool2_kernel<<<(unsigned)blocks, 256, 0, st>>>(op.in, op.out, n_img, op.in_h, op.in_w, op.c);
+        maxpool2_kernel<<<(unsigned)blocks, 256, 0, st>>>(op.in.base, op.in.c_total, op.in.img_stride, op.out.base, op.out.img_stride,
+                                                          n_img, op.in_h, op.in_w, op.c);
         RCU_LAUNCH_CHECK();
         ++launches;
       } else {
         const ConvLayer& L = net->convs[op.conv];
+        if (net->conv_impl == 0 && L.halo.ok && ((net->halo_mask >> op.conv) & 1ull)) {
+          int rc = run_conv_halo(net, L, n_img, cs, (long long)s0, (long long)n_slices, logits, st, &launches);
+          if (rc) return rc;
+          continue;
+        }
         ConvParams prm;
         std::memset(&prm, 0, sizeof(prm));
         prm.n_img = n_img;
@@ -593,30 +868,32 @@ extern "C" int rcu_unet_forward(rcu_unet* net, const float* images, int64_t n_sl
         std::memcpy(prm.dy, L.dy, sizeof(prm.dy));
         std::memcpy(prm.dx, L.dx, sizeof(prm.dx));
         prm.out_mul = L.out_mul;
-        prm.out_h = L.in_h * L.out_mul; prm.out_w = L.in_w * L.out_mul; prm.out_c = L.c_out;
-        prm.out = L.dst;
+        prm.out_h = L.in_h * L.out_mul; prm.out_w = L.in_w * L.out_mul;
+        prm.out_c = L.dst.c_total;
+        prm.out_img_stride = L.dst.img_stride;
+        prm.out = L.dst.base;
         prm.coef = net->d_coef; prm.coef_stride = net->n_cols; prm.coef_off = L.coef_off;
         prm.relu = L.relu;
         prm.head = nullptr; prm.logits = logits;
         prm.chunk_slices = cs; prm.slice0 = s0; prm.n_slices_total = n_slices;
-        if (net->conv_impl == 0) {
+        if (net->conv_impl != 1) {
           if (L.head) prm.head = net->d_head;
           int rc = dispatch_conv_tc(L, prm, st);
           if (rc) return rc;
           ++launches;
         } else {
-          if (L.head) prm.out = net->head_feat;
           const long long total = (long long)n_img * L.n_phases * L.in_h * L.in_w * L.c_out;
           long long blocks = (total + 255) / 256;
           if (blocks > (long long)sm_count() * 32) blocks = (long long)sm_count() * 32;
-          conv_check_kernel<<<(unsigned)blocks, 256, 0, st>>>(L.src0, L.src1, L.c0, L.c1, L.d_weights, L.c_out, prm);
+          conv_check_kernel<<<(unsigned)blocks, 256, 0, st>>>(L.src.base, L.c0, L.src.c_total, L.src.img_stride, L.d_weights, L.c_out, prm);
           RCU_LAUNCH_CHECK();
           ++launches;
           if (L.head) {
             const long long px = (long long)n_img * H * W;
             long long hb = (px + 255) / 256;
             if (hb > (long long)sm_count() * 32) hb = (long long)sm_count() * 32;
-            head_check_kernel<<<(unsigned)hb, 256, 0, st>>>(net->head_feat, net->d_head, logits, n_img, H, W, sf, cs, (long long)s0, (long long)n_slices);
+            head_check_kernel<<<(unsigned)hb, 256, 0, st>>>(net->head_feat.base, net->head_feat.img_stride, net->d_head, logits, n_img, H, W,
+                                                           sf, cs, (long long)s0, (long long)n_slices);
             RCU_LAUNCH_CHECK();
             ++launches;
           }
@@ -632,7 +909,7 @@ extern "C" int rcu_unet_debug_activation(rcu_unet* net, int index, float* out, s
   RCU_CHECK_ARG(net != nullptr && out != nullptr, "NULL argument");
   RCU_CHECK_ARG(index >= 0 && index < (int)net->ops.size(), "activation index %d out of range [0, %d)", index, (int)net->ops.size());
   const Op& op = net->ops[index];
-  if (op.kind == OP_CONV && net->convs[op.conv].head && net->conv_impl == 0) {
+  if (op.kind == OP_CONV && net->convs[op.conv].head && net->conv_impl != 1) {
     set_error("activation %d is fused away (conv_cls.0 feeds the head in registers on the tcgen05 path)", index);
     return RCU_ENOTSUP;
   }
@@ -641,7 +918,8 @@ extern "C" int rcu_unet_debug_activation(rcu_unet* net, int index, float* out, s
   if (n == 0) return RCU_OK;
   long long blocks = (n + 255) / 256;
   if (blocks > 4096) blocks = 4096;
-  bf16_to_f32_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(op.out, out, n);
+  bf16_to_f32_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(op.out.base, op.out.c_total, op.out.img_stride,
+                                                                        (long long)op.h * op.w, op.c, out, n);
   RCU_LAUNCH_CHECK();
   return RCU_OK;
 }

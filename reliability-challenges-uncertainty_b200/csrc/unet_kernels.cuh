@@ -65,7 +65,7 @@ template <int C_OUT>
 __global__ void __launch_bounds__(256)
 first_conv_kernel(const float* __restrict__ images, int c_in, int h, int w, long long slice0, int chunk_slices, int n_samples,
                   const float* __restrict__ weight /* [c_in*9][C_OUT] */, const float2* __restrict__ coef, long long coef_stride,
-                  int coef_off, __nv_bfloat16* __restrict__ out) {
+                  int coef_off, __nv_bfloat16* __restrict__ out, long long out_img_stride) {
   extern __shared__ float s_first[];
   float* s_w = s_first;                                  // [c_in*9][C_OUT]
   float* s_in = s_first + c_in * 9 * C_OUT;              // [c_in][18][18]
@@ -104,7 +104,7 @@ first_conv_kernel(const float* __restrict__ images, int c_in, int h, int w, long
   for (int t = 0; t < n_samples; ++t) {
     const int im = t * chunk_slices + sl;
     const float2* cf = coef + (long long)im * coef_stride + coef_off;
-    uint4* dst = reinterpret_cast<uint4*>(out + (((long long)im * h + y) * w + x) * C_OUT);
+    uint4* dst = reinterpret_cast<uint4*>(out + (long long)im * out_img_stride + ((long long)y * w + x) * C_OUT);
 #pragma unroll
     for (int c8 = 0; c8 < C_OUT / 8; ++c8) {
       uint32_t pk[4];
@@ -135,7 +135,9 @@ __device__ __forceinline__ uint4 bf16x8_max(uint4 a, uint4 b) {
 }
 
 __global__ void __launch_bounds__(256)
-maxpool2_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n_img, int h, int w, int c) {
+maxpool2_kernel(const __nv_bfloat16* __restrict__ in, int in_px_stride, long long in_img_stride, __nv_bfloat16* __restrict__ out,
+                long long out_img_stride, long long n_img, int h, int w, int c) {
+  // `in` may be a channel slice of a wider tensor (the skip half of a concat buffer): pixel stride in_px_stride
   const int oh = h >> 1, ow = w >> 1, c8 = c >> 3;
   const long long total = n_img * oh * ow * c8;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
@@ -144,10 +146,11 @@ maxpool2_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict_
     const int ox = (int)(r % ow); r /= ow;
     const int oy = (int)(r % oh);
     const long long im = r / oh;
-    const uint4* p = reinterpret_cast<const uint4*>(in + ((im * h + 2 * oy) * w + 2 * ox) * c) + cc;
-    const long long row = (long long)w * c8, px = c8;
-    const uint4 m = bf16x8_max(bf16x8_max(__ldg(p), __ldg(p + px)), bf16x8_max(__ldg(p + row), __ldg(p + row + px)));
-    reinterpret_cast<uint4*>(out)[i] = m;
+    const __nv_bfloat16* p0 = in + im * in_img_stride + ((long long)(2 * oy) * w + 2 * ox) * in_px_stride + cc * 8;
+    const long long row = (long long)w * in_px_stride;
+    const uint4 m = bf16x8_max(bf16x8_max(__ldg(reinterpret_cast<const uint4*>(p0)), __ldg(reinterpret_cast<const uint4*>(p0 + in_px_stride))),
+                               bf16x8_max(__ldg(reinterpret_cast<const uint4*>(p0 + row)), __ldg(reinterpret_cast<const uint4*>(p0 + row + in_px_stride))));
+    *reinterpret_cast<uint4*>(out + im * out_img_stride + ((long long)oy * ow + ox) * c + cc * 8) = m;
   }
 }
 
@@ -156,9 +159,8 @@ maxpool2_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict_
 // One thread = one output pixel x one output channel.  Debug only: rcu_unet_set_conv_impl(net, 1).
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-conv_check_kernel(const __nv_bfloat16* __restrict__ src0, const __nv_bfloat16* __restrict__ src1, int c0, int c1,
+conv_check_kernel(const __nv_bfloat16* __restrict__ src, int c_in, int src_px_stride, long long src_img_stride,
                   const __nv_bfloat16* __restrict__ weights, int c_out, const ConvParams prm) {
-  const int c_in = c0 + c1;
   const long long total = (long long)prm.n_img * prm.n_phases * prm.in_h * prm.in_w * c_out;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
     long long r = i;
@@ -172,31 +174,27 @@ conv_check_kernel(const __nv_bfloat16* __restrict__ src0, const __nv_bfloat16* _
       const int yy = y + prm.dy[ph][tap], xx = x + prm.dx[ph][tap];
       if (yy < 0 || yy >= prm.in_h || xx < 0 || xx >= prm.in_w) continue;
       const __nv_bfloat16* wrow = weights + ((long long)(ph * prm.n_taps + tap) * c_out + co) * c_in;
-      const __nv_bfloat16* a0 = src0 + (((long long)img * prm.in_h + yy) * prm.in_w + xx) * c0;
-      for (int k = 0; k < c0; ++k) acc = fmaf(__bfloat162float(a0[k]), __bfloat162float(wrow[k]), acc);
-      if (c1 > 0) {
-        const __nv_bfloat16* a1 = src1 + (((long long)img * prm.in_h + yy) * prm.in_w + xx) * c1;
-        for (int k = 0; k < c1; ++k) acc = fmaf(__bfloat162float(a1[k]), __bfloat162float(wrow[c0 + k]), acc);
-      }
+      const __nv_bfloat16* a0 = src + (long long)img * src_img_stride + ((long long)yy * prm.in_w + xx) * src_px_stride;
+      for (int k = 0; k < c_in; ++k) acc = fmaf(__bfloat162float(a0[k]), __bfloat162float(wrow[k]), acc);
     }
     const float2 cf = prm.coef[(long long)img * prm.coef_stride + prm.coef_off + co];
     float v = fmaf(acc, cf.x, cf.y);
     if (prm.relu) v = fmaxf(v, 0.0f);
     const int oy = prm.out_mul * y + (ph >> 1), ox = prm.out_mul * x + (ph & 1);
-    prm.out[(((long long)img * prm.out_h + oy) * prm.out_w + ox) * prm.out_c + co] = __float2bfloat16_rn(v);
+    prm.out[(long long)img * prm.out_img_stride + ((long long)oy * prm.out_w + ox) * prm.out_c + co] = __float2bfloat16_rn(v);
   }
 }
 
 // 1x1 head for the cross-check path: bf16 features [img][h][w][32] -> logits (the tcgen05 path fuses this).
 __global__ void __launch_bounds__(256)
-head_check_kernel(const __nv_bfloat16* __restrict__ feat, const float* __restrict__ head, float* __restrict__ logits, int n_img,
-                  int h, int w, int c, int chunk_slices, long long slice0, long long n_slices_total) {
+head_check_kernel(const __nv_bfloat16* __restrict__ feat, long long feat_img_stride, const float* __restrict__ head,
+                  float* __restrict__ logits, int n_img, int h, int w, int c, int chunk_slices, long long slice0, long long n_slices_total) {
   const long long total = (long long)n_img * h * w;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
     const long long img = i / ((long long)h * w), px = i - img * h * w;
     float l0 = head[2 * c], l1 = head[2 * c + 1];
     for (int k = 0; k < c; ++k) {
-      const float a = __bfloat162float(feat[i * c + k]);
+      const float a = __bfloat162float(feat[img * feat_img_stride + px * c + k]);
       l0 = fmaf(a, head[k], l0);
       l1 = fmaf(a, head[c + k], l1);
     }
@@ -206,10 +204,14 @@ head_check_kernel(const __nv_bfloat16* __restrict__ feat, const float* __restric
   }
 }
 
-// NHWC bf16 -> fp32 copy used by rcu_unet_debug_activation.
-__global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, long long n) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    out[i] = __bfloat162float(in[i]);
+// (strided) NHWC bf16 -> dense fp32 copy used by rcu_unet_debug_activation.
+__global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, int px_stride, long long img_stride, long long hw, int c,
+                                   float* __restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % c);
+    const long long px = (i / c) % hw, img = i / c / hw;
+    out[i] = __bfloat162float(in[img * img_stride + px * px_stride + ch]);
+  }
 }
 
 }  // namespace rcu

@@ -201,8 +201,12 @@ class B200UNet(nn.Module):
         return int(sum(self.site_channels))
 
     def set_conv_impl(self, impl):
-        """0 = tcgen05 (product path), 1 = CUDA-core cross-check kernels (tests only)."""
+        """0 = tcgen05 (product path), 1 = CUDA-core cross-check kernels (tests only), 2 = tcgen05 per-tap kernel only."""
         _lib.check(_lib.lib().rcu_unet_set_conv_impl(self._handle, int(impl)))
+
+    def set_halo_mask(self, mask):
+        """Debug: bit i lets conv i (execution order) use the halo-tile kernel; default all ones."""
+        _lib.check(_lib.lib().rcu_unet_set_halo_mask(self._handle, int(mask) & 0xFFFFFFFFFFFFFFFF))
 
     def last_launch_count(self):
         return int(_lib.lib().rcu_unet_last_launch_count(self._handle))

@@ -234,10 +234,45 @@ def stage_unet_full():
     return True
 
 
+def stage_halo_layers():
+    """Each halo-eligible conv alone against the per-tap tcgen05 kernel (identical inputs: every other layer is per-tap)."""
+    cfg, sd = make_net()
+    n, h, w = 3, 48, 64
+    x = torch.randn(n, 4, h, w, generator=torch.Generator().manual_seed(3))
+    ref = model.B200UNet(sd, in_channels=4, dropout=cfg.dropout, chunk_images=64)
+    ref.set_conv_impl(2)
+    out_ref = ref.forward_samples(x, 2, dropout_mode=1, det_first=True, seed=5)
+    ops = ref.op_table()
+    conv_ops = [i for i, o in enumerate(ops) if o['kind'] == 'conv_tc']
+    ok = True
+    for ci, op_i in enumerate(conv_ops):
+        o = ops[op_i]
+        if o['c_out'] > 64:
+            continue
+        net = model.B200UNet(sd, in_channels=4, dropout=cfg.dropout, chunk_images=64)
+        net.set_halo_mask(1 << ci)
+        out = net.forward_samples(x, 2, dropout_mode=1, det_first=True, seed=5)
+        shape = (2 * n, o['h'], o['w'], o['c_out'])
+        if ci == len(conv_ops) - 1:
+            d = (out - out_ref).abs().max().item()
+            s = out_ref.abs().max().item()
+            ok &= report('halo conv %2d (head) %s' % (ci, o), d <= 2e-2 * s, 'logits maxdiff %.4g scale %.3g' % (d, s))
+            continue
+        a = ref.debug_activation(op_i, shape).cpu()
+        b = net.debug_activation(op_i, shape).cpu()
+        d = (a - b).abs()
+        s = a.abs().max().item()
+        bad = d > 2 ** -7 * max(s, 1.0)
+        ok &= report('halo conv %2d c_in=%d c_out=%d %dx%d' % (ci, o['c_in'], o['c_out'], o['h'], o['w']), not bad.any().item(),
+                     'maxdiff %.4g scale %.3g nbad %d first_bad %s' % (d.max().item(), s, int(bad.sum()),
+                                                                       tuple(bad.nonzero()[0].tolist()) if bad.any() else ''))
+    return ok
+
+
 if __name__ == '__main__':
     stage = sys.argv[1]
     fn = {'metrics': stage_metrics, 'aggregate': stage_aggregate, 'unet_check': lambda: stage_unet(1),
-          'unet_tc_e2e': lambda: stage_unet(0), 'unet_tc': stage_unet_tc, 'unet_full': stage_unet_full}[stage]
+          'unet_tc_e2e': lambda: stage_unet(0), 'unet_tc': stage_unet_tc, 'unet_full': stage_unet_full, 'halo_layers': stage_halo_layers}[stage]
     good = fn()
     print('STAGE %s %s' % (stage, 'OK' if good else 'FAILED'))
     sys.exit(0 if good else 1)

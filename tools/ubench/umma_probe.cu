@@ -22,6 +22,12 @@ using namespace rcu;
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
 
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred;
+}
+
 __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout, uint32_t base_off) {
   return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
          (uint64_t(1) << 46) | ((uint64_t)base_off << 49) | ((uint64_t)layout << 61);
@@ -38,9 +44,12 @@ __global__ void __launch_bounds__(128, 1) shift_kernel(const __nv_bfloat16* __re
   uint8_t* sp = smem_raw + (base - smem_u32(smem_raw));
   __shared__ uint64_t bar;
   __shared__ uint32_t s_tmem;
-  const int C = mode == 0 ? 32 : 64;
-  const int P = mode == 0 ? 10 : 16;
+  // mode 3: SWIZZLE_128B rows, C = 64, DENSE halo 18 x 10 (pitch 10, what one TMA box writes), base_offset 0
+  // mode 4: SWIZZLE_64B rows, C = 32, dense halo 18 x 10, base_offset 0
+  const int C = (mode == 0 || mode == 4) ? 32 : 64;
+  const int P = (mode == 1 || mode == 2) ? 16 : 10;
   const int N = 32;
+  const int RB = C * 2;  // row bytes
   const uint32_t a_bytes = mode == 0 ? 4 * 18 * 10 * 16 : 18 * 16 * 128;
   const uint32_t sA = base, sB = (base + a_bytes + 1023u) & ~1023u;
   uint8_t* pA = sp;
@@ -51,7 +60,11 @@ __global__ void __launch_bounds__(128, 1) shift_kernel(const __nv_bfloat16* __re
     const uint4 v = *reinterpret_cast<const uint4*>(x + ((size_t)(py * 10 + px) * C + g * 8));
     uint32_t off;
     if (mode == 0) off = (uint32_t)g * (18 * 10 * 16) + (uint32_t)(py * P + px) * 16;
-    else off = (uint32_t)(py * P + px) * 128 + (uint32_t)((g ^ (px & 7)) * 16);
+    else {
+      const uint32_t row = (uint32_t)(py * P + px) * RB;             // byte address of the row (tile base is 1024-aligned)
+      const uint32_t x7 = mode == 4 ? ((row >> 7) & 3u) : ((row >> 7) & 7u);  // SW64: bits[4:5] ^= bits[7:8]; SW128: bits[4:6] ^= bits[7:9]
+      off = row + (uint32_t)((g ^ x7) * 16);
+    }
     *reinterpret_cast<uint4*>(pA + off) = v;
   }
   // ---- fill B: w[tap][n][ci]
@@ -60,7 +73,11 @@ __global__ void __launch_bounds__(128, 1) shift_kernel(const __nv_bfloat16* __re
     const uint4 v = *reinterpret_cast<const uint4*>(w + ((size_t)(tap * N + n) * C + g * 8));
     uint32_t off;
     if (mode == 0) off = (uint32_t)(tap * (C / 8) + g) * (N * 16) + (uint32_t)n * 16;
-    else off = (uint32_t)tap * (N * 128) + (uint32_t)n * 128 + (uint32_t)((g ^ (n & 7)) * 16);
+    else {
+      const uint32_t row = (uint32_t)tap * (N * RB) + (uint32_t)n * RB;
+      const uint32_t x7 = mode == 4 ? ((row >> 7) & 3u) : ((row >> 7) & 7u);
+      off = row + (uint32_t)((g ^ x7) * 16);
+    }
     *reinterpret_cast<uint4*>(pB + off) = v;
   }
   if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
@@ -81,9 +98,10 @@ __global__ void __launch_bounds__(128, 1) shift_kernel(const __nv_bfloat16* __re
           da = make_desc(sA + (uint32_t)(2 * ks) * (18 * 10 * 16) + (uint32_t)(ty * P + tx) * 16, 18 * 10 * 16, P * 16, 0, 0);
           db = make_desc(sB + (uint32_t)(tap * (C / 8) + 2 * ks) * (N * 16), N * 16, 128, 0, 0);
         } else {
-          const uint32_t start = sA + (uint32_t)(ty * P + tx) * 128 + (uint32_t)ks * 32;
-          da = make_desc(start, 16, P * 128, 2, mode == 1 ? ((start >> 7) & 7u) : 0u);
-          db = make_desc(sB + (uint32_t)tap * (N * 128) + (uint32_t)ks * 32, 16, 1024, 2, 0);
+          const uint32_t start = sA + (uint32_t)(ty * P + tx) * RB + (uint32_t)ks * 32;
+          const uint32_t lay = mode == 4 ? 4u : 2u;
+          da = make_desc(start, 16, P * RB, lay, mode == 1 ? ((start >> 7) & 7u) : 0u);
+          db = make_desc(sB + (uint32_t)tap * (N * RB) + (uint32_t)ks * 32, 16, 8 * RB, lay, 0);
         }
         umma_bf16(tmem, da, db, idesc, first ? 0u : 1u);
         first = 0;
@@ -104,7 +122,7 @@ __global__ void __launch_bounds__(128, 1) shift_kernel(const __nv_bfloat16* __re
 }
 
 static void run_shift(int mode) {
-  const int C = mode == 0 ? 32 : 64, N = 32;
+  const int C = (mode == 0 || mode == 4) ? 32 : 64, N = 32;
   std::vector<__nv_bfloat16> hx(18 * 10 * C), hw(9 * N * C);
   std::vector<float> fx(hx.size()), fw(hw.size());
   srand(1234 + mode);
@@ -139,7 +157,7 @@ static void run_shift(int mode) {
     }
   }
   printf("SHIFT mode %d (%s): mismatches %d / %d, max |diff| %.3f -> %s\n", mode,
-         mode == 0 ? "SWIZZLE_NONE planes, 16B-granular start" : (mode == 1 ? "SWIZZLE_128B rows, base_offset=(addr>>7)&7" : "SWIZZLE_128B rows, base_offset=0"),
+         mode == 0 ? "SWIZZLE_NONE planes, 16B-granular start" : (mode == 1 ? "SWIZZLE_128B rows pitch 16, base_offset=(addr>>7)&7" : (mode == 2 ? "SWIZZLE_128B rows pitch 16, base_offset=0" : (mode == 3 ? "SWIZZLE_128B rows DENSE pitch 10, base_offset=0" : "SWIZZLE_64B rows DENSE pitch 10, base_offset=0"))),
          bad, 128 * N, maxd, bad == 0 ? "OK" : "WRONG");
   cudaFree(dx); cudaFree(dw); cudaFree(dout);
 }
@@ -185,9 +203,153 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int N, int layout, int
   if (threadIdx.x < 32) tmem_dealloc(tmem, 512);
 }
 
+// Unrolled issue loop with precomputed descriptors: one or two issuing warps (each with its own accumulator).
+template <int N>
+__global__ void __launch_bounds__(128, 1) mma_rate2_kernel(int n_issuers, int iters, int rowbytes, long long* cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ uint64_t bar[2];
+  __shared__ uint32_t s_tmem;
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar[0]), 1); mbar_init(smem_u32(&bar[1]), 1); fence_barrier_init(); }
+  if (threadIdx.x < 32) { tmem_alloc(smem_u32(&s_tmem), 512); tmem_relinquish(); }
+  for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem_raw + (base - smem_u32(smem_raw)))[i] = 0;
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  const int warp = threadIdx.x >> 5;
+  if (warp < n_issuers) {   // warp-uniform control flow + elect.sync keeps the descriptors in uniform registers
+    const bool leader = elect_one() != 0;
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(N >> 3) << 17) | (uint32_t(128 >> 4) << 24);
+    const uint32_t lay = rowbytes == 128 ? 2u : 4u;
+    const uint64_t a0 = make_desc(base + warp * 32768, 16, 10 * rowbytes, lay, 0);
+    const uint64_t b0 = make_desc(base + 96 * 1024, 16, 8 * rowbytes, lay, 0);
+    const uint32_t tm = tmem + (uint32_t)(warp * 256);
+    const int kk = rowbytes / 32;   // k16 steps per row
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const uint32_t aoff = (uint32_t)(((tap / 3) * 10 + tap % 3) * rowbytes) >> 4;
+        const uint32_t boff = (uint32_t)(tap * N * rowbytes) >> 4;
+#pragma unroll 4
+        for (int ks = 0; ks < kk; ++ks)
+          if (leader) umma_bf16(tm, a0 + aoff + 2 * ks, b0 + boff + 2 * ks, idesc, 1u);
+      }
+    }
+    if (leader) umma_commit(smem_u32(&bar[warp]));
+    mbar_wait(smem_u32(&bar[warp]), 0);
+    const long long t1 = clock64();
+    if (leader) cycles[blockIdx.x * 2 + warp] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc(tmem, 512);
+}
+
+// A operand in SWIZZLE_NONE planes ([cgroup][18][10][16B], C = 64 -> 8 planes), B in SWIZZLE_128B rows.
+// mode 0: one issuer, one accumulator; 1: one issuer alternating two accumulators; 2: two issuers
+template <int N>
+__global__ void __launch_bounds__(128, 1) mma_rate3_kernel(int mode, int a_none, int iters, long long* cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ uint64_t bar[2];
+  __shared__ uint32_t s_tmem;
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar[0]), 1); mbar_init(smem_u32(&bar[1]), 1); fence_barrier_init(); }
+  if (threadIdx.x < 32) { tmem_alloc(smem_u32(&s_tmem), 512); tmem_relinquish(); }
+  for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem_raw + (base - smem_u32(smem_raw)))[i] = 0;
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  const int warp = threadIdx.x >> 5;
+  const int n_issuers = mode == 2 ? 2 : 1;
+  if (warp < n_issuers) {
+    const bool leader = elect_one() != 0;
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(N >> 3) << 17) | (uint32_t(128 >> 4) << 24);
+    const uint32_t plane = 18 * 10 * 16;
+    const uint64_t a0 = a_none ? make_desc(base + warp * 32768, plane, 160, 0, 0) : make_desc(base + warp * 32768, 16, 1280, 2, 0);
+    const uint64_t b0 = make_desc(base + 96 * 1024, 16, 1024, 2, 0);
+    const uint32_t tm = tmem + (uint32_t)(warp * 256);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const uint32_t tmi = tm + (mode == 1 ? (uint32_t)((it & 1) * 256) : 0u);
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const uint32_t aoff = a_none ? (uint32_t)(((tap / 3) * 10 + tap % 3) * 16) >> 4 : (uint32_t)(((tap / 3) * 10 + tap % 3) * 128) >> 4;
+        const uint32_t boff = (uint32_t)(tap * N * 128) >> 4;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          if (leader) umma_bf16(tmi, a0 + aoff + (a_none ? (uint32_t)(2 * ks) * (plane >> 4) : (uint32_t)(2 * ks)), b0 + boff + 2 * ks, idesc, 1u);
+      }
+    }
+    if (leader) umma_commit(smem_u32(&bar[warp]));
+    mbar_wait(smem_u32(&bar[warp]), 0);
+    const long long t1 = clock64();
+    if (leader) cycles[blockIdx.x * 2 + warp] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc(tmem, 512);
+}
+
+template <int N>
+static void run_rate3(int sms, long long* dcyc) {
+  const int smem = 200 * 1024;
+  CK(cudaFuncSetAttribute(mma_rate3_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  for (int a_none = 0; a_none <= 1; ++a_none)
+    for (int mode = 0; mode <= 2; ++mode) {
+      const int iters = 200;
+      CK(cudaMemset(dcyc, 0, sms * 2 * sizeof(long long)));
+      mma_rate3_kernel<N><<<sms, 128, smem>>>(mode, a_none, iters, dcyc);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("MMA rate3 N=%d failed: %s\n", N, cudaGetErrorString(e)); exit(3); }
+      std::vector<long long> h(sms * 2);
+      CK(cudaMemcpy(h.data(), dcyc, sms * 2 * sizeof(long long), cudaMemcpyDeviceToHost));
+      long long mx = 0;
+      for (long long c : h) mx = c > mx ? c : mx;
+      const double n_mma = (double)iters * 36 * (mode == 2 ? 2 : 1);
+      const double cyc = (double)mx / n_mma;
+      printf("MMA_RATE3 A=%s mode=%s N=%3d: %.1f clk/MMA -> %.0f MAC/clk/SM (floor %d clk); smem operand %.0f B/clk\n", a_none ? "NONE " : "SW128",
+             mode == 0 ? "1 issuer/1 acc " : (mode == 1 ? "1 issuer/2 accs" : "2 issuers      "), N, cyc, 128.0 * N * 16 / cyc, 128 * N / 256, (4096 + N * 32) / cyc);
+    }
+}
+
+template <int N>
+static void run_rate2(int sms, long long* dcyc) {
+  const int smem = 200 * 1024;
+  CK(cudaFuncSetAttribute(mma_rate2_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  for (int rowbytes = 64; rowbytes <= 128; rowbytes *= 2)
+    for (int issuers = 1; issuers <= 2; ++issuers) {
+      if (N * rowbytes * 9 > 100 * 1024) continue;
+      const int iters = 200;
+      CK(cudaMemset(dcyc, 0, sms * 2 * sizeof(long long)));
+      mma_rate2_kernel<N><<<sms, 128, smem>>>(issuers, iters, rowbytes, dcyc);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("MMA rate2 N=%d failed: %s\n", N, cudaGetErrorString(e)); exit(3); }
+      std::vector<long long> h(sms * 2);
+      CK(cudaMemcpy(h.data(), dcyc, sms * 2 * sizeof(long long), cudaMemcpyDeviceToHost));
+      long long mx = 0;
+      for (long long c : h) mx = c > mx ? c : mx;
+      const double n_mma = (double)iters * 9 * (rowbytes / 32) * issuers;
+      const double cyc = (double)mx / n_mma;
+      printf("MMA_RATE2 row=%3dB issuers=%d M=128 N=%3d K=16: %.1f clk/MMA -> %.0f MAC/clk/SM (floor %d clk); smem operand %.0f B/clk\n", rowbytes, issuers, N, cyc,
+             128.0 * N * 16 / cyc, 128 * N / 256, (4096 + N * 32) / cyc);
+    }
+}
+
 static void run_mma_rate(int sms) {
   long long* dcyc;
-  CK(cudaMalloc(&dcyc, sms * sizeof(long long)));
+  CK(cudaMalloc(&dcyc, sms * 2 * sizeof(long long)));
+  run_rate3<32>(sms, dcyc);
+  run_rate3<64>(sms, dcyc);
+  run_rate3<128>(sms, dcyc);
+  run_rate2<32>(sms, dcyc);
+  run_rate2<64>(sms, dcyc);
+  run_rate2<128>(sms, dcyc);
+  run_rate2<256>(sms, dcyc);
   const int smem = 200 * 1024;
   CK(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int iters = 4096;
@@ -290,6 +452,88 @@ static void run_bw(int sms) {
   cudaFree(src); cudaFree(dcyc);
 }
 
+// ------------------------------------------------------------------------------------------------ 5: what does a 5-D pair box look like in smem?
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+__global__ void __launch_bounds__(128, 1) tma5d_kernel(const __grid_constant__ CUtensorMap map, uint16_t* out, int bytes, int x0, int y0) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sp = smem_raw + (base - smem_u32(smem_raw));
+  __shared__ uint64_t bar;
+  for (int i = threadIdx.x; i < bytes / 2; i += blockDim.x) reinterpret_cast<uint16_t*>(sp)[i] = 0xFFFF;
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+  fence_proxy_async();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(smem_u32(&bar), (uint32_t)bytes);
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(base), "l"(reinterpret_cast<uint64_t>(&map)), "r"(smem_u32(&bar)), "r"(0), "r"(0), "r"(x0), "r"(y0), "r"(0)
+        : "memory");
+  }
+  mbar_wait(smem_u32(&bar), 0);
+  for (int i = threadIdx.x; i < bytes / 2; i += blockDim.x) out[i] = reinterpret_cast<uint16_t*>(sp)[i];
+}
+
+static void run_tma5d() {
+  const int H = 20, W = 16, C = 32, BOXX = 10, BOXY = 17;
+  // rows: one zero row above, H image rows, one zero row below; ids are unique 16-bit patterns (0 reserved for zero rows)
+  std::vector<uint16_t> h((size_t)(H + 2) * W * C, 0);
+  for (int y = 0; y < H; ++y)
+    for (int x = 0; x < W; ++x)
+      for (int c = 0; c < C; ++c) h[((size_t)(y + 1) * W + x) * C + c] = (uint16_t)(1 + (y * W + x) * C + c);
+  uint16_t *d, *dout;
+  CK(cudaMalloc(&d, h.size() * 2));
+  CK(cudaMemcpy(d, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+  const int bytes = C * 2 * 2 * BOXX * BOXY;
+  CK(cudaMalloc(&dout, bytes));
+  void* fp = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q));
+  EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(fp);
+  const cuuint64_t row_bytes = (cuuint64_t)W * C * 2;
+  CUtensorMap map;
+  cuuint64_t dims[5] = {32, 2, (cuuint64_t)W, (cuuint64_t)H + 1, 1};
+  cuuint64_t strides[4] = {row_bytes, (cuuint64_t)C * 2, row_bytes, (cuuint64_t)(H + 1) * row_bytes};
+  cuuint32_t box[5] = {32, 2, BOXX, BOXY, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, d, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  printf("TMA5D encode rc=%d\n", (int)r);
+  if (r != CUDA_SUCCESS) return;
+  CK(cudaFuncSetAttribute(tma5d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  const int x0 = 3, y0 = 2;   // interior window: y' = 2..18, x = 3..12
+  tma5d_kernel<<<1, 128, 64 * 1024>>>(map, dout, bytes, x0, y0);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("TMA5D kernel failed: %s\n", cudaGetErrorString(e)); exit(4); }
+  std::vector<uint16_t> got(bytes / 2);
+  CK(cudaMemcpy(got.data(), dout, bytes, cudaMemcpyDeviceToHost));
+  // hypothesis A: dense [y'][x][pair][c] with 16-byte chunk index XOR ((byte_offset >> 7) & 7)
+  int badA = 0;
+  for (int yy = 0; yy < BOXY; ++yy)
+    for (int xx = 0; xx < BOXX; ++xx)
+      for (int pr = 0; pr < 2; ++pr)
+        for (int c = 0; c < C; ++c) {
+          const int img_row = (y0 + yy) + pr - 1;   // image row
+          const uint16_t want = (img_row < 0 || img_row >= H) ? 0 : (uint16_t)(1 + (img_row * W + (x0 + xx)) * C + c);
+          const int line = yy * BOXX + xx;
+          const int chunk = pr * 4 + c / 8;
+          const int off = line * 64 + ((chunk ^ (line & 7)) * 8) + (c & 7);   // in uint16 units
+          if (got[off] != want) ++badA;
+        }
+  printf("TMA5D hypothesis A (dense rows, address-based XOR): %d mismatches of %d\n", badA, BOXY * BOXX * 2 * C);
+  // dump where the first elements of the first two lines ended up
+  for (int slot = 0; slot < 2 * 64; slot += 8) {
+    const uint16_t v = got[slot];
+    if (v == 0 || v == 0xFFFF) { printf("  smem u16[%3d] = %s\n", slot, v ? "untouched" : "zero"); continue; }
+    const int id = v - 1, c = id % C, x = (id / C) % W, y = id / C / W;
+    printf("  smem u16[%3d] <- image row %d, x %d, c %d\n", slot, y, x, c);
+  }
+  cudaFree(d); cudaFree(dout);
+}
+
 int main(int argc, char** argv) {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, 0));
@@ -299,6 +543,9 @@ int main(int argc, char** argv) {
   if (all || std::string(what) == "shift0") run_shift(0);
   if (all || std::string(what) == "shift1") run_shift(1);
   if (all || std::string(what) == "shift2") run_shift(2);
+  if (all || std::string(what) == "shift3") run_shift(3);
+  if (all || std::string(what) == "shift4") run_shift(4);
+  if (all || std::string(what) == "tma5d") run_tma5d();
   if (all || std::string(what) == "rate") run_mma_rate(prop.multiProcessorCount);
   if (all || std::string(what) == "bw") run_bw(prop.multiProcessorCount);
   return 0;
