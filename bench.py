@@ -288,8 +288,9 @@ def run_gpu_arm(args):
         return float(t.item())
 
     # ---------------- warm-up (also builds the plan / workspaces)
+    keep = None
     for i in range(max(args.warmup, 3)):
-        device_step(i)
+        keep = device_step(i)   # hold the previous step's outputs like the timed loop does: the caching allocator reaches steady state
     torch.cuda.synchronize()
 
     # ---------------- timed region: K device-resident steps
@@ -305,7 +306,6 @@ def run_gpu_arm(args):
     w0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    keep = None
     for i in range(args.steps):
         ev = []
         keep = device_step(100 + i, ev)

@@ -31,7 +31,7 @@ constexpr int kHaloTileW = 8;
 constexpr int kHaloPitch = kHaloTileW + 2;   // window pixels per row
 constexpr int kHaloRows = kHaloTileH + 2;    // window rows
 constexpr int kHaloMaxEntries = 20;
-constexpr int kHaloThreads = 192;
+enum HaloMode { HALO_CONV64 = 0, HALO_CONV32 = 1, HALO_UP64 = 2 };   // 3x3 conv over 64-ch chunks / a 32-ch source / one up-path phase
 constexpr int kHaloSmemBudget = 225 * 1024;
 
 struct HaloEntry {
@@ -48,10 +48,10 @@ struct HaloParams {
   uint32_t chunk_bytes;      // bytes one box delivers
   uint32_t chunk_stride;     // slot size (multiple of 1024)
   int n_stages;
-  int e_split;               // entries [0, e_split) read chunk 0, [e_split, n_entries) chunk 1
-  int n_entries;
-  HaloEntry entries[kHaloMaxEntries];
-  const void* w_image;       // pre-swizzled weight tiles in global memory
+  int dbg;                   // experiment switches (RCU_HALO_DBG): 1 epilogue skips TMEM loads/stores, 16 no TMA loads,
+                             // 32 one MMA per chunk — timing experiments only, results are wrong
+  uint32_t up_base16;        // HALO_UP64: window offset of the phase's first tap, (a * 10 + b) * 8 sixteen-byte units
+  const void* w_image;       // pre-swizzled weight tiles in global memory, in the order the MMA loop walks them
   uint32_t w_bytes;
   // output addressing: pixel (y, x) lands at (out_mul*y + out_dy, out_mul*x + out_dx)
   int out_mul, out_dy, out_dx, out_h, out_w;
@@ -89,20 +89,23 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
 
 __device__ __forceinline__ uint64_t desc_from(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 
-template <int N>
+template <int N, int G>
 struct HaloSmem {
-  static constexpr int kCoefBytes = 2 * N * (int)sizeof(float2);
+  static constexpr int kCoefBytes = G * N * (int)sizeof(float2);
   static constexpr int kHeadBytes = 2 * 32 * 4 + 16;
   static constexpr int kMaxStages = 8;
-  static constexpr int kBarBytes = (2 * kMaxStages + 5) * 8 + 16;
+  static constexpr int kBarBytes = (2 * kMaxStages + 2 * G + 1) * 8 + 16;
   static constexpr int kFixed = 1024 + kCoefBytes + kHeadBytes + kBarBytes;
-  static constexpr int kTmemCols = 2 * N < 32 ? 32 : 2 * N;
+  static constexpr int kTmemCols = G * N < 32 ? 32 : G * N;   // 64, 128 or 256: powers of two
+  static constexpr int kThreads = 96 + 128 * G;   // producer warp, two MMA warps, G epilogue groups of four warps
 };
 
-template <int N>
-__global__ void __launch_bounds__(kHaloThreads, 1)
+// G = number of TMEM accumulator stages = number of 4-warp epilogue groups (group g drains the tiles whose index in
+// the CTA's range is g mod G), so G epilogues are in flight while the MMA warp works on the next tile.
+template <int N, int G, int MODE>
+__global__ void __launch_bounds__(96 + 128 * G, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ HaloParams prm) {
-  using S = HaloSmem<N>;
+  using S = HaloSmem<N, G>;
   static_assert(N == 32 || N == 64, "halo kernel serves c_out = 32 / 64");
   extern __shared__ uint8_t smem_dyn[];
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
@@ -116,10 +119,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   uint8_t* bar_ptr = base_ptr + tail + S::kCoefBytes + S::kHeadBytes;
   const uint32_t bar_full = smem_u32(bar_ptr);                      // [kMaxStages]
   const uint32_t bar_empty = bar_full + S::kMaxStages * 8;          // [kMaxStages]
-  const uint32_t bar_tfull = bar_empty + S::kMaxStages * 8;         // [2]
-  const uint32_t bar_tempty = bar_tfull + 16;                       // [2]
-  const uint32_t bar_w = bar_tempty + 16;                           // [1]
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_ptr + (2 * S::kMaxStages + 5) * 8);
+  const uint32_t bar_tfull = bar_empty + S::kMaxStages * 8;         // [G]
+  const uint32_t bar_tempty = bar_tfull + G * 8;                    // [G]
+  const uint32_t bar_w = bar_tempty + G * 8;                        // [1]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_ptr + (2 * S::kMaxStages + 2 * G + 1) * 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -130,7 +133,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < G; ++s) {
       mbar_init(bar_tfull + 8 * s, 1);
       mbar_init(bar_tempty + 8 * s, 128);
     }
@@ -141,14 +144,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     tmem_alloc(smem_u32(s_tmem), S::kTmemCols);
     tmem_relinquish();
   }
-  if (prm.head != nullptr && threadIdx.x >= 64 && threadIdx.x < 64 + 66) s_head[threadIdx.x - 64] = prm.head[threadIdx.x - 64];
+  if (prm.head != nullptr && threadIdx.x >= 96 && threadIdx.x < 96 + 66) s_head[threadIdx.x - 96] = prm.head[threadIdx.x - 96];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
-  const long long tiles_per_img = (long long)prm.tiles_y * prm.tiles_x;
-  const long long total_tiles = (long long)prm.n_img * tiles_per_img;
+  // contiguous tile range of this CTA: neighbouring tiles share halo rows in L2 and, above all, the same image, so the
+  // per-image epilogue coefficients are re-staged only a handful of times per launch
+  const int tiles_per_img = prm.tiles_y * prm.tiles_x;
+  const long long total_tiles = (long long)prm.n_img * tiles_per_img;   // < 2^31 (checked on the host)
+  const int t_begin = (int)(total_tiles * blockIdx.x / gridDim.x);
+  const int t_end = (int)(total_tiles * (blockIdx.x + 1) / gridDim.x);
 
   if (warp == 0) {
     // ===================== producer: weights once, then one halo box per (tile, chunk) =====================
@@ -160,23 +167,33 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
       int stage = 0;
       uint32_t phase = 0;
-      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        long long r = tile;
-        const int tx = (int)(r % prm.tiles_x); r /= prm.tiles_x;
-        const int ty = (int)(r % prm.tiles_y);
-        const int img = (int)(r / prm.tiles_y);
+      int img = t_begin / tiles_per_img;
+      int ty = (t_begin - img * tiles_per_img) / prm.tiles_x;
+      int tx = t_begin - img * tiles_per_img - ty * prm.tiles_x;
+      for (int tile = t_begin; tile < t_end; ++tile) {
         const int x0 = tx * kHaloTileW - 1, y0 = ty * kHaloTileH;
         for (int j = 0; j < prm.n_chunks; ++j) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
-          mbar_expect_tx(bar_full + 8 * stage, prm.chunk_bytes);
           const uint32_t dst = smem_a + (uint32_t)stage * prm.chunk_stride;
-          tma_load_4d(dst, &map_a, bar_full + 8 * stage, j * 64, x0, y0 - 1, img);
+          if (prm.dbg & 16) {
+            mbar_arrive(bar_full + 8 * stage);   // experiment: no loads at all
+          } else {
+            mbar_expect_tx(bar_full + 8 * stage, prm.chunk_bytes);
+            tma_load_4d(dst, &map_a, bar_full + 8 * stage, j * 64, x0, y0 - 1, img);
+          }
           if (++stage == prm.n_stages) { stage = 0; phase ^= 1u; }
         }
+        if (++tx == prm.tiles_x) { tx = 0; if (++ty == prm.tiles_y) { ty = 0; ++img; } }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer: warp-uniform flow, elect.sync-predicated tcgen05.mma =====================
+  } else if (warp <= 2) {
+    // ===================== two MMA issuers (warps 1, 2), alternating tiles =====================
+    // One warp's per-tile fixed cost (two mbarrier waits at ~90 clk each even when complete, two commits, loop
+    // overhead: ~500 clk measured) is as long as the MMAs of a thin tile (18 x 40 clk) and the tensor pipe's queue is
+    // shallow, so a single issuer leaves the pipe idle half of the time; with two issuers one warp's bookkeeping
+    // hides behind the other's MMAs.  Control flow is warp-uniform, only the tcgen05 instructions are predicated on
+    // elect.sync, so descriptors live in uniform registers and MMAs issue back to back.
+    const int mw = warp - 1;
     const bool leader = elect_one() != 0;
     constexpr uint32_t idesc = make_idesc<N>();
     // descriptor halves: [0,14) addr>>4, [16,30) LBO>>4 (=1, unused), hi: [0,14) SBO>>4, [14,16) version 1, [29,32) SWIZZLE_128B
@@ -185,69 +202,89 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const uint32_t lo_b0 = ((smem_w & 0x3FFFFu) >> 4) | (1u << 16);
     mbar_wait(bar_w, 0);
     tc_fence_after();
-    int stage = 0;
-    uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    constexpr int kTaps = MODE == HALO_UP64 ? 4 : 9;
+    constexpr int kK16 = MODE == HALO_CONV32 ? 2 : 4;
+    constexpr uint32_t kTile16 = (uint32_t)(N * 128) >> 4;              // one [N][64] weight tile in 16-byte units
+    constexpr uint32_t kChunkW16 = (MODE == HALO_CONV32 ? 5u : (uint32_t)kTaps) * kTile16;
+    // this warp's position in the shared stage / accumulator sequences (tile index t_begin + mw, then every second tile)
+    int stage = (mw * prm.n_chunks) % prm.n_stages;
+    uint32_t phase = (uint32_t)((mw * prm.n_chunks) / prm.n_stages) & 1u;
+    int acc = mw % G;
+    uint32_t acc_phase = (uint32_t)(mw / G) & 1u;
+    for (int tile = t_begin + mw; tile < t_end; tile += 2) {
       mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * N);
-      uint32_t accumulate = 0;
       for (int j = 0; j < prm.n_chunks; ++j) {
         mbar_wait(bar_full + 8 * stage, phase);
         tc_fence_after();
-        const uint32_t lo_a0 = (((smem_a + (uint32_t)stage * prm.chunk_stride) & 0x3FFFFu) >> 4) | (1u << 16);
-        const int e0 = j == 0 ? 0 : prm.e_split, e1 = j == 0 ? prm.e_split : prm.n_entries;
-        for (int e = e0; e < e1; ++e) {
-          const uint32_t la = lo_a0 + prm.entries[e].a_off16, lb = lo_b0 + prm.entries[e].b_off16;
-          if (leader) {
-            umma_bf16(tmem_d, desc_from(la, hi_a), desc_from(lb, hi_b), idesc, accumulate);
-            umma_bf16(tmem_d, desc_from(la + 2, hi_a), desc_from(lb + 2, hi_b), idesc, 1u);
-          }
-          accumulate = 1u;
-          if (prm.entries[e].n_k16 == 4) {
-            if (leader) {
-              umma_bf16(tmem_d, desc_from(la + 4, hi_a), desc_from(lb + 4, hi_b), idesc, 1u);
-              umma_bf16(tmem_d, desc_from(la + 6, hi_a), desc_from(lb + 6, hi_b), idesc, 1u);
-            }
+        const uint32_t lo_a0 = ((((smem_a + (uint32_t)stage * prm.chunk_stride) & 0x3FFFFu) >> 4) | (1u << 16)) +
+                               (MODE == HALO_UP64 ? prm.up_base16 : 0u);
+        const uint32_t lo_bj = lo_b0 + (uint32_t)j * kChunkW16;
+        // every offset below is a compile-time constant: the loop unrolls into back-to-back UTCHMMA with uniform adds
+#pragma unroll
+        for (int tap = 0; tap < kTaps; ++tap) {
+          const uint32_t a_off = MODE == HALO_UP64 ? (uint32_t)(((tap >> 1) * kHaloPitch + (tap & 1)) * 8)
+                                                   : (uint32_t)(((tap / 3) * kHaloPitch + tap % 3) * 8);
+          const uint32_t b_off = MODE == HALO_CONV32 ? (uint32_t)(tap >> 1) * kTile16 + (uint32_t)(tap & 1) * 4u : (uint32_t)tap * kTile16;
+#pragma unroll
+          for (int ks = 0; ks < kK16; ++ks) {
+            const uint32_t accumulate = (tap > 0 || ks > 0) ? 1u : (j > 0 ? 1u : 0u);
+            if ((prm.dbg & 32) && (tap > 0 || ks > 0)) continue;   // experiment: one MMA per chunk
+            if (leader) umma_bf16(tmem_d, desc_from(lo_a0 + a_off + 2 * ks, hi_a), desc_from(lo_bj + b_off + 2 * ks, hi_b), idesc, accumulate);
           }
         }
         if (leader) umma_commit(bar_empty + 8 * stage);
         if (++stage == prm.n_stages) { stage = 0; phase ^= 1u; }
       }
       if (leader) umma_commit(bar_tfull + 8 * acc);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      // skip the other issuer's tile
+      stage += prm.n_chunks;
+      if (stage >= prm.n_stages) { stage -= prm.n_stages; phase ^= 1u; }
+      acc += 2;
+      if (acc >= G) { acc -= G; acc_phase ^= 1u; }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;
+    // ===================== epilogue: G groups of 4 warps; group g owns accumulator stage g =====================
+    const int group = (warp - 3) >> 2;
+    const int q = warp & 3;               // TMEM lane quarter this warp may access (each group holds all four)
     const int row = q * 32 + lane;
-    const int et = threadIdx.x - 64;
-    int acc = 0;
+    const int gt = threadIdx.x - 96 - group * 128;   // 0..127 inside the group
+    float2* coef = s_coef + group * N;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(group * N);
     uint32_t acc_phase = 0;
-    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      long long r = tile;
-      const int tx = (int)(r % prm.tiles_x); r /= prm.tiles_x;
-      const int ty = (int)(r % prm.tiles_y);
-      const int img = (int)(r / prm.tiles_y);
+    int cur_img = -1;
+    for (int tile = t_begin + group; tile < t_end; tile += G) {
+      const int img = tile / tiles_per_img;
+      const int rem = tile - img * tiles_per_img;
+      const int ty = rem / prm.tiles_x, tx = rem - ty * prm.tiles_x;
 
-      float2* coef = s_coef + acc * N;
-      if (et < N) coef[et] = __ldg(prm.coef + (long long)img * prm.coef_stride + prm.coef_off + et);
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (img != cur_img) {   // group-uniform
+        asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");   // everyone is done with the old coefficients
+        if (gt < N) coef[gt] = __ldg(prm.coef + (long long)img * prm.coef_stride + prm.coef_off + gt);
+        asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
+        cur_img = img;
+      }
 
-      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      mbar_wait(bar_tfull + 8 * group, acc_phase);
       tc_fence_after();
+      if (prm.dbg & 1) {
+        tc_fence_before();
+        mbar_arrive(bar_tempty + 8 * group);
+        acc_phase ^= 1u;
+        continue;
+      }
 
       const int y = ty * kHaloTileH + (row >> 3), x = tx * kHaloTileW + (row & 7);
       const bool valid = (y < prm.in_h) && (x < prm.in_w);
       const int oy = prm.out_mul * y + prm.out_dy, ox = prm.out_mul * x + prm.out_dx;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * N);
 
       if (prm.head != nullptr) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr, v);
         tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(bar_tempty + 8 * group);   // accumulator is in registers: the MMA warp may reuse the stage
         float l0 = s_head[64], l1 = s_head[65];
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
@@ -270,6 +307,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           uint32_t v[32];
           tmem_ld_32x32b_x32(taddr + (uint32_t)cb, v);
           tmem_ld_wait();
+          if (cb + 32 == N) {
+            tc_fence_before();
+            mbar_arrive(bar_tempty + 8 * group);
+          }
           uint32_t packed[16];
 #pragma unroll
           for (int c = 0; c < 32; c += 2) {
@@ -287,9 +328,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           }
         }
       }
-      tc_fence_before();
-      mbar_arrive(bar_tempty + 8 * acc);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      acc_phase ^= 1u;
     }
   }
 

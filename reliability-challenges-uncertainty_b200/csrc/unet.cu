@@ -7,6 +7,7 @@
 #include <cuda_bf16.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -418,17 +419,20 @@ static uint32_t halo_chunk_stride(bool /*half_rows*/) {
   return (bytes + 1023u) & ~1023u;
 }
 
+constexpr int kHaloGroups = 4;   // TMEM accumulator stages = epilogue warp groups
+
 template <int N>
 static int halo_stage_count(uint32_t w_bytes, bool pair) {
-  const int64_t room = (int64_t)kHaloSmemBudget - HaloSmem<N>::kFixed - (int64_t)((w_bytes + 1023u) & ~1023u);
+  const int64_t room = (int64_t)kHaloSmemBudget - HaloSmem<N, kHaloGroups>::kFixed - (int64_t)((w_bytes + 1023u) & ~1023u);
   int64_t st = room / halo_chunk_stride(pair);
-  if (st > HaloSmem<N>::kMaxStages) st = HaloSmem<N>::kMaxStages;
+  if (st > HaloSmem<N, kHaloGroups>::kMaxStages) st = HaloSmem<N, kHaloGroups>::kMaxStages;
   return (int)st;
 }
 
-template <int N>
+template <int N, int MODE>
 static int launch_conv_halo(const ConvLayer& L, const HaloParams& prm, cudaStream_t st) {
-  auto kern = conv_halo_kernel<N>;
+  auto kern = conv_halo_kernel<N, kHaloGroups, MODE>;
+  using HS = HaloSmem<N, kHaloGroups>;
   static bool configured[64] = {false};
   int dev = 0;
   RCU_CUDA(cudaGetDevice(&dev));
@@ -437,12 +441,12 @@ static int launch_conv_halo(const ConvLayer& L, const HaloParams& prm, cudaStrea
     RCU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmemBudget));
     configured[dev] = true;
   }
-  const size_t smem = (size_t)HaloSmem<N>::kFixed + ((prm.w_bytes + 1023u) & ~1023u) + (size_t)prm.n_stages * prm.chunk_stride;
+  const size_t smem = (size_t)HS::kFixed + ((prm.w_bytes + 1023u) & ~1023u) + (size_t)prm.n_stages * prm.chunk_stride;
   const long long total_tiles = (long long)prm.n_img * prm.tiles_y * prm.tiles_x;
   long long grid = sm_count();
   if (grid > total_tiles) grid = total_tiles;
   if (grid < 1) return RCU_OK;
-  kern<<<(unsigned)grid, kHaloThreads, smem, st>>>(L.map_halo, prm);
+  kern<<<(unsigned)grid, HS::kThreads, smem, st>>>(L.map_halo, prm);
   RCU_LAUNCH_CHECK();
   return RCU_OK;
 }
@@ -766,9 +770,11 @@ static int run_conv_halo(rcu_unet* net, const ConvLayer& L, int n_img, int cs, l
     prm.chunk_bytes = (uint32_t)(kHaloRows * kHaloPitch * (hp.pair ? 64 : 128));   // bytes TMA delivers (complete_tx counts data bytes)
     prm.chunk_stride = halo_chunk_stride(hp.pair);
     prm.n_stages = L.halo_stages;
-    prm.e_split = hp.e_split;
-    prm.n_entries = hp.n_entries;
-    std::memcpy(prm.entries, hp.entries[ph], sizeof(HaloEntry) * hp.n_entries);
+    {
+      static const int dbg = [] { const char* e = std::getenv("RCU_HALO_DBG"); return e ? std::atoi(e) : 0; }();
+      prm.dbg = dbg;
+    }
+    prm.up_base16 = hp.n_phases == 4 ? (uint32_t)(((ph >> 1) * kHaloPitch + (ph & 1)) * 8) : 0u;
     prm.w_image = hp.d_wimg[ph];
     prm.w_bytes = hp.w_bytes;
     prm.out_mul = L.out_mul;
@@ -783,7 +789,10 @@ static int run_conv_halo(rcu_unet* net, const ConvLayer& L, int n_img, int cs, l
     prm.head = L.head ? net->d_head : nullptr;
     prm.logits = logits;
     prm.chunk_slices = cs; prm.slice0 = s0; prm.n_slices_total = n_slices;
-    int rc = L.c_out == 32 ? launch_conv_halo<32>(L, prm, st) : launch_conv_halo<64>(L, prm, st);
+    int rc;
+    if (hp.n_phases == 4) rc = L.c_out == 32 ? launch_conv_halo<32, HALO_UP64>(L, prm, st) : launch_conv_halo<64, HALO_UP64>(L, prm, st);
+    else if (hp.pair) rc = L.c_out == 32 ? launch_conv_halo<32, HALO_CONV32>(L, prm, st) : launch_conv_halo<64, HALO_CONV32>(L, prm, st);
+    else rc = L.c_out == 32 ? launch_conv_halo<32, HALO_CONV64>(L, prm, st) : launch_conv_halo<64, HALO_CONV64>(L, prm, st);
     if (rc) return rc;
     ++*launches;
   }

@@ -180,13 +180,13 @@ class B200UNet(nn.Module):
         del keep
 
     def __del__(self):
-        h = getattr(self, '_handle', None)
-        if h:
-            try:
+        try:
+            h = self.__dict__.get('_handle')
+            if h:
+                self.__dict__['_handle'] = None
                 _lib.lib().rcu_unet_destroy(h)
-            except Exception:  # interpreter shutdown
-                pass
-            self._handle = None
+        except Exception:  # interpreter shutdown
+            pass
 
     # ------------------------------------------------------------------ nn.Module surface
     def to(self, *args, **kwargs):  # weights already live on the device chosen at construction

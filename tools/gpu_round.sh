@@ -11,4 +11,4 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 26 -c 26 -o gpurun_out/prof_conv -f python tools/prof_forward.py 16 > gpurun_out/ncu_full.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:'aggregate_kernel|fused|hist' -c 4 -o gpurun_out/prof_hbm -f python tools/prof_forward.py 16 > gpurun_out/ncu_hbm.log 2>&1
 fi
-tail -3 gpurun_out/pytest.log gpurun_out/smoke.log
+tail -n 3 gpurun_out/pytest.log; tail -n 3 gpurun_out/smoke.log

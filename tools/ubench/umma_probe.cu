@@ -534,6 +534,73 @@ static void run_tma5d() {
   cudaFree(d); cudaFree(dout);
 }
 
+// ------------------------------------------------------------------------------------------------ 6: TMA halo-box load throughput
+__global__ void __launch_bounds__(32, 1) tma_box_kernel(const __grid_constant__ CUtensorMap map, int n_img, int tiles_x, int tiles_y, int stages,
+                                                        uint32_t box_bytes, uint32_t slot, long long* cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ uint64_t bars[16];
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < stages; ++i) mbar_init(smem_u32(&bars[i]), 1);
+    fence_barrier_init();
+    const int tiles_per_img = tiles_x * tiles_y;
+    const long long total = (long long)n_img * tiles_per_img;
+    const int t0i = (int)(total * blockIdx.x / gridDim.x), t1i = (int)(total * (blockIdx.x + 1) / gridDim.x);
+    const long long t0 = clock64();
+    int n = 0;
+    for (int tile = t0i; tile < t1i; ++tile, ++n) {
+      const int img = tile / tiles_per_img, rem = tile - img * tiles_per_img, ty = rem / tiles_x, tx = rem - ty * tiles_x;
+      const int s = n % stages;
+      if (n >= stages) mbar_wait(smem_u32(&bars[s]), (uint32_t)(((n / stages) - 1) & 1));
+      mbar_expect_tx(smem_u32(&bars[s]), box_bytes);
+      tma_load_4d(base + (uint32_t)s * slot, &map, smem_u32(&bars[s]), 0, tx * 8 - 1, ty * 16 - 1, img);
+    }
+    for (int k = (n >= stages ? n - stages : 0); k < n; ++k) mbar_wait(smem_u32(&bars[k % stages]), (uint32_t)((k / stages) & 1));
+    cycles[blockIdx.x] = clock64() - t0;
+  }
+}
+
+static void run_tma_box(int sms) {
+  void* fp = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q));
+  EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(fp);
+  long long* dcyc;
+  CK(cudaMalloc(&dcyc, sms * sizeof(long long)));
+  CK(cudaFuncSetAttribute(tma_box_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  const int H = 240, W = 240;
+  for (int C = 32; C <= 64; C *= 2)
+    for (int n_img = 8; n_img <= 128; n_img *= 16) {    // 8 images: L2 resident after one pass; 128: streams from HBM
+      uint8_t* d;
+      const size_t bytes = (size_t)n_img * H * W * C * 2;
+      CK(cudaMalloc(&d, bytes));
+      CK(cudaMemset(d, 1, bytes));
+      CUtensorMap map;
+      cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img};
+      cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+      cuuint32_t box[4] = {(cuuint32_t)C, 10, 18, 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, d, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { printf("TMA_BOX encode failed %d\n", (int)r); exit(5); }
+      for (int stages = 2; stages <= 8; stages *= 2) {
+        std::vector<long long> h(sms);
+        for (int rep = 0; rep < 2; ++rep) {
+          tma_box_kernel<<<sms, 32, 200 * 1024>>>(map, n_img, 30, 15, stages, (uint32_t)(C * 2 * 180), 23552u, dcyc);
+          CK(cudaDeviceSynchronize());
+        }
+        CK(cudaMemcpy(h.data(), dcyc, sms * sizeof(long long), cudaMemcpyDeviceToHost));
+        long long mx = 0;
+        for (long long c : h) mx = c > mx ? c : mx;
+        const double tiles_per_sm = (double)n_img * 450 / sms;
+        printf("TMA_BOX C=%d (%d B rows) images=%3d (%s) stages=%d: %.0f clk/box, %.1f B/clk/SM\n", C, C * 2, n_img,
+               n_img <= 8 ? "L2" : "HBM", stages, mx / tiles_per_sm, (double)C * 2 * 180 * tiles_per_sm / mx);
+      }
+      cudaFree(d);
+    }
+  cudaFree(dcyc);
+}
+
 int main(int argc, char** argv) {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, 0));
@@ -546,6 +613,7 @@ int main(int argc, char** argv) {
   if (all || std::string(what) == "shift3") run_shift(3);
   if (all || std::string(what) == "shift4") run_shift(4);
   if (all || std::string(what) == "tma5d") run_tma5d();
+  if (all || std::string(what) == "tmabox") run_tma_box(prop.multiProcessorCount);
   if (all || std::string(what) == "rate") run_mma_rate(prop.multiProcessorCount);
   if (all || std::string(what) == "bw") run_bw(prop.multiProcessorCount);
   return 0;
