@@ -94,7 +94,7 @@ struct HaloSmem {
   static constexpr int kCoefBytes = G * N * (int)sizeof(float2);
   static constexpr int kHeadBytes = 2 * 32 * 4 + 16;
   static constexpr int kMaxStages = 8;
-  static constexpr int kBarBytes = (2 * kMaxStages + 2 * G + 1) * 8 + 16;
+  static constexpr int kBarBytes = (2 * kMaxStages + 2 * G + 3) * 8 + 16;
   static constexpr int kFixed = 1024 + kCoefBytes + kHeadBytes + kBarBytes;
   static constexpr int kTmemCols = G * N < 32 ? 32 : G * N;   // 64, 128 or 256: powers of two
   static constexpr int kThreads = 96 + 128 * G;   // producer warp, two MMA warps, G epilogue groups of four warps
@@ -122,7 +122,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const uint32_t bar_tfull = bar_empty + S::kMaxStages * 8;         // [G]
   const uint32_t bar_tempty = bar_tfull + G * 8;                    // [G]
   const uint32_t bar_w = bar_tempty + G * 8;                        // [1]
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_ptr + (2 * S::kMaxStages + 2 * G + 1) * 8);
+  const uint32_t bar_turn = bar_w + 8;                              // [2] issue-turn hand-off between the two MMA warps
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_ptr + (2 * S::kMaxStages + 2 * G + 3) * 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -138,6 +139,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       mbar_init(bar_tempty + 8 * s, 128);
     }
     mbar_init(bar_w, 1);
+    mbar_init(bar_turn, 1);
+    mbar_init(bar_turn + 8, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -193,6 +196,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // shallow, so a single issuer leaves the pipe idle half of the time; with two issuers one warp's bookkeeping
     // hides behind the other's MMAs.  Control flow is warp-uniform, only the tcgen05 instructions are predicated on
     // elect.sync, so descriptors live in uniform registers and MMAs issue back to back.
+    const int n_issuers = (prm.dbg & 128) ? 1 : 2;   // experiment: single issuer
     const int mw = warp - 1;
     const bool leader = elect_one() != 0;
     constexpr uint32_t idesc = make_idesc<N>();
@@ -211,12 +215,21 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint32_t phase = (uint32_t)((mw * prm.n_chunks) / prm.n_stages) & 1u;
     int acc = mw % G;
     uint32_t acc_phase = (uint32_t)(mw / G) & 1u;
-    for (int tile = t_begin + mw; tile < t_end; tile += 2) {
+    // The two warps never issue at the same time (concurrent tcgen05.mma streams from two warps of one CTA fault
+    // intermittently on B200): warp mw owns the issue turn for its tile and hands it over right after its last MMA;
+    // its commits and the waits for its NEXT tile then overlap the other warp's MMAs.
+    uint32_t turn_phase = 0;
+    for (int tile = t_begin + mw; tile < t_end && mw < n_issuers; tile += n_issuers) {
       mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1u);
+      if (prm.n_chunks > 0) mbar_wait(bar_full + 8 * stage, phase);   // first chunk's data before taking the turn
+      if (n_issuers == 2 && !(mw == 0 && tile == t_begin)) {
+        mbar_wait(bar_turn + 8 * mw, turn_phase);
+        turn_phase ^= 1u;
+      }
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * N);
       for (int j = 0; j < prm.n_chunks; ++j) {
-        mbar_wait(bar_full + 8 * stage, phase);
+        if (j > 0) mbar_wait(bar_full + 8 * stage, phase);
         tc_fence_after();
         const uint32_t lo_a0 = ((((smem_a + (uint32_t)stage * prm.chunk_stride) & 0x3FFFFu) >> 4) | (1u << 16)) +
                                (MODE == HALO_UP64 ? prm.up_base16 : 0u);
@@ -234,14 +247,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             if (leader) umma_bf16(tmem_d, desc_from(lo_a0 + a_off + 2 * ks, hi_a), desc_from(lo_bj + b_off + 2 * ks, hi_b), idesc, accumulate);
           }
         }
+        if (j + 1 == prm.n_chunks && n_issuers == 2 && leader) mbar_arrive(bar_turn + 8 * (mw ^ 1));   // hand the turn over
         if (leader) umma_commit(bar_empty + 8 * stage);
         if (++stage == prm.n_stages) { stage = 0; phase ^= 1u; }
       }
       if (leader) umma_commit(bar_tfull + 8 * acc);
       // skip the other issuer's tile
-      stage += prm.n_chunks;
-      if (stage >= prm.n_stages) { stage -= prm.n_stages; phase ^= 1u; }
-      acc += 2;
+      if (n_issuers == 2) {
+        stage += prm.n_chunks;
+        if (stage >= prm.n_stages) { stage -= prm.n_stages; phase ^= 1u; }
+      }
+      acc += n_issuers;
       if (acc >= G) { acc -= G; acc_phase ^= 1u; }
     }
   } else {
