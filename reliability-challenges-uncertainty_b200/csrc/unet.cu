@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "conv_tc.cuh"
 #include "conv_halo.cuh"
+#include "conv_wide.cuh"
 #include "philox.cuh"
 #include "unet_kernels.cuh"
 
@@ -62,6 +63,12 @@ struct HaloPack {                  // create-time description of a layer the hal
   uint32_t w_bytes = 0;
 };
 
+struct WidePack {                  // create-time description of a layer the wide kernel can run (c_out % 128 == 0)
+  bool ok = false;
+  int n_chunks = 0, n_ntiles = 0, n_phases = 1;
+  uint8_t* d_wimg = nullptr;       // [phase][ntile][chunk][tap][128][64] pre-swizzled tiles
+};
+
 struct ConvLayer {
   int c0 = 0, c1 = 0, c_out = 0;        // c1 is always 0 now (concat buffers), kept for the kernel's two-map interface
   int n_taps = 9, n_phases = 1, out_mul = 1, relu = 1;
@@ -72,10 +79,11 @@ struct ConvLayer {
   int block_n = 0, kc = 0;
   bool head = false;
   HaloPack halo;
+  WidePack wide;
   // plan-time
   int in_h = 0, in_w = 0;
   Act src, dst;
-  CUtensorMap map_a0, map_a1, map_w, map_halo;
+  CUtensorMap map_a0, map_a1, map_w, map_halo, map_wide;
   int halo_stages = 0;
 };
 
@@ -414,6 +422,76 @@ static int pack_halo_upconv(rcu_unet* net, const rcu_conv_unit& u, HaloPack& hp)
   return RCU_OK;
 }
 
+// Wide-kernel weight image: [phase][ntile][chunk][tap] tiles of [128][64] bf16 in the SWIZZLE_128B smem layout.
+static int pack_wide(rcu_unet* net, const rcu_conv_unit& u, bool upconv, WidePack& wp) {
+  if (u.c_out % kWideN != 0 || u.c_in % 64 != 0) return RCU_OK;
+  wp.n_chunks = u.c_in / 64; wp.n_ntiles = u.c_out / kWideN; wp.n_phases = upconv ? 4 : 1;
+  const int taps = upconv ? 4 : 9;
+  std::vector<uint16_t> img((size_t)wp.n_phases * wp.n_ntiles * wp.n_chunks * taps * kWideN * 64);
+  size_t tile = 0;
+  for (int ph = 0; ph < wp.n_phases; ++ph) {
+    const int a = ph >> 1, b = ph & 1;
+    for (int nt = 0; nt < wp.n_ntiles; ++nt)
+      for (int c = 0; c < wp.n_chunks; ++c)
+        for (int tap = 0; tap < taps; ++tap, ++tile) {
+          int ky0 = tap / 3, ky1 = tap / 3, kx0 = tap % 3, kx1 = tap % 3;
+          if (upconv) {   // pre-summed 2x2 phase weights, see pack_upconv_phases
+            const int i2 = tap >> 1, j2 = tap & 1;
+            if (a == 0) { ky0 = i2 == 0 ? 0 : 1; ky1 = i2 == 0 ? 0 : 2; } else { ky0 = i2 == 0 ? 0 : 2; ky1 = i2 == 0 ? 1 : 2; }
+            if (b == 0) { kx0 = j2 == 0 ? 0 : 1; kx1 = j2 == 0 ? 0 : 2; } else { kx0 = j2 == 0 ? 0 : 2; kx1 = j2 == 0 ? 1 : 2; }
+          }
+          uint16_t* t = img.data() + tile * kWideN * 64;
+          for (int n = 0; n < kWideN; ++n)
+            for (int k = 0; k < 64; ++k) {
+              float sum = 0.0f;
+              for (int ky = ky0; ky <= ky1; ++ky)
+                for (int kx = kx0; kx <= kx1; ++kx) sum += u.weight[((size_t)(nt * kWideN + n) * u.c_in + c * 64 + k) * 9 + ky * 3 + kx];
+              t[sw128_index(n, k)] = f32_to_bf16_rn(sum);
+            }
+        }
+  }
+  uint16_t* d;
+  int rc = dev_upload(net, img, &d);
+  if (rc) return rc;
+  wp.d_wimg = reinterpret_cast<uint8_t*>(d);
+  wp.ok = true;
+  return RCU_OK;
+}
+
+static int make_wide_map(CUtensorMap* map, const Act& a, int n) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available (driver too old?)"); return RCU_ECUDA; }
+  cuuint64_t dims[4] = {(cuuint64_t)a.c, (cuuint64_t)a.w, (cuuint64_t)a.h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)a.c_total * 2, (cuuint64_t)a.w * a.c_total * 2, (cuuint64_t)a.img_stride * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)kWidePitch, (cuuint32_t)kWidePitch, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a.base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(wide c=%d w=%d h=%d n=%d) failed: %d", a.c, a.w, a.h, n, (int)r); return RCU_ECUDA; }
+  return RCU_OK;
+}
+
+template <int TAPS>
+static int launch_conv_wide(const ConvLayer& L, const WideParams& prm, cudaStream_t st) {
+  auto kern = conv_wide_kernel<TAPS>;
+  using C = WideCfg<TAPS>;
+  static bool configured[64] = {false};
+  int dev = 0;
+  RCU_CUDA(cudaGetDevice(&dev));
+  dev = dev < 0 || dev >= 64 ? 0 : dev;
+  if (!configured[dev]) {
+    RCU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
+    configured[dev] = true;
+  }
+  const long long total = (long long)prm.n_img * prm.tiles_y * prm.tiles_x * prm.n_ntiles * prm.n_phases;
+  long long grid = sm_count();
+  if (grid > total) grid = total;
+  if (grid < 1) return RCU_OK;
+  kern<<<(unsigned)grid, kWideThreads, C::kSmem, st>>>(L.map_wide, prm);
+  RCU_LAUNCH_CHECK();
+  return RCU_OK;
+}
+
 static uint32_t halo_chunk_stride(bool /*half_rows*/) {
   const uint32_t bytes = (uint32_t)(kHaloRows * kHaloPitch * 128);   // footprint: 128-byte rows even when only 64 are filled
   return (bytes + 1023u) & ~1023u;
@@ -554,6 +632,8 @@ extern "C" int rcu_unet_create(const rcu_unet_desc* d, int device, rcu_unet** ou
     L.d_weights = reinterpret_cast<__nv_bfloat16*>(dw);
     rc2 = pack_halo_conv3x3(net, cu, L.halo);
     if (rc2) return rc2;
+    rc2 = pack_wide(net, cu, false, L.wide);
+    if (rc2) return rc2;
     net->convs.push_back(L);
     return RCU_OK;
   };
@@ -571,6 +651,8 @@ extern "C" int rcu_unet_create(const rcu_unet_desc* d, int device, rcu_unet** ou
     if (rc2) return rc2;
     L.d_weights = reinterpret_cast<__nv_bfloat16*>(dw);
     rc2 = pack_halo_upconv(net, cu, L.halo);
+    if (rc2) return rc2;
+    rc2 = pack_wide(net, cu, true, L.wide);
     if (rc2) return rc2;
     net->convs.push_back(L);
     return RCU_OK;
@@ -714,6 +796,10 @@ extern "C" int rcu_unet_plan(rcu_unet* net, int height, int width, int max_image
         rc = make_halo_map(&L.map_halo, src, (int)N, L.halo.pair ? 32 : 64);
         if (rc) return rc;
       }
+    }
+    if (L.wide.ok) {
+      rc = make_wide_map(&L.map_wide, src, (int)N);
+      if (rc) return rc;
     }
     Op op;
     op.kind = OP_CONV; op.conv = ci; op.out = L.head ? net->head_feat : dst;
@@ -863,6 +949,24 @@ extern "C" int rcu_unet_forward(rcu_unet* net, const float* images, int64_t n_sl
         if (net->conv_impl == 0 && L.halo.ok && ((net->halo_mask >> op.conv) & 1ull)) {
           int rc = run_conv_halo(net, L, n_img, cs, (long long)s0, (long long)n_slices, logits, st, &launches);
           if (rc) return rc;
+          continue;
+        }
+        if (net->conv_impl == 0 && L.wide.ok && !L.head && ((net->halo_mask >> op.conv) & 1ull)) {
+          WideParams wp;
+          std::memset(&wp, 0, sizeof(wp));
+          wp.n_img = n_img; wp.in_h = L.in_h; wp.in_w = L.in_w;
+          wp.tiles_x = (L.in_w + kWideTile - 1) / kWideTile;
+          wp.tiles_y = (L.in_h + kWideTile - 1) / kWideTile;
+          wp.n_chunks = L.wide.n_chunks; wp.n_ntiles = L.wide.n_ntiles; wp.n_phases = L.wide.n_phases;
+          wp.w_image = L.wide.d_wimg;
+          wp.out_mul = L.out_mul;
+          wp.out_h = L.in_h * L.out_mul; wp.out_w = L.in_w * L.out_mul;
+          wp.out_c = L.dst.c_total; wp.out_img_stride = L.dst.img_stride; wp.out = L.dst.base;
+          wp.coef = net->d_coef; wp.coef_stride = net->n_cols; wp.coef_off = L.coef_off;
+          wp.relu = L.relu;
+          int rc = L.wide.n_phases == 4 ? launch_conv_wide<4>(L, wp, st) : launch_conv_wide<9>(L, wp, st);
+          if (rc) return rc;
+          ++launches;
           continue;
         }
         ConvParams prm;

@@ -65,7 +65,7 @@ def _f32(t):
 class B200UNet(nn.Module):
     """See module docstring.  Not trainable: there are no parameters, only a device handle."""
 
-    DEFAULT_CHUNK_IMAGES = int(os.environ.get('RCU_B200_CHUNK_IMAGES', '168'))
+    DEFAULT_CHUNK_IMAGES = int(os.environ.get('RCU_B200_CHUNK_IMAGES', '147'))
 
     def __init__(self, state_dict, nb_classes=2, in_channels=4, depth=4, start_filters=32, dropout=0.05,
                  dropout_center=None, device=None, seed=20, chunk_images=None):

@@ -247,8 +247,6 @@ def stage_halo_layers():
     ok = True
     for ci, op_i in enumerate(conv_ops):
         o = ops[op_i]
-        if o['c_out'] > 64:
-            continue
         net = model.B200UNet(sd, in_channels=4, dropout=cfg.dropout, chunk_images=64)
         net.set_halo_mask(1 << ci)
         out = net.forward_samples(x, 2, dropout_mode=1, det_first=True, seed=5)
