@@ -48,6 +48,7 @@ aggregate_kernel(const float* __restrict__ in, int n_samples, long long n_images
     const long long px = (pair - img * pairs_per_image) * 2;
     const float* src = in + img * hw * 2 + (KIND == 0 ? px * 2 : px);
     AggAcc a[2] = {};
+#pragma unroll 4
     for (int t = 0; t < n_samples; ++t) {
       float v00, v01, v10, v11;  // [pixel][class]
       if (KIND == 0) {

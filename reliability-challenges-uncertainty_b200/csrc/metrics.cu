@@ -263,10 +263,19 @@ eval_hist_kernel(const float* __restrict__ p, const double* __restrict__ u64v, c
     const bool is_conf = (s >= 2 * nb1 && s < 3 * nb1);
     unsigned long long iacc = 0;
     double dacc = 0.0;
-    for (int b = lane; b < blocks_per_subject; b += 32) {
-      const unsigned long long v = __ldcg(sp + (long long)b * kPartialSlots + s);
-      if (is_conf) dacc += __longlong_as_double((long long)v);
-      else iacc += v;
+    // same summation order as a plain loop (b = lane, lane + 32, ...), but eight L2 loads in flight per lane
+    for (int b0 = lane; b0 < blocks_per_subject; b0 += 32 * 8) {
+      unsigned long long v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int b = b0 + 32 * u;
+        v[u] = b < blocks_per_subject ? __ldcg(sp + (long long)b * kPartialSlots + s) : 0ull;   // +0.0 / 0: neutral
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (is_conf) dacc += __longlong_as_double((long long)v[u]);
+        else iacc += v[u];
+      }
     }
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) {
@@ -342,7 +351,9 @@ static int launch_hist(const float* p, const double* u64v, const uint8_t* pred, 
   RCU_CHECK_ARG(workspace_bytes >= rcu_metrics_workspace_bytes(n_subjects), "metrics workspace too small: %zu < %zu",
                 workspace_bytes, rcu_metrics_workspace_bytes(n_subjects));
   const int sms = sm_count();
-  long long bps = ((long long)sms * 6 + n_subjects - 1) / n_subjects;  // ~2 waves at 3 resident blocks / SM
+  // one wave of fat blocks: the per-block fixed cost (zeroing ~60 KB of private counters, the column reduction) and the
+  // last block's fold over all partials are what a small launch pays, the streaming part is short
+  long long bps = ((long long)sms * 2 + n_subjects - 1) / n_subjects;
   const long long groups = (vps + 3) / 4;
   const long long min_groups_per_block = 256;  // do not shred small subjects into blocks with < 1 group / thread
   if (bps * min_groups_per_block > groups) bps = groups / min_groups_per_block;

@@ -83,6 +83,7 @@ struct ConvLayer {
   // plan-time
   int in_h = 0, in_w = 0;
   Act src, dst;
+  Act pool_dst;                          // when set: the halo kernel also writes MaxPool2d(2) of the output here
   CUtensorMap map_a0, map_a1, map_w, map_halo, map_wide;
   int halo_stages = 0;
 };
@@ -818,13 +819,16 @@ extern "C" int rcu_unet_plan(rcu_unet* net, int height, int width, int max_image
     first.kind = OP_FIRST; first.out = E[0]; first.h = height; first.w = width; first.c = sf;
     net->ops.push_back(first);
   }
+  for (ConvLayer& L : net->convs) L.pool_dst = Act();
   int rc = push_conv(E[0], slice(CAT[0], sf, sf));
   if (rc) return rc;
+  net->convs[ci - 1].pool_dst = P[0];     // the pool that follows can ride in this conv's epilogue (halo kernel only)
   for (int l = 1; l <= depth; ++l) {
     const int cp = sf << (l - 1), c = sf << l;
     push_pool(slice(CAT[l - 1], cp, cp), P[l - 1]);
     if ((rc = push_conv(P[l - 1], E[l]))) return rc;
     if ((rc = push_conv(E[l], l < depth ? slice(CAT[l], c, c) : SB))) return rc;
+    if (l < depth) net->convs[ci - 1].pool_dst = P[l];
   }
   Act cur = SB;
   for (int l = depth - 1; l >= 0; --l) {
@@ -870,6 +874,8 @@ static int run_conv_halo(rcu_unet* net, const ConvLayer& L, int n_img, int cs, l
     prm.out_c = L.dst.c_total;
     prm.out_img_stride = L.dst.img_stride;
     prm.out = L.dst.base;
+    prm.pool_out = L.pool_dst.base;
+    prm.pool_img_stride = L.pool_dst.img_stride;
     prm.coef = net->d_coef; prm.coef_stride = net->n_cols; prm.coef_off = L.coef_off;
     prm.relu = L.relu;
     prm.head = L.head ? net->d_head : nullptr;
@@ -919,8 +925,11 @@ extern "C" int rcu_unet_forward(rcu_unet* net, const float* images, int64_t n_sl
       RCU_LAUNCH_CHECK();
       ++launches;
     }
+    bool pool_done = false;   // the previous conv's epilogue already produced the pooled tensor
     for (size_t op_index = 0; op_index < net->ops.size(); ++op_index) {
       const Op& op = net->ops[op_index];
+      if (op.kind == OP_POOL && pool_done) { pool_done = false; continue; }
+      pool_done = false;
       OpTimer timer(net, (int)op_index, st);
       if (op.kind == OP_FIRST) {
         const int tiles = ((H + kFirstTile - 1) / kFirstTile) * ((W + kFirstTile - 1) / kFirstTile);
@@ -949,6 +958,7 @@ extern "C" int rcu_unet_forward(rcu_unet* net, const float* images, int64_t n_sl
         if (net->conv_impl == 0 && L.halo.ok && ((net->halo_mask >> op.conv) & 1ull)) {
           int rc = run_conv_halo(net, L, n_img, cs, (long long)s0, (long long)n_slices, logits, st, &launches);
           if (rc) return rc;
+          pool_done = L.pool_dst.base != nullptr;
           continue;
         }
         if (net->conv_impl == 0 && L.wide.ok && !L.head && ((net->halo_mask >> op.conv) & 1ull)) {

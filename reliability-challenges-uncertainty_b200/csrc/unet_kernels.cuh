@@ -56,8 +56,10 @@ __global__ void coef_kernel(CoefColumns cols, float2* __restrict__ coef, int n_i
 // ---------------------------------------------------------------------------------------------------------
 // First conv: fp32 NCHW slices (C_in = 3 or 4) -> bf16 NHWC, 32*k output channels.  K = 9*C_in <= 36 is too
 // thin for a tensor-core tile; the convolution itself does not depend on the MC sample (dropout acts after it),
-// so each thread convolves its pixel ONCE and then only re-applies the per-sample coefficients: the layer is
-// store-bound (64 B per pixel-sample).
+// so each thread convolves its pixels ONCE and then only re-applies the per-sample coefficients: the layer is
+// store-bound (64 B per pixel-sample).  Thread t owns 8 output channels (group t % CG) of CG pixels, so the
+// lanes of a warp write 32 consecutive 16-byte pieces (8 x-adjacent pixels x 64 B): fully coalesced stores, and
+// only 8 coefficient pairs per thread and sample.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kFirstTile = 16;  // 16x16 pixels per block, 256 threads
 
@@ -66,6 +68,8 @@ __global__ void __launch_bounds__(256)
 first_conv_kernel(const float* __restrict__ images, int c_in, int h, int w, long long slice0, int chunk_slices, int n_samples,
                   const float* __restrict__ weight /* [c_in*9][C_OUT] */, const float2* __restrict__ coef, long long coef_stride,
                   int coef_off, __nv_bfloat16* __restrict__ out, long long out_img_stride) {
+  constexpr int CG = C_OUT / 8;      // channel groups = pixels per thread
+  constexpr int PG = 256 / CG;       // pixel groups
   extern __shared__ float s_first[];
   float* s_w = s_first;                                  // [c_in*9][C_OUT]
   float* s_in = s_first + c_in * 9 * C_OUT;              // [c_in][18][18]
@@ -81,42 +85,46 @@ first_conv_kernel(const float* __restrict__ images, int c_in, int h, int w, long
     s_in[i] = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? img[((long long)c * h + yy) * w + xx] : 0.0f;
   }
   __syncthreads();
-  const int ly = threadIdx.x >> 4, lx = threadIdx.x & 15;
-  const int y = ty0 + ly, x = tx0 + lx;
-  float acc[C_OUT];
+  const int cg = threadIdx.x % CG, pg = threadIdx.x / CG;
+  float acc[CG][8];
 #pragma unroll
-  for (int c = 0; c < C_OUT; ++c) acc[c] = 0.0f;
+  for (int j = 0; j < CG; ++j)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[j][c] = 0.0f;
   for (int ci = 0; ci < c_in; ++ci)
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
-      const float v = s_in[ci * 324 + (ly + k / 3) * 18 + lx + k % 3];
-      const float4* wr = reinterpret_cast<const float4*>(s_w + (ci * 9 + k) * C_OUT);
+      const float4 w0 = *reinterpret_cast<const float4*>(s_w + (ci * 9 + k) * C_OUT + cg * 8);
+      const float4 w1 = *reinterpret_cast<const float4*>(s_w + (ci * 9 + k) * C_OUT + cg * 8 + 4);
 #pragma unroll
-      for (int c4 = 0; c4 < C_OUT / 4; ++c4) {
-        const float4 wv = wr[c4];
-        acc[4 * c4 + 0] = fmaf(v, wv.x, acc[4 * c4 + 0]);
-        acc[4 * c4 + 1] = fmaf(v, wv.y, acc[4 * c4 + 1]);
-        acc[4 * c4 + 2] = fmaf(v, wv.z, acc[4 * c4 + 2]);
-        acc[4 * c4 + 3] = fmaf(v, wv.w, acc[4 * c4 + 3]);
+      for (int j = 0; j < CG; ++j) {
+        const int p = pg + PG * j, ly = p >> 4, lx = p & 15;
+        const float v = s_in[ci * 324 + (ly + k / 3) * 18 + lx + k % 3];
+        acc[j][0] = fmaf(v, w0.x, acc[j][0]); acc[j][1] = fmaf(v, w0.y, acc[j][1]);
+        acc[j][2] = fmaf(v, w0.z, acc[j][2]); acc[j][3] = fmaf(v, w0.w, acc[j][3]);
+        acc[j][4] = fmaf(v, w1.x, acc[j][4]); acc[j][5] = fmaf(v, w1.y, acc[j][5]);
+        acc[j][6] = fmaf(v, w1.z, acc[j][6]); acc[j][7] = fmaf(v, w1.w, acc[j][7]);
       }
     }
-  if (y >= h || x >= w) return;
   for (int t = 0; t < n_samples; ++t) {
     const int im = t * chunk_slices + sl;
-    const float2* cf = coef + (long long)im * coef_stride + coef_off;
-    uint4* dst = reinterpret_cast<uint4*>(out + (long long)im * out_img_stride + ((long long)y * w + x) * C_OUT);
+    const float2* cf = coef + (long long)im * coef_stride + coef_off + cg * 8;
+    float2 c8[8];
 #pragma unroll
-    for (int c8 = 0; c8 < C_OUT / 8; ++c8) {
+    for (int c = 0; c < 8; ++c) c8[c] = __ldg(cf + c);
+#pragma unroll
+    for (int j = 0; j < CG; ++j) {
+      const int p = pg + PG * j, y = ty0 + (p >> 4), x = tx0 + (p & 15);
+      if (y >= h || x >= w) continue;
       uint32_t pk[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 c0 = __ldg(cf + 8 * c8 + 2 * j), c1 = __ldg(cf + 8 * c8 + 2 * j + 1);
-        const float a0 = fmaxf(fmaf(acc[8 * c8 + 2 * j], c0.x, c0.y), 0.0f);
-        const float a1 = fmaxf(fmaf(acc[8 * c8 + 2 * j + 1], c1.x, c1.y), 0.0f);
+      for (int c = 0; c < 4; ++c) {
+        const float a0 = fmaxf(fmaf(acc[j][2 * c], c8[2 * c].x, c8[2 * c].y), 0.0f);
+        const float a1 = fmaxf(fmaf(acc[j][2 * c + 1], c8[2 * c + 1].x, c8[2 * c + 1].y), 0.0f);
         __nv_bfloat162 b = __floats2bfloat162_rn(a0, a1);
-        pk[j] = *reinterpret_cast<uint32_t*>(&b);
+        pk[c] = *reinterpret_cast<uint32_t*>(&b);
       }
-      dst[c8] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      *reinterpret_cast<uint4*>(out + (long long)im * out_img_stride + ((long long)y * w + x) * C_OUT + cg * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
   }
 }

@@ -55,10 +55,10 @@ class DeviceMetricsHook:
         row = {'subject': subject}
         bins = {}
         row['ece'] = tables.ece_from_tables(count[0, :self.n_bins], positives[0, :self.n_bins], conf[0, :self.n_bins],
-                                            n_dim=np.ndim(target), out_bins=bins)
+                                            n_dim=target.ndim, out_bins=bins)
         row.update(bins)
         tp, tn, fp, fn = (ue[0, i].sum() for i in range(4))
-        row.update(tp=tp, tn=tn, fp=fp, fn=fn, n=int(np.size(target)), dice=tables.dice_from_counts(tp, fp, fn))
+        row.update(tp=tp, tn=tn, fp=fp, fn=fn, n=int(target.numel() if hasattr(target, 'numel') else np.size(target)), dice=tables.dice_from_counts(tp, fp, fn))
         row['sweep'] = {}
         for k_sorted, idx in enumerate(order):
             r = tables.correction_results(*tables.counts_at_threshold(ue[0], k_sorted))

@@ -115,7 +115,7 @@ class SegmentationPredictStep(_BatchStepBase):
 
     def __call__(self, batch_context, task_context, context) -> None:
         _check_context(context)
-        batch_context.input['images'] = batch_context.input['images'].float().to(context.device)
+        batch_context.input['images'] = batch_context.input['images'].float().to(context.device, non_blocking=True)
         if self.has_labels:
             batch_context.input['labels'] = batch_context.input['labels'].long().to(context.device)
         engine = engine_for(context.model, context.device)
@@ -135,7 +135,7 @@ class McPredictStep(_BatchStepBase):
 
     def __call__(self, batch_context, task_context, context) -> None:
         _check_context(context)
-        batch_context.input['images'] = batch_context.input['images'].float().to(context.device)
+        batch_context.input['images'] = batch_context.input['images'].float().to(context.device, non_blocking=True)
         images = batch_context.input['images']
         engine = engine_for(context.model, context.device, _context_seed(context))
         mode = 1 if engine.dropout else 0
@@ -154,7 +154,7 @@ class EnsemblePredictionStep(_BatchStepBase):
 
     def __call__(self, batch_context, task_context, context) -> None:
         _check_context(context)
-        batch_context.input['images'] = batch_context.input['images'].float().to(context.device)
+        batch_context.input['images'] = batch_context.input['images'].float().to(context.device, non_blocking=True)
         images = batch_context.input['images']
         members = [context.model] + list(self.additional_models)
         n, _, h, w = images.shape
