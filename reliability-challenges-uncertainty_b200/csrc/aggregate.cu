@@ -14,12 +14,16 @@ namespace rcu {
 constexpr int kAggThreads = 256;
 
 __device__ __forceinline__ void softmax2(float l0, float l1, float& p0, float& p1) {
-  // same formulation as torch: exp(l - max) / sum
-  const float m = fmaxf(l0, l1);
-  const float e0 = expf(l0 - m), e1 = expf(l1 - m);
-  const float s = e0 + e1;
-  p0 = __fdiv_rn(e0, s);
-  p1 = __fdiv_rn(e1, s);
+  // torch's formulation, exp(l - max) / sum, for two classes: the larger logit contributes exp(0) = 1 exactly, the
+  // other e = exp(-|l0 - l1|); p_max = 1 / (1 + e) is the correctly rounded quotient torch computes, p_min = e * p_max
+  // differs from e / (1 + e) by at most one ulp.  One expf and one reciprocal per pixel-sample instead of two each.
+  const float d = l0 - l1;
+  const float e = expf(-fabsf(d));
+  const float r = __frcp_rn(1.0f + e);
+  const float q = e * r;
+  const bool first = d >= 0.0f;      // NaN logits give NaN probabilities either way
+  p0 = first ? r : q;
+  p1 = first ? q : r;
 }
 
 __device__ __forceinline__ float plogp(float p) { return p > 0.0f ? p * logf(p) : 0.0f; }

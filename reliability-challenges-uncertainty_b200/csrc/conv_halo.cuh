@@ -50,11 +50,14 @@ struct HaloParams {
   int n_stages;
   int dbg;                   // experiment switches (RCU_HALO_DBG): 1 epilogue skips TMEM loads/stores, 16 no TMA loads,
                              // 32 one MMA per chunk — timing experiments only, results are wrong
-  uint32_t up_base16;        // HALO_UP64: window offset of the phase's first tap, (a * 10 + b) * 8 sixteen-byte units
+  // HALO_UP64: the PH up-path phases this launch computes per tile (one accumulator each).  Phase (a, b) reads the
+  // window from (a * 10 + b) * 8 sixteen-byte units on and writes output pixel (2y + a, 2x + b).
+  uint32_t up_base16[4];
+  int up_dy[4], up_dx[4];
   const void* w_image;       // pre-swizzled weight tiles in global memory, in the order the MMA loop walks them
   uint32_t w_bytes;
-  // output addressing: pixel (y, x) lands at (out_mul*y + out_dy, out_mul*x + out_dx)
-  int out_mul, out_dy, out_dx, out_h, out_w;
+  // output addressing: pixel (y, x) lands at (out_mul*y + dy, out_mul*x + dx), (dy, dx) = the phase offset (0 for plain convs)
+  int out_mul, out_h, out_w;
   int out_c;                 // pixel stride in elements (the channel offset is folded into `out`)
   long long out_img_stride;  // elements between images
   __nv_bfloat16* out;
@@ -92,23 +95,26 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
 
 __device__ __forceinline__ uint64_t desc_from(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 
-template <int N, int G>
+template <int N, int G, int PH = 1>
 struct HaloSmem {
   static constexpr int kCoefBytes = G * N * (int)sizeof(float2);
   static constexpr int kHeadBytes = 2 * 32 * 4 + 16;
   static constexpr int kMaxStages = 8;
   static constexpr int kBarBytes = (2 * kMaxStages + 2 * G + 3) * 8 + 16;
   static constexpr int kFixed = 1024 + kCoefBytes + kHeadBytes + kBarBytes;
-  static constexpr int kTmemCols = G * N < 32 ? 32 : G * N;   // 64, 128 or 256: powers of two
+  static constexpr int kAccCols = PH * N;                      // TMEM columns of one accumulator stage
+  static constexpr int kTmemCols = G * kAccCols < 32 ? 32 : G * kAccCols;   // 128, 256 or 512: powers of two
   static constexpr int kThreads = 96 + 128 * G;   // producer warp, two MMA warps, G epilogue groups of four warps
 };
 
 // G = number of TMEM accumulator stages = number of 4-warp epilogue groups (group g drains the tiles whose index in
 // the CTA's range is g mod G), so G epilogues are in flight while the MMA warp works on the next tile.
-template <int N, int G, int MODE>
+template <int N, int G, int MODE, int PH = 1>
 __global__ void __launch_bounds__(96 + 128 * G, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ HaloParams prm) {
-  using S = HaloSmem<N, G>;
+  using S = HaloSmem<N, G, PH>;
+  static_assert(PH == 1 || MODE == HALO_UP64, "several phases per tile only exist on the up path");
+  static_assert(S::kTmemCols <= 512, "accumulator stages exceed TMEM");
   static_assert(N == 32 || N == 64, "halo kernel serves c_out = 32 / 64");
   extern __shared__ uint8_t smem_dyn[];
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
@@ -230,24 +236,29 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         turn_phase ^= 1u;
       }
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * N);
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * S::kAccCols);
       for (int j = 0; j < prm.n_chunks; ++j) {
         if (j > 0) mbar_wait(bar_full + 8 * stage, phase);
         tc_fence_after();
-        const uint32_t lo_a0 = ((((smem_a + (uint32_t)stage * prm.chunk_stride) & 0x3FFFFu) >> 4) | (1u << 16)) +
-                               (MODE == HALO_UP64 ? prm.up_base16 : 0u);
-        const uint32_t lo_bj = lo_b0 + (uint32_t)j * kChunkW16;
-        // every offset below is a compile-time constant: the loop unrolls into back-to-back UTCHMMA with uniform adds
+        const uint32_t lo_a = (((smem_a + (uint32_t)stage * prm.chunk_stride) & 0x3FFFFu) >> 4) | (1u << 16);
+        // every offset below is a compile-time constant: the loops unroll into back-to-back UTCHMMA with uniform adds
 #pragma unroll
-        for (int tap = 0; tap < kTaps; ++tap) {
-          const uint32_t a_off = MODE == HALO_UP64 ? (uint32_t)(((tap >> 1) * kHaloPitch + (tap & 1)) * 8)
-                                                   : (uint32_t)(((tap / 3) * kHaloPitch + tap % 3) * 8);
-          const uint32_t b_off = MODE == HALO_CONV32 ? (uint32_t)(tap >> 1) * kTile16 + (uint32_t)(tap & 1) * 4u : (uint32_t)tap * kTile16;
+        for (int p = 0; p < PH; ++p) {
+          const uint32_t lo_a0 = lo_a + (MODE == HALO_UP64 ? prm.up_base16[p] : 0u);
+          // weight tiles are stored [phase][chunk][tap]
+          const uint32_t lo_bj = lo_b0 + (uint32_t)(p * prm.n_chunks + j) * kChunkW16;
 #pragma unroll
-          for (int ks = 0; ks < kK16; ++ks) {
-            const uint32_t accumulate = (tap > 0 || ks > 0) ? 1u : (j > 0 ? 1u : 0u);
-            if ((prm.dbg & 32) && (tap > 0 || ks > 0)) continue;   // experiment: one MMA per chunk
-            if (leader) umma_bf16(tmem_d, desc_from(lo_a0 + a_off + 2 * ks, hi_a), desc_from(lo_bj + b_off + 2 * ks, hi_b), idesc, accumulate);
+          for (int tap = 0; tap < kTaps; ++tap) {
+            const uint32_t a_off = MODE == HALO_UP64 ? (uint32_t)(((tap >> 1) * kHaloPitch + (tap & 1)) * 8)
+                                                     : (uint32_t)(((tap / 3) * kHaloPitch + tap % 3) * 8);
+            const uint32_t b_off = MODE == HALO_CONV32 ? (uint32_t)(tap >> 1) * kTile16 + (uint32_t)(tap & 1) * 4u : (uint32_t)tap * kTile16;
+#pragma unroll
+            for (int ks = 0; ks < kK16; ++ks) {
+              const uint32_t accumulate = (tap > 0 || ks > 0) ? 1u : (j > 0 ? 1u : 0u);
+              if ((prm.dbg & 32) && (tap > 0 || ks > 0)) continue;   // experiment: one MMA per chunk
+              if (leader)
+                umma_bf16(tmem_d + (uint32_t)(p * N), desc_from(lo_a0 + a_off + 2 * ks, hi_a), desc_from(lo_bj + b_off + 2 * ks, hi_b), idesc, accumulate);
+            }
           }
         }
         if (j + 1 == prm.n_chunks && n_issuers == 2 && leader) mbar_arrive(bar_turn + 8 * (mw ^ 1));   // hand the turn over
@@ -270,7 +281,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int row = q * 32 + lane;
     const int gt = threadIdx.x - 96 - group * 128;   // 0..127 inside the group
     float2* coef = s_coef + group * N;
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(group * N);
+    const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(group * S::kAccCols);
     uint32_t acc_phase = 0;
     int cur_img = -1;
     for (int tile = t_begin + group; tile < t_end; tile += G) {
@@ -296,7 +307,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
       const int y = ty * kHaloTileH + (row >> 3), x = tx * kHaloTileW + (row & 7);
       const bool valid = (y < prm.in_h) && (x < prm.in_w);
-      const int oy = prm.out_mul * y + prm.out_dy, ox = prm.out_mul * x + prm.out_dx;
+#pragma unroll 1
+      for (int p = 0; p < PH; ++p) {
+      const uint32_t taddr = taddr0 + (uint32_t)(p * N);
+      const int oy = prm.out_mul * y + (MODE == HALO_UP64 ? prm.up_dy[p] : 0), ox = prm.out_mul * x + (MODE == HALO_UP64 ? prm.up_dx[p] : 0);
 
       if (prm.head != nullptr) {
         uint32_t v[32];
@@ -326,7 +340,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           uint32_t v[32];
           tmem_ld_32x32b_x32(taddr + (uint32_t)cb, v);
           tmem_ld_wait();
-          if (cb + 32 == N) {
+          if (cb + 32 == N && p + 1 == PH) {
             tc_fence_before();
             mbar_arrive(bar_tempty + 8 * group);
           }
@@ -373,6 +387,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           }
         }
       }
+      }  // phases
       acc_phase ^= 1u;
     }
   }

@@ -59,8 +59,9 @@ struct HaloPack {                  // create-time description of a layer the hal
   int n_phases = 1;
   int n_entries = 0, e_split = 0;
   HaloEntry entries[kMaxPhases][kHaloMaxEntries];
-  uint8_t* d_wimg[kMaxPhases] = {nullptr, nullptr, nullptr, nullptr};
-  uint32_t w_bytes = 0;
+  uint8_t* d_wimg[kMaxPhases] = {nullptr, nullptr, nullptr, nullptr};   // per-phase views into one contiguous image
+  uint32_t w_bytes = 0;            // bytes of ONE phase
+  int phases_per_launch = 1;       // up path: 4, 2 or 1 phases share a launch (weights of all of them resident)
 };
 
 struct WidePack {                  // create-time description of a layer the wide kernel can run (c_out % 128 == 0)
@@ -383,16 +384,24 @@ static int pack_halo_conv3x3(rcu_unet* net, const rcu_conv_unit& u, HaloPack& hp
 }
 
 // nearest-x2 + conv3x3 as four 2x2-tap phase convolutions (see pack_upconv_phases): one weight image per phase
+constexpr int kHaloGroups = 4;   // TMEM accumulator stages = epilogue warp groups
+static size_t halo_chunk_stride_bytes() { return ((size_t)kHaloRows * kHaloPitch * 128 + 1023) & ~size_t(1023); }
+
 static int pack_halo_upconv(rcu_unet* net, const rcu_conv_unit& u, HaloPack& hp) {
   const int N = u.c_out;
   if (!(N == 32 || N == 64) || !(u.c_in == 64 || u.c_in == 128)) return RCU_OK;
   hp.pair = false; hp.n_chunks = u.c_in / 64; hp.n_phases = 4;
   hp.w_bytes = (uint32_t)(hp.n_chunks * 4 * N * 128);
   if (hp.w_bytes > kHaloMaxWeightBytes) return RCU_OK;
+  // as many phases per launch as TMEM (4 stages x PH x N <= 512 columns) and shared memory (weights + >= 3 halo slots) allow
+  hp.phases_per_launch = 1;
+  for (int phs = 4; phs >= 2; phs >>= 1)
+    if (kHaloGroups * phs * N <= 512 && (size_t)phs * hp.w_bytes + 3 * halo_chunk_stride_bytes() + 4096 <= (size_t)kHaloSmemBudget) { hp.phases_per_launch = phs; break; }
+  std::vector<uint16_t> all((size_t)4 * hp.n_chunks * 4 * N * 64, 0);
   for (int a = 0; a < 2; ++a)
     for (int b = 0; b < 2; ++b) {
       const int ph = a * 2 + b;
-      std::vector<uint16_t> img((size_t)hp.n_chunks * 4 * N * 64, 0);
+      uint16_t* img = all.data() + (size_t)ph * hp.n_chunks * 4 * N * 64;
       int t = 0, ne = 0;
       for (int j = 0; j < hp.n_chunks; ++j) {
         for (int i2 = 0; i2 < 2; ++i2)
@@ -414,11 +423,11 @@ static int pack_halo_upconv(rcu_unet* net, const rcu_conv_unit& u, HaloPack& hp)
         if (j == 0) hp.e_split = ne;
       }
       hp.n_entries = ne;
-      uint16_t* d;
-      int rc = dev_upload(net, img, &d);
-      if (rc) return rc;
-      hp.d_wimg[ph] = reinterpret_cast<uint8_t*>(d);
     }
+  uint16_t* d;
+  int rc = dev_upload(net, all, &d);
+  if (rc) return rc;
+  for (int ph = 0; ph < 4; ++ph) hp.d_wimg[ph] = reinterpret_cast<uint8_t*>(d) + (size_t)ph * hp.w_bytes;
   hp.ok = true;
   return RCU_OK;
 }
@@ -498,8 +507,6 @@ static uint32_t halo_chunk_stride(bool /*half_rows*/) {
   return (bytes + 1023u) & ~1023u;
 }
 
-constexpr int kHaloGroups = 4;   // TMEM accumulator stages = epilogue warp groups
-
 template <int N>
 static int halo_stage_count(uint32_t w_bytes, bool pair) {
   const int64_t room = (int64_t)kHaloSmemBudget - HaloSmem<N, kHaloGroups>::kFixed - (int64_t)((w_bytes + 1023u) & ~1023u);
@@ -508,10 +515,10 @@ static int halo_stage_count(uint32_t w_bytes, bool pair) {
   return (int)st;
 }
 
-template <int N, int MODE>
+template <int N, int MODE, int PH = 1>
 static int launch_conv_halo(const ConvLayer& L, const HaloParams& prm, cudaStream_t st) {
-  auto kern = conv_halo_kernel<N, kHaloGroups, MODE>;
-  using HS = HaloSmem<N, kHaloGroups>;
+  auto kern = conv_halo_kernel<N, kHaloGroups, MODE, PH>;
+  using HS = HaloSmem<N, kHaloGroups, PH>;
   static bool configured[64] = {false};
   int dev = 0;
   RCU_CUDA(cudaGetDevice(&dev));
@@ -790,7 +797,8 @@ extern "C" int rcu_unet_plan(rcu_unet* net, int height, int width, int max_image
     rc = make_weight_map(&L.map_w, L.d_weights, L.c0 + L.c1, L.c_out, L.n_taps * L.n_phases, L.kc, L.block_n);
     if (rc) return rc;
     if (L.halo.ok) {
-      L.halo_stages = L.c_out == 32 ? halo_stage_count<32>(L.halo.w_bytes, L.halo.pair) : halo_stage_count<64>(L.halo.w_bytes, L.halo.pair);
+      const uint32_t resident = L.halo.w_bytes * (uint32_t)(L.halo.n_phases == 4 ? L.halo.phases_per_launch : 1);
+      L.halo_stages = L.c_out == 32 ? halo_stage_count<32>(resident, L.halo.pair) : halo_stage_count<64>(resident, L.halo.pair);
       if (L.halo_stages < 2) {
         L.halo.ok = false;
       } else {
@@ -848,7 +856,8 @@ namespace rcu {
 static int run_conv_halo(rcu_unet* net, const ConvLayer& L, int n_img, int cs, long long s0, long long n_slices, float* logits,
                          cudaStream_t st, long long* launches) {
   const HaloPack& hp = L.halo;
-  for (int ph = 0; ph < hp.n_phases; ++ph) {
+  const int ppl = hp.n_phases == 4 ? hp.phases_per_launch : 1;
+  for (int ph = 0; ph < hp.n_phases; ph += ppl) {
     HaloParams prm;
     std::memset(&prm, 0, sizeof(prm));
     prm.n_img = n_img;
@@ -864,12 +873,14 @@ static int run_conv_halo(rcu_unet* net, const ConvLayer& L, int n_img, int cs, l
       static const int dbg = [] { const char* e = std::getenv("RCU_HALO_DBG"); return e ? std::atoi(e) : 0; }();
       prm.dbg = dbg;
     }
-    prm.up_base16 = hp.n_phases == 4 ? (uint32_t)(((ph >> 1) * kHaloPitch + (ph & 1)) * 8) : 0u;
+    for (int i = 0; i < ppl && hp.n_phases == 4; ++i) {
+      const int a = (ph + i) >> 1, b = (ph + i) & 1;
+      prm.up_base16[i] = (uint32_t)((a * kHaloPitch + b) * 8);
+      prm.up_dy[i] = a; prm.up_dx[i] = b;
+    }
     prm.w_image = hp.d_wimg[ph];
-    prm.w_bytes = hp.w_bytes;
+    prm.w_bytes = hp.w_bytes * (uint32_t)ppl;
     prm.out_mul = L.out_mul;
-    prm.out_dy = hp.n_phases == 4 ? (ph >> 1) : 0;
-    prm.out_dx = hp.n_phases == 4 ? (ph & 1) : 0;
     prm.out_h = L.in_h * L.out_mul; prm.out_w = L.in_w * L.out_mul;
     prm.out_c = L.dst.c_total;
     prm.out_img_stride = L.dst.img_stride;
@@ -882,8 +893,11 @@ static int run_conv_halo(rcu_unet* net, const ConvLayer& L, int n_img, int cs, l
     prm.logits = logits;
     prm.chunk_slices = cs; prm.slice0 = s0; prm.n_slices_total = n_slices;
     int rc;
-    if (hp.n_phases == 4) rc = L.c_out == 32 ? launch_conv_halo<32, HALO_UP64>(L, prm, st) : launch_conv_halo<64, HALO_UP64>(L, prm, st);
-    else if (hp.pair) rc = L.c_out == 32 ? launch_conv_halo<32, HALO_CONV32>(L, prm, st) : launch_conv_halo<64, HALO_CONV32>(L, prm, st);
+    if (hp.n_phases == 4) {
+      if (ppl == 4) rc = L.c_out == 32 ? launch_conv_halo<32, HALO_UP64, 4>(L, prm, st) : RCU_ENOTSUP;
+      else if (ppl == 2) rc = L.c_out == 32 ? launch_conv_halo<32, HALO_UP64, 2>(L, prm, st) : launch_conv_halo<64, HALO_UP64, 2>(L, prm, st);
+      else rc = L.c_out == 32 ? launch_conv_halo<32, HALO_UP64>(L, prm, st) : launch_conv_halo<64, HALO_UP64>(L, prm, st);
+    } else if (hp.pair) rc = L.c_out == 32 ? launch_conv_halo<32, HALO_CONV32>(L, prm, st) : launch_conv_halo<64, HALO_CONV32>(L, prm, st);
     else rc = L.c_out == 32 ? launch_conv_halo<32, HALO_CONV64>(L, prm, st) : launch_conv_halo<64, HALO_CONV64>(L, prm, st);
     if (rc) return rc;
     ++*launches;
