@@ -8,6 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'librcu_b200.so')
+LIB_PATH = os.environ.get('RCU_B200_LIB', LIB_PATH)   # developer override (A/B builds)
 
 RCU_OK, RCU_EINVAL, RCU_ECUDA, RCU_ENOTSUP, RCU_ENOMEM = 0, -1, -2, -3, -4
 RCU_MAX_BINS, RCU_MAX_UE_CLASSES, RCU_MAX_BREAKS = 32, 32, 96

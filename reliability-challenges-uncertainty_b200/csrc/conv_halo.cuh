@@ -48,6 +48,7 @@ struct HaloParams {
   uint32_t chunk_bytes;      // bytes one box delivers
   uint32_t chunk_stride;     // slot size (multiple of 1024)
   int n_stages;
+  int tiles_per_turn;        // consecutive tiles an MMA issuer handles per issue turn (1 or 2)
   int dbg;                   // experiment switches (RCU_HALO_DBG): 1 epilogue skips TMEM loads/stores, 16 no TMA loads,
                              // 32 one MMA per chunk — timing experiments only, results are wrong
   // HALO_UP64: the PH up-path phases this launch computes per tile (one accumulator each).  Phase (a, b) reads the
@@ -219,60 +220,82 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     constexpr int kK16 = MODE == HALO_CONV32 ? 2 : 4;
     constexpr uint32_t kTile16 = (uint32_t)(N * 128) >> 4;              // one [N][64] weight tile in 16-byte units
     constexpr uint32_t kChunkW16 = (MODE == HALO_CONV32 ? 5u : (uint32_t)kTaps) * kTile16;
-    // this warp's position in the shared stage / accumulator sequences (tile index t_begin + mw, then every second tile)
-    int stage = (mw * prm.n_chunks) % prm.n_stages;
-    uint32_t phase = (uint32_t)((mw * prm.n_chunks) / prm.n_stages) & 1u;
-    int acc = mw % G;
-    uint32_t acc_phase = (uint32_t)(mw / G) & 1u;
     // The two warps never issue at the same time (concurrent tcgen05.mma streams from two warps of one CTA fault
-    // intermittently on B200): warp mw owns the issue turn for its tile and hands it over right after its last MMA;
-    // its commits and the waits for its NEXT tile then overlap the other warp's MMAs.
+    // intermittently on B200): an issuer owns the issue turn for TT consecutive tiles and hands it over right after
+    // its last MMA; its commits and the barrier waits for its NEXT turn then overlap the other warp's MMAs.  The
+    // hand-off itself costs ~200 clk of idle tensor pipe, so TT = 2 when the smem ring is deep enough.
+    const int TT = prm.tiles_per_turn;
+    const int n_tiles = t_end - t_begin;
     uint32_t turn_phase = 0;
-    for (int tile = t_begin + mw; tile < t_end && mw < n_issuers; tile += n_issuers) {
-      mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1u);
-      if (prm.n_chunks > 0) mbar_wait(bar_full + 8 * stage, phase);   // first chunk's data before taking the turn
-      if (n_issuers == 2 && !(mw == 0 && tile == t_begin)) {
+    // ring positions of this issuer's next tile, advanced incrementally (no divisions on the issue path)
+    int stage = (mw * TT * prm.n_chunks) % prm.n_stages;
+    uint32_t phase = (uint32_t)((mw * TT * prm.n_chunks) / prm.n_stages) & 1u;
+    int acc = (mw * TT) % G;
+    uint32_t acc_phase = (uint32_t)((mw * TT) / G) & 1u;
+    for (int k0 = mw * TT; k0 < n_tiles && mw < n_issuers; k0 += n_issuers * TT) {
+      const int nt = n_tiles - k0 < TT ? n_tiles - k0 : TT;
+      // everything this turn needs, before asking for the turn
+      {
+        int st = stage, ac = acc;
+        uint32_t ph = phase, aph = acc_phase;
+        for (int i = 0; i < nt; ++i) {
+          mbar_wait(bar_tempty + 8 * ac, aph ^ 1u);
+          mbar_wait(bar_full + 8 * st, ph);
+          st += prm.n_chunks;
+          if (st >= prm.n_stages) { st -= prm.n_stages; ph ^= 1u; }
+          if (++ac == G) { ac = 0; aph ^= 1u; }
+        }
+      }
+      if (n_issuers == 2 && k0 != 0) {
         mbar_wait(bar_turn + 8 * mw, turn_phase);
         turn_phase ^= 1u;
       }
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * S::kAccCols);
-      for (int j = 0; j < prm.n_chunks; ++j) {
-        if (j > 0) mbar_wait(bar_full + 8 * stage, phase);
-        tc_fence_after();
-        const uint32_t lo_a = (((smem_a + (uint32_t)stage * prm.chunk_stride) & 0x3FFFFu) >> 4) | (1u << 16);
-        // every offset below is a compile-time constant: the loops unroll into back-to-back UTCHMMA with uniform adds
+      for (int i = 0; i < nt; ++i) {
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * S::kAccCols);
+        for (int j = 0; j < prm.n_chunks; ++j) {
+          if (j > 0) {
+            mbar_wait(bar_full + 8 * stage, phase);
+            tc_fence_after();
+          }
+          const uint32_t lo_a = (((smem_a + (uint32_t)stage * prm.chunk_stride) & 0x3FFFFu) >> 4) | (1u << 16);
+          // every offset below is a compile-time constant: the loops unroll into back-to-back UTCHMMA with uniform adds
 #pragma unroll
-        for (int p = 0; p < PH; ++p) {
-          const uint32_t lo_a0 = lo_a + (MODE == HALO_UP64 ? prm.up_base16[p] : 0u);
-          // weight tiles are stored [phase][chunk][tap]
-          const uint32_t lo_bj = lo_b0 + (uint32_t)(p * prm.n_chunks + j) * kChunkW16;
+          for (int p = 0; p < PH; ++p) {
+            const uint32_t lo_a0 = lo_a + (MODE == HALO_UP64 ? prm.up_base16[p] : 0u);
+            // weight tiles are stored [phase][chunk][tap]
+            const uint32_t lo_bj = lo_b0 + (uint32_t)(p * prm.n_chunks + j) * kChunkW16;
 #pragma unroll
-          for (int tap = 0; tap < kTaps; ++tap) {
-            const uint32_t a_off = MODE == HALO_UP64 ? (uint32_t)(((tap >> 1) * kHaloPitch + (tap & 1)) * 8)
-                                                     : (uint32_t)(((tap / 3) * kHaloPitch + tap % 3) * 8);
-            const uint32_t b_off = MODE == HALO_CONV32 ? (uint32_t)(tap >> 1) * kTile16 + (uint32_t)(tap & 1) * 4u : (uint32_t)tap * kTile16;
+            for (int tap = 0; tap < kTaps; ++tap) {
+              const uint32_t a_off = MODE == HALO_UP64 ? (uint32_t)(((tap >> 1) * kHaloPitch + (tap & 1)) * 8)
+                                                       : (uint32_t)(((tap / 3) * kHaloPitch + tap % 3) * 8);
+              const uint32_t b_off = MODE == HALO_CONV32 ? (uint32_t)(tap >> 1) * kTile16 + (uint32_t)(tap & 1) * 4u : (uint32_t)tap * kTile16;
 #pragma unroll
-            for (int ks = 0; ks < kK16; ++ks) {
-              const uint32_t accumulate = (tap > 0 || ks > 0) ? 1u : (j > 0 ? 1u : 0u);
-              if ((prm.dbg & 32) && (tap > 0 || ks > 0)) continue;   // experiment: one MMA per chunk
-              if (leader)
-                umma_bf16(tmem_d + (uint32_t)(p * N), desc_from(lo_a0 + a_off + 2 * ks, hi_a), desc_from(lo_bj + b_off + 2 * ks, hi_b), idesc, accumulate);
+              for (int ks = 0; ks < kK16; ++ks) {
+                const uint32_t accumulate = (tap > 0 || ks > 0) ? 1u : (j > 0 ? 1u : 0u);
+                if (leader)
+                  umma_bf16(tmem_d + (uint32_t)(p * N), desc_from(lo_a0 + a_off + 2 * ks, hi_a), desc_from(lo_bj + b_off + 2 * ks, hi_b), idesc, accumulate);
+              }
             }
           }
+          if (i + 1 == nt && j + 1 == prm.n_chunks && n_issuers == 2 && leader) mbar_arrive(bar_turn + 8 * (mw ^ 1));   // hand the turn over
+          if (leader) umma_commit(bar_empty + 8 * stage);
+          if (++stage == prm.n_stages) { stage = 0; phase ^= 1u; }
         }
-        if (j + 1 == prm.n_chunks && n_issuers == 2 && leader) mbar_arrive(bar_turn + 8 * (mw ^ 1));   // hand the turn over
-        if (leader) umma_commit(bar_empty + 8 * stage);
-        if (++stage == prm.n_stages) { stage = 0; phase ^= 1u; }
+        if (leader) umma_commit(bar_tfull + 8 * acc);
+        if (++acc == G) { acc = 0; acc_phase ^= 1u; }
       }
-      if (leader) umma_commit(bar_tfull + 8 * acc);
-      // skip the other issuer's tile
+      // skip the other issuer's turn
       if (n_issuers == 2) {
-        stage += prm.n_chunks;
-        if (stage >= prm.n_stages) { stage -= prm.n_stages; phase ^= 1u; }
+        int skip = TT * prm.n_chunks;
+        while (skip > 0) {
+          const int step = skip < prm.n_stages - stage ? skip : prm.n_stages - stage;
+          stage += step; skip -= step;
+          if (stage == prm.n_stages) { stage = 0; phase ^= 1u; }
+        }
+        for (int i = 0; i < TT; ++i)
+          if (++acc == G) { acc = 0; acc_phase ^= 1u; }
       }
-      acc += n_issuers;
-      if (acc >= G) { acc -= G; acc_phase ^= 1u; }
     }
   } else {
     // ===================== epilogue: G groups of 4 warps; group g owns accumulator stage g =====================

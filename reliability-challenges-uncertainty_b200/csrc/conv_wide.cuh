@@ -46,11 +46,17 @@ struct WideParams {
 
 template <int TAPS>   // 9: conv3x3, 4: one up-path phase per unit
 struct WideCfg {
-  static constexpr int kTps = TAPS == 9 ? 3 : 2;           // taps per weight stage
-  static constexpr int kWg = TAPS / kTps + (TAPS % kTps ? 1 : 0);   // weight stages per chunk: 3 or 2
+#ifndef RCU_WIDE_TPS
+#define RCU_WIDE_TPS 3
+#endif
+#ifndef RCU_WIDE_WSTAGES
+#define RCU_WIDE_WSTAGES 2
+#endif
+  static constexpr int kTps = TAPS == 9 ? RCU_WIDE_TPS : 2;           // taps per weight stage
+  static constexpr int kWg = TAPS / kTps + (TAPS % kTps ? 1 : 0);   // weight stages per chunk
   static constexpr uint32_t kWSlot = kTps * kWideWTile;    // 48 KB / 32 KB
   static constexpr int kAStages = 2;
-  static constexpr int kWStages = 2;
+  static constexpr int kWStages = TAPS == 9 ? RCU_WIDE_WSTAGES : 3;
   static constexpr int kCoefBytes = 2 * kWideN * (int)sizeof(float2);
   static constexpr int kBarBytes = (2 * kAStages + 2 * kWStages + 4) * 8 + 16;
   static constexpr int kSmem = 1024 + kAStages * kWideASlot + kWStages * kWSlot + kCoefBytes + kBarBytes;

@@ -869,6 +869,11 @@ static int run_conv_halo(rcu_unet* net, const ConvLayer& L, int n_img, int cs, l
     prm.chunk_bytes = (uint32_t)(kHaloRows * kHaloPitch * (hp.pair ? 64 : 128));   // bytes TMA delivers (complete_tx counts data bytes)
     prm.chunk_stride = halo_chunk_stride(hp.pair);
     prm.n_stages = L.halo_stages;
+    prm.tiles_per_turn = 1;   // measured: two tiles per turn is no faster (the hand-off is not what is exposed)
+    {
+      static const int tt = [] { const char* e = std::getenv("RCU_HALO_TT"); return e ? std::atoi(e) : 0; }();
+      if (tt == 2 && L.halo_stages >= 4 * hp.n_chunks) prm.tiles_per_turn = 2;
+    }
     {
       static const int dbg = [] { const char* e = std::getenv("RCU_HALO_DBG"); return e ? std::atoi(e) : 0; }();
       prm.dbg = dbg;
