@@ -10,6 +10,8 @@
 // private column of shared-memory counters (no atomics, no bank conflicts: bank == lane), blocks reduce their
 // columns in a fixed order and the last block of each subject (ticket) folds the per-block partials in a fixed
 // order, so the float64 confidence sums are deterministic run to run.  Integer tables are exact.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace rcu {
@@ -34,6 +36,11 @@ struct UeParams {
   int n_breaks;
   int n_classes;
   int search_top;   // first step of the branch-free search (power of two)
+  // fused kernel (calibration + U-E on the same float32 p): ONE search over the merged, sorted edge / break list;
+  // segment s = #{merged entries <= p}; joint_kj[s] = calibration bin | (U-E class << 8) of that segment
+  float joint[kBreakPad];
+  unsigned short joint_kj[kBreakPad + 1];
+  int joint_n, joint_top;
   int check_range;  // count values outside [0, 1] (value_kind 0: p must be a probability)
 };
 
@@ -59,10 +66,13 @@ template <typename T, bool STRICT>
 __device__ __forceinline__ int count_breaks(T x, const T* s_breaks, int top) {
   // number of (sorted, +inf padded) breaks b with b <= x (or b < x when STRICT); NaN compares false -> 0
   int lo = 0;
-  for (int step = top; step >= 1; step >>= 1) {
-    const T b = s_breaks[lo + step - 1];
-    const bool take = STRICT ? (b < x) : (b <= x);
-    lo += take ? step : 0;
+#pragma unroll
+  for (int step = kBreakPad / 2; step >= 1; step >>= 1) {
+    if (step <= top) {   // warp-uniform
+      const T b = s_breaks[lo + step - 1];
+      const bool take = STRICT ? (b < x) : (b <= x);
+      lo += take ? step : 0;
+    }
   }
   return lo;
 }
@@ -82,15 +92,22 @@ eval_hist_kernel(const float* __restrict__ p, const double* __restrict__ u64v, c
   const int ncls = UE ? up.n_classes : 0;
 
   // shared layout: conf (double) | cntpos (u32) | ue (u16) | edges (float) | breaks (float/double) | seg (u8)
+  // (offsets are computed as integers and added to smem_raw: a pointer -> integer -> pointer round trip would turn
+  // every access below into a generic load)
+  const int conf_bytes = nb1 * kHistThreads * (int)sizeof(double);
+  const int cntpos_bytes = nb1 * kHistThreads * (int)sizeof(unsigned int);
+  const int ue_bytes = 4 * ncls * kHistThreads * (int)sizeof(unsigned short);
+  const int tail_off = (conf_bytes + cntpos_bytes + ue_bytes + 15) & ~15;
+  const int breaks_d_bytes = (VK == 2 ? RCU_MAX_UE_CLASSES : 0) * (int)sizeof(double);
+  const int breaks_f_bytes = (VK == 0 ? kBreakPad : 0) * (int)sizeof(float);
+  const int edges_bytes = (CALIB ? RCU_MAX_BINS + 1 : 0) * (int)sizeof(float);
   double* s_conf = reinterpret_cast<double*>(smem_raw);
-  unsigned int* s_cntpos = reinterpret_cast<unsigned int*>(s_conf + nb1 * kHistThreads);
-  unsigned short* s_ue = reinterpret_cast<unsigned short*>(s_cntpos + nb1 * kHistThreads);
-  unsigned char* tail = reinterpret_cast<unsigned char*>(s_ue + 4 * ncls * kHistThreads);
-  tail = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tail) + 15) & ~uintptr_t(15));
-  double* s_breaks_d = reinterpret_cast<double*>(tail);
-  float* s_breaks_f = reinterpret_cast<float*>(s_breaks_d + (VK == 2 ? RCU_MAX_UE_CLASSES : 0));
-  float* s_edges = s_breaks_f + (VK == 0 ? kBreakPad : 0);
-  unsigned char* s_seg = reinterpret_cast<unsigned char*>(s_edges + (CALIB ? RCU_MAX_BINS + 1 : 0));
+  unsigned int* s_cntpos = reinterpret_cast<unsigned int*>(smem_raw + conf_bytes);
+  unsigned short* s_ue = reinterpret_cast<unsigned short*>(smem_raw + conf_bytes + cntpos_bytes);
+  double* s_breaks_d = reinterpret_cast<double*>(smem_raw + tail_off);
+  float* s_breaks_f = reinterpret_cast<float*>(smem_raw + tail_off + breaks_d_bytes);
+  float* s_edges = reinterpret_cast<float*>(smem_raw + tail_off + breaks_d_bytes + breaks_f_bytes);
+  unsigned char* s_seg = smem_raw + tail_off + breaks_d_bytes + breaks_f_bytes + edges_bytes;
   __shared__ int s_is_last;
 
   for (int i = tid; i < nb1 * kHistThreads; i += kHistThreads) {
@@ -100,7 +117,12 @@ eval_hist_kernel(const float* __restrict__ p, const double* __restrict__ u64v, c
   for (int i = tid; i < 4 * ncls * kHistThreads; i += kHistThreads) s_ue[i] = 0;
   if (CALIB)
     for (int i = tid; i <= cp.n_bins; i += kHistThreads) s_edges[i] = cp.edges[i];
-  if (VK == 0)
+  constexpr bool JOINT = CALIB && VK == 0;   // one merged search for the calibration bin and the U-E class
+  unsigned short* s_kj = reinterpret_cast<unsigned short*>(smem_raw + tail_off + breaks_d_bytes + breaks_f_bytes + edges_bytes + 128);
+  if (JOINT) {
+    for (int i = tid; i < kBreakPad; i += kHistThreads) s_breaks_f[i] = i < up.joint_n ? up.joint[i] : __int_as_float(0x7f800000);
+    for (int i = tid; i <= up.joint_n; i += kHistThreads) s_kj[i] = up.joint_kj[i];
+  } else if (VK == 0)
     for (int i = tid; i < kBreakPad; i += kHistThreads) s_breaks_f[i] = i < up.n_breaks ? up.breaks32[i] : __int_as_float(0x7f800000);
   if (VK == 2)
     for (int i = tid; i < RCU_MAX_UE_CLASSES; i += kHistThreads) s_breaks_d[i] = i < up.n_breaks ? up.breaks64[i] : __longlong_as_double(0x7ff0000000000000LL);
@@ -118,34 +140,57 @@ eval_hist_kernel(const float* __restrict__ p, const double* __restrict__ u64v, c
   const float n_bins_f = (float)cp.n_bins;
   unsigned int n_invalid = 0;
 
-  auto one = [&](float pv, double uv, unsigned int t, unsigned int d, unsigned int m) {
-    if (CALIB) {
-      bool use = HAS_MASK ? (m != 0) : true;
-      if (cp.has_range) use = use && (pv < cp.range_hi) && (pv > cp.range_lo);
-      if (use) {
-        const int k = calib_bin(pv, s_edges, cp.n_bins, n_bins_f);
-        s_cntpos[k * kHistThreads + tid] += 1u + ((t != 0) ? 65536u : 0u);
-        s_conf[k * kHistThreads + tid] += (double)pv;
-      }
-    }
-    if (UE) {
-      // U-E tables are unmasked in the fused kernel (mask belongs to the calibration part); in the
-      // U-E-only kernel HAS_MASK applies to them (UncertaintyErrorDiceNumpy(with_mask=True)).
-      const bool use = (HAS_MASK && !CALIB) ? (m != 0) : true;
-      if (use) {
-        int idx;
-        if (VK == 2) {
-          idx = count_breaks<double, true>(uv, s_breaks_d, up.search_top);
-        } else {
-          idx = count_breaks<float, false>(pv, s_breaks_f, up.search_top);
-          n_invalid += up.check_range ? (!(pv >= 0.0f && pv <= 1.0f) ? 1u : 0u) : (!(pv == pv) ? 1u : 0u);
-        }
-        const int j = s_seg[idx];
-        const int row = (t != 0) ? ((d != 0) ? 0 : 3) : ((d != 0) ? 2 : 1);  // tp, tn, fp, fn
-        s_ue[(row * ncls + j) * kHistThreads + tid] += 1;
-      }
-    }
-  };
+  // One voxel, branch-free: every voxel performs the same read-modify-writes on this thread's private counters, with a
+  // zero increment when it is masked out (the private columns are bank == lane, so the RMWs are conflict-free; a
+  // predicated-off voxel is cheaper than a divergent branch).  A macro, not a lambda: the counters must be addressed
+  // as shared memory (LDS/STS), which a by-reference capture degrades to generic loads/stores.
+  const float e_last = CALIB ? s_edges[cp.n_bins] : 0.0f;
+  const int nbm1 = cp.n_bins - 1;
+  const bool has_range = CALIB && cp.has_range;
+#define RCU_HIST_ONE(PV, UV, T, D, M)                                                                                   \
+  do {                                                                                                                  \
+    const float pv_ = (PV);                                                                                             \
+    const unsigned int t_ = (T), d_ = (D), m_ = (M);                                                                    \
+    if (JOINT) {                                                                                                        \
+      const unsigned int kj_ = s_kj[count_breaks<float, false>(pv_, s_breaks_f, up.joint_top)];                         \
+      bool use_ = HAS_MASK ? (m_ != 0u) : true;                                                                         \
+      if (has_range) use_ = use_ && (pv_ < cp.range_hi) && (pv_ > cp.range_lo);                                         \
+      const bool inr_ = (pv_ >= 0.0f) && (pv_ < e_last);                                                                \
+      const int ci_ = (inr_ ? (int)(kj_ & 0xffu) : cp.n_bins) * kHistThreads + tid;                                     \
+      s_cntpos[ci_] += use_ ? (1u + ((t_ != 0u) ? 65536u : 0u)) : 0u;                                                   \
+      s_conf[ci_] += use_ ? (double)pv_ : 0.0;                                                                          \
+      n_invalid += !(pv_ >= 0.0f && pv_ <= 1.0f) ? 1u : 0u;                                                             \
+      const int row_ = (t_ != 0u) ? ((d_ != 0u) ? 0 : 3) : ((d_ != 0u) ? 2 : 1);                                        \
+      s_ue[(row_ * ncls + (int)(kj_ >> 8)) * kHistThreads + tid] += 1;                                                  \
+    } else if (CALIB) {                                                                                                 \
+      bool use_ = HAS_MASK ? (m_ != 0u) : true;                                                                         \
+      if (has_range) use_ = use_ && (pv_ < cp.range_hi) && (pv_ > cp.range_lo);                                         \
+      const bool inr_ = (pv_ >= 0.0f) && (pv_ < e_last);          /* NaN / negative / >= last edge -> slot n_bins */     \
+      int k_ = max(0, min(__float2int_rz(pv_ * n_bins_f), nbm1)); /* floor(p * n) is right up to +-1 ...           */     \
+      k_ += (pv_ >= s_edges[k_ + 1]) ? 1 : 0;                     /* ... the float32-rounded-up edges settle it     */     \
+      k_ -= (pv_ < s_edges[min(k_, nbm1 + 1)]) ? 1 : 0;                                                                 \
+      k_ = inr_ ? k_ : cp.n_bins;                                                                                       \
+      const int ci_ = k_ * kHistThreads + tid;                                                                          \
+      s_cntpos[ci_] += use_ ? (1u + ((t_ != 0u) ? 65536u : 0u)) : 0u;                                                   \
+      s_conf[ci_] += use_ ? (double)pv_ : 0.0;                                                                          \
+    }                                                                                                                   \
+    if (UE && !JOINT) {                                                                                                 \
+      /* U-E tables are unmasked in the fused kernel (the mask belongs to the calibration part); in the U-E-only */      \
+      /* kernel HAS_MASK applies to them (UncertaintyErrorDiceNumpy(with_mask=True)).                              */      \
+      const bool useu_ = (HAS_MASK && !CALIB) ? (m_ != 0u) : true;                                                      \
+      int idx_;                                                                                                         \
+      if (VK == 2) {                                                                                                    \
+        idx_ = count_breaks<double, true>((UV), s_breaks_d, up.search_top);                                             \
+      } else {                                                                                                          \
+        idx_ = count_breaks<float, false>(pv_, s_breaks_f, up.search_top);                                              \
+        const bool bad_ = up.check_range ? !(pv_ >= 0.0f && pv_ <= 1.0f) : !(pv_ == pv_);                               \
+        n_invalid += (useu_ && bad_) ? 1u : 0u;                                                                         \
+      }                                                                                                                 \
+      const int j_ = s_seg[idx_];                                                                                       \
+      const int row_ = (t_ != 0u) ? ((d_ != 0u) ? 0 : 3) : ((d_ != 0u) ? 2 : 1); /* tp, tn, fp, fn */                    \
+      s_ue[(row_ * ncls + j_) * kHistThreads + tid] += useu_ ? 1 : 0;                                                   \
+    }                                                                                                                   \
+  } while (0)
 
   if (vec_ok) {
     constexpr int U = 4;
@@ -182,11 +227,11 @@ eval_hist_kernel(const float* __restrict__ p, const double* __restrict__ u64v, c
           if (VK == 2) { ue[0] = uv[u][0].x; ue[1] = uv[u][0].y; ue[2] = uv[u][1].x; ue[3] = uv[u][1].y; }
 #pragma unroll
           for (int e = 0; e < 4; ++e)
-            one(pe[e], ue[e], (tv[u] >> (8 * e)) & 0xffu, (dv[u] >> (8 * e)) & 0xffu, (mv[u] >> (8 * e)) & 0xffu);
+            RCU_HIST_ONE(pe[e], ue[e], (tv[u] >> (8 * e)) & 0xffu, (dv[u] >> (8 * e)) & 0xffu, (mv[u] >> (8 * e)) & 0xffu);
         } else {  // ragged last group of the subject
           for (long long v = gg * 4; v < voxels_per_subject; ++v) {
             const long long a = base + v;
-            one(VK != 2 ? p[a] : 0.f, VK == 2 ? u64v[a] : 0., target[a], UE ? pred[a] : 0, HAS_MASK ? mask[a] : 1);
+            RCU_HIST_ONE(VK != 2 ? p[a] : 0.f, VK == 2 ? u64v[a] : 0., target[a], UE ? pred[a] : 0, HAS_MASK ? mask[a] : 1);
           }
         }
       }
@@ -196,10 +241,11 @@ eval_hist_kernel(const float* __restrict__ p, const double* __restrict__ u64v, c
       const long long vend = min(voxels_per_subject, g * 4 + 4);
       for (long long v = g * 4; v < vend; ++v) {
         const long long a = base + v;
-        one(VK != 2 ? p[a] : 0.f, VK == 2 ? u64v[a] : 0., target[a], UE ? pred[a] : 0, HAS_MASK ? mask[a] : 1);
+        RCU_HIST_ONE(VK != 2 ? p[a] : 0.f, VK == 2 ? u64v[a] : 0., target[a], UE ? pred[a] : 0, HAS_MASK ? mask[a] : 1);
       }
     }
   }
+#undef RCU_HIST_ONE
   __syncthreads();
 
   // ---- block reduction of the private columns, fixed order ----
@@ -340,7 +386,7 @@ static size_t hist_smem_bytes(bool calib, int vk, int n_bins, int n_classes) {
   size_t b = (size_t)nb1 * kHistThreads * (sizeof(double) + sizeof(unsigned int)) + (size_t)4 * ncls * kHistThreads * sizeof(unsigned short);
   b = (b + 15) & ~size_t(15);
   b += (vk == 2 ? RCU_MAX_UE_CLASSES * sizeof(double) : 0) + (vk == 0 ? kBreakPad * sizeof(float) : 0) +
-       (calib ? (RCU_MAX_BINS + 1) * sizeof(float) : 0) + (RCU_MAX_BREAKS + 1) + 64;
+       (calib ? (RCU_MAX_BINS + 1) * sizeof(float) : 0) + 128 + (kBreakPad + 1) * sizeof(unsigned short) + 64;
   return b < 64 ? 64 : b;
 }
 
@@ -353,7 +399,8 @@ static int launch_hist(const float* p, const double* u64v, const uint8_t* pred, 
   const int sms = sm_count();
   // one wave of fat blocks: the per-block fixed cost (zeroing ~60 KB of private counters, the column reduction) and the
   // last block's fold over all partials are what a small launch pays, the streaming part is short
-  long long bps = ((long long)sms * 2 + n_subjects - 1) / n_subjects;
+  static const int blocks_per_sm = [] { const char* e = std::getenv("RCU_HIST_BPSM"); return e ? std::atoi(e) : 3; }();
+  long long bps = ((long long)sms * blocks_per_sm + n_subjects - 1) / n_subjects;
   const long long groups = (vps + 3) / 4;
   const long long min_groups_per_block = 256;  // do not shred small subjects into blocks with < 1 group / thread
   if (bps * min_groups_per_block > groups) bps = groups / min_groups_per_block;
@@ -501,6 +548,24 @@ extern "C" int rcu_eval_fused(const float* p, const uint8_t* prediction, const u
   if (rc) return rc;
   rc = fill_ue(up, 0, breaks_f32, nullptr, n_breaks, seg_class, n_classes);
   if (rc) return rc;
+  {
+    // merged list of the inner calibration edges (bin k = #{edges[1..n_bins-1] <= p} for p inside [0, last edge)) and the
+    // U-E breaks (class = seg_class[#{breaks <= p}]): both are "count of entries <= p", so one search serves both
+    RCU_CHECK_ARG((n_bins - 1) + n_breaks <= kBreakPad - 1, "too many bins + break points for the fused kernel");
+    int ie = 1, ib = 0, n = 0;
+    up.joint_kj[0] = (unsigned short)(0 | (up.seg_class[0] << 8));
+    while (ie < n_bins || ib < n_breaks) {
+      const bool take_edge = ib >= n_breaks || (ie < n_bins && cp.edges[ie] <= up.breaks32[ib]);
+      up.joint[n] = take_edge ? cp.edges[ie] : up.breaks32[ib];
+      if (take_edge) ++ie; else ++ib;
+      ++n;
+      up.joint_kj[n] = (unsigned short)((ie - 1) | (up.seg_class[ib] << 8));
+    }
+    up.joint_n = n;
+    int top = 1;
+    while (2 * top - 1 < n) top *= 2;
+    up.joint_top = top;
+  }
   HistOut out = {reinterpret_cast<unsigned long long*>(count), reinterpret_cast<unsigned long long*>(positives), conf_sum,
                  reinterpret_cast<unsigned long long*>(ue_counts), reinterpret_cast<unsigned long long*>(invalid)};
   cudaStream_t st = (cudaStream_t)stream;
