@@ -9,9 +9,20 @@
 //   bin-dl/brats_test_default.py:97  prediction = np.argmax(probabilities, -1)   (ties -> class 0)
 #include "common.cuh"
 
+#ifndef RCU_AGG_TU
+#define RCU_AGG_TU 2
+#endif
+#ifndef RCU_AGG_P
+#define RCU_AGG_P 4
+#endif
+#ifndef RCU_AGG_MINB
+#define RCU_AGG_MINB 4
+#endif
+
 namespace rcu {
 
 constexpr int kAggThreads = 256;
+constexpr int kAggSampleUnroll = RCU_AGG_TU;
 
 __device__ __forceinline__ void softmax2(float l0, float l1, float& p0, float& p1) {
   // torch's formulation, exp(l - max) / sum, for two classes: the larger logit contributes exp(0) = 1 exactly, the
@@ -35,10 +46,13 @@ struct AggAcc {
   float q0, q1;      // sum of squared deviations
 };
 
-// One thread = 2 adjacent pixels (float4 of interleaved logits, or two float2 of planar values).
+// One thread = P pixel pairs (a float4 of interleaved logits, or two float2 of planar values, per pair and sample).
+// Pair (thread, k) = warp_base + k * 32 + lane: every load instruction of a warp reads 512 contiguous bytes of one
+// sample, and with P = 4 the P loads of a sample are issued back to back, so a warp walks 2 KB runs of each of the
+// n_samples streams (long DRAM bursts; deeper unrolling over samples instead opens more streams at once and is slower).
 // KIND 0: interleaved logits [t][n][hw][2];  1: planar probabilities [t][n][2][hw];  2: planar logits.
-template <int KIND, bool MI, bool VAR, bool PARTIAL>
-__global__ void __launch_bounds__(kAggThreads)
+template <int KIND, bool MI, bool VAR, bool PARTIAL, int P>
+__global__ void __launch_bounds__(kAggThreads, P > 1 ? RCU_AGG_MINB : 1)
 aggregate_kernel(const float* __restrict__ in, int n_samples, long long n_images, long long hw, float inv_or_scale,
                  float* __restrict__ mean, float* __restrict__ entropy, float* __restrict__ mutual_info,
                  float* __restrict__ variance, unsigned char* __restrict__ prediction, float* __restrict__ foreground,
@@ -46,96 +60,119 @@ aggregate_kernel(const float* __restrict__ in, int n_samples, long long n_images
   const long long pairs_per_image = hw >> 1;  // hw is even (checked on the host)
   const long long total_pairs = n_images * pairs_per_image;
   const long long sample_stride = n_images * hw * 2;
-  for (long long pair = (long long)blockIdx.x * kAggThreads + threadIdx.x; pair < total_pairs;
-       pair += (long long)gridDim.x * kAggThreads) {
-    const long long img = pair / pairs_per_image;
-    const long long px = (pair - img * pairs_per_image) * 2;
-    const float* src = in + img * hw * 2 + (KIND == 0 ? px * 2 : px);
-    AggAcc a[2] = {};
-#pragma unroll 4
+  const int lane = threadIdx.x & 31;
+  const long long warp_id = ((long long)blockIdx.x * kAggThreads + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * kAggThreads) >> 5;
+  for (long long wbase = warp_id * (32 * P); wbase < total_pairs; wbase += n_warps * (32 * P)) {
+    AggAcc a[P][2] = {};
+    const float* src[P];
+    long long img_k[P], px_k[P];
+    bool on[P];
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+      const long long pair = wbase + k * 32 + lane;
+      on[k] = pair < total_pairs;
+      const long long pr = on[k] ? pair : 0;
+      img_k[k] = pr / pairs_per_image;
+      px_k[k] = (pr - img_k[k] * pairs_per_image) * 2;
+      src[k] = in + img_k[k] * hw * 2 + (KIND == 0 ? px_k[k] * 2 : px_k[k]);
+    }
+#pragma unroll kAggSampleUnroll
     for (int t = 0; t < n_samples; ++t) {
-      float v00, v01, v10, v11;  // [pixel][class]
-      if (KIND == 0) {
-        const float4 v = ld_stream_f4(src + (long long)t * sample_stride);
-        v00 = v.x; v01 = v.y; v10 = v.z; v11 = v.w;
-      } else {
-        const float2 c0 = ld_stream_f2(src + (long long)t * sample_stride);
-        const float2 c1 = ld_stream_f2(src + (long long)t * sample_stride + hw);
-        v00 = c0.x; v10 = c0.y; v01 = c1.x; v11 = c1.y;
-      }
-      float p[2][2];
-      if (KIND == 1) {
-        p[0][0] = v00; p[0][1] = v01; p[1][0] = v10; p[1][1] = v11;
-      } else {
-        softmax2(v00, v01, p[0][0], p[0][1]);
-        softmax2(v10, v11, p[1][0], p[1][1]);
-      }
-      if (multi_out != nullptr) {
-        float* dst = multi_out + (long long)t * sample_stride + img * hw * 2 + px;
-        *reinterpret_cast<float2*>(dst) = make_float2(p[0][0], p[1][0]);
-        *reinterpret_cast<float2*>(dst + hw) = make_float2(p[0][1], p[1][1]);
+      float v[P][4];  // [pair][pixel * 2 + class]
+#pragma unroll
+      for (int k = 0; k < P; ++k) {
+        if (!on[k]) { v[k][0] = v[k][1] = v[k][2] = v[k][3] = 0.0f; continue; }
+        if (KIND == 0) {
+          const float4 q = ld_stream_f4(src[k] + (long long)t * sample_stride);
+          v[k][0] = q.x; v[k][1] = q.y; v[k][2] = q.z; v[k][3] = q.w;
+        } else {
+          const float2 c0 = ld_stream_f2(src[k] + (long long)t * sample_stride);
+          const float2 c1 = ld_stream_f2(src[k] + (long long)t * sample_stride + hw);
+          v[k][0] = c0.x; v[k][2] = c0.y; v[k][1] = c1.x; v[k][3] = c1.y;
+        }
       }
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        a[k].s0 += p[k][0];
-        a[k].s1 += p[k][1];
-        if (MI) a[k].h += -(plogp(p[k][0]) + plogp(p[k][1]));
-        if (VAR) {
-          if (PARTIAL) {  // raw second moments, combined across ranks later
-            a[k].q0 += p[k][0] * p[k][0];
-            a[k].q1 += p[k][1] * p[k][1];
-          } else {
-            const float inv = 1.0f / (float)(t + 1);
-            const float d0 = p[k][0] - a[k].m0, d1 = p[k][1] - a[k].m1;
-            a[k].m0 += d0 * inv;
-            a[k].m1 += d1 * inv;
-            a[k].q0 += d0 * (p[k][0] - a[k].m0);
-            a[k].q1 += d1 * (p[k][1] - a[k].m1);
+      for (int k = 0; k < P; ++k) {
+        float p[2][2];
+        if (KIND == 1) {
+          p[0][0] = v[k][0]; p[0][1] = v[k][1]; p[1][0] = v[k][2]; p[1][1] = v[k][3];
+        } else {
+          softmax2(v[k][0], v[k][1], p[0][0], p[0][1]);
+          softmax2(v[k][2], v[k][3], p[1][0], p[1][1]);
+        }
+        if (multi_out != nullptr && on[k]) {
+          float* dst = multi_out + (long long)t * sample_stride + img_k[k] * hw * 2 + px_k[k];
+          *reinterpret_cast<float2*>(dst) = make_float2(p[0][0], p[1][0]);
+          *reinterpret_cast<float2*>(dst + hw) = make_float2(p[0][1], p[1][1]);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          AggAcc& acc = a[k][j];
+          acc.s0 += p[j][0];
+          acc.s1 += p[j][1];
+          if (MI) acc.h += -(plogp(p[j][0]) + plogp(p[j][1]));
+          if (VAR) {
+            if (PARTIAL) {  // raw second moments, combined across ranks later
+              acc.q0 += p[j][0] * p[j][0];
+              acc.q1 += p[j][1] * p[j][1];
+            } else {
+              const float inv = 1.0f / (float)(t + 1);
+              const float d0 = p[j][0] - acc.m0, d1 = p[j][1] - acc.m1;
+              acc.m0 += d0 * inv;
+              acc.m1 += d1 * inv;
+              acc.q0 += d0 * (p[j][0] - acc.m0);
+              acc.q1 += d1 * (p[j][1] - acc.m1);
+            }
           }
         }
       }
     }
-    if (PARTIAL) {
-      const int planes = 2 + (MI ? 1 : 0) + (VAR ? 2 : 0);
-      float* dst = sums + img * planes * hw + px;
-      *reinterpret_cast<float2*>(dst) = make_float2(a[0].s0, a[1].s0);
-      *reinterpret_cast<float2*>(dst + hw) = make_float2(a[0].s1, a[1].s1);
-      int pl = 2;
-      if (MI) { *reinterpret_cast<float2*>(dst + pl * hw) = make_float2(a[0].h, a[1].h); ++pl; }
-      if (VAR) {
-        *reinterpret_cast<float2*>(dst + pl * hw) = make_float2(a[0].q0, a[1].q0);
-        *reinterpret_cast<float2*>(dst + (pl + 1) * hw) = make_float2(a[0].q1, a[1].q1);
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+      if (!on[k]) continue;
+      const long long img = img_k[k], px = px_k[k];
+      if (PARTIAL) {
+        const int planes = 2 + (MI ? 1 : 0) + (VAR ? 2 : 0);
+        float* dst = sums + img * planes * hw + px;
+        *reinterpret_cast<float2*>(dst) = make_float2(a[k][0].s0, a[k][1].s0);
+        *reinterpret_cast<float2*>(dst + hw) = make_float2(a[k][0].s1, a[k][1].s1);
+        int pl = 2;
+        if (MI) { *reinterpret_cast<float2*>(dst + pl * hw) = make_float2(a[k][0].h, a[k][1].h); ++pl; }
+        if (VAR) {
+          *reinterpret_cast<float2*>(dst + pl * hw) = make_float2(a[k][0].q0, a[k][1].q0);
+          *reinterpret_cast<float2*>(dst + (pl + 1) * hw) = make_float2(a[k][0].q1, a[k][1].q1);
+        }
+      } else {
+        float m0[2], m1[2], ent[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          // torch: sum then divide by T
+          m0[j] = __fdiv_rn(a[k][j].s0, inv_or_scale);
+          m1[j] = __fdiv_rn(a[k][j].s1, inv_or_scale);
+          ent[j] = -(plogp(m0[j]) + plogp(m1[j]));
+        }
+        float* mdst = mean + img * hw * 2 + px;
+        *reinterpret_cast<float2*>(mdst) = make_float2(m0[0], m0[1]);
+        *reinterpret_cast<float2*>(mdst + hw) = make_float2(m1[0], m1[1]);
+        const long long o = img * hw + px;
+        if (entropy) *reinterpret_cast<float2*>(entropy + o) = make_float2(ent[0], ent[1]);
+        if (MI) *reinterpret_cast<float2*>(mutual_info + o) =
+            make_float2(ent[0] - __fdiv_rn(a[k][0].h, inv_or_scale), ent[1] - __fdiv_rn(a[k][1].h, inv_or_scale));
+        if (VAR) {
+          const float dn = (float)(n_samples - 1);
+          *reinterpret_cast<float2*>(variance + o) =
+              make_float2(0.5f * (a[k][0].q0 / dn + a[k][0].q1 / dn), 0.5f * (a[k][1].q0 / dn + a[k][1].q1 / dn));
+        }
+        if (prediction) {
+          uchar2 pr;
+          pr.x = m1[0] > m0[0] ? 1 : 0;
+          pr.y = m1[1] > m0[1] ? 1 : 0;
+          *reinterpret_cast<uchar2*>(prediction + o) = pr;
+        }
+        if (foreground) *reinterpret_cast<float2*>(foreground + o) = make_float2(m1[0], m1[1]);
       }
     }
-    if (!PARTIAL) {
-    float m0[2], m1[2], ent[2];
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      // torch: sum then divide by T
-      m0[k] = __fdiv_rn(a[k].s0, inv_or_scale);
-      m1[k] = __fdiv_rn(a[k].s1, inv_or_scale);
-      ent[k] = -(plogp(m0[k]) + plogp(m1[k]));
-    }
-    float* mdst = mean + img * hw * 2 + px;
-    *reinterpret_cast<float2*>(mdst) = make_float2(m0[0], m0[1]);
-    *reinterpret_cast<float2*>(mdst + hw) = make_float2(m1[0], m1[1]);
-    const long long o = img * hw + px;
-    if (entropy) *reinterpret_cast<float2*>(entropy + o) = make_float2(ent[0], ent[1]);
-    if (MI) *reinterpret_cast<float2*>(mutual_info + o) =
-        make_float2(ent[0] - __fdiv_rn(a[0].h, inv_or_scale), ent[1] - __fdiv_rn(a[1].h, inv_or_scale));
-    if (VAR) {
-      const float dn = (float)(n_samples - 1);
-      *reinterpret_cast<float2*>(variance + o) =
-          make_float2(0.5f * (a[0].q0 / dn + a[0].q1 / dn), 0.5f * (a[1].q0 / dn + a[1].q1 / dn));
-    }
-    if (prediction) {
-      uchar2 pr;
-      pr.x = m1[0] > m0[0] ? 1 : 0;
-      pr.y = m1[1] > m0[1] ? 1 : 0;
-      *reinterpret_cast<uchar2*>(prediction + o) = pr;
-    }
-    if (foreground) *reinterpret_cast<float2*>(foreground + o) = make_float2(m1[0], m1[1]);
-    }  // !PARTIAL
   }
 }
 
@@ -177,11 +214,21 @@ static int launch_aggregate(bool mi, bool var, const float* in, int n_samples, i
                             float* foreground, float* multi_out, float* sums, cudaStream_t st) {
   const long long total_pairs = n_images * (hw / 2);
   if (total_pairs == 0) return RCU_OK;
-  long long blocks = (total_pairs + kAggThreads - 1) / kAggThreads;
+  // the plain summary (no MI / variance) runs four pairs per thread; the variants with more accumulators keep one
+  const bool wide = !mi && !var && total_pairs >= (long long)sm_count() * kAggThreads * 8;
+  const int per_thread = wide ? RCU_AGG_P : 1;
+  long long blocks = (total_pairs + (long long)kAggThreads * per_thread - 1) / ((long long)kAggThreads * per_thread);
   const long long cap = (long long)sm_count() * 16;
   if (blocks > cap) blocks = cap;
+  if (wide) {
+    aggregate_kernel<KIND, false, false, PARTIAL, RCU_AGG_P><<<(unsigned)blocks, kAggThreads, 0, st>>>(
+        in, n_samples, (long long)n_images, (long long)hw, denom, mean, entropy, mutual_info, variance, prediction, foreground,
+        multi_out, sums);
+    RCU_LAUNCH_CHECK();
+    return RCU_OK;
+  }
 #define RCU_AGG_LAUNCH(MI_, VAR_)                                                                                    \
-  aggregate_kernel<KIND, MI_, VAR_, PARTIAL><<<(unsigned)blocks, kAggThreads, 0, st>>>(                               \
+  aggregate_kernel<KIND, MI_, VAR_, PARTIAL, 1><<<(unsigned)blocks, kAggThreads, 0, st>>>(                            \
       in, n_samples, (long long)n_images, (long long)hw, denom, mean, entropy, mutual_info, variance, prediction,     \
       foreground, multi_out, sums)
   if (mi && var) RCU_AGG_LAUNCH(true, true);
