@@ -77,6 +77,105 @@ __device__ __forceinline__ int count_breaks(T x, const T* s_breaks, int top) {
   return lo;
 }
 
+// Block reduction of the per-thread private columns (fixed order), per-block partials to global memory, and the fold of
+// all partials by the subject's last block (ticket) — shared by the generic and the LUT kernels.
+__device__ __forceinline__ void hist_block_finish(unsigned char* smem_raw, double* s_conf, unsigned int* s_cntpos, unsigned short* s_ue,
+                                                  int nb1, int ncls, unsigned int n_invalid, int subject, int blocks_per_subject,
+                                                  HistOut out, unsigned int* __restrict__ tickets,
+                                                  unsigned long long* __restrict__ partials) {
+  const int tid = threadIdx.x;
+  __shared__ int s_is_last;
+  // ---- block reduction of the private columns, fixed order ----
+  const int warp = tid >> 5, lane = tid & 31;
+  const int n_slots = 3 * nb1 + 4 * ncls + 1;
+  unsigned long long* my_partial = partials + ((long long)subject * blocks_per_subject + blockIdx.x) * kPartialSlots;
+  for (int s = warp; s < n_slots - 1; s += kHistThreads / 32) {
+    if (s >= 2 * nb1 && s < 3 * nb1) {
+      const double* col = s_conf + (s - 2 * nb1) * kHistThreads;
+      double acc = 0.0;
+#pragma unroll
+      for (int i = 0; i < kHistThreads / 32; ++i) acc += col[lane + 32 * i];
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+      if (lane == 0) my_partial[s] = (unsigned long long)__double_as_longlong(acc);
+    } else {
+      unsigned long long acc = 0;
+      if (s < 2 * nb1) {
+        const unsigned int* col = s_cntpos + (s < nb1 ? s : s - nb1) * kHistThreads;
+        const int sh = s < nb1 ? 0 : 16;
+#pragma unroll
+        for (int i = 0; i < kHistThreads / 32; ++i) acc += (col[lane + 32 * i] >> sh) & 0xffffu;
+      } else {
+        const unsigned short* col = s_ue + (s - 3 * nb1) * kHistThreads;
+#pragma unroll
+        for (int i = 0; i < kHistThreads / 32; ++i) acc += col[lane + 32 * i];
+      }
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+      if (lane == 0) my_partial[s] = acc;
+    }
+  }
+  // invalid-key count lives in registers: block-wide sum through a scratch word per warp (the columns are dead now)
+  __syncthreads();
+  unsigned int* s_scratch = reinterpret_cast<unsigned int*>(smem_raw);
+  {
+    unsigned int v = n_invalid;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) s_scratch[warp] = v;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long tot = 0;
+    for (int w = 0; w < kHistThreads / 32; ++w) tot += s_scratch[w];
+    my_partial[n_slots - 1] = tot;
+  }
+
+  // ---- last block of the subject folds the partials in block order ----
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int t = atomicAdd(&tickets[subject], 1u);
+    s_is_last = (t == (unsigned int)blocks_per_subject - 1u);
+  }
+  __syncthreads();
+  if (!s_is_last) return;
+  __threadfence();
+  const unsigned long long* sp = partials + (long long)subject * blocks_per_subject * kPartialSlots;
+  for (int s = warp; s < n_slots; s += kHistThreads / 32) {
+    const bool is_conf = (s >= 2 * nb1 && s < 3 * nb1);
+    unsigned long long iacc = 0;
+    double dacc = 0.0;
+    // same summation order as a plain loop (b = lane, lane + 32, ...), but eight L2 loads in flight per lane
+    for (int b0 = lane; b0 < blocks_per_subject; b0 += 32 * 8) {
+      unsigned long long v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int b = b0 + 32 * u;
+        v[u] = b < blocks_per_subject ? __ldcg(sp + (long long)b * kPartialSlots + s) : 0ull;   // +0.0 / 0: neutral
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (is_conf) dacc += __longlong_as_double((long long)v[u]);
+        else iacc += v[u];
+      }
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      iacc += __shfl_down_sync(0xffffffffu, iacc, o);
+      dacc += __shfl_down_sync(0xffffffffu, dacc, o);
+    }
+    if (lane == 0) {
+      if (s < nb1) out.count[(long long)subject * nb1 + s] = iacc;
+      else if (s < 2 * nb1) out.positives[(long long)subject * nb1 + (s - nb1)] = iacc;
+      else if (s < 3 * nb1) out.conf_sum[(long long)subject * nb1 + (s - 2 * nb1)] = dacc;
+      else if (s < n_slots - 1) out.ue_counts[(long long)subject * 4 * ncls + (s - 3 * nb1)] = iacc;
+      else if (out.invalid) out.invalid[subject] = iacc;
+    }
+  }
+  if (tid == 0) tickets[subject] = 0u;  // workspace is reusable by the next stream-ordered call
+}
+
 // VK: 0 = float32 p (or float32 uncertainty, same search), 2 = float64 uncertainty; -1 = no U-E part.
 template <bool CALIB, int VK, bool HAS_MASK>
 __global__ void __launch_bounds__(kHistThreads)
@@ -108,7 +207,6 @@ eval_hist_kernel(const float* __restrict__ p, const double* __restrict__ u64v, c
   float* s_breaks_f = reinterpret_cast<float*>(smem_raw + tail_off + breaks_d_bytes);
   float* s_edges = reinterpret_cast<float*>(smem_raw + tail_off + breaks_d_bytes + breaks_f_bytes);
   unsigned char* s_seg = smem_raw + tail_off + breaks_d_bytes + breaks_f_bytes + edges_bytes;
-  __shared__ int s_is_last;
 
   for (int i = tid; i < nb1 * kHistThreads; i += kHistThreads) {
     s_conf[i] = 0.0;
@@ -248,97 +346,133 @@ eval_hist_kernel(const float* __restrict__ p, const double* __restrict__ u64v, c
 #undef RCU_HIST_ONE
   __syncthreads();
 
-  // ---- block reduction of the private columns, fixed order ----
-  const int warp = tid >> 5, lane = tid & 31;
-  const int n_slots = 3 * nb1 + 4 * ncls + 1;
-  unsigned long long* my_partial = partials + ((long long)subject * blocks_per_subject + blockIdx.x) * kPartialSlots;
-  for (int s = warp; s < n_slots - 1; s += kHistThreads / 32) {
-    if (s >= 2 * nb1 && s < 3 * nb1) {
-      const double* col = s_conf + (s - 2 * nb1) * kHistThreads;
-      double acc = 0.0;
-#pragma unroll
-      for (int i = 0; i < kHistThreads / 32; ++i) acc += col[lane + 32 * i];
-#pragma unroll
-      for (int o = 16; o >= 1; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-      if (lane == 0) my_partial[s] = (unsigned long long)__double_as_longlong(acc);
-    } else {
-      unsigned long long acc = 0;
-      if (s < 2 * nb1) {
-        const unsigned int* col = s_cntpos + (s < nb1 ? s : s - nb1) * kHistThreads;
-        const int sh = s < nb1 ? 0 : 16;
-#pragma unroll
-        for (int i = 0; i < kHistThreads / 32; ++i) acc += (col[lane + 32 * i] >> sh) & 0xffffu;
-      } else {
-        const unsigned short* col = s_ue + (s - 3 * nb1) * kHistThreads;
-#pragma unroll
-        for (int i = 0; i < kHistThreads / 32; ++i) acc += col[lane + 32 * i];
-      }
-#pragma unroll
-      for (int o = 16; o >= 1; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-      if (lane == 0) my_partial[s] = acc;
-    }
-  }
-  // invalid-key count lives in registers: block-wide sum through a scratch word per warp (the columns are dead now)
-  __syncthreads();
-  unsigned int* s_scratch = reinterpret_cast<unsigned int*>(smem_raw);
-  {
-    unsigned int v = n_invalid;
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if (lane == 0) s_scratch[warp] = v;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    unsigned long long tot = 0;
-    for (int w = 0; w < kHistThreads / 32; ++w) tot += s_scratch[w];
-    my_partial[n_slots - 1] = tot;
-  }
-
-  // ---- last block of the subject folds the partials in block order ----
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    const unsigned int t = atomicAdd(&tickets[subject], 1u);
-    s_is_last = (t == (unsigned int)blocks_per_subject - 1u);
-  }
-  __syncthreads();
-  if (!s_is_last) return;
-  __threadfence();
-  const unsigned long long* sp = partials + (long long)subject * blocks_per_subject * kPartialSlots;
-  for (int s = warp; s < n_slots; s += kHistThreads / 32) {
-    const bool is_conf = (s >= 2 * nb1 && s < 3 * nb1);
-    unsigned long long iacc = 0;
-    double dacc = 0.0;
-    // same summation order as a plain loop (b = lane, lane + 32, ...), but eight L2 loads in flight per lane
-    for (int b0 = lane; b0 < blocks_per_subject; b0 += 32 * 8) {
-      unsigned long long v[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int b = b0 + 32 * u;
-        v[u] = b < blocks_per_subject ? __ldcg(sp + (long long)b * kPartialSlots + s) : 0ull;   // +0.0 / 0: neutral
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        if (is_conf) dacc += __longlong_as_double((long long)v[u]);
-        else iacc += v[u];
-      }
-    }
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
-      iacc += __shfl_down_sync(0xffffffffu, iacc, o);
-      dacc += __shfl_down_sync(0xffffffffu, dacc, o);
-    }
-    if (lane == 0) {
-      if (s < nb1) out.count[(long long)subject * nb1 + s] = iacc;
-      else if (s < 2 * nb1) out.positives[(long long)subject * nb1 + (s - nb1)] = iacc;
-      else if (s < 3 * nb1) out.conf_sum[(long long)subject * nb1 + (s - 2 * nb1)] = dacc;
-      else if (s < n_slots - 1) out.ue_counts[(long long)subject * 4 * ncls + (s - 3 * nb1)] = iacc;
-      else if (out.invalid) out.invalid[subject] = iacc;
-    }
-  }
-  if (tid == 0) tickets[subject] = 0u;  // workspace is reusable by the next stream-ordered call
+  hist_block_finish(smem_raw, s_conf, s_cntpos, s_ue, nb1, ncls, n_invalid, subject, blocks_per_subject, out, tickets, partials);
 }
 
+
+// Fused calibration + U-E pass, lean variant for the common case (float32 p, 16-byte aligned inputs, no threshold_range,
+// at most one merged edge / break point per 1/NB-wide bucket of p).  The generic kernel is instruction bound at ~105
+// instructions per voxel (two searches, index arithmetic); here the joint segment of p comes from a bucket table —
+// s = base[bucket] + (p >= break[bucket]), exact because p * NB is exact for a power-of-two NB — and the per-segment
+// table holds the counter offsets pre-multiplied, which leaves ~45 instructions per voxel.  Same private-column counters,
+// same reduction, bit-identical tables.
+template <bool HAS_MASK>
+__global__ void __launch_bounds__(kHistThreads)
+eval_fused_lut_kernel(const float* __restrict__ p, const unsigned char* __restrict__ pred, const unsigned char* __restrict__ target,
+                      const unsigned char* __restrict__ mask, long long voxels_per_subject, int blocks_per_subject,
+                      const __grid_constant__ CalibParams cp, const __grid_constant__ UeParams up, int n_buckets, HistOut out,
+                      unsigned int* __restrict__ tickets, unsigned long long* __restrict__ partials) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x;
+  const int nb1 = cp.n_bins + 1;
+  const int ncls = up.n_classes;
+  const int conf_bytes = nb1 * kHistThreads * (int)sizeof(double);
+  const int cntpos_bytes = nb1 * kHistThreads * (int)sizeof(unsigned int);
+  const int ue_bytes = 4 * ncls * kHistThreads * (int)sizeof(unsigned short);
+  const int tail_off = (conf_bytes + cntpos_bytes + ue_bytes + 15) & ~15;
+  double* s_conf = reinterpret_cast<double*>(smem_raw);
+  unsigned int* s_cntpos = reinterpret_cast<unsigned int*>(smem_raw + conf_bytes);
+  unsigned short* s_ue = reinterpret_cast<unsigned short*>(smem_raw + conf_bytes + cntpos_bytes);
+  float* s_joint = reinterpret_cast<float*>(smem_raw + tail_off);                           // [kBreakPad] merged list, +inf padded
+  unsigned int* s_seg2 = reinterpret_cast<unsigned int*>(smem_raw + tail_off + kBreakPad * 4);   // [kBreakPad + 1] k*T | (j*T) << 16
+  unsigned int* s_lut = reinterpret_cast<unsigned int*>(smem_raw + tail_off + kBreakPad * 4 + (kBreakPad + 8) * 4);   // [n_buckets] base | n_inside << 8
+
+  for (int i = tid; i < nb1 * kHistThreads; i += kHistThreads) {
+    s_conf[i] = 0.0;
+    s_cntpos[i] = 0u;
+  }
+  for (int i = tid; i < 4 * ncls * kHistThreads; i += kHistThreads) s_ue[i] = 0;
+  for (int i = tid; i < kBreakPad; i += kHistThreads) s_joint[i] = i < up.joint_n ? up.joint[i] : __int_as_float(0x7f800000);
+  for (int i = tid; i <= up.joint_n; i += kHistThreads) {
+    const unsigned int kj = up.joint_kj[i];
+    s_seg2[i] = ((kj & 0xffu) * kHistThreads) | (((kj >> 8) * kHistThreads) << 16);
+  }
+  __syncthreads();
+  const float nb_f = (float)n_buckets, inv_nb = 1.0f / nb_f;
+  for (int b = tid; b < n_buckets; b += kHistThreads) {
+    const float lo = (float)b * inv_nb;                                            // exact (power-of-two bucket count)
+    const float hi = b + 1 < n_buckets ? (float)(b + 1) * inv_nb : __int_as_float(0x7f800000);
+    const int base = count_breaks<float, false>(lo, s_joint, up.joint_top);        // entries <= lo
+    // entries strictly inside (lo, hi): the break points of the float arithmetic cluster a few ulps apart around each
+    // threshold, so a bucket may hold several; they are resolved by a short scan (most buckets hold none)
+    const int upto = b + 1 < n_buckets ? count_breaks<float, false>(__uint_as_float(__float_as_uint(hi) - 1u), s_joint, up.joint_top) : up.joint_n;
+    s_lut[b] = (unsigned int)base | ((unsigned int)(upto - base) << 8);
+  }
+  __syncthreads();
+
+  const int subject = blockIdx.y;
+  const long long base_v = (long long)subject * voxels_per_subject;
+  const long long groups = (voxels_per_subject + 3) >> 2;
+  const long long gpb = (groups + blocks_per_subject - 1) / blocks_per_subject;
+  const long long g0 = (long long)blockIdx.x * gpb;
+  const long long g1 = min(groups, g0 + gpb);
+  const float e_last = cp.edges[cp.n_bins];
+  const unsigned int nb_off = (unsigned int)cp.n_bins * kHistThreads;
+  const int row_stride = ncls * kHistThreads;
+  unsigned int* cnt_col = s_cntpos + tid;
+  double* conf_col = s_conf + tid;
+  unsigned short* ue_col = s_ue + tid;
+  unsigned int n_invalid = 0;
+
+#define RCU_LUT_ONE(PV, T, D, M)                                                                                        \
+  do {                                                                                                                  \
+    const float pv_ = (PV);                                                                                             \
+    const unsigned int t_ = (T), d_ = (D), m_ = (M);                                                                    \
+    const int b_ = max(0, min(__float2int_rz(pv_ * nb_f), n_buckets - 1));                                              \
+    const unsigned int le_ = s_lut[b_];                                                                                 \
+    const bool nonneg_ = pv_ >= 0.0f;                                 /* false for NaN */                               \
+    int s_ = (int)(le_ & 0xffu);                                                                                        \
+    for (int i_ = (int)(le_ & 0xffu), e_ = i_ + (int)(le_ >> 8); i_ < e_; ++i_) s_ += (pv_ >= s_joint[i_]) ? 1 : 0;    \
+    s_ = nonneg_ ? s_ : 0;                                            /* the search counts 0 entries for p < 0 / NaN */ \
+    const unsigned int sg_ = s_seg2[s_];                                                                                \
+    const bool use_ = HAS_MASK ? (m_ != 0u) : true;                                                                     \
+    const unsigned int ko_ = (nonneg_ && pv_ < e_last) ? (sg_ & 0xffffu) : nb_off;                                      \
+    cnt_col[ko_] += use_ ? (1u + ((t_ != 0u) ? 65536u : 0u)) : 0u;                                                      \
+    conf_col[ko_] += use_ ? (double)pv_ : 0.0;                                                                          \
+    n_invalid += !(nonneg_ && pv_ <= 1.0f) ? 1u : 0u;                                                                   \
+    const int row_ = (t_ != 0u) ? ((d_ != 0u) ? 0 : 3) : ((d_ != 0u) ? 2 : 1);     /* tp, tn, fp, fn */                 \
+    ue_col[row_ * row_stride + (int)(sg_ >> 16)] += 1;                                                                  \
+  } while (0)
+
+  constexpr int U = 4;
+  for (long long g = g0 + tid; g < g1; g += (long long)kHistThreads * U) {
+    float4 pv[U];
+    unsigned int tv[U], dv[U], mv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long gg = g + (long long)u * kHistThreads;
+      const bool in = gg < g1 && (gg * 4 + 3 < voxels_per_subject);
+      pv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      tv[u] = dv[u] = mv[u] = 0u;
+      if (in) {
+        const long long v = base_v + gg * 4;
+        pv[u] = ld_stream_f4(p + v);
+        tv[u] = ld_stream_u32(target + v);
+        dv[u] = ld_stream_u32(pred + v);
+        if (HAS_MASK) mv[u] = ld_stream_u32(mask + v);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long gg = g + (long long)u * kHistThreads;
+      if (gg >= g1) break;
+      if (gg * 4 + 3 < voxels_per_subject) {
+        const float pe[4] = {pv[u].x, pv[u].y, pv[u].z, pv[u].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          RCU_LUT_ONE(pe[e], (tv[u] >> (8 * e)) & 0xffu, (dv[u] >> (8 * e)) & 0xffu, (mv[u] >> (8 * e)) & 0xffu);
+      } else {  // ragged last group of the subject
+        for (long long v = gg * 4; v < voxels_per_subject; ++v) {
+          const long long a = base_v + v;
+          RCU_LUT_ONE(p[a], target[a], pred[a], HAS_MASK ? mask[a] : 1);
+        }
+      }
+    }
+  }
+#undef RCU_LUT_ONE
+  __syncthreads();
+  hist_block_finish(smem_raw, s_conf, s_cntpos, s_ue, nb1, ncls, n_invalid, subject, blocks_per_subject, out, tickets, partials);
+}
 
 // Confusion matrix with pymia 0.2.1 semantics (ConfusionMatrix: prediction == 1 / == 0 against label == 1 / == 0),
 // reached from np_fn.dice / confusion_matrx / accuracy (common/evalutation/numpyfunctions.py:128-151).  2 B/voxel.
@@ -569,6 +703,46 @@ extern "C" int rcu_eval_fused(const float* p, const uint8_t* prediction, const u
   HistOut out = {reinterpret_cast<unsigned long long*>(count), reinterpret_cast<unsigned long long*>(positives), conf_sum,
                  reinterpret_cast<unsigned long long*>(ue_counts), reinterpret_cast<unsigned long long*>(invalid)};
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    // lean bucket-table kernel for aligned inputs (the generic kernel handles the rest)
+    static const bool allow_lut = [] { const char* e = std::getenv("RCU_HIST_LUT"); return !(e && e[0] == '0'); }();
+    const bool aligned = reinterpret_cast<uintptr_t>(p) % 16 == 0 && reinterpret_cast<uintptr_t>(target) % 4 == 0 &&
+                         reinterpret_cast<uintptr_t>(prediction) % 4 == 0 && (mask == nullptr || reinterpret_cast<uintptr_t>(mask) % 4 == 0);
+    const int n_buckets = (allow_lut && aligned && (n_subjects == 1 || vps % 4 == 0)) ? 1024 : 0;
+    if (n_buckets > 0) {
+      RCU_CHECK_ARG(workspace_bytes >= rcu_metrics_workspace_bytes(n_subjects), "metrics workspace too small");
+      const int sms = sm_count();
+      long long bps = ((long long)sms * 3 + n_subjects - 1) / n_subjects;
+      const long long groups = (vps + 3) / 4;
+      if (bps * 256 > groups) bps = groups / 256;
+      if (bps < 1) bps = 1;
+      if (bps > kMaxBlocksPerSubject) bps = kMaxBlocksPerSubject;
+      if (bps * n_subjects > partial_blocks_cap(n_subjects)) bps = partial_blocks_cap(n_subjects) / n_subjects;
+      if (bps < 1) bps = 1;
+      const long long per_thread = ((groups + bps - 1) / bps + kHistThreads - 1) / kHistThreads * 4;
+      RCU_CHECK_ARG(per_thread <= kMaxVoxelsPerThread, "subject of %lld voxels is too large for one launch (split it)", (long long)vps);
+      RCU_CHECK_ARG(n_subjects <= 65535, "n_subjects %d exceeds grid.y limit", n_subjects);
+      const int nb1 = n_bins + 1;
+      size_t smem = (size_t)nb1 * kHistThreads * 12 + (size_t)4 * n_classes * kHistThreads * 2;
+      smem = ((smem + 15) & ~size_t(15)) + kBreakPad * 4 + (kBreakPad + 8) * 4 + (size_t)n_buckets * 4 + 64;
+      unsigned int* tickets = reinterpret_cast<unsigned int*>(workspace);
+      unsigned long long* partials = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(workspace) + tickets_bytes(n_subjects));
+      dim3 grid((unsigned)bps, (unsigned)n_subjects);
+      static size_t configured[2][64] = {{0}};
+      int dev = 0;
+      RCU_CUDA(cudaGetDevice(&dev));
+      const int mi = mask ? 1 : 0;
+      if (dev < 0 || dev >= 64 || smem > configured[mi][dev]) {
+        if (mask) RCU_CUDA(cudaFuncSetAttribute(eval_fused_lut_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else RCU_CUDA(cudaFuncSetAttribute(eval_fused_lut_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (dev >= 0 && dev < 64) configured[mi][dev] = smem;
+      }
+      if (mask) eval_fused_lut_kernel<true><<<grid, kHistThreads, smem, st>>>(p, prediction, target, mask, (long long)vps, (int)bps, cp, up, n_buckets, out, tickets, partials);
+      else eval_fused_lut_kernel<false><<<grid, kHistThreads, smem, st>>>(p, prediction, target, nullptr, (long long)vps, (int)bps, cp, up, n_buckets, out, tickets, partials);
+      RCU_LAUNCH_CHECK();
+      return RCU_OK;
+    }
+  }
   if (mask) return launch_hist<true, 0, true>(p, nullptr, prediction, target, mask, vps, n_subjects, cp, up, out, workspace, workspace_bytes, st);
   return launch_hist<true, 0, false>(p, nullptr, prediction, target, nullptr, vps, n_subjects, cp, up, out, workspace, workspace_bytes, st);
 }
