@@ -48,6 +48,7 @@ struct HaloParams {
   uint32_t chunk_bytes;      // bytes one box delivers
   uint32_t chunk_stride;     // slot size (multiple of 1024)
   int n_stages;
+  int tma_store;             // epilogue stages bf16 tiles in shared memory and writes them with TMA tensor stores
   int tiles_per_turn;        // consecutive tiles an MMA issuer handles per issue turn (1 or 2)
   int dbg;                   // experiment switches (RCU_HALO_DBG): 1 epilogue skips TMEM loads/stores, 16 no TMA loads,
                              // 32 one MMA per chunk — timing experiments only, results are wrong
@@ -94,12 +95,24 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
                : "memory");
 }
 
+struct HaloOutMaps { CUtensorMap m[4]; };   // destination views, one per up-path phase of the launch (m[0] for plain convs)
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 __device__ __forceinline__ uint64_t desc_from(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 
 template <int N, int G, int PH = 1>
 struct HaloSmem {
   static constexpr int kCoefBytes = G * N * (int)sizeof(float2);
   static constexpr int kHeadBytes = 2 * 32 * 4 + 16;
+  static constexpr int kOutSlot = 128 * 64;                    // one 128-pixel x 32-channel bf16 tile per epilogue group
+  static constexpr int kOutBytes = G * kOutSlot;               // only reserved when the launch uses TMA stores
   static constexpr int kMaxStages = 8;
   static constexpr int kBarBytes = (2 * kMaxStages + 2 * G + 3) * 8 + 16;
   static constexpr int kFixed = 1024 + kCoefBytes + kHeadBytes + kBarBytes;
@@ -112,7 +125,8 @@ struct HaloSmem {
 // the CTA's range is g mod G), so G epilogues are in flight while the MMA warp works on the next tile.
 template <int N, int G, int MODE, int PH = 1>
 __global__ void __launch_bounds__(96 + 128 * G, 1)
-conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ HaloParams prm) {
+conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ HaloOutMaps out_maps,
+                 const __grid_constant__ HaloParams prm) {
   using S = HaloSmem<N, G, PH>;
   static_assert(PH == 1 || MODE == HALO_UP64, "several phases per tile only exist on the up path");
   static_assert(S::kTmemCols <= 512, "accumulator stages exceed TMEM");
@@ -123,7 +137,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const uint32_t w_span = (prm.w_bytes + 1023u) & ~1023u;
   const uint32_t smem_w = base;
   const uint32_t smem_a = base + w_span;
-  const uint32_t tail = w_span + (uint32_t)prm.n_stages * prm.chunk_stride;
+  const uint32_t smem_out = base + w_span + (uint32_t)prm.n_stages * prm.chunk_stride;   // 1024-aligned
+  const uint32_t tail = w_span + (uint32_t)prm.n_stages * prm.chunk_stride + (prm.tma_store ? (uint32_t)S::kOutBytes : 0u);
   float2* s_coef = reinterpret_cast<float2*>(base_ptr + tail);
   float* s_head = reinterpret_cast<float*>(base_ptr + tail + S::kCoefBytes);
   uint8_t* bar_ptr = base_ptr + tail + S::kCoefBytes + S::kHeadBytes;
@@ -140,6 +155,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
+    if (prm.tma_store)
+      for (int i = 0; i < PH; ++i) tma_prefetch_desc(&out_maps.m[i]);
     for (int s = 0; s < S::kMaxStages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
@@ -377,7 +394,27 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             __nv_bfloat162 b = __floats2bfloat162_rn(a0, a1);
             packed[c >> 1] = *reinterpret_cast<uint32_t*>(&b);
           }
-          if (valid) {
+          if (prm.tma_store) {
+            // stage the 128 x 32 tile in shared memory (64-byte rows, SWIZZLE_64B: 16-byte chunk ^= (row >> 1) & 3, which
+            // also makes the 4 x STS.128 of a warp conflict-free) and let ONE TMA tensor store write it: the direct path
+            // costs 32 LSU wavefronts per STG.128 (every lane its own line), and TMA clips tiles that overhang the image
+            const uint32_t so = smem_out + (uint32_t)group * S::kOutSlot;
+            if (gt == 0) bulk_wait_group_read0();                         // the previous store has finished reading the slot
+            asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
+            const uint32_t rowa = so + (uint32_t)row * 64u;
+            const uint32_t sw = (uint32_t)(row >> 1) & 3u;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + (((uint32_t)i ^ sw) << 4)), "r"(packed[4 * i]),
+                           "r"(packed[4 * i + 1]), "r"(packed[4 * i + 2]), "r"(packed[4 * i + 3])
+                           : "memory");
+            fence_proxy_async();
+            asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
+            if (gt == 0) {
+              tma_store_4d(&out_maps.m[p], so, cb, tx * kHaloTileW, ty * kHaloTileH, img);
+              bulk_commit_group();
+            }
+          } else if (valid) {
             uint4* d4 = reinterpret_cast<uint4*>(dst + cb);
 #pragma unroll
             for (int i = 0; i < 4; ++i) d4[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
@@ -413,6 +450,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }  // phases
       acc_phase ^= 1u;
     }
+    if (prm.tma_store && gt == 0) bulk_wait_group_read0();   // shared memory must outlive the last store's read
   }
 
   tc_fence_before();

@@ -86,6 +86,8 @@ struct ConvLayer {
   Act src, dst;
   Act pool_dst;                          // when set: the halo kernel also writes MaxPool2d(2) of the output here
   CUtensorMap map_a0, map_a1, map_w, map_halo, map_wide;
+  CUtensorMap map_out[kMaxPhases];       // halo kernel: TMA-store views of the destination (one per up-path phase)
+  bool tma_store = false;
   int halo_stages = 0;
 };
 
@@ -267,6 +269,22 @@ static int make_halo_map(CUtensorMap* map, const Act& a, int n, int box_c) {
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a.base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(halo c=%d w=%d h=%d n=%d) failed: %d", a.c, a.w, a.h, n, (int)r); return RCU_ECUDA; }
+  return RCU_OK;
+}
+
+// Destination view for the halo kernel's TMA tensor stores: 128-pixel x 32-channel boxes, SWIZZLE_64B.  For an up-path
+// phase (a, b) the view is the (2y + a, 2x + b) sub-lattice of the high-resolution tensor (doubled strides).
+static int make_out_map(CUtensorMap* map, const Act& d, int n, int out_mul, int a, int b) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available (driver too old?)"); return RCU_ECUDA; }
+  cuuint64_t dims[4] = {(cuuint64_t)d.c, (cuuint64_t)(d.w / out_mul), (cuuint64_t)(d.h / out_mul), (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)d.c_total * 2 * out_mul, (cuuint64_t)d.w * d.c_total * 2 * out_mul, (cuuint64_t)d.img_stride * 2};
+  cuuint32_t box[4] = {32, (cuuint32_t)kHaloTileW, (cuuint32_t)kHaloTileH, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  void* base = d.base + ((size_t)a * d.w + b) * d.c_total;
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(out c=%d w=%d h=%d n=%d) failed: %d", d.c, d.w, d.h, n, (int)r); return RCU_ECUDA; }
   return RCU_OK;
 }
 
@@ -508,15 +526,16 @@ static uint32_t halo_chunk_stride(bool /*half_rows*/) {
 }
 
 template <int N>
-static int halo_stage_count(uint32_t w_bytes, bool pair) {
-  const int64_t room = (int64_t)kHaloSmemBudget - HaloSmem<N, kHaloGroups>::kFixed - (int64_t)((w_bytes + 1023u) & ~1023u);
+static int halo_stage_count(uint32_t w_bytes, bool pair, bool tma_store = false) {
+  const int64_t room = (int64_t)kHaloSmemBudget - HaloSmem<N, kHaloGroups>::kFixed - (int64_t)((w_bytes + 1023u) & ~1023u) -
+                       (tma_store ? HaloSmem<N, kHaloGroups>::kOutBytes : 0);
   int64_t st = room / halo_chunk_stride(pair);
   if (st > HaloSmem<N, kHaloGroups>::kMaxStages) st = HaloSmem<N, kHaloGroups>::kMaxStages;
   return (int)st;
 }
 
 template <int N, int MODE, int PH = 1>
-static int launch_conv_halo(const ConvLayer& L, const HaloParams& prm, cudaStream_t st) {
+static int launch_conv_halo(const ConvLayer& L, const HaloParams& prm, const HaloOutMaps& maps, cudaStream_t st) {
   auto kern = conv_halo_kernel<N, kHaloGroups, MODE, PH>;
   using HS = HaloSmem<N, kHaloGroups, PH>;
   static bool configured[64] = {false};
@@ -527,12 +546,13 @@ static int launch_conv_halo(const ConvLayer& L, const HaloParams& prm, cudaStrea
     RCU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmemBudget));
     configured[dev] = true;
   }
-  const size_t smem = (size_t)HS::kFixed + ((prm.w_bytes + 1023u) & ~1023u) + (size_t)prm.n_stages * prm.chunk_stride;
+  const size_t smem = (size_t)HS::kFixed + ((prm.w_bytes + 1023u) & ~1023u) + (size_t)prm.n_stages * prm.chunk_stride +
+                      (prm.tma_store ? HS::kOutBytes : 0);
   const long long total_tiles = (long long)prm.n_img * prm.tiles_y * prm.tiles_x;
   long long grid = sm_count();
   if (grid > total_tiles) grid = total_tiles;
   if (grid < 1) return RCU_OK;
-  kern<<<(unsigned)grid, HS::kThreads, smem, st>>>(L.map_halo, prm);
+  kern<<<(unsigned)grid, HS::kThreads, smem, st>>>(L.map_halo, maps, prm);
   RCU_LAUNCH_CHECK();
   return RCU_OK;
 }
@@ -798,12 +818,21 @@ extern "C" int rcu_unet_plan(rcu_unet* net, int height, int width, int max_image
     if (rc) return rc;
     if (L.halo.ok) {
       const uint32_t resident = L.halo.w_bytes * (uint32_t)(L.halo.n_phases == 4 ? L.halo.phases_per_launch : 1);
-      L.halo_stages = L.c_out == 32 ? halo_stage_count<32>(resident, L.halo.pair) : halo_stage_count<64>(resident, L.halo.pair);
+      // TMA-store epilogue when the staging slots still leave a deep enough ring
+      static const bool allow_tma_store = [] { const char* e = std::getenv("RCU_HALO_TMA_STORE"); return !(e && e[0] == '0'); }();
+      const int with_out = L.c_out == 32 ? halo_stage_count<32>(resident, L.halo.pair, true) : halo_stage_count<64>(resident, L.halo.pair, true);
+      L.tma_store = allow_tma_store && !L.head && with_out >= 2 * L.halo.n_chunks + 2;
+      L.halo_stages = L.tma_store ? with_out
+                                  : (L.c_out == 32 ? halo_stage_count<32>(resident, L.halo.pair) : halo_stage_count<64>(resident, L.halo.pair));
       if (L.halo_stages < 2) {
         L.halo.ok = false;
       } else {
         rc = make_halo_map(&L.map_halo, src, (int)N, L.halo.pair ? 32 : 64);
         if (rc) return rc;
+        for (int ph = 0; ph < L.halo.n_phases && L.tma_store; ++ph) {
+          rc = make_out_map(&L.map_out[ph], dst, (int)N, L.out_mul, L.halo.n_phases == 4 ? (ph >> 1) : 0, L.halo.n_phases == 4 ? (ph & 1) : 0);
+          if (rc) return rc;
+        }
       }
     }
     if (L.wide.ok) {
@@ -869,6 +898,9 @@ static int run_conv_halo(rcu_unet* net, const ConvLayer& L, int n_img, int cs, l
     prm.chunk_bytes = (uint32_t)(kHaloRows * kHaloPitch * (hp.pair ? 64 : 128));   // bytes TMA delivers (complete_tx counts data bytes)
     prm.chunk_stride = halo_chunk_stride(hp.pair);
     prm.n_stages = L.halo_stages;
+    prm.tma_store = L.tma_store ? 1 : 0;
+    HaloOutMaps maps;
+    for (int i = 0; i < ppl; ++i) maps.m[i] = L.map_out[ph + i];
     prm.tiles_per_turn = 1;   // measured: two tiles per turn is no faster (the hand-off is not what is exposed)
     {
       static const int tt = [] { const char* e = std::getenv("RCU_HALO_TT"); return e ? std::atoi(e) : 0; }();
@@ -899,11 +931,11 @@ static int run_conv_halo(rcu_unet* net, const ConvLayer& L, int n_img, int cs, l
     prm.chunk_slices = cs; prm.slice0 = s0; prm.n_slices_total = n_slices;
     int rc;
     if (hp.n_phases == 4) {
-      if (ppl == 4) rc = L.c_out == 32 ? launch_conv_halo<32, HALO_UP64, 4>(L, prm, st) : RCU_ENOTSUP;
-      else if (ppl == 2) rc = L.c_out == 32 ? launch_conv_halo<32, HALO_UP64, 2>(L, prm, st) : launch_conv_halo<64, HALO_UP64, 2>(L, prm, st);
-      else rc = L.c_out == 32 ? launch_conv_halo<32, HALO_UP64>(L, prm, st) : launch_conv_halo<64, HALO_UP64>(L, prm, st);
-    } else if (hp.pair) rc = L.c_out == 32 ? launch_conv_halo<32, HALO_CONV32>(L, prm, st) : launch_conv_halo<64, HALO_CONV32>(L, prm, st);
-    else rc = L.c_out == 32 ? launch_conv_halo<32, HALO_CONV64>(L, prm, st) : launch_conv_halo<64, HALO_CONV64>(L, prm, st);
+      if (ppl == 4) rc = L.c_out == 32 ? launch_conv_halo<32, HALO_UP64, 4>(L, prm, maps, st) : RCU_ENOTSUP;
+      else if (ppl == 2) rc = L.c_out == 32 ? launch_conv_halo<32, HALO_UP64, 2>(L, prm, maps, st) : launch_conv_halo<64, HALO_UP64, 2>(L, prm, maps, st);
+      else rc = L.c_out == 32 ? launch_conv_halo<32, HALO_UP64>(L, prm, maps, st) : launch_conv_halo<64, HALO_UP64>(L, prm, maps, st);
+    } else if (hp.pair) rc = L.c_out == 32 ? launch_conv_halo<32, HALO_CONV32>(L, prm, maps, st) : launch_conv_halo<64, HALO_CONV32>(L, prm, maps, st);
+    else rc = L.c_out == 32 ? launch_conv_halo<32, HALO_CONV64>(L, prm, maps, st) : launch_conv_halo<64, HALO_CONV64>(L, prm, maps, st);
     if (rc) return rc;
     ++*launches;
   }
