@@ -42,6 +42,7 @@ struct WideParams {
   long long coef_stride;
   int coef_off;
   int relu;
+  int tma_store;             // epilogue writes through swizzled smem staging + TMA tensor stores (see conv_halo.cuh)
 };
 
 template <int TAPS>   // 9: conv3x3, 4: one up-path phase per unit
@@ -59,19 +60,22 @@ struct WideCfg {
   static constexpr int kWStages = TAPS == 9 ? RCU_WIDE_WSTAGES : 3;
   static constexpr int kCoefBytes = 2 * kWideN * (int)sizeof(float2);
   static constexpr int kBarBytes = (2 * kAStages + 2 * kWStages + 4) * 8 + 16;
-  static constexpr int kSmem = 1024 + kAStages * kWideASlot + kWStages * kWSlot + kCoefBytes + kBarBytes;
+  static constexpr int kOutSlot = 128 * 64;                // 128 pixels x 32 channels, bf16, one per epilogue group
+  static constexpr int kSmem = 1024 + kAStages * kWideASlot + kWStages * kWSlot + 2 * kOutSlot + kCoefBytes + kBarBytes;
 };
 
 template <int TAPS>
 __global__ void __launch_bounds__(kWideThreads, 1)
-conv_wide_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ WideParams prm) {
+conv_wide_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ HaloOutMaps out_maps,
+                 const __grid_constant__ WideParams prm) {
   using C = WideCfg<TAPS>;
   extern __shared__ uint8_t smem_dyn[];
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_dyn + (base - smem_u32(smem_dyn));
   const uint32_t smem_a = base;
   const uint32_t smem_w = base + C::kAStages * kWideASlot;
-  const uint32_t tail = C::kAStages * kWideASlot + C::kWStages * C::kWSlot;
+  const uint32_t smem_out = base + C::kAStages * kWideASlot + C::kWStages * C::kWSlot;   // 1024-aligned
+  const uint32_t tail = C::kAStages * kWideASlot + C::kWStages * C::kWSlot + 2 * C::kOutSlot;
   float2* s_coef = reinterpret_cast<float2*>(base_ptr + tail);
   uint8_t* bar_ptr = base_ptr + tail + C::kCoefBytes;
   const uint32_t bar_afull = smem_u32(bar_ptr);
@@ -240,7 +244,24 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             __nv_bfloat162 b = __floats2bfloat162_rn(a0, a1);
             packed[c >> 1] = *reinterpret_cast<uint32_t*>(&b);
           }
-          if (valid) {
+          if (prm.tma_store) {
+            const uint32_t so = smem_out + (uint32_t)group * C::kOutSlot;
+            if (gt == 0) bulk_wait_group_read0();
+            asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
+            const uint32_t rowa = so + (uint32_t)row * 64u;
+            const uint32_t sw = (uint32_t)(row >> 1) & 3u;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + (((uint32_t)i ^ sw) << 4)), "r"(packed[4 * i]),
+                           "r"(packed[4 * i + 1]), "r"(packed[4 * i + 2]), "r"(packed[4 * i + 3])
+                           : "memory");
+            fence_proxy_async();
+            asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
+            if (gt == 0) {
+              tma_store_4d(&out_maps.m[TAPS == 4 ? ph : 0], so, nt * kWideN + cb, tx * kWideTile + s * 8, ty * kWideTile, img);
+              bulk_commit_group();
+            }
+          } else if (valid) {
             uint4* d4 = reinterpret_cast<uint4*>(dst + cb);
 #pragma unroll
             for (int i = 0; i < 4; ++i) d4[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
@@ -249,6 +270,7 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
       acc_phase ^= 1u;
     }
+    if (prm.tma_store && gt == 0) bulk_wait_group_read0();
   }
 
   tc_fence_before();

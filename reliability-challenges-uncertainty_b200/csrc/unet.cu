@@ -500,7 +500,7 @@ static int make_wide_map(CUtensorMap* map, const Act& a, int n) {
 }
 
 template <int TAPS>
-static int launch_conv_wide(const ConvLayer& L, const WideParams& prm, cudaStream_t st) {
+static int launch_conv_wide(const ConvLayer& L, const WideParams& prm, const HaloOutMaps& maps, cudaStream_t st) {
   auto kern = conv_wide_kernel<TAPS>;
   using C = WideCfg<TAPS>;
   static bool configured[64] = {false};
@@ -515,7 +515,7 @@ static int launch_conv_wide(const ConvLayer& L, const WideParams& prm, cudaStrea
   long long grid = sm_count();
   if (grid > total) grid = total;
   if (grid < 1) return RCU_OK;
-  kern<<<(unsigned)grid, kWideThreads, C::kSmem, st>>>(L.map_wide, prm);
+  kern<<<(unsigned)grid, kWideThreads, C::kSmem, st>>>(L.map_wide, maps, prm);
   RCU_LAUNCH_CHECK();
   return RCU_OK;
 }
@@ -838,6 +838,11 @@ extern "C" int rcu_unet_plan(rcu_unet* net, int height, int width, int max_image
     if (L.wide.ok) {
       rc = make_wide_map(&L.map_wide, src, (int)N);
       if (rc) return rc;
+      if (!L.halo.ok)
+        for (int ph = 0; ph < L.wide.n_phases; ++ph) {
+          rc = make_out_map(&L.map_out[ph], dst, (int)N, L.out_mul, L.wide.n_phases == 4 ? (ph >> 1) : 0, L.wide.n_phases == 4 ? (ph & 1) : 0);
+          if (rc) return rc;
+        }
     }
     Op op;
     op.kind = OP_CONV; op.conv = ci; op.out = L.head ? net->head_feat : dst;
@@ -1025,7 +1030,13 @@ extern "C" int rcu_unet_forward(rcu_unet* net, const float* images, int64_t n_sl
           wp.out_c = L.dst.c_total; wp.out_img_stride = L.dst.img_stride; wp.out = L.dst.base;
           wp.coef = net->d_coef; wp.coef_stride = net->n_cols; wp.coef_off = L.coef_off;
           wp.relu = L.relu;
-          int rc = L.wide.n_phases == 4 ? launch_conv_wide<4>(L, wp, st) : launch_conv_wide<9>(L, wp, st);
+          {
+            static const bool allow = [] { const char* e = std::getenv("RCU_WIDE_TMA_STORE"); return !(e && e[0] == '0'); }();
+            wp.tma_store = allow ? 1 : 0;
+          }
+          HaloOutMaps maps;
+          for (int i = 0; i < L.wide.n_phases; ++i) maps.m[i] = L.map_out[i];
+          int rc = L.wide.n_phases == 4 ? launch_conv_wide<4>(L, wp, maps, st) : launch_conv_wide<9>(L, wp, maps, st);
           if (rc) return rc;
           ++launches;
           continue;
