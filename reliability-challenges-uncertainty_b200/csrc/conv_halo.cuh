@@ -30,28 +30,17 @@ constexpr int kHaloTileH = 16;
 constexpr int kHaloTileW = 8;
 constexpr int kHaloPitch = kHaloTileW + 2;   // window pixels per row
 constexpr int kHaloRows = kHaloTileH + 2;    // window rows
-constexpr int kHaloMaxEntries = 20;
 enum HaloMode { HALO_CONV64 = 0, HALO_CONV32 = 1, HALO_UP64 = 2 };   // 3x3 conv over 64-ch chunks / a 32-ch source / one up-path phase
 constexpr int kHaloSmemBudget = 225 * 1024;
-
-struct HaloEntry {
-  uint32_t a_off16;   // offset of the A view inside a stage slot, 16-byte units
-  uint32_t b_off16;   // offset of the weight tile inside the weight image, 16-byte units
-  int n_k16;          // K = 16 steps to issue (4 = a full 128-byte row, 2 = half)
-  int pad;
-};
 
 struct HaloParams {
   int n_img, in_h, in_w, tiles_x, tiles_y;
   int n_chunks;              // TMA boxes (pipeline slots) per tile: c_in / 64, or 1 for a 32-channel source
-  int pair;                  // 32-channel source (informational: the entries carry n_k16 = 2)
   uint32_t chunk_bytes;      // bytes one box delivers
   uint32_t chunk_stride;     // slot size (multiple of 1024)
   int n_stages;
   int tma_store;             // epilogue stages bf16 tiles in shared memory and writes them with TMA tensor stores
   int tiles_per_turn;        // consecutive tiles an MMA issuer handles per issue turn (1 or 2)
-  int dbg;                   // experiment switches (RCU_HALO_DBG): 1 epilogue skips TMEM loads/stores, 16 no TMA loads,
-                             // 32 one MMA per chunk — timing experiments only, results are wrong
   // HALO_UP64: the PH up-path phases this launch computes per tile (one accumulator each).  Phase (a, b) reads the
   // window from (a * 10 + b) * 8 sixteen-byte units on and writes output pixel (2y + a, 2x + b).
   uint32_t up_base16[4];
@@ -80,13 +69,6 @@ __device__ __forceinline__ uint32_t elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
   return pred;
-}
-
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
 }
 
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -205,12 +187,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         for (int j = 0; j < prm.n_chunks; ++j) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
           const uint32_t dst = smem_a + (uint32_t)stage * prm.chunk_stride;
-          if (prm.dbg & 16) {
-            mbar_arrive(bar_full + 8 * stage);   // experiment: no loads at all
-          } else {
-            mbar_expect_tx(bar_full + 8 * stage, prm.chunk_bytes);
-            tma_load_4d(dst, &map_a, bar_full + 8 * stage, j * 64, x0, y0 - 1, img);
-          }
+          mbar_expect_tx(bar_full + 8 * stage, prm.chunk_bytes);
+          tma_load_4d(dst, &map_a, bar_full + 8 * stage, j * 64, x0, y0 - 1, img);
           if (++stage == prm.n_stages) { stage = 0; phase ^= 1u; }
         }
         if (++tx == prm.tiles_x) { tx = 0; if (++ty == prm.tiles_y) { ty = 0; ++img; } }
@@ -223,7 +201,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // shallow, so a single issuer leaves the pipe idle half of the time; with two issuers one warp's bookkeeping
     // hides behind the other's MMAs.  Control flow is warp-uniform, only the tcgen05 instructions are predicated on
     // elect.sync, so descriptors live in uniform registers and MMAs issue back to back.
-    const int n_issuers = (prm.dbg & 128) ? 1 : 2;   // experiment: single issuer
+    constexpr int n_issuers = 2;
     const int mw = warp - 1;
     const bool leader = elect_one() != 0;
     constexpr uint32_t idesc = make_idesc<N>();
@@ -338,12 +316,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
       mbar_wait(bar_tfull + 8 * group, acc_phase);
       tc_fence_after();
-      if (prm.dbg & 1) {
-        tc_fence_before();
-        mbar_arrive(bar_tempty + 8 * group);
-        acc_phase ^= 1u;
-        continue;
-      }
 
       const int y = ty * kHaloTileH + (row >> 3), x = tx * kHaloTileW + (row & 7);
       const bool valid = (y < prm.in_h) && (x < prm.in_w);

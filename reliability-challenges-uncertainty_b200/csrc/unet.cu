@@ -57,8 +57,6 @@ struct HaloPack {                  // create-time description of a layer the hal
   bool pair = false;               // 32-channel source: 64-byte pixel rows, two K = 16 steps per tap
   int n_chunks = 0;
   int n_phases = 1;
-  int n_entries = 0, e_split = 0;
-  HaloEntry entries[kMaxPhases][kHaloMaxEntries];
   uint8_t* d_wimg[kMaxPhases] = {nullptr, nullptr, nullptr, nullptr};   // per-phase views into one contiguous image
   uint32_t w_bytes = 0;            // bytes of ONE phase
   int phases_per_launch = 1;       // up path: 4, 2 or 1 phases share a launch (weights of all of them resident)
@@ -346,13 +344,12 @@ static int dispatch_conv_tc(const ConvLayer& L, const ConvParams& prm, cudaStrea
 
 // ---------------------------------------------------------------------------------------------------------
 // Halo-kernel weight images: a sequence of [c_out][64] bf16 tiles in the SWIZZLE_128B K-major shared-memory layout
-// (16-byte chunk index XOR (row & 7)), one tile per HaloEntry, copied verbatim into shared memory by the kernel.
+// (16-byte chunk index XOR (row & 7)), in the order the kernel's MMA loop walks them ([phase][chunk][tap]; two taps per tile for a
+// 32-channel source), copied verbatim into shared memory by the kernel.
 // ---------------------------------------------------------------------------------------------------------
 static inline size_t sw128_index(int n, int k) {  // element index inside a tile
   return (size_t)n * 64 + (size_t)((((k >> 3) ^ (n & 7)) << 3) + (k & 7));
 }
-
-static inline uint32_t halo_a_off16(int row, int col, int byte_in_row) { return (uint32_t)(((row * kHaloPitch + col) * 128 + byte_in_row) >> 4); }
 
 constexpr uint32_t kHaloMaxWeightBytes = 150 * 1024;
 
@@ -372,9 +369,7 @@ static int pack_halo_conv3x3(rcu_unet* net, const rcu_conv_unit& u, HaloPack& hp
       for (int n = 0; n < N; ++n)
         for (int k = 0; k < 32; ++k)
           img[(size_t)t * N * 64 + sw128_index(n, (tap & 1) * 32 + k)] = f32_to_bf16_rn(u.weight[((size_t)n * 32 + k) * 9 + tap]);
-      hp.entries[0][hp.n_entries++] = HaloEntry{halo_a_off16(tap / 3, tap % 3, 0), (uint32_t)(((size_t)t * N * 128 + (tap & 1) * 64) >> 4), 2, 0};
     }
-    hp.e_split = hp.n_entries;
   } else if (u.c_in == 64 || u.c_in == 128) {
     hp.pair = false; hp.n_chunks = u.c_in / 64;
     for (int j = 0; j < hp.n_chunks; ++j) {
@@ -383,9 +378,7 @@ static int pack_halo_conv3x3(rcu_unet* net, const rcu_conv_unit& u, HaloPack& hp
         for (int n = 0; n < N; ++n)
           for (int k = 0; k < 64; ++k)
             img[(size_t)t * N * 64 + sw128_index(n, k)] = f32_to_bf16_rn(u.weight[((size_t)n * u.c_in + j * 64 + k) * 9 + tap]);
-        hp.entries[0][hp.n_entries++] = HaloEntry{halo_a_off16(tap / 3, tap % 3, 0), (uint32_t)((size_t)t * N * 128 >> 4), 4, 0};
       }
-      if (j == 0) hp.e_split = hp.n_entries;
     }
   } else {
     return RCU_OK;
@@ -420,11 +413,11 @@ static int pack_halo_upconv(rcu_unet* net, const rcu_conv_unit& u, HaloPack& hp)
     for (int b = 0; b < 2; ++b) {
       const int ph = a * 2 + b;
       uint16_t* img = all.data() + (size_t)ph * hp.n_chunks * 4 * N * 64;
-      int t = 0, ne = 0;
+      int t = 0;
       for (int j = 0; j < hp.n_chunks; ++j) {
         for (int i2 = 0; i2 < 2; ++i2)
           for (int j2 = 0; j2 < 2; ++j2) {
-            const int dy = a == 0 ? i2 - 1 : i2, dx = b == 0 ? j2 - 1 : j2;
+            // tap (i2, j2) of phase (a, b) reads window row a + i2, column b + j2 (see pack_upconv_phases for the kernel sums)
             int ky0, ky1, kx0, kx1;
             if (a == 0) { ky0 = i2 == 0 ? 0 : 1; ky1 = i2 == 0 ? 0 : 2; } else { ky0 = i2 == 0 ? 0 : 2; ky1 = i2 == 0 ? 1 : 2; }
             if (b == 0) { kx0 = j2 == 0 ? 0 : 1; kx1 = j2 == 0 ? 0 : 2; } else { kx0 = j2 == 0 ? 0 : 2; kx1 = j2 == 0 ? 1 : 2; }
@@ -435,12 +428,9 @@ static int pack_halo_upconv(rcu_unet* net, const rcu_conv_unit& u, HaloPack& hp)
                   for (int kx = kx0; kx <= kx1; ++kx) sum += u.weight[((size_t)n * u.c_in + j * 64 + k) * 9 + ky * 3 + kx];
                 img[(size_t)t * N * 64 + sw128_index(n, k)] = f32_to_bf16_rn(sum);
               }
-            hp.entries[ph][ne++] = HaloEntry{halo_a_off16(dy + 1, dx + 1, 0), (uint32_t)((size_t)t * N * 128 >> 4), 4, 0};
             ++t;
           }
-        if (j == 0) hp.e_split = ne;
       }
-      hp.n_entries = ne;
     }
   uint16_t* d;
   int rc = dev_upload(net, all, &d);
@@ -899,7 +889,6 @@ static int run_conv_halo(rcu_unet* net, const ConvLayer& L, int n_img, int cs, l
     prm.tiles_x = (L.in_w + kHaloTileW - 1) / kHaloTileW;
     prm.tiles_y = (L.in_h + kHaloTileH - 1) / kHaloTileH;
     prm.n_chunks = hp.n_chunks;
-    prm.pair = hp.pair ? 1 : 0;
     prm.chunk_bytes = (uint32_t)(kHaloRows * kHaloPitch * (hp.pair ? 64 : 128));   // bytes TMA delivers (complete_tx counts data bytes)
     prm.chunk_stride = halo_chunk_stride(hp.pair);
     prm.n_stages = L.halo_stages;
@@ -910,10 +899,6 @@ static int run_conv_halo(rcu_unet* net, const ConvLayer& L, int n_img, int cs, l
     {
       static const int tt = [] { const char* e = std::getenv("RCU_HALO_TT"); return e ? std::atoi(e) : 0; }();
       if (tt == 2 && L.halo_stages >= 4 * hp.n_chunks) prm.tiles_per_turn = 2;
-    }
-    {
-      static const int dbg = [] { const char* e = std::getenv("RCU_HALO_DBG"); return e ? std::atoi(e) : 0; }();
-      prm.dbg = dbg;
     }
     for (int i = 0; i < ppl && hp.n_phases == 4; ++i) {
       const int a = (ph + i) >> 1, b = (ph + i) & 1;

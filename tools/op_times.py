@@ -1,4 +1,4 @@
-"""Per-op device time of a few chunks of the BraTS MC forward (timing experiments: RCU_HALO_DBG=n python tools/halo_dbg.py)."""
+"""Per-op device time of a few chunks of the BraTS MC forward: python tools/op_times.py [n_slices]."""
 import os
 import sys
 
@@ -27,13 +27,13 @@ for _ in range(reps):
 ms, launches = net.read_timing()
 ops = net.op_table()
 chunks = launches[0] / reps
-print('RCU_HALO_DBG=%s  chunks/forward=%d' % (os.environ.get('RCU_HALO_DBG', '0'), chunks))
+print('chunks/forward=%d (chunk_images=%d)' % (chunks, net.chunk_images))
 tot = 0.0
 for i, o in enumerate(ops):
     if launches[i] == 0:
         continue
     per = ms[i] / reps / chunks
     tot += per
-    tf = 2.0 * o['macs_per_image'] * 168 / (per * 1e-3) / 1e12 if o['macs_per_image'] else 0
+    tf = 2.0 * o['macs_per_image'] * (n_slices * 21.0 / chunks) / (per * 1e-3) / 1e12 if o['macs_per_image'] else 0
     print('op %2d %-10s %3d->%3d %3dx%-3d  %.4f ms/chunk  %6.0f TF' % (i, o['kind'], o['c_in'], o['c_out'], o['h'], o['w'], per, tf))
 print('total %.3f ms/chunk' % tot)
