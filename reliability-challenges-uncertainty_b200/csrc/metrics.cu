@@ -708,11 +708,13 @@ extern "C" int rcu_eval_fused(const float* p, const uint8_t* prediction, const u
     static const bool allow_lut = [] { const char* e = std::getenv("RCU_HIST_LUT"); return !(e && e[0] == '0'); }();
     const bool aligned = reinterpret_cast<uintptr_t>(p) % 16 == 0 && reinterpret_cast<uintptr_t>(target) % 4 == 0 &&
                          reinterpret_cast<uintptr_t>(prediction) % 4 == 0 && (mask == nullptr || reinterpret_cast<uintptr_t>(mask) % 4 == 0);
-    const int n_buckets = (allow_lut && aligned && (n_subjects == 1 || vps % 4 == 0)) ? 1024 : 0;
+    static const int lut_buckets = [] { const char* e = std::getenv("RCU_HIST_BUCKETS"); return e ? std::atoi(e) : 1024; }();
+    const int n_buckets = (allow_lut && aligned && (n_subjects == 1 || vps % 4 == 0)) ? lut_buckets : 0;
     if (n_buckets > 0) {
       RCU_CHECK_ARG(workspace_bytes >= rcu_metrics_workspace_bytes(n_subjects), "metrics workspace too small");
       const int sms = sm_count();
-      long long bps = ((long long)sms * 3 + n_subjects - 1) / n_subjects;
+      static const int lut_bpsm = [] { const char* e = std::getenv("RCU_HIST_BPSM"); return e ? std::atoi(e) : 2; }();
+      long long bps = ((long long)sms * lut_bpsm + n_subjects - 1) / n_subjects;
       const long long groups = (vps + 3) / 4;
       if (bps * 256 > groups) bps = groups / 256;
       if (bps < 1) bps = 1;

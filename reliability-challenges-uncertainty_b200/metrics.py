@@ -167,11 +167,17 @@ def eval_fused(p, prediction, target, mask=None, n_bins=10, thresholds=tables.SW
     vps = n // max(n_subjects, 1)
     _check_lengths(n, vps, n_subjects, prediction=d_d, target=t_d, mask=m_d)
     dev = p_d.device
-    count = torch.zeros((n_subjects, n_bins + 1), dtype=torch.int64, device=dev)
-    positives = torch.zeros_like(count)
-    conf = torch.zeros((n_subjects, n_bins + 1), dtype=torch.float64, device=dev)
-    table = torch.zeros((n_subjects, 4, n_classes), dtype=torch.int64, device=dev)
-    invalid = torch.zeros((n_subjects,), dtype=torch.int64, device=dev)
+    # one allocation for all five result tables (the kernel's last block writes every slot, nothing needs zeroing):
+    # the single-subject call is otherwise bound by five tiny memset launches
+    nb1 = n_bins + 1
+    width = 3 * nb1 + 4 * n_classes + 1
+    flat = (torch.empty if n > 0 else torch.zeros)((n_subjects * width,), dtype=torch.int64, device=dev)
+    o1, o2, o3, o4 = n_subjects * nb1, 2 * n_subjects * nb1, 3 * n_subjects * nb1, 3 * n_subjects * nb1 + n_subjects * 4 * n_classes
+    count = flat[:o1].view(n_subjects, nb1)
+    positives = flat[o1:o2].view(n_subjects, nb1)
+    conf = flat[o2:o3].view(torch.float64).view(n_subjects, nb1)
+    table = flat[o3:o4].view(n_subjects, 4, n_classes)
+    invalid = flat[o4:]
     if n > 0:
         edges, edges_p = _f32_array(tables.calibration_edges_f32(n_bins))
         b32, b32_p = _f32_array(breaks)

@@ -119,7 +119,10 @@ def test_fused_equals_separate_and_confusion(s):
     c, po, cf, tab, inv, _ = metrics.eval_fused(p, pred, target, mask, n_subjects=s)
     c2, po2, cf2 = metrics.calibration_tables(p, target, mask, n_subjects=s)
     tab2, _, _ = metrics.ue_tables(p, pred, target, kind='p', n_subjects=s)
-    assert np.array_equal(c, c2) and np.array_equal(po, po2) and np.array_equal(cf, cf2) and np.array_equal(tab, tab2)
+    assert np.array_equal(c, c2) and np.array_equal(po, po2) and np.array_equal(tab, tab2)
+    # float64 confidence sums: the fused and the separate kernels split a subject into different block ranges, which
+    # changes the summation order only
+    assert np.allclose(cf, cf2, rtol=CONF_RTOL, atol=0)
     cm = metrics.confusion_counts(pred, target, n_subjects=s)
     assert np.array_equal(cm, tab.sum(axis=2))
     vps = n // s
