@@ -161,6 +161,30 @@ int rcu_philox_masks_host(uint64_t seed, float p_drop, const int* site_channels,
                           int64_t n_slices, int sample0, int n_samples, float* scale_host);
 
 /* ------------------------------------------------------------------------------------------------
+ * Evaluation-side preparations (between the saved maps and the metric kernels)
+ * ------------------------------------------------------------------------------------------------ */
+
+/* common/utils/labelhelper.py:12-20 boarder_mask(binary_label_map, distance_in, distance_out) as used by
+ * rechun/eval/analysis.py:109-116 (distance_in = distance_out = 1): mask[v] = (dist_in[v] <= distance_in) *
+ * (dist_out[v] <= distance_out) with the Euclidean distance transforms of the map and its complement, unit spacing.
+ * label / mask: uint8[d0][d1][d2] device arrays (a 2-D map is d0 = 1).  Maps without any voxel of the opposite class
+ * give an all-zero mask (scipy's transform is not defined there). */
+int rcu_border_mask(const uint8_t* label, int d0, int d1, int d2, int distance_in, int distance_out, uint8_t* mask, void* stream);
+
+/* entry_np.min() / entry_np.max() of RescaleSubjectMinMax (rechun/eval/analysis.py:169-178).  out3 is a DEVICE array of
+ * three uint32: order-preserving keys of min and max (decode with rcu_minmax_decode) and the number of NaNs skipped. */
+int rcu_minmax(const float* values, int64_t n, uint32_t* out3, void* stream);
+float rcu_minmax_decode(uint32_t key);
+
+/* rechun/eval/helper.py:18-21 rescale_uncertainties followed by helper.py:7-15 uncertainty_to_foreground_probabilities:
+ *   p = ((u - lo) / range) * scale + epsilon      (only when rescale != 0; each operation rounded to float32 like numpy)
+ *   foreground = prediction == 1 ? 1 - p * 0.5 : p * 0.5
+ * invalid2 (device, 2 x uint64): [0] values of p outside [0, 1] or NaN, [1] predictions > 1 — the two conditions the
+ * reference raises ValueError for (helper.py:10-12,30-46). */
+int rcu_confidence_to_foreground(const float* uncertainty, const uint8_t* prediction, int64_t n, int rescale, float lo, float range,
+                                 float scale, float epsilon, float* foreground, uint64_t* invalid2, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * U-Net forward (tcgen05 implicit-GEMM convolutions)
  * ------------------------------------------------------------------------------------------------ */
 
@@ -179,7 +203,7 @@ typedef struct rcu_conv_unit {
 } rcu_conv_unit;
 
 /* Topology and weights of common/model/unet.py:123-186 UNet(nb_classes=2, in_channels, depth, start_filters,
- * dropout, dropout_center) with residual=False, sigma_out=False, bn=True.  Arrays are host pointers.
+ * dropout, dropout_center[, sigma_out]) with residual=False, bn=True.  Arrays are host pointers.
  *   units   : 2*depth + 2 + 2*depth + 1 Conv2dBnRelu units in forward order (down blocks, bottom, up blocks, conv_cls.0)
  *   upconvs : depth plain 3x3 convs `up_convs.i.upconv.1` (bias only, applied after nearest x2), bn_* = NULL
  *   head    : `conv_cls.1`, 1x1, c_in = start_filters, c_out = 2 (weight [2][c_in][1][1])
@@ -193,6 +217,10 @@ typedef struct rcu_unet_desc {
   const rcu_conv_unit* upconvs;
   int n_upconvs;
   rcu_conv_unit head;
+  /* sigma_out=True nets (unet.py:162-164, config/train_brats_aleatoric.yaml:12): `conv_sigma.0` (a Conv2dBnRelu on the
+   * same features as conv_cls.0) and `conv_sigma.1` (1x1 -> 2).  Both NULL for sigma_out=False. */
+  const rcu_conv_unit* sigma_unit;
+  const rcu_conv_unit* sigma_head;
 } rcu_unet_desc;
 
 /* Folds BN into per-channel scale/shift, converts weights to the device layout, uploads them. */
@@ -220,6 +248,34 @@ int rcu_unet_plan(rcu_unet* net, int height, int width, int max_images_per_chunk
 int rcu_unet_forward(rcu_unet* net, const float* images, int64_t n_slices, int n_samples, int dropout_mode,
                      int det_first, uint64_t seed, int64_t slice_index0, int sample0, const float* scale,
                      float* logits, void* stream);
+
+/* PostNet (common/model/postnet.py:6-17): n_units 1x1 Conv2dBnRelu units (c_in = c_out = 32, weight [32][32][1][1],
+ * eval mode) followed by a 1x1 logits conv 32 -> 2; the auxiliary-feature method runs it on `UNet.features`
+ * (bin-dl/brats_test_auxiliary_feat.py:61-80). */
+typedef struct rcu_postnet rcu_postnet;
+int rcu_postnet_create(const rcu_conv_unit* units, int n_units, const rcu_conv_unit* head, float bn_eps, int device, rcu_postnet** out);
+void rcu_postnet_destroy(rcu_postnet* post);
+/* Stand-alone call on a materialised feature tensor: float32[n_images][32][hw] (NCHW) -> pixel-interleaved logits
+ * float32[n_images][hw][2].  Stands behind `context.model(self.test_model.features)` (brats_test_auxiliary_feat.py:77). */
+int rcu_postnet_forward(const rcu_postnet* post, const float* features, int64_t n_images, int64_t hw, float* logits, void* stream);
+
+/* Optional outputs of rcu_unet_forward_ex; NULL members are skipped (and cost nothing).
+ *   logits          as rcu_unet_forward (required)
+ *   sigma           `out_sigma` of a sigma_out net (unet.py:185-186), raw conv_sigma output, same layout as logits;
+ *                   AleatoricPredictStep's abs()/exp() (bin-dl/brats_test_aleatoric.py:62-66) is left to the caller
+ *   features        `UNet.features` (unet.py:178-179): float32[n_samples][n_slices][start_filters][H][W]
+ *   postnet/postnet_logits   run `postnet` on the features while they are still in the workspace (bf16, never
+ *                   materialised as float32) and write its logits, same layout as `logits` */
+typedef struct rcu_unet_outputs {
+  float* logits;
+  float* sigma;
+  float* features;
+  const rcu_postnet* postnet;
+  float* postnet_logits;
+} rcu_unet_outputs;
+int rcu_unet_forward_ex(rcu_unet* net, const float* images, int64_t n_slices, int n_samples, int dropout_mode,
+                        int det_first, uint64_t seed, int64_t slice_index0, int sample0, const float* scale,
+                        const rcu_unet_outputs* out, void* stream);
 
 /* Introspection used by tests and the benchmark. */
 int rcu_unet_total_dropout_channels(const rcu_unet* net);

@@ -19,6 +19,11 @@ Reference citations (path:line relative to the reference root):
   Dice / accuracy / cm ..... common/evalutation/numpyfunctions.py:128-151 (+ pymia 0.2.1 metric classes, restated)
   eval-side preparation .... rechun/eval/helper.py:25-47; rechun/eval/analysis.py:147-151,189-203
   threshold sweep / table .. bin-eval/eval_uncertainty.py:176-202,239; bin-analysis/table_ece_ue_bnf_dice.py:56-59
+  sigma head / aleatoric ... common/model/unet.py:162-164,181-186; bin-dl/brats_test_aleatoric.py:51-73
+  features / PostNet ....... common/model/unet.py:178-179; common/model/postnet.py:6-17; bin-dl/brats_test_auxiliary_feat.py:61-80
+  auxiliary segm input ..... bin-dl/brats_test_auxiliary_segm.py:48-69
+  border mask .............. common/utils/labelhelper.py:12-20
+  confidence -> p .......... rechun/eval/helper.py:7-22
 """
 import math
 from collections import OrderedDict
@@ -37,7 +42,9 @@ SWEEP_THRESHOLDS = (0.05, 0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9, 0.95)  # 
 class UNetConfig:
     """Constructor arguments of the reference UNet that the hot path supports."""
 
-    def __init__(self, nb_classes=2, in_channels=4, depth=4, start_filters=32, dropout=0.05, dropout_center=None):
+    def __init__(self, nb_classes=2, in_channels=4, depth=4, start_filters=32, dropout=0.05, dropout_center=None,
+                 sigma_out=False):
+        self.sigma_out = sigma_out
         self.nb_classes = nb_classes
         self.in_channels = in_channels
         self.depth = depth
@@ -86,9 +93,16 @@ def conv_sites(cfg):
     return sites
 
 
+SIGMA_PREFIX = 'conv_sigma.0.conv2d_batch_relu'
+
+
 def dropout_sites(cfg):
-    """[(prefix, channels)] of the units that own a Dropout2d, in forward order."""
-    return [(p, co) for (p, ci, co, d) in conv_sites(cfg) if d]
+    """[(prefix, channels)] of the units that own a Dropout2d, in forward order (conv_sigma.0 of a sigma_out net
+    runs after conv_cls, unet.py:181-185)."""
+    sites = [(p, co) for (p, ci, co, d) in conv_sites(cfg) if d]
+    if cfg.sigma_out and cfg.dropout is not None:
+        sites.append((SIGMA_PREFIX, cfg.start_filters))
+    return sites
 
 
 def init_state_dict(cfg, seed):
@@ -135,6 +149,9 @@ def init_state_dict(cfg, seed):
     p, ci, co, _ = sites[k]
     unit(p, ci, co)
     conv('conv_cls.1', cfg.nb_classes, co, 1)
+    if cfg.sigma_out:  # unet.py:162-164
+        unit(SIGMA_PREFIX, co, co)
+        conv('conv_sigma.1', cfg.nb_classes, co, 1)
     torch.random.set_rng_state(gen_state)
 
     # state_dict order of the reference module tree: inside UpConv, `block` is registered before `upconv`
@@ -179,11 +196,13 @@ def _unit(x, sd, prefix, p_drop, keep):
     return F.relu(y)
 
 
-def unet_forward(sd, x, cfg, keep_masks=None):
+def unet_forward(sd, x, cfg, keep_masks=None, return_all=False):
     """Logits (N, nb_classes, H, W) of the reference UNet in eval mode.
 
     keep_masks: None (all Dropout2d in eval mode = identity) or a list, one entry per dropout site in
     forward order, of (N, C) {0,1} tensors = the Bernoulli keep decisions of Dropout2d in train mode.
+    return_all: a dict with 'logits', 'features' (the conv_cls input, unet.py:178-179) and, for sigma_out nets,
+    'sigma' (unet.py:185-186).
     """
     sites = conv_sites(cfg)
     masks = iter(keep_masks) if keep_masks is not None else None
@@ -216,8 +235,17 @@ def unet_forward(sd, x, cfg, keep_masks=None):
         x = run(x, idx)
         x = run(x, idx + 1)
         idx += 2
-    x = run(x, idx)
-    return F.conv2d(x, sd['conv_cls.1.weight'], sd['conv_cls.1.bias'])
+    features = x
+    x = run(features, idx)
+    logits = F.conv2d(x, sd['conv_cls.1.weight'], sd['conv_cls.1.bias'])
+    if not return_all:
+        return logits
+    out = {'logits': logits, 'features': features}
+    if cfg.sigma_out:
+        keep = next(masks) if (masks is not None and cfg.dropout is not None) else None
+        y = _unit(features, sd, SIGMA_PREFIX, cfg.dropout, keep)
+        out['sigma'] = F.conv2d(y, sd['conv_sigma.1.weight'], sd['conv_sigma.1.bias'])
+    return out
 
 
 def predict_deterministic(sd, images, cfg):
@@ -244,6 +272,68 @@ def predict_ensemble(state_dicts, images, cfg):
     """EnsemblePredictionStep (bin-dl/brats_test_ensemble.py:78-94)."""
     images = images.float()
     return {'multi_probabilities': torch.stack([F.softmax(unet_forward(sd, images, cfg), 1) for sd in state_dicts])}
+
+
+def predict_aleatoric(sd, images, cfg, is_log_sigma=False):
+    """AleatoricPredictStep (bin-dl/brats_test_aleatoric.py:51-73)."""
+    out = unet_forward(sd, images.float(), cfg, return_all=True)
+    sigma = out['sigma'].exp() if is_log_sigma else out['sigma'].abs()
+    return {'logits': out['logits'], 'sigma': sigma, 'probabilities': F.softmax(out['logits'], 1)}
+
+
+def postnet_init_state_dict(in_channels, nb_classes, nb_convs, seed):
+    """`torch.manual_seed(seed); PostNet(in_channels, nb_classes, nb_convs).state_dict()` (common/model/postnet.py:8-12)."""
+    gen_state = torch.random.get_rng_state()
+    torch.manual_seed(seed)
+    sd = OrderedDict()
+
+    def conv(prefix, c_out, c_in):
+        w = torch.empty(c_out, c_in, 1, 1)
+        torch.nn.init.kaiming_uniform_(w, a=math.sqrt(5))
+        bound = 1 / math.sqrt(c_in)
+        b = torch.empty(c_out)
+        torch.nn.init.uniform_(b, -bound, bound)
+        sd[prefix + '.weight'] = w
+        sd[prefix + '.bias'] = b
+    for i in range(nb_convs):
+        p = 'convs.%d.conv2d_batch_relu' % i
+        conv(p + '.conv', in_channels, in_channels)
+        sd[p + '.bn.weight'] = torch.ones(in_channels)
+        sd[p + '.bn.bias'] = torch.zeros(in_channels)
+        sd[p + '.bn.running_mean'] = torch.zeros(in_channels)
+        sd[p + '.bn.running_var'] = torch.ones(in_channels)
+        sd[p + '.bn.num_batches_tracked'] = torch.tensor(0, dtype=torch.long)
+    conv('conv_logits', nb_classes, in_channels)
+    torch.random.set_rng_state(gen_state)
+    return sd
+
+
+def postnet_forward(sd, x):
+    """PostNet.forward in eval mode (common/model/postnet.py:14-17)."""
+    i = 0
+    while 'convs.%d.conv2d_batch_relu.conv.weight' % i in sd:
+        p = 'convs.%d.conv2d_batch_relu' % i
+        x = F.conv2d(x, sd[p + '.conv.weight'], sd[p + '.conv.bias'])
+        x = F.batch_norm(x, sd[p + '.bn.running_mean'], sd[p + '.bn.running_var'], sd[p + '.bn.weight'], sd[p + '.bn.bias'],
+                         False, 0.0, BN_EPS)
+        x = F.relu(x)
+        i += 1
+    return F.conv2d(x, sd['conv_logits.weight'], sd['conv_logits.bias'])
+
+
+def predict_aux_feat(sd_unet, cfg, sd_postnet, images):
+    """SegmentationPredictStep(test_model) of bin-dl/brats_test_auxiliary_feat.py:61-80."""
+    out = unet_forward(sd_unet, images.float(), cfg, return_all=True)
+    return {'segm_probabilities': F.softmax(out['logits'], 1), 'features': out['features'],
+            'probabilities': F.softmax(postnet_forward(sd_postnet, out['features']), 1)}
+
+
+def predict_aux_segm(sd, images, labels, cfg):
+    """SegmentationPredictStep of bin-dl/brats_test_auxiliary_segm.py:48-69 (cfg.in_channels = image channels + 1)."""
+    pred = labels.long()[:, 1]
+    inpt = torch.cat([images.float(), pred.unsqueeze(1).float()], dim=1)
+    logits = unet_forward(sd, inpt, cfg)
+    return {'logits': logits, 'probabilities': F.softmax(logits, 1), 'orig_prediction': pred.unsqueeze(1)}
 
 
 def torch_entropy(p, dim=-1, keepdim=False):
@@ -405,6 +495,33 @@ def normalized_entropy(prob_2class):
 # ------------------------------------------------------------------------------------------------
 # Confusion / Dice / accuracy (numpyfunctions.py:128-151 via pymia 0.2.1 metric classes)
 # ------------------------------------------------------------------------------------------------
+def boarder_mask(binary_label_map, distance_in=1, distance_out=1):
+    """common/utils/labelhelper.py:12-20: voxels within `distance_in` of the background (inside the object) and within
+    `distance_out` of the object (outside).  Returns (dist_in + dist_out, mask)."""
+    import scipy.ndimage
+    m = np.asarray(binary_label_map).astype(bool)
+    dist_in = scipy.ndimage.distance_transform_edt(m)
+    dist_out = scipy.ndimage.distance_transform_edt(~m)
+    return dist_in + dist_out, (dist_in <= distance_in) * (dist_out <= distance_out)
+
+
+def rescale_uncertainties(uncertainty, min_, max_, epsilon=1e-5):
+    """rechun/eval/helper.py:18-21."""
+    rescaled = (uncertainty - min_) / (max_ - min_)
+    return rescaled * (1 - 2 * epsilon) + epsilon
+
+
+def uncertainty_to_foreground_probabilities(uncertainty, prediction):
+    """rechun/eval/helper.py:7-15."""
+    if prediction.shape != uncertainty.shape:
+        raise ValueError('shapes must agree. Found {} and {}'.format(uncertainty.shape, prediction.shape))
+    if uncertainty.max() > 1 or uncertainty.min() < 0 or prediction.max() > 1:
+        raise ValueError('values outside the valid range')
+    p = uncertainty * 0.5
+    p[prediction == 1] = 1 - p[prediction == 1]
+    return p
+
+
 def confusion(prediction, target):
     tp = np.sum(np.logical_and(prediction == 1, target == 1))
     tn = np.sum(np.logical_and(prediction == 0, target == 0))

@@ -29,7 +29,13 @@ class RcuConvUnit(ctypes.Structure):
 class RcuUnetDesc(ctypes.Structure):
     _fields_ = [('in_channels', c_int), ('depth', c_int), ('start_filters', c_int), ('nb_classes', c_int),
                 ('p_drop', c_float), ('bn_eps', c_float), ('units', ctypes.POINTER(RcuConvUnit)), ('n_units', c_int),
-                ('upconvs', ctypes.POINTER(RcuConvUnit)), ('n_upconvs', c_int), ('head', RcuConvUnit)]
+                ('upconvs', ctypes.POINTER(RcuConvUnit)), ('n_upconvs', c_int), ('head', RcuConvUnit),
+                ('sigma_unit', ctypes.POINTER(RcuConvUnit)), ('sigma_head', ctypes.POINTER(RcuConvUnit))]
+
+
+class RcuUnetOutputs(ctypes.Structure):
+    _fields_ = [('logits', c_void_p), ('sigma', c_void_p), ('features', c_void_p), ('postnet', c_void_p),
+                ('postnet_logits', c_void_p)]
 
 
 # name -> (restype, argtypes); mirrors include/rcu_b200.h one to one
@@ -54,11 +60,22 @@ PROTOTYPES = {
                                      c_void_p, c_void_p, c_void_p]),
     'rcu_philox_masks': (c_int, [c_uint64, c_float, c_int_p, c_int, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p]),
     'rcu_philox_masks_host': (c_int, [c_uint64, c_float, c_int_p, c_int, c_int64, c_int64, c_int, c_int, c_float_p]),
+    'rcu_border_mask': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'rcu_minmax': (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    'rcu_minmax_decode': (c_float, [ctypes.c_uint32]),
+    'rcu_confidence_to_foreground': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_float, c_float, c_float, c_float, c_void_p,
+                                             c_void_p, c_void_p]),
     'rcu_unet_create': (c_int, [ctypes.POINTER(RcuUnetDesc), c_int, ctypes.POINTER(c_void_p)]),
     'rcu_unet_destroy': (None, [c_void_p]),
     'rcu_unet_plan': (c_int, [c_void_p, c_int, c_int, c_int, ctypes.POINTER(c_size_t)]),
     'rcu_unet_forward': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_uint64, c_int64, c_int, c_void_p,
                                  c_void_p, c_void_p]),
+    'rcu_unet_forward_ex': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_uint64, c_int64, c_int, c_void_p,
+                                    ctypes.POINTER(RcuUnetOutputs), c_void_p]),
+    'rcu_postnet_create': (c_int, [ctypes.POINTER(RcuConvUnit), c_int, ctypes.POINTER(RcuConvUnit), c_float, c_int,
+                                   ctypes.POINTER(c_void_p)]),
+    'rcu_postnet_destroy': (None, [c_void_p]),
+    'rcu_postnet_forward': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     'rcu_unet_total_dropout_channels': (c_int, [c_void_p]),
     'rcu_unet_debug_activation': (c_int, [c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     'rcu_unet_set_conv_impl': (c_int, [c_void_p, c_int]),

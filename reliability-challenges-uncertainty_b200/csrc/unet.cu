@@ -18,6 +18,7 @@
 #include "conv_wide.cuh"
 #include "philox.cuh"
 #include "unet_kernels.cuh"
+#include "postnet.cuh"
 
 namespace rcu {
 
@@ -77,6 +78,8 @@ struct ConvLayer {
   int coef_off = 0;
   int block_n = 0, kc = 0;
   bool head = false;
+  const float* d_head = nullptr;         // fused 1x1 head of this layer: [2][c_out] + [2]
+  int out_slot = 0;                      // 0: class logits (conv_cls), 1: sigma logits (conv_sigma, unet.py:162-164)
   HaloPack halo;
   WidePack wide;
   // plan-time
@@ -111,7 +114,9 @@ struct rcu_unet {
   // device constants
   float* d_first_w = nullptr;            // [c_in*9][sf]
   int first_coef_off = 0;
-  float* d_head = nullptr;               // [2][sf] + [2]
+  float* d_head = nullptr;               // conv_cls.1:   [2][sf] + [2]
+  float* d_sigma_head = nullptr;         // conv_sigma.1: [2][sf] + [2] (sigma_out nets only)
+  bool has_sigma = false;
   std::vector<ConvLayer> convs;          // execution order
   CoefColumns cols{};
   std::vector<void*> owned;              // device allocations freed in destroy
@@ -123,6 +128,8 @@ struct rcu_unet {
   float2* d_coef = nullptr;
   Act first_out;
   Act head_feat;                         // features of conv_cls.0 for the cross-check path
+  Act sigma_feat;                        // same for conv_sigma.0
+  Act features;                          // input of conv_cls = `UNet.features` (unet.py:178-179)
   std::vector<Op> ops;
   int conv_impl = 0;
   unsigned long long halo_mask = ~0ull;  // debug: bit i enables the halo kernel for conv i (execution order)
@@ -134,6 +141,36 @@ struct rcu_unet {
   std::vector<int> ev_op;      // op index of every recorded pair since the last read
   size_t ev_used = 0;
 };
+
+struct rcu_postnet {
+  int device = 0;
+  int n_convs = 0;
+  rcu::PostNetWeights w;   // host copy; passed by value as a __grid_constant__ kernel parameter
+};
+
+namespace rcu {
+static int launch_postnet(const rcu_postnet* post, bool src_bf16, const void* src, int px_stride, long long img_stride, int hw, int n_img,
+                          int chunk_slices, long long slice0, long long n_slices_total, float* logits, cudaStream_t st) {
+  const long long total = (long long)n_img * hw;
+  if (total == 0) return RCU_OK;
+  long long blocks = (total + 127) / 128;
+  if (blocks > (long long)sm_count() * 64) blocks = (long long)sm_count() * 64;
+#define RCU_POSTNET_CASE(NC)                                                                                                      \
+  case NC:                                                                                                                        \
+    if (src_bf16) postnet_kernel<NC, true><<<(unsigned)blocks, 128, 0, st>>>(post->w, src, px_stride, img_stride, hw, n_img,      \
+                                                                              chunk_slices, slice0, n_slices_total, logits);      \
+    else postnet_kernel<NC, false><<<(unsigned)blocks, 128, 0, st>>>(post->w, src, px_stride, img_stride, hw, n_img, chunk_slices, \
+                                                                     slice0, n_slices_total, logits);                              \
+    break;
+  switch (post->n_convs) {
+    RCU_POSTNET_CASE(1) RCU_POSTNET_CASE(2) RCU_POSTNET_CASE(3) RCU_POSTNET_CASE(4)
+    default: set_error("PostNet with %d convs", post->n_convs); return RCU_ENOTSUP;
+  }
+#undef RCU_POSTNET_CASE
+  RCU_LAUNCH_CHECK();
+  return RCU_OK;
+}
+}  // namespace rcu
 
 namespace rcu {
 struct OpTimer {  // brackets one launch with events when timing is on
@@ -574,10 +611,17 @@ extern "C" int rcu_unet_create(const rcu_unet_desc* d, int device, rcu_unet** ou
   // ---- column tables (units first, then upconvs) ----
   std::vector<float> fa, fba, fd;
   std::vector<int> site, chin, scol;
-  std::vector<int> unit_off(d->n_units), up_off(d->n_upconvs);
+  // sigma_out nets (unet.py:162-164) carry one more Conv2dBnRelu + 1x1 head on the same features; its unit (and its
+  // Dropout2d site) come after conv_cls.0, the order the reference's forward visits them in (unet.py:181-185)
+  const bool has_sigma = d->sigma_unit != nullptr;
+  if (has_sigma && d->sigma_head == nullptr) { set_error("sigma_unit without sigma_head"); rcu_unet_destroy(net); return RCU_EINVAL; }
+  net->has_sigma = has_sigma;
+  const int n_all_units = d->n_units + (has_sigma ? 1 : 0);
+  auto unit_at = [&](int u) -> const rcu_conv_unit& { return u < d->n_units ? d->units[u] : *d->sigma_unit; };
+  std::vector<int> unit_off(n_all_units), up_off(d->n_upconvs);
   int n_sites = 0, drop_cols = 0;
-  for (int u = 0; u < d->n_units; ++u) {
-    const rcu_conv_unit& cu = d->units[u];
+  for (int u = 0; u < n_all_units; ++u) {
+    const rcu_conv_unit& cu = unit_at(u);
     if (!(cu.weight && cu.bias && cu.bn_weight && cu.bn_bias && cu.bn_mean && cu.bn_var)) {
       set_error("unit %d: NULL weight/bn pointer (bn=False nets are outside the hot path)", u);
       rcu_unet_destroy(net);
@@ -622,24 +666,27 @@ extern "C" int rcu_unet_create(const rcu_unet_desc* d, int device, rcu_unet** ou
     RCU_TRY(dev_upload(net, w, &net->d_first_w));
     net->first_coef_off = unit_off[0];
   }
-  // ---- head ----
-  {
-    const rcu_conv_unit& h = d->head;
-    if (!(h.weight && h.bias) || h.c_in != sf || h.c_out != 2) { set_error("head must be a 1x1 conv start_filters -> 2"); rcu_unet_destroy(net); return RCU_EINVAL; }
+  // ---- 1x1 heads ----
+  auto upload_head = [&](const rcu_conv_unit& h, float** out_ptr) -> int {
+    if (!(h.weight && h.bias) || h.c_in != sf || h.c_out != 2) { set_error("head must be a 1x1 conv start_filters -> 2"); return RCU_EINVAL; }
     std::vector<float> hw((size_t)2 * sf + 2);
     for (int i = 0; i < 2 * sf; ++i) hw[i] = h.weight[i];
     hw[2 * sf] = h.bias[0];
     hw[2 * sf + 1] = h.bias[1];
-    RCU_TRY(dev_upload(net, hw, &net->d_head));
-  }
+    return dev_upload(net, hw, out_ptr);
+  };
+  RCU_TRY(upload_head(d->head, &net->d_head));
+  if (has_sigma) RCU_TRY(upload_head(*d->sigma_head, &net->d_sigma_head));
   // ---- tensor-core conv layers in execution order ----
-  auto add_unit = [&](int u, int c0, int c1, bool head) -> int {
-    const rcu_conv_unit& cu = d->units[u];
+  auto add_unit = [&](int u, int c0, int c1, bool head, int out_slot = 0) -> int {
+    const rcu_conv_unit& cu = unit_at(u);
     if (cu.c_in != c0 + c1) { set_error("unit %d: c_in=%d does not match the topology (%d)", u, cu.c_in, c0 + c1); return RCU_EINVAL; }
     ConvLayer L;
     L.c0 = c0; L.c1 = c1; L.c_out = cu.c_out; L.n_taps = 9; L.n_phases = 1; L.out_mul = 1; L.relu = 1; L.head = head;
     for (int t = 0; t < 9; ++t) { L.dy[0][t] = (signed char)(t / 3 - 1); L.dx[0][t] = (signed char)(t % 3 - 1); }
     L.coef_off = unit_off[u];
+    L.out_slot = out_slot;
+    L.d_head = out_slot ? net->d_sigma_head : net->d_head;
     int rc2 = pick_tiles(c1 > 0 ? (c0 < c1 ? c0 : c1) : c0, cu.c_out, &L.block_n, &L.kc);
     if (rc2) return rc2;
     if (head && (L.block_n != 32 || cu.c_out != 32)) { set_error("fused head needs start_filters == 32"); return RCU_ENOTSUP; }
@@ -695,6 +742,7 @@ extern "C" int rcu_unet_create(const rcu_unet_desc* d, int device, rcu_unet** ou
     }
     const bool fuse_head = (sf == 32);
     RCU_TRY(add_unit(u++, c, 0, fuse_head));             // conv_cls.0
+    if (has_sigma) RCU_TRY(add_unit(u++, c, 0, fuse_head, 1));   // conv_sigma.0
   }
 #undef RCU_TRY
   *out = net;
@@ -745,7 +793,7 @@ extern "C" int rcu_unet_plan(rcu_unet* net, int height, int width, int max_image
   // (2*C_l channels; the encoder's second conv writes the skip half, the decoder's upconv the up half), P[l] pooled
   // skip (input of level l+1), DA/DB[l] the decoder block's two convs.
   std::vector<Act> E(depth + 1), CAT(depth), P(depth), DA(depth), DB(depth);
-  Act SB, HF;
+  Act SB, HF, HF2;
   size_t off = 0;
   uint8_t* base = nullptr;
   auto tensor = [&](int c_total, int h, int w) {
@@ -782,6 +830,7 @@ extern "C" int rcu_unet_plan(rcu_unet* net, int height, int width, int max_image
       }
     }
     HF = tensor(sf, height, width);   // conv_cls.0 features (cross-check path only; the tcgen05 paths fuse the head)
+    if (net->has_sigma) HF2 = tensor(sf, height, width);
     o_coef = off;
     off += ((size_t)N * net->n_cols * sizeof(float2) + 1023) & ~size_t(1023);
     if (pass == 0) {
@@ -794,6 +843,7 @@ extern "C" int rcu_unet_plan(rcu_unet* net, int height, int width, int max_image
   net->d_coef = reinterpret_cast<float2*>(base + o_coef);
   net->first_out = E[0];
   net->head_feat = HF;
+  net->sigma_feat = HF2;
 
   // ---- schedule ----
   int ci = 0;
@@ -835,7 +885,7 @@ extern "C" int rcu_unet_plan(rcu_unet* net, int height, int width, int max_image
         }
     }
     Op op;
-    op.kind = OP_CONV; op.conv = ci; op.out = L.head ? net->head_feat : dst;
+    op.kind = OP_CONV; op.conv = ci; op.out = dst;
     op.h = src.h * L.out_mul; op.w = src.w * L.out_mul; op.c = L.c_out;
     net->ops.push_back(op);
     ++ci;
@@ -870,7 +920,9 @@ extern "C" int rcu_unet_plan(rcu_unet* net, int height, int width, int max_image
     if ((rc = push_conv(DA[l], DB[l]))) return rc;
     cur = DB[l];
   }
+  net->features = cur;
   if ((rc = push_conv(cur, net->head_feat))) return rc;             // conv_cls.0 (+ fused head)
+  if (net->has_sigma && (rc = push_conv(cur, net->sigma_feat))) return rc;   // conv_sigma.0 (+ fused head)
   if (workspace_bytes) *workspace_bytes = off;
   return RCU_OK;
 }
@@ -916,7 +968,7 @@ static int run_conv_halo(rcu_unet* net, const ConvLayer& L, int n_img, int cs, l
     prm.pool_img_stride = L.pool_dst.img_stride;
     prm.coef = net->d_coef; prm.coef_stride = net->n_cols; prm.coef_off = L.coef_off;
     prm.relu = L.relu;
-    prm.head = L.head ? net->d_head : nullptr;
+    prm.head = L.head ? L.d_head : nullptr;
     prm.logits = logits;
     prm.chunk_slices = cs; prm.slice0 = s0; prm.n_slices_total = n_slices;
     int rc;
@@ -937,7 +989,23 @@ static int run_conv_halo(rcu_unet* net, const ConvLayer& L, int n_img, int cs, l
 extern "C" int rcu_unet_forward(rcu_unet* net, const float* images, int64_t n_slices, int n_samples, int dropout_mode,
                                 int det_first, uint64_t seed, int64_t slice_index0, int sample0, const float* scale,
                                 float* logits, void* stream) {
-  RCU_CHECK_ARG(net != nullptr && images != nullptr && logits != nullptr, "NULL argument");
+  rcu_unet_outputs out;
+  std::memset(&out, 0, sizeof(out));
+  out.logits = logits;
+  return rcu_unet_forward_ex(net, images, n_slices, n_samples, dropout_mode, det_first, seed, slice_index0, sample0, scale, &out, stream);
+}
+
+extern "C" int rcu_unet_forward_ex(rcu_unet* net, const float* images, int64_t n_slices, int n_samples, int dropout_mode,
+                                   int det_first, uint64_t seed, int64_t slice_index0, int sample0, const float* scale,
+                                   const rcu_unet_outputs* outputs, void* stream) {
+  RCU_CHECK_ARG(net != nullptr && images != nullptr && outputs != nullptr && outputs->logits != nullptr, "NULL argument");
+  float* const logits = outputs->logits;
+  float* const sigma = outputs->sigma;
+  float* const features = outputs->features;
+  const rcu_postnet* const post = outputs->postnet;
+  RCU_CHECK_ARG(sigma == nullptr || net->has_sigma, "sigma output requested from a net without conv_sigma (sigma_out=False)");
+  RCU_CHECK_ARG(post == nullptr || outputs->postnet_logits != nullptr, "postnet without postnet_logits");
+  RCU_CHECK_ARG(post == nullptr || (post->device == net->device && net->start_filters == kPostC), "postnet does not match this net");
   RCU_CHECK_ARG(!net->ops.empty(), "rcu_unet_plan has not been called");
   RCU_CHECK_ARG(n_slices >= 0 && n_samples >= 1, "bad sizes: n_slices=%lld n_samples=%d", (long long)n_slices, n_samples);
   RCU_CHECK_ARG(dropout_mode >= 0 && dropout_mode <= 2, "dropout_mode must be 0, 1 or 2");
@@ -996,8 +1064,10 @@ extern "C" int rcu_unet_forward(rcu_unet* net, const float* images, int64_t n_sl
         ++launches;
       } else {
         const ConvLayer& L = net->convs[op.conv];
+        float* const head_out = L.out_slot ? sigma : logits;
+        if (L.out_slot && sigma == nullptr) continue;   // nobody asked for the sigma branch
         if (net->conv_impl == 0 && L.halo.ok && ((net->halo_mask >> op.conv) & 1ull)) {
-          int rc = run_conv_halo(net, L, n_img, cs, (long long)s0, (long long)n_slices, logits, st, &launches);
+          int rc = run_conv_halo(net, L, n_img, cs, (long long)s0, (long long)n_slices, head_out, st, &launches);
           if (rc) return rc;
           pool_done = L.pool_dst.base != nullptr;
           continue;
@@ -1044,10 +1114,10 @@ extern "C" int rcu_unet_forward(rcu_unet* net, const float* images, int64_t n_sl
         prm.out = L.dst.base;
         prm.coef = net->d_coef; prm.coef_stride = net->n_cols; prm.coef_off = L.coef_off;
         prm.relu = L.relu;
-        prm.head = nullptr; prm.logits = logits;
+        prm.head = nullptr; prm.logits = head_out;
         prm.chunk_slices = cs; prm.slice0 = s0; prm.n_slices_total = n_slices;
         if (net->conv_impl != 1) {
-          if (L.head) prm.head = net->d_head;
+          if (L.head) prm.head = L.d_head;
           int rc = dispatch_conv_tc(L, prm, st);
           if (rc) return rc;
           ++launches;
@@ -1062,7 +1132,7 @@ extern "C" int rcu_unet_forward(rcu_unet* net, const float* images, int64_t n_sl
             const long long px = (long long)n_img * H * W;
             long long hb = (px + 255) / 256;
             if (hb > (long long)sm_count() * 32) hb = (long long)sm_count() * 32;
-            head_check_kernel<<<(unsigned)hb, 256, 0, st>>>(net->head_feat.base, net->head_feat.img_stride, net->d_head, logits, n_img, H, W,
+            head_check_kernel<<<(unsigned)hb, 256, 0, st>>>(L.dst.base, L.dst.img_stride, L.d_head, head_out, n_img, H, W,
                                                            sf, cs, (long long)s0, (long long)n_slices);
             RCU_LAUNCH_CHECK();
             ++launches;
@@ -1070,9 +1140,70 @@ extern "C" int rcu_unet_forward(rcu_unet* net, const float* images, int64_t n_sl
         }
       }
     }
+    if (features != nullptr) {
+      // `UNet.features` (unet.py:178-179): the decoder output that feeds conv_cls, as float32 NCHW per (sample, slice)
+      const Act& f = net->features;
+      const int runs = (H * W + kFeatRun - 1) / kFeatRun;
+      dim3 grid((unsigned)runs, (unsigned)n_img);
+      OpTimer timer(net, (int)net->ops.size(), st);
+      if (sf == 32)
+        features_export_kernel<32><<<grid, 256, 0, st>>>(f.base, f.c_total, f.img_stride, features, H * W, cs, (long long)s0, (long long)n_slices);
+      else
+        features_export_kernel<64><<<grid, 256, 0, st>>>(f.base, f.c_total, f.img_stride, features, H * W, cs, (long long)s0, (long long)n_slices);
+      RCU_LAUNCH_CHECK();
+      ++launches;
+    }
+    if (post != nullptr) {
+      const Act& f = net->features;
+      OpTimer timer(net, (int)net->ops.size(), st);
+      int rc = launch_postnet(post, true, f.base, f.c_total, f.img_stride, H * W, n_img, cs, (long long)s0, (long long)n_slices,
+                              outputs->postnet_logits, st);
+      if (rc) return rc;
+      ++launches;
+    }
   }
   net->last_launches = launches;
   return RCU_OK;
+}
+
+extern "C" int rcu_postnet_create(const rcu_conv_unit* units, int n_units, const rcu_conv_unit* head, float bn_eps, int device, rcu_postnet** out) {
+  RCU_CHECK_ARG(out != nullptr && head != nullptr && (units != nullptr || n_units == 0), "NULL argument");
+  *out = nullptr;
+  int rc = rcu_device_check(device);
+  if (rc) return rc;
+  if (n_units < 1 || n_units > kPostMaxConvs) { set_error("PostNet nb_convs=%d: supported 1..%d", n_units, kPostMaxConvs); return RCU_ENOTSUP; }
+  rcu_postnet* post = new rcu_postnet();
+  post->device = device;
+  post->n_convs = n_units;
+  std::memset(&post->w, 0, sizeof(post->w));
+  for (int l = 0; l < n_units; ++l) {
+    const rcu_conv_unit& u = units[l];
+    if (u.c_in != kPostC || u.c_out != kPostC) { set_error("PostNet unit %d: %d -> %d channels, supported 32 -> 32", l, u.c_in, u.c_out); delete post; return RCU_ENOTSUP; }
+    if (!(u.weight && u.bias && u.bn_weight && u.bn_bias && u.bn_mean && u.bn_var)) { set_error("PostNet unit %d: NULL weight/bn pointer", l); delete post; return RCU_EINVAL; }
+    for (int co = 0; co < kPostC; ++co) {
+      // y = relu(a * (W x + b - mean) + beta): fold a into the row and the bias
+      const float a = u.bn_weight[co] / std::sqrt(u.bn_var[co] + bn_eps);
+      for (int ci = 0; ci < kPostC; ++ci) post->w.w[l][co][ci] = a * u.weight[co * kPostC + ci];
+      post->w.b[l][co] = a * (u.bias[co] - u.bn_mean[co]) + u.bn_bias[co];
+    }
+  }
+  if (!(head->weight && head->bias) || head->c_in != kPostC || head->c_out != 2) { set_error("PostNet head must be a 1x1 conv 32 -> 2"); delete post; return RCU_EINVAL; }
+  for (int k = 0; k < 2; ++k) {
+    for (int c = 0; c < kPostC; ++c) post->w.hw[k][c] = head->weight[k * kPostC + c];
+    post->w.hb[k] = head->bias[k];
+  }
+  *out = post;
+  return RCU_OK;
+}
+
+extern "C" void rcu_postnet_destroy(rcu_postnet* post) { delete post; }
+
+extern "C" int rcu_postnet_forward(const rcu_postnet* post, const float* features, int64_t n_images, int64_t hw, float* logits, void* stream) {
+  RCU_CHECK_ARG(post != nullptr && features != nullptr && logits != nullptr, "NULL argument");
+  RCU_CHECK_ARG(n_images >= 0 && hw >= 0 && hw < (1ll << 31) && n_images < (1ll << 31), "bad sizes");
+  if (n_images == 0 || hw == 0) return RCU_OK;
+  RCU_CUDA(cudaSetDevice(post->device));
+  return launch_postnet(post, false, features, 0, 0, (int)hw, (int)n_images, (int)n_images, 0, n_images, logits, (cudaStream_t)stream);
 }
 
 extern "C" int rcu_unet_debug_activation(rcu_unet* net, int index, float* out, size_t out_elems, void* stream) {

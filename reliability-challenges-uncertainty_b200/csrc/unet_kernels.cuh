@@ -212,6 +212,40 @@ head_check_kernel(const __nv_bfloat16* __restrict__ feat, long long feat_img_str
   }
 }
 
+// `UNet.features` export (common/model/unet.py:178-179): (strided) NHWC bf16 [image in chunk][hw][C] -> float32 NCHW
+// [sample][slice][C][hw].  A block transposes kFeatRun pixels x C channels through shared memory: 16-byte coalesced
+// loads, 256-byte coalesced store runs per channel.
+constexpr int kFeatRun = 64;
+
+template <int C>
+__global__ void __launch_bounds__(256)
+features_export_kernel(const __nv_bfloat16* __restrict__ feat, int px_stride, long long img_stride, float* __restrict__ out, int hw,
+                       int chunk_slices, long long slice0, long long n_slices_total) {
+  __shared__ float tile[C][kFeatRun + 1];
+  constexpr int V = C / 8;
+  const int img = blockIdx.y, px0 = blockIdx.x * kFeatRun;
+  for (int i = threadIdx.x; i < kFeatRun * V; i += 256) {
+    const int px = i / V, v = i % V;
+    if (px0 + px < hw) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(feat + (long long)img * img_stride + (long long)(px0 + px) * px_stride + v * 8));
+      const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(b2[j]);
+        tile[v * 8 + 2 * j][px] = f.x;
+        tile[v * 8 + 2 * j + 1][px] = f.y;
+      }
+    }
+  }
+  __syncthreads();
+  const int t = img / chunk_slices, sl = img - t * chunk_slices;
+  float* o = out + ((long long)t * n_slices_total + slice0 + sl) * (long long)C * hw;
+  for (int i = threadIdx.x; i < C * kFeatRun; i += 256) {
+    const int c = i / kFeatRun, px = i % kFeatRun;
+    if (px0 + px < hw) o[(long long)c * hw + px0 + px] = tile[c][px];
+  }
+}
+
 // (strided) NHWC bf16 -> dense fp32 copy used by rcu_unet_debug_activation.
 __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, int px_stride, long long img_stride, long long hw, int c,
                                    float* __restrict__ out, long long n) {

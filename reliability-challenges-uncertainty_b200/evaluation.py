@@ -82,6 +82,22 @@ error_recall = tables.error_recall
 error_precision = tables.error_precision
 
 
+def boarder_mask(binary_label_map, distance_in: int, distance_out: int):
+    """common/utils/labelhelper.py:12-20 — the mask only (the summed distance map has no consumer on this path);
+    numpy in -> numpy bool out, CUDA tensor in -> uint8 CUDA tensor out."""
+    _check_ndarray(binary_label_map)
+    mask = metrics.border_mask(binary_label_map, distance_in, distance_out)
+    return mask if torch.is_tensor(binary_label_map) else mask.cpu().numpy().astype(bool)
+
+
+def uncertainty_to_foreground_probabilities(uncertainty, prediction, rescale=None, epsilon=1e-5):
+    """rechun/eval/helper.py:7-22 (optionally preceded by rescale_uncertainties, see metrics.confidence_to_foreground)."""
+    _check_ndarray(uncertainty)
+    _check_ndarray(prediction)
+    out = metrics.confidence_to_foreground(uncertainty, prediction, rescale, epsilon)
+    return out if torch.is_tensor(uncertainty) else out.cpu().numpy()
+
+
 def confusion_matrx(prediction, target):
     _check_ndarray(prediction)
     _check_ndarray(target)

@@ -6,9 +6,27 @@ anything) and can be composed with the reference's hooks through ReducedComposeT
 Rows carry the entries the `ece_dice`, `calib` and `bnf_ue` actions write (bin-eval/eval_uncertainty.py:112-202).
 """
 import numpy as np
+import torch
 
 from . import metrics
 from . import tables
+
+
+def subject_outputs(probabilities, prediction=None):
+    """(foreground p float32, argmax prediction uint8) of an assembled subject — the two volumes WriteHook stores
+    (bin-dl/brats_test_default.py:96-98; np.argmax ties -> class 0).  numpy in -> numpy out, tensor in -> tensor out."""
+    if torch.is_tensor(probabilities):
+        if probabilities.shape[-1] == 2:
+            return probabilities[..., 1].float().contiguous(), (probabilities[..., 1] > probabilities[..., 0]).to(torch.uint8)
+        if prediction is None:
+            raise ValueError('foreground probabilities need a "prediction" entry')
+        return probabilities.float().contiguous(), (prediction != 0).to(torch.uint8)
+    if probabilities.shape[-1] == 2:
+        return (np.ascontiguousarray(probabilities[..., 1], dtype=np.float32),
+                (probabilities[..., 1] > probabilities[..., 0]).astype(np.uint8))
+    if prediction is None:
+        raise ValueError('foreground probabilities need a "prediction" entry')
+    return np.ascontiguousarray(probabilities, dtype=np.float32), np.asarray(prediction, dtype=np.uint8)
 
 
 class DeviceMetricsHook:
@@ -36,15 +54,15 @@ class DeviceMetricsHook:
     def on_test_subject_end(self, subject_context, task_context, context):
         data = subject_context.subject_data
         prob = data[self.probability_entry]
-        # what WriteHook saves and the eval script reloads (bin-dl/brats_test_default.py:96-98): argmax + foreground p
-        if prob.shape[-1] == 2:
-            prediction = (prob[..., 1] > prob[..., 0]).astype(np.uint8)
-            p = np.ascontiguousarray(prob[..., 1], dtype=np.float32)
-        else:
-            p = np.ascontiguousarray(prob, dtype=np.float32)
-            prediction = np.asarray(data['prediction'], dtype=np.uint8)
-        target = (np.asarray(data[self.label_entry]) != 0).astype(np.uint8)
-        mask = None if self.mask_entry is None else np.asarray(data[self.mask_entry]).astype(bool)
+        # what WriteHook saves and the eval script reloads (bin-dl/brats_test_default.py:96-98): argmax + foreground p.
+        # Entries assembled by assembly.DeviceSubjectAssembler are CUDA tensors and never leave the device.
+        p, prediction = subject_outputs(prob, data.get('prediction'))
+        target = data[self.label_entry]
+        target = (target != 0).to(torch.uint8) if torch.is_tensor(target) else (np.asarray(target) != 0).astype(np.uint8)
+        mask = None
+        if self.mask_entry is not None:
+            mask = data[self.mask_entry]
+            mask = (mask != 0) if torch.is_tensor(mask) else np.asarray(mask).astype(bool)
         self.rows.append(self.evaluate(subject_context.subject_index, p, prediction, target, mask))
 
     def evaluate(self, subject, p, prediction, target, mask=None):

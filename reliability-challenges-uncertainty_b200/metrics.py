@@ -220,3 +220,61 @@ def confusion_counts(prediction, target, n_subjects=1, sync=True):
     out = torch.zeros((n_subjects, 4), dtype=torch.int64, device=d_d.device)
     _lib.check(_lib.lib().rcu_confusion(_lib.ptr(d_d), _lib.ptr(t_d), vps, n_subjects, _lib.ptr(out), _lib.current_stream()))
     return out.cpu().numpy() if sync else out
+
+
+# --------------------------------------------------------------------------------------------------
+# evaluation-side preparations (csrc/prepare.cu)
+# --------------------------------------------------------------------------------------------------
+def border_mask(binary_label_map, distance_in=1, distance_out=1):
+    """common/utils/labelhelper.py:12-20 `boarder_mask` (mask only): uint8 CUDA tensor of the map's shape."""
+    shape = tuple(binary_label_map.shape)
+    if len(shape) not in (2, 3):
+        raise ValueError('border mask needs a 2-D or 3-D label map, got shape {}'.format(shape))
+    label = _to_device(binary_label_map if torch.is_tensor(binary_label_map) else np.asarray(binary_label_map) != 0, torch.uint8, 'label')
+    d = (1,) * (3 - len(shape)) + shape
+    out = torch.empty(label.numel(), dtype=torch.uint8, device=label.device)
+    _lib.check(_lib.lib().rcu_border_mask(_lib.ptr(label), int(d[0]), int(d[1]), int(d[2]), int(distance_in), int(distance_out),
+                                          _lib.ptr(out), _lib.current_stream()))
+    return out.view(shape)
+
+
+def minmax(values):
+    """(min, max) as numpy float32 scalars — `entry_np.min(), entry_np.max()` (rechun/eval/analysis.py:176)."""
+    v = _to_device(values, torch.float32, 'values')
+    out = torch.empty(3, dtype=torch.int32, device=v.device)
+    _lib.check(_lib.lib().rcu_minmax(_lib.ptr(v), v.numel(), _lib.ptr(out), _lib.current_stream()))
+    k = out.cpu().numpy().view(np.uint32)
+    if k[2]:
+        return np.float32('nan'), np.float32('nan')   # numpy's min / max propagate NaN
+    return np.float32(_lib.lib().rcu_minmax_decode(int(k[0]))), np.float32(_lib.lib().rcu_minmax_decode(int(k[1])))
+
+
+def confidence_to_foreground(uncertainty, prediction, rescale='subject', epsilon=1e-5):
+    """`rescale_uncertainties` + `uncertainty_to_foreground_probabilities` (rechun/eval/helper.py:7-22) in one pass.
+
+    rescale: 'subject' (RescaleSubjectMinMax, analysis.py:169-178: float32 min / max of this map), a (min, max) pair of
+    Python floats (RescaleLinear, analysis.py:154-166) or None (the map is already in [0, 1]).  Returns the foreground
+    pseudo-probability as a float32 CUDA tensor of the input's shape; raises ValueError where the reference does."""
+    shape = tuple(uncertainty.shape)
+    if tuple(prediction.shape) != shape:
+        raise ValueError('shapes must agree. Found {} and {}'.format(shape, tuple(prediction.shape)))
+    u = _to_device(uncertainty, torch.float32, 'uncertainty')
+    pred = _to_device(prediction, torch.uint8, 'prediction')
+    lo = rng = 0.0
+    if rescale == 'subject':
+        mn, mx = minmax(u)
+        lo, rng = float(mn), float(np.float32(mx) - np.float32(mn))          # float32 scalars: float32 arithmetic
+    elif rescale is not None:
+        mn, mx = rescale
+        lo, rng = float(np.float32(mn)), float(np.float32(float(mx) - float(mn)))   # Python floats: range in double, then weak-cast
+    out = torch.empty_like(u)
+    invalid = torch.empty(2, dtype=torch.int64, device=u.device)
+    _lib.check(_lib.lib().rcu_confidence_to_foreground(_lib.ptr(u), _lib.ptr(pred), u.numel(), int(rescale is not None), lo, rng,
+                                                       float(np.float32(1 - 2 * epsilon)), float(np.float32(epsilon)), _lib.ptr(out),
+                                                       _lib.ptr(invalid), _lib.current_stream()))
+    bad, bad_pred = (int(v) for v in invalid.cpu())
+    if bad_pred:
+        raise ValueError('Found class larger than 1. Only works for binary problems')
+    if bad:
+        raise ValueError('Found {} values outside [0, 1] (rescale the uncertainty first)'.format(bad))
+    return out.view(shape)

@@ -68,21 +68,25 @@ class B200UNet(nn.Module):
     DEFAULT_CHUNK_IMAGES = int(os.environ.get('RCU_B200_CHUNK_IMAGES', '147'))
 
     def __init__(self, state_dict, nb_classes=2, in_channels=4, depth=4, start_filters=32, dropout=0.05,
-                 dropout_center=None, device=None, seed=20, chunk_images=None):
+                 dropout_center=None, device=None, seed=20, chunk_images=None, sigma_out=None, provide_features=False):
         super().__init__()
         if nb_classes != 2:
             raise NotImplementedError('the B200 hot path is binary (nb_classes == 2)')
         state_dict = {(k[len('module.'):] if k.startswith('module.') else k): v for k, v in state_dict.items()}
-        for bad, why in (('conv_sigma', 'sigma_out=True'), ('.residual.', 'residual=True')):
-            if any(bad in k for k in state_dict):
-                raise NotImplementedError('{} nets are outside the B200 hot path'.format(why))
+        if any('.residual.' in k for k in state_dict):
+            raise NotImplementedError('residual=True nets are outside the B200 hot path')
+        has_sigma_weights = any(k.startswith('conv_sigma.') for k in state_dict)
+        # sigma_out=True (unet.py:162-164): a second head on the same features, forward returns (logits, sigma)
+        self.sigma_out = has_sigma_weights if sigma_out is None else bool(sigma_out)
+        if self.sigma_out and not has_sigma_weights:
+            raise ValueError('sigma_out=True but the state_dict has no conv_sigma weights')
         self.nb_classes, self.in_channels, self.depth, self.start_filters = nb_classes, in_channels, depth, start_filters
         self.dropout, self.dropout_center = dropout, dropout_center
         self.seed = int(seed)
         self.chunk_images = int(chunk_images or self.DEFAULT_CHUNK_IMAGES)
         # the reference toggles MC dropout by flipping nn.Dropout2d modules (torchhelper.py:44-50); this is ours
         self.mc_dropout_switch = nn.Dropout2d(p=dropout if dropout is not None else 0.0)
-        self.provide_features = False
+        self.provide_features = bool(provide_features)   # unet.py:178-179: forward() keeps the conv_cls input in .features
         self.features = None
         self._next_sample = 0      # Philox sample index of the next free-running stochastic forward() call
         self._next_slice = 0       # run-global slice counter for forward() calls
@@ -100,8 +104,6 @@ class B200UNet(nn.Module):
         """Build from a loaded reference `common.model.unet.UNet` (any object with its attribute layout)."""
         if isinstance(module, nn.DataParallel):
             module = module.module
-        if getattr(module, 'conv_sigma', None) is not None:
-            raise NotImplementedError('sigma_out=True nets are outside the B200 hot path')
         sd = module.state_dict()
         depth = len(module.down_convs)
         w0 = sd['down_convs.0.block.block.0.conv2d_batch_relu.conv.weight']
@@ -132,11 +134,10 @@ class B200UNet(nn.Module):
         if device is None:
             p0 = next(module.parameters())
             device = p0.device if p0.is_cuda else None
-        net = cls(sd, nb_classes, in_channels, depth, start_filters, dropout, dropout_center, device, seed, chunk_images)
+        net = cls(sd, nb_classes, in_channels, depth, start_filters, dropout, dropout_center, device, seed, chunk_images,
+                  sigma_out=getattr(module, 'conv_sigma', None) is not None,
+                  provide_features=bool(getattr(module, 'provide_features', False)))
         net.mc_dropout_switch.train(any(m.training for m in module.modules() if isinstance(m, nn.Dropout2d)))
-        net.provide_features = bool(getattr(module, 'provide_features', False))
-        if net.provide_features:
-            raise NotImplementedError('provide_features=True (auxiliary feature nets) is outside the B200 hot path')
         return net
 
     def _create(self, sd, units, upconvs):
@@ -173,6 +174,13 @@ class B200UNet(nn.Module):
         desc.units, desc.n_units = unit_arr, len(units)
         desc.upconvs, desc.n_upconvs = up_arr, len(upconvs)
         desc.head = unit_struct('conv_cls.1', self.start_filters, self.nb_classes, False, bn=False, conv_key='')
+        if self.sigma_out:
+            sf = self.start_filters
+            sigma_unit = unit_struct('conv_sigma.0.conv2d_batch_relu', sf, sf, self.dropout is not None)
+            sigma_head = unit_struct('conv_sigma.1', sf, self.nb_classes, False, bn=False, conv_key='')
+            desc.sigma_unit, desc.sigma_head = ctypes.pointer(sigma_unit), ctypes.pointer(sigma_head)
+            if self.dropout is not None:
+                self.site_channels.append(sf)   # conv_sigma.0's Dropout2d is the last site in forward order
         handle = ctypes.c_void_p()
         dev_index = self._device.index if self._device.index is not None else torch.cuda.current_device()
         _lib.check(_lib.lib().rcu_unet_create(ctypes.byref(desc), int(dev_index), ctypes.byref(handle)))
@@ -231,12 +239,37 @@ class B200UNet(nn.Module):
         images: (N, C, H, W) tensor (moved to the device as float32).  Returns pixel-interleaved logits
         float32 (n_samples, N, H, W, 2).  dropout_mode: 0 eval, 1 Philox MC dropout (sample ids sample0...),
         2 caller-supplied keep-scale table `scale` float32 (n_stochastic, N, total_dropout_channels)."""
+        return self.forward_outputs(images, n_samples, dropout_mode, det_first, seed, slice_index0, sample0, scale)['logits']
+
+    def forward_outputs(self, images, n_samples=1, dropout_mode=0, det_first=False, seed=None, slice_index0=0, sample0=0,
+                        scale=None, sigma=False, features=False, postnet=None):
+        """forward_samples plus the optional outputs of rcu_unet_forward_ex, as a dict:
+          'logits'          (n_samples, N, H, W, 2) interleaved
+          'sigma'           same layout, raw conv_sigma output (sigma=True, sigma_out nets)
+          'features'        (n_samples, N, start_filters, H, W) float32 = UNet.features (features=True)
+          'postnet_logits'  (n_samples, N, H, W, 2): `postnet` (a B200PostNet) applied to the features inside the same
+                            call, while they are still bf16 in the workspace"""
         if images.dim() != 4 or images.shape[1] != self.in_channels:
             raise ValueError('expected images of shape (N, {}, H, W), got {}'.format(self.in_channels, tuple(images.shape)))
         x = images.to(self._device, torch.float32).contiguous()
         n, _, h, w = x.shape
         self._ensure_plan(h, w, n_samples)
         logits = torch.empty((n_samples, n, h, w, 2), dtype=torch.float32, device=self._device)
+        result = {'logits': logits}
+        outputs = _lib.RcuUnetOutputs()
+        outputs.logits = logits.data_ptr()
+        if sigma:
+            if not self.sigma_out:
+                raise ValueError('this net has no sigma head (sigma_out=False)')
+            result['sigma'] = torch.empty_like(logits)
+            outputs.sigma = result['sigma'].data_ptr()
+        if features:
+            result['features'] = torch.empty((n_samples, n, self.start_filters, h, w), dtype=torch.float32, device=self._device)
+            outputs.features = result['features'].data_ptr()
+        if postnet is not None:
+            result['postnet_logits'] = torch.empty_like(logits)
+            outputs.postnet = postnet._handle
+            outputs.postnet_logits = result['postnet_logits'].data_ptr()
         scale_d = None
         if dropout_mode == 2:
             n_stoch = n_samples - (1 if det_first else 0)
@@ -244,22 +277,31 @@ class B200UNet(nn.Module):
             if tuple(scale_d.shape) != (n_stoch, n, self.total_dropout_channels):
                 raise ValueError('scale must have shape {}, got {}'.format((n_stoch, n, self.total_dropout_channels), tuple(scale_d.shape)))
         with torch.cuda.device(self._device):
-            _lib.check(_lib.lib().rcu_unet_forward(self._handle, _lib.ptr(x), n, int(n_samples), int(dropout_mode), int(bool(det_first)),
-                                                   int(self.seed if seed is None else seed), int(slice_index0), int(sample0),
-                                                   _lib.ptr(scale_d), _lib.ptr(logits), _lib.current_stream()))
-        return logits
+            _lib.check(_lib.lib().rcu_unet_forward_ex(self._handle, _lib.ptr(x), n, int(n_samples), int(dropout_mode),
+                                                      int(bool(det_first)), int(self.seed if seed is None else seed),
+                                                      int(slice_index0), int(sample0), _lib.ptr(scale_d), ctypes.byref(outputs),
+                                                      _lib.current_stream()))
+        return result
 
     def forward(self, x):
-        """`model(images)` of the reference: logits (N, 2, H, W) float32 (a channels-last strided view).
+        """`model(images)` of the reference: logits (N, 2, H, W) float32 (a channels-last strided view), or
+        `(logits, sigma)` for a sigma_out net (unet.py:181-186); with provide_features the conv_cls input is kept in
+        `self.features` as (N, start_filters, H, W) float32 (unet.py:178-179).
 
         Deterministic while the Dropout2d switch is in eval mode; in train mode (th.set_dropout_mode(model, True))
         every call is the next MC sample of the Philox stream for these slices."""
+        kw = dict(sigma=self.sigma_out, features=self.provide_features)
         if self.mc_dropout_switch.training and self.dropout:
-            logits = self.forward_samples(x, 1, dropout_mode=1, slice_index0=self._next_slice, sample0=self._next_sample)
+            out = self.forward_outputs(x, 1, dropout_mode=1, slice_index0=self._next_slice, sample0=self._next_sample, **kw)
             self._next_sample += 1
         else:
-            logits = self.forward_samples(x, 1, dropout_mode=0)
-        return logits[0].permute(0, 3, 1, 2)
+            out = self.forward_outputs(x, 1, dropout_mode=0, **kw)
+        if self.provide_features:
+            self.features = out['features'][0]
+        logits = out['logits'][0].permute(0, 3, 1, 2)
+        if self.sigma_out:
+            return logits, out['sigma'][0].permute(0, 3, 1, 2)
+        return logits
 
     def enable_timing(self, enable=True):
         """Bracket every kernel launch of the forward with CUDA events (read them with read_timing)."""
@@ -292,3 +334,83 @@ class B200UNet(nn.Module):
         out = torch.empty(shape, dtype=torch.float32, device=self._device)
         _lib.check(_lib.lib().rcu_unet_debug_activation(self._handle, int(index), _lib.ptr(out), out.numel(), _lib.current_stream()))
         return out
+
+
+class B200PostNet(nn.Module):
+    """`context.model` drop-in for common/model/postnet.py:6-17 PostNet(in_channels=32, nb_classes=2, nb_convs, dropout):
+    the auxiliary-feature method's per-pixel stack of 1x1 Conv2dBnRelu units + 1x1 logits conv, in eval mode
+    (bin-dl/brats_test_auxiliary_feat.py:61-80).  `forward(features)` takes the (N, 32, H, W) tensor UNet.features holds;
+    `B200UNet.forward_outputs(..., postnet=self)` runs it fused with the U-Net forward instead."""
+
+    def __init__(self, state_dict, device=None):
+        super().__init__()
+        sd = {(k[len('module.'):] if k.startswith('module.') else k): v for k, v in state_dict.items()}
+        self._handle = None
+        self._device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
+        n_convs = 0
+        while 'convs.{}.conv2d_batch_relu.conv.weight'.format(n_convs) in sd:
+            n_convs += 1
+        if n_convs == 0 or 'conv_logits.weight' not in sd:
+            raise ValueError('state_dict is not a PostNet (convs.N.conv2d_batch_relu.*, conv_logits.*)')
+        if int(sd['conv_logits.weight'].shape[0]) != 2:
+            raise NotImplementedError('the B200 hot path is binary (nb_classes == 2)')
+        self.nb_convs = n_convs
+        self.in_channels = int(sd['conv_logits.weight'].shape[1])
+        keep = []
+
+        def arr(key):
+            a = _f32(sd[key])
+            keep.append(a)
+            return a.ctypes.data_as(_lib.c_float_p)
+
+        def unit(prefix, conv_key, bn, c_in, c_out):
+            u = _lib.RcuConvUnit()
+            u.weight, u.bias = arr(prefix + conv_key + '.weight'), arr(prefix + conv_key + '.bias')
+            if bn:
+                u.bn_weight, u.bn_bias = arr(prefix + '.bn.weight'), arr(prefix + '.bn.bias')
+                u.bn_mean, u.bn_var = arr(prefix + '.bn.running_mean'), arr(prefix + '.bn.running_var')
+            u.c_in, u.c_out, u.has_dropout = c_in, c_out, 0
+            return u
+        c = self.in_channels
+        for i in range(n_convs):
+            w = sd['convs.{}.conv2d_batch_relu.conv.weight'.format(i)]
+            if tuple(w.shape) != (c, c, 1, 1):
+                raise ValueError('convs.{}: weight shape {} is not ({}, {}, 1, 1)'.format(i, tuple(w.shape), c, c))
+        units = (_lib.RcuConvUnit * n_convs)(*[unit('convs.{}.conv2d_batch_relu'.format(i), '.conv', True, c, c) for i in range(n_convs)])
+        head = unit('conv_logits', '', False, c, 2)
+        handle = ctypes.c_void_p()
+        dev_index = self._device.index if self._device.index is not None else torch.cuda.current_device()
+        _lib.check(_lib.lib().rcu_postnet_create(units, n_convs, ctypes.byref(head), BN_EPS, int(dev_index), ctypes.byref(handle)))
+        self._handle = handle
+        self.eval()
+
+    @classmethod
+    def from_reference(cls, module, device=None):
+        if isinstance(module, nn.DataParallel):
+            module = module.module
+        if device is None:
+            p0 = next(module.parameters())
+            device = p0.device if p0.is_cuda else None
+        return cls(module.state_dict(), device)
+
+    def __del__(self):
+        try:
+            h = self.__dict__.get('_handle')
+            if h:
+                self.__dict__['_handle'] = None
+                _lib.lib().rcu_postnet_destroy(h)
+        except Exception:  # interpreter shutdown
+            pass
+
+    def to(self, *args, **kwargs):
+        return self
+
+    def forward(self, features):
+        if features.dim() != 4 or features.shape[1] != self.in_channels:
+            raise ValueError('expected features of shape (N, {}, H, W), got {}'.format(self.in_channels, tuple(features.shape)))
+        x = features.to(self._device, torch.float32).contiguous()
+        n, _, h, w = x.shape
+        logits = torch.empty((n, h, w, 2), dtype=torch.float32, device=self._device)
+        with torch.cuda.device(self._device):
+            _lib.check(_lib.lib().rcu_postnet_forward(self._handle, _lib.ptr(x), n, h * w, _lib.ptr(logits), _lib.current_stream()))
+        return logits.permute(0, 3, 1, 2)

@@ -6,6 +6,9 @@ dtypes and device placement as
   McPredictStep             rechun/dl/customsteps.py:10-39
   MultiPredictionSummary    rechun/dl/customsteps.py:42-71
   EnsemblePredictionStep    bin-dl/brats_test_ensemble.py:72-94 (ISIC twin bin-dl/isic_test_ensemble.py:73-95)
+  AleatoricPredictStep      bin-dl/brats_test_aleatoric.py:51-73 (sigma_out nets)
+  AuxiliaryFeatPredictStep  bin-dl/brats_test_auxiliary_feat.py:61-80 (`SegmentationPredictStep(test_model)` there)
+  AuxiliarySegmPredictStep  bin-dl/brats_test_auxiliary_segm.py:48-69 (`SegmentationPredictStep()` there)
 but the T+1 (or M) forwards run folded into one batch on the tcgen05 engine and softmax / mean / entropy are one
 fused pass over the logits.  `batch_context.output['multi_probabilities']` is a LazyMultiProbabilities: the fused
 summary consumes the logits behind it directly; anything else that touches it gets the real (T, N, C, H, W) tensor.
@@ -15,7 +18,7 @@ import abc
 import torch
 
 from . import _lib
-from .model import B200UNet
+from .model import B200UNet, B200PostNet
 
 try:  # inside the reference tree the real protocol classes are used, so isinstance checks keep working
     import common.trainloop.steps as _ref_steps
@@ -125,6 +128,77 @@ class SegmentationPredictStep(_BatchStepBase):
             batch_context.output['probabilities'] = softmax_planar(logits)
 
 
+class AleatoricPredictStep(_BatchStepBase):
+    """One deterministic forward of a sigma_out net: 'logits', 'sigma' (= |out_sigma| or exp(out_sigma)) and
+    'probabilities' = softmax(logits) (bin-dl/brats_test_aleatoric.py:51-73)."""
+
+    def __init__(self, is_log_sigma=False) -> None:
+        super().__init__()
+        self.is_log_sigma = is_log_sigma
+
+    def __call__(self, batch_context, task_context, context) -> None:
+        _check_context(context)
+        batch_context.input['images'] = batch_context.input['images'].float().to(context.device, non_blocking=True)
+        engine = engine_for(context.model, context.device)
+        out = engine.forward_outputs(batch_context.input['images'], 1, dropout_mode=0, sigma=True)
+        logits, sigma = out['logits'][0], out['sigma'][0].permute(0, 3, 1, 2)
+        batch_context.output['logits'] = logits.permute(0, 3, 1, 2)
+        batch_context.output['sigma'] = sigma.exp_() if self.is_log_sigma else sigma.abs_()
+        batch_context.output['probabilities'] = softmax_planar(logits)
+
+
+_POSTNETS = {}
+
+
+def postnet_for(model, device=None):
+    """The B200PostNet behind an auxiliary model: the model itself, or a cached conversion of a reference PostNet."""
+    if isinstance(model, B200PostNet):
+        return model
+    key = id(model)
+    post = _POSTNETS.get(key)
+    if post is None or post[0] is not model:
+        post = (model, B200PostNet.from_reference(model, device=device))
+        _POSTNETS[key] = post
+    return post[1]
+
+
+class AuxiliaryFeatPredictStep(_BatchStepBase):
+    """The auxiliary-feature method (bin-dl/brats_test_auxiliary_feat.py:61-80): the segmentation net's probabilities
+    ('segm_probabilities') and the PostNet's probabilities on the segmentation net's features ('probabilities').  The
+    PostNet runs inside the same engine call on the bf16 features in the workspace; the (N, 32, H, W) float32
+    `features` tensor of the reference is never materialised."""
+
+    def __init__(self, test_model) -> None:
+        super().__init__()
+        self.test_model = test_model
+
+    def __call__(self, batch_context, task_context, context) -> None:
+        _check_context(context)
+        batch_context.input['images'] = batch_context.input['images'].float().to(context.device, non_blocking=True)
+        engine = engine_for(self.test_model, context.device)
+        post = postnet_for(context.model, context.device)
+        out = engine.forward_outputs(batch_context.input['images'], 1, dropout_mode=0, postnet=post)
+        batch_context.output['segm_probabilities'] = softmax_planar(out['logits'][0])
+        batch_context.output['probabilities'] = softmax_planar(out['postnet_logits'][0])
+
+
+class AuxiliarySegmPredictStep(_BatchStepBase):
+    """The auxiliary-segmentation method (bin-dl/brats_test_auxiliary_segm.py:48-69): the net sees the images plus the
+    existing prediction (`labels[:, 1]`) as one more input channel."""
+
+    def __call__(self, batch_context, task_context, context) -> None:
+        _check_context(context)
+        batch_context.input['images'] = batch_context.input['images'].float().to(context.device, non_blocking=True)
+        batch_context.input['labels'] = batch_context.input['labels'].long().to(context.device)
+        pred = batch_context.input['labels'][:, 1]
+        inpt = torch.cat([batch_context.input['images'], pred.unsqueeze(1).float()], dim=1)
+        engine = engine_for(context.model, context.device)
+        logits = engine.forward_samples(inpt, 1, dropout_mode=0)[0]
+        batch_context.output['logits'] = logits.permute(0, 3, 1, 2)
+        batch_context.output['probabilities'] = softmax_planar(logits)
+        batch_context.output['orig_prediction'] = pred.unsqueeze(1)
+
+
 class McPredictStep(_BatchStepBase):
     """T stochastic forwards + the deterministic weight-scaling forward, as ONE folded batch of (T+1)·N images."""
 
@@ -218,6 +292,29 @@ def summarize(multi, do_mi=False, do_var=False, emit_prediction=False, emit_fore
     if emit_foreground:
         out['foreground'] = fg
     return out
+
+
+class EvalSubjectStep:
+    """Drop-in for the subject step of the test scripts (common/trainloop/steps.py:117-131,
+    bin-dl/brats_test_default.py:63-77): prediction = argmax of the assembled probabilities, Dice against the
+    subject's labels.  Works on what assembly.DeviceSubjectAssembler produces (CUDA tensors: argmax and the confusion
+    counts run on the device, only four integers come back) as well as on the numpy arrays of the stock assembler."""
+
+    def __init__(self) -> None:
+        from . import evaluation
+        self.evaluate = evaluation.ComposeEvaluation([evaluation.DiceNumpy()])
+
+    def __call__(self, subject_context, task_context, context) -> None:
+        probabilities = subject_context.subject_data['probabilities']
+        if torch.is_tensor(probabilities):
+            prediction = (probabilities[..., 1] > probabilities[..., 0]).to(torch.uint8)  # np.argmax: ties -> class 0
+        else:
+            import numpy as np
+            prediction = np.argmax(probabilities, axis=-1)
+        to_eval = {'prediction': prediction, 'probabilities': probabilities, 'target': subject_context.subject_data['labels']}
+        results = {}
+        self.evaluate(to_eval, results)
+        subject_context.metrics.update(results)
 
 
 def _context_seed(context):

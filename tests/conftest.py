@@ -47,3 +47,9 @@ def golden_unet():
 def golden_metrics():
     import numpy as np
     return np.load(os.path.join(ROOT, 'tests', 'golden', 'metrics_golden.npz'), allow_pickle=False)
+
+
+@pytest.fixture(scope='session')
+def golden_aux():
+    import numpy as np
+    return np.load(os.path.join(ROOT, 'tests', 'golden', 'aux_golden.npz'), allow_pickle=False)

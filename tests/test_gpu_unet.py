@@ -150,9 +150,15 @@ def test_unsupported_configurations_fail_loudly():
     with pytest.raises(NotImplementedError):
         model.B200UNet(sd, nb_classes=3)
     bad = dict(sd)
-    bad['conv_sigma.1.weight'] = torch.zeros(2, 32, 1, 1)
-    with pytest.raises(NotImplementedError):
+    bad['conv_sigma.1.weight'] = torch.zeros(2, 32, 1, 1)     # a sigma head without its conv_sigma.0 unit
+    with pytest.raises(ValueError):
         model.B200UNet(bad)
+    bad = dict(sd)
+    bad['down_convs.0.block.residual.weight'] = torch.zeros(32, 4, 1, 1)
+    with pytest.raises(NotImplementedError):
+        model.B200UNet(bad)                                    # residual=True blocks (no shipped config uses them)
+    with pytest.raises(ValueError):
+        net.forward_outputs(torch.randn(1, 4, 32, 32), sigma=True)   # sigma requested from a sigma_out=False net
     missing = {k: v for k, v in sd.items() if 'bottom_convs.block.1' not in k}
     with pytest.raises(ValueError):
         model.B200UNet(missing)
