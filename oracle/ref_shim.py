@@ -176,6 +176,17 @@ def _install_shims():
         sys.modules['tensorboardX'] = tbx
     if 'SimpleITK' not in sys.modules:
         sys.modules['SimpleITK'] = _permissive_module('SimpleITK')
+    try:  # rechun/eval/hook.py:4-5 imports matplotlib for its PDF hooks; the CSV hooks next to them do not use it
+        import matplotlib  # noqa: F401
+    except ImportError:
+        mpl = _permissive_module('matplotlib')
+        mpl.__path__ = []
+        backends = _permissive_module('matplotlib.backends')
+        backends.__path__ = []
+        backends.backend_pdf = _permissive_module('matplotlib.backends.backend_pdf')
+        mpl.backends, mpl.pyplot = backends, _permissive_module('matplotlib.pyplot')
+        sys.modules.update({'matplotlib': mpl, 'matplotlib.backends': backends,
+                            'matplotlib.backends.backend_pdf': backends.backend_pdf, 'matplotlib.pyplot': mpl.pyplot})
     if 'h5py' not in sys.modules:
         try:
             import h5py  # noqa: F401

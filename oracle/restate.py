@@ -24,6 +24,9 @@ Reference citations (path:line relative to the reference root):
   auxiliary segm input ..... bin-dl/brats_test_auxiliary_segm.py:48-69
   border mask .............. common/utils/labelhelper.py:12-20
   confidence -> p .......... rechun/eval/helper.py:7-22
+  CSV rows / report tables . rechun/eval/hook.py:27-93; bin-analysis/table_supplmat_ece_dataset_vs_meansubject.py:59-104;
+                             bin-analysis/table_ece_ue_bnf_dice.py:30-73,132-143 (the last one UNPINNED: the installed
+                             pandas 3 rejects the reference's groupby.mean over string columns, so it cannot be run)
 """
 import math
 from collections import OrderedDict
@@ -630,3 +633,64 @@ def ue_table_row(r):
     denom = r['fn'] + r['fp'] + r['fnu'] + r['fpu'] + r['tnu'] + r['tpu']
     return {'benefit': r['corrected_dice'] > r['dice'],
             'ue': (2 * (r['fnu'] + r['fpu'])) / denom if denom else float('nan')}
+
+
+# ------------------------------------------------------------------------------------------------
+# Report-side reductions
+# ------------------------------------------------------------------------------------------------
+def bins_csv_row(results):
+    """WriteBinsCsvHook.on_subject + WriteCsvHook._unfold_results (rechun/eval/hook.py:49-62,75-93) -> {column: value}."""
+    nz = np.asarray(results['bins_non_zero'])
+    row = {}
+    for key, value in results.items():
+        if key in ('bins_count', 'bins_avg_confidence', 'bins_positive_fraction'):
+            full = np.zeros_like(nz, dtype=np.asarray(value).dtype)
+            full[nz] = value
+            value = full
+        if isinstance(value, np.ndarray):
+            value = value.tolist()
+        if isinstance(value, (list, tuple)):
+            digits = len(str(len(value)))
+            for i, v in enumerate(value):
+                row['{}_{:0{}d}'.format(key, i, digits)] = v
+        else:
+            row[key] = value
+    return row
+
+
+def dataset_vs_mean_subject_ece(rows):
+    """table_supplmat_ece_dataset_vs_meansubject.py:59-104 on the unfolded calibration rows of one test id."""
+    def block(prefix, dtype):
+        return np.array([[r['%s_%02d' % (prefix, b)] for b in range(10)] for r in rows], dtype=dtype)
+    nonzero = block('bins_non_zero', bool)
+    conf = np.ma.array(block('bins_avg_confidence', np.float64), mask=~nonzero)
+    pos = np.ma.array(block('bins_positive_fraction', np.float64), mask=~nonzero)
+    cnt = np.ma.array(block('bins_count', np.int64), mask=~nonzero)
+    bin_sum = cnt.sum(axis=0)
+    avg_conf = (conf * cnt).sum(axis=0) / bin_sum
+    pos_frac = (pos * cnt).sum(axis=0) / bin_sum
+    ece = (np.abs(conf - pos) * (cnt / cnt.sum(axis=1, keepdims=True))).sum(axis=1)
+    assert np.allclose(ece.data, [r['ece'] for r in rows])      # the reference's own consistency check (:77-78)
+    return {'ece': ece.mean(), 'ds_ece': (np.abs(avg_conf - pos_frac) * bin_sum / bin_sum.sum()).sum()}
+
+
+def best_threshold_summary(sweeps, ece, dice, thresholds=SWEEP_THRESHOLDS):
+    """table_ece_ue_bnf_dice.py:30-73,132-143 for one test id.  sweeps[s][threshold] = uncertainty_and_correction()."""
+    table = {}
+    for name in ('benefit', 'error'):
+        per_th = []
+        for th in thresholds:
+            vals = []
+            for s in sweeps:
+                r = s[th]
+                if name == 'benefit':
+                    vals.append(float((r['corrected_dice'] - r['dice']) > 0))
+                else:
+                    with np.errstate(divide='ignore', invalid='ignore'):
+                        vals.append((2 * (r['fnu'] + r['fpu'])) / np.float64(r['fn'] + r['fp'] + r['fnu'] + r['fpu'] + r['tnu'] + r['tpu']))
+            per_th.append(np.mean(vals))
+        per_th = np.array(per_th)
+        k = int(np.nanargmax(per_th))                            # Series.idxmax: first maximum, NaN skipped
+        table[name], table[name + '_threshold'] = per_th[k], float(thresholds[k])
+    table['ece'], table['dice'] = float(np.mean(ece)), float(np.mean(dice))
+    return table

@@ -255,3 +255,84 @@ def ue_table_columns(r):
     with np.errstate(divide='ignore', invalid='ignore'):
         ue = (2 * (r['fnu'] + r['fpu'])) / np.float64(denom)
     return {'benefit': r['corrected_dice'] > r['dice'], 'ue': ue}
+
+
+# --------------------------------------------------------------------------------------------------
+# Report-side reductions: what the eval hooks write and what the analysis tables compute from it
+# --------------------------------------------------------------------------------------------------
+def expand_bins(results):
+    """WriteBinsCsvHook.on_subject (rechun/eval/hook.py:75-93): the compacted `bins_*` arrays of `return_bins=True`
+    re-expanded to full length with zeros in the empty bins (`bins_non_zero` says which)."""
+    out = dict(results)
+    non_zero = np.asarray(results['bins_non_zero'], dtype=bool)
+    for key in ('bins_count', 'bins_avg_confidence', 'bins_positive_fraction'):
+        value = np.asarray(results[key])
+        full = np.zeros(non_zero.shape, dtype=value.dtype)
+        full[non_zero] = value
+        out[key] = full
+    return out
+
+
+def unfold_results(results):
+    """WriteCsvHook._unfold_results (rechun/eval/hook.py:49-62): sequences become `key_00 ... key_NN` columns."""
+    unfolded = {}
+    for key, value in results.items():
+        if isinstance(value, np.ndarray):
+            value = value.tolist()
+        if isinstance(value, (list, tuple)):
+            nb_digits = len(str(len(value)))
+            for i in range(len(value)):
+                unfolded['{}_{:0{}d}'.format(key, i, nb_digits)] = value[i]
+        else:
+            unfolded[key] = value
+    return unfolded
+
+
+def csv_rows(results_per_subject, subject_names, run_id, entries=None, bins=False):
+    """(header, rows) exactly as WriteCsvHook / WriteBinsCsvHook (hook.py:27-47,75-93) would write them."""
+    header, rows = None, []
+    for results, name in zip(results_per_subject, subject_names):
+        unfolded = unfold_results(expand_bins(results) if bins else results)
+        if entries is None:
+            entries = list(unfolded.keys())
+        if header is None:
+            header = ['test_id', 'subject_name'] + list(entries)
+        rows.append([run_id, name] + [unfolded[e] for e in entries])
+    return header, rows
+
+
+def dataset_vs_mean_subject_ece(count, positives, conf_sum):
+    """bin-analysis/table_supplmat_ece_dataset_vs_meansubject.py:59-86 from the per-subject tables themselves
+    ((S, n_bins) arrays, e.g. the batched output of rcu_calib_hist / rcu_eval_fused): the mean of the per-subject
+    ECEs and the ECE of the pooled data set (bins summed over subjects before the ratio)."""
+    count = np.asarray(count, dtype=np.int64)
+    positives = np.asarray(positives, dtype=np.int64)
+    conf_sum = np.asarray(conf_sum, dtype=np.float64)
+    if count.ndim != 2 or count.shape != positives.shape or count.shape != conf_sum.shape:
+        raise ValueError('expected three (subjects, n_bins) tables')
+    ece = np.array([ece_from_tables(c, p, s) for c, p, s in zip(count, positives, conf_sum)])
+    return {'ece': ece.mean(), 'ds_ece': ece_from_tables(count.sum(0), positives.sum(0), conf_sum.sum(0))}
+
+
+def best_threshold_summary(sweeps, ece, dice, thresholds=None):
+    """The row bin-analysis/table_ece_ue_bnf_dice.py:30-73 prints for one test id.
+
+    sweeps: per subject, {threshold: UncertaintyAndCorrectionEvalNumpy results} (what DeviceMetricsHook rows hold under
+    'sweep'); ece / dice: per-subject values.  `benefit` = corrected_dice > dice, `error` = the U-E Dice (:56-59); for
+    each of the two the threshold with the best subject-mean is chosen (`get_best_thresholds`, :132-143; first maximum
+    in threshold order, NaNs skipped) and the subject-mean at that threshold reported."""
+    if thresholds is None:
+        thresholds = list(sweeps[0].keys())
+    benefit = np.array([[float(s[th]['corrected_dice'] - s[th]['dice'] > 0) for s in sweeps] for th in thresholds])
+    error = np.array([[ue_table_columns(s[th])['ue'] for s in sweeps] for th in thresholds], dtype=np.float64)
+
+    def best(table):
+        means = table.mean(axis=1)           # per threshold over subjects (a NaN subject makes the threshold NaN)
+        if np.all(np.isnan(means)):
+            return float('nan'), float('nan')
+        k = int(np.nanargmax(means))
+        return means[k], float(thresholds[k])
+    b_mean, b_th = best(benefit)
+    e_mean, e_th = best(error)
+    return {'ece': float(np.mean(ece)), 'dice': float(np.mean(dice)), 'benefit': b_mean, 'benefit_threshold': b_th,
+            'error': e_mean, 'error_threshold': e_th}

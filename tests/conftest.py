@@ -53,3 +53,9 @@ def golden_metrics():
 def golden_aux():
     import numpy as np
     return np.load(os.path.join(ROOT, 'tests', 'golden', 'aux_golden.npz'), allow_pickle=False)
+
+
+@pytest.fixture(scope='session')
+def golden_tables():
+    import numpy as np
+    return np.load(os.path.join(ROOT, 'tests', 'golden', 'tables_golden.npz'), allow_pickle=False)
