@@ -17,31 +17,47 @@ namespace rcu {
 // and of its complement (unit spacing).  For a foreground voxel dist_out = 0 and dist_in <= d_in  <=>  some background
 // voxel lies within the ball of radius d_in; symmetrically for a background voxel.  With the radii the reference
 // uses (1, 1: analysis.py:113) that is the 6-neighbourhood.  Voxels outside the volume are neither class (scipy's
-// transform only sees the array).
+// transform only sees the array).  The ball offsets come sorted by distance as a kernel parameter (nearest first:
+// interior voxels of a border-free region still visit all of them, border voxels stop at the first hit).
+constexpr int kMaxBallOffsets = 124;   // radius 3: 123 offsets
+
+struct BallOffsets {
+  int n_in, n_out;
+  char4 in[kMaxBallOffsets];    // (dx, dy, dz, -)
+  char4 out[kMaxBallOffsets];
+};
+
 __global__ void __launch_bounds__(256)
-border_mask_kernel(const uint8_t* __restrict__ label, int d0, int d1, int d2, int r_in, int r_out, uint8_t* __restrict__ mask) {
-  const long long n = (long long)d0 * d1 * d2;
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
-    const int x = (int)(i % d2), y = (int)((i / d2) % d1), z = (int)(i / ((long long)d1 * d2));
-    const bool fg = label[i] != 0;
-    const int r = fg ? r_in : r_out;
-    const int rr = r * r;
-    bool hit = false;
-    for (int dz = -r; dz <= r && !hit; ++dz) {
-      const int zz = z + dz;
-      if (zz < 0 || zz >= d0) continue;
-      for (int dy = -r; dy <= r && !hit; ++dy) {
-        const int yy = y + dy;
-        if (yy < 0 || yy >= d1 || dz * dz + dy * dy > rr) continue;
-        for (int dx = -r; dx <= r; ++dx) {
-          const int xx = x + dx;
-          if (xx < 0 || xx >= d2 || dz * dz + dy * dy + dx * dx > rr) continue;
-          if ((label[((long long)zz * d1 + yy) * d2 + xx] != 0) != fg) { hit = true; break; }
-        }
+border_mask_kernel(const uint8_t* __restrict__ label, int d0, int d1, int d2, const __grid_constant__ BallOffsets ball,
+                   uint8_t* __restrict__ mask) {
+  // one block row per (z, y) line: the index arithmetic is per line, the neighbour loads of a line hit L1
+  for (long long row = blockIdx.y; row < (long long)d0 * d1; row += gridDim.y) {
+    const int z = (int)(row / d1), y = (int)(row - (long long)z * d1);
+    for (int x = blockIdx.x * 256 + threadIdx.x; x < d2; x += gridDim.x * 256) {
+      const long long i = row * d2 + x;
+      const bool fg = __ldg(label + i) != 0;
+      const int cnt = fg ? ball.n_in : ball.n_out;
+      const char4* offs = fg ? ball.in : ball.out;
+      bool hit = false;
+      for (int k = 0; k < cnt && !hit; ++k) {
+        const char4 o = offs[k];
+        const int xx = x + o.x, yy = y + o.y, zz = z + o.z;
+        if (xx < 0 || xx >= d2 || yy < 0 || yy >= d1 || zz < 0 || zz >= d0) continue;
+        hit = (__ldg(label + i + ((long long)o.z * d1 + o.y) * d2 + o.x) != 0) != fg;
       }
+      mask[i] = hit ? 1 : 0;
     }
-    mask[i] = hit ? 1 : 0;
   }
+}
+
+static int fill_ball(int r, char4* out) {   // offsets of the ball of radius r without the centre, nearest first
+  int n = 0;
+  for (int d2 = 1; d2 <= r * r; ++d2)
+    for (int dz = -r; dz <= r; ++dz)
+      for (int dy = -r; dy <= r; ++dy)
+        for (int dx = -r; dx <= r; ++dx)
+          if (dz * dz + dy * dy + dx * dx == d2) out[n++] = make_char4((signed char)dx, (signed char)dy, (signed char)dz, 0);
+  return n;
 }
 
 __device__ __forceinline__ uint32_t ordered_key(float v) {
@@ -110,8 +126,13 @@ extern "C" int rcu_border_mask(const uint8_t* label, int d0, int d1, int d2, int
   RCU_CHECK_ARG(label != nullptr && mask != nullptr, "NULL argument");
   RCU_CHECK_ARG(d0 >= 1 && d1 >= 1 && d2 >= 1, "bad shape %d x %d x %d", d0, d1, d2);
   RCU_CHECK_ARG(distance_in >= 0 && distance_out >= 0, "distances must be >= 0");
-  if (distance_in > 8 || distance_out > 8) { set_error("border distances above 8 voxels are not supported"); return RCU_ENOTSUP; }
-  border_mask_kernel<<<grid_for((long long)d0 * d1 * d2, 16), 256, 0, (cudaStream_t)stream>>>(label, d0, d1, d2, distance_in, distance_out, mask);
+  if (distance_in > 3 || distance_out > 3) { set_error("border distances above 3 voxels are not supported"); return RCU_ENOTSUP; }
+  BallOffsets ball;
+  ball.n_in = fill_ball(distance_in, ball.in);
+  ball.n_out = fill_ball(distance_out, ball.out);
+  const long long rows = (long long)d0 * d1;
+  dim3 grid((unsigned)((d2 + 255) / 256 > 64 ? 64 : (d2 + 255) / 256), (unsigned)(rows > 65535 ? 65535 : rows));
+  border_mask_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(label, d0, d1, d2, ball, mask);
   RCU_LAUNCH_CHECK();
   return RCU_OK;
 }
