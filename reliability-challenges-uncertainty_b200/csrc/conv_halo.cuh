@@ -71,6 +71,13 @@ __device__ __forceinline__ uint32_t elect_one() {
   return pred;
 }
 
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may become
+// resident while its predecessor in the stream drains.  Everything before griddep_wait() (barrier init, TMEM allocation,
+// descriptor prefetch, the resident weight image: constant data) overlaps the predecessor's tail; the first load of
+// an activation comes after it, and every global store of the kernel is downstream of those loads.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
                "r"(bytes), "r"(bar)
@@ -135,6 +142,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  if (threadIdx.x == 0) griddep_launch_dependents();   // the next layer's CTA may take this SM as soon as this one exits
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     if (prm.tma_store)
@@ -177,6 +185,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const uint32_t n = prm.w_bytes - off < 32768u ? prm.w_bytes - off : 32768u;
         bulk_load(smem_w + off, reinterpret_cast<const uint8_t*>(prm.w_image) + off, n, bar_w);
       }
+      griddep_wait();                                    // the previous layer's output is complete and visible from here on
       int stage = 0;
       uint32_t phase = 0;
       int img = t_begin / tiles_per_img;

@@ -89,6 +89,7 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  if (threadIdx.x == 0) griddep_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     for (int s = 0; s < C::kAStages; ++s) { mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, 1); }
@@ -113,6 +114,7 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (warp == 0) {
     // ===================== producer =====================
     if (lane == 0) {
+      griddep_wait();   // see conv_halo.cuh: everything above overlapped the previous layer's tail
       int as = 0, ws = 0;
       uint32_t aph = 0, wph = 0;
       for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {

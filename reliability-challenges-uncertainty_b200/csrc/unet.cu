@@ -526,6 +526,26 @@ static int make_wide_map(CUtensorMap* map, const Act& a, int n) {
   return RCU_OK;
 }
 
+// Launch with programmatic stream serialization (the kernels call griddepcontrol.wait before their first dependent
+// access, see conv_halo.cuh).  RCU_PDL=0 falls back to plain stream order.
+template <typename Kern, typename... Args>
+static int launch_pdl(Kern kern, unsigned grid, unsigned threads, size_t smem, cudaStream_t st, const Args&... args) {
+  static const bool pdl = [] { const char* e = std::getenv("RCU_PDL"); return !(e && e[0] == '0'); }();
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  RCU_CUDA(cudaLaunchKernelEx(&cfg, kern, args...));
+  return RCU_OK;
+}
+
 template <int TAPS>
 static int launch_conv_wide(const ConvLayer& L, const WideParams& prm, const HaloOutMaps& maps, cudaStream_t st) {
   auto kern = conv_wide_kernel<TAPS>;
@@ -542,9 +562,7 @@ static int launch_conv_wide(const ConvLayer& L, const WideParams& prm, const Hal
   long long grid = sm_count();
   if (grid > total) grid = total;
   if (grid < 1) return RCU_OK;
-  kern<<<(unsigned)grid, kWideThreads, C::kSmem, st>>>(L.map_wide, maps, prm);
-  RCU_LAUNCH_CHECK();
-  return RCU_OK;
+  return launch_pdl(kern, (unsigned)grid, kWideThreads, (size_t)C::kSmem, st, L.map_wide, maps, prm);
 }
 
 static uint32_t halo_chunk_stride(bool /*half_rows*/) {
@@ -579,9 +597,7 @@ static int launch_conv_halo(const ConvLayer& L, const HaloParams& prm, const Hal
   long long grid = sm_count();
   if (grid > total_tiles) grid = total_tiles;
   if (grid < 1) return RCU_OK;
-  kern<<<(unsigned)grid, HS::kThreads, smem, st>>>(L.map_halo, maps, prm);
-  RCU_LAUNCH_CHECK();
-  return RCU_OK;
+  return launch_pdl(kern, (unsigned)grid, HS::kThreads, smem, st, L.map_halo, maps, prm);
 }
 
 }  // namespace rcu
