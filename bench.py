@@ -364,7 +364,9 @@ def run_gpu_arm(args):
     # ---------------- ECE-eval ms (second half of BASELINE's metric): full metric set per subject, device resident
     for _ in range(3):
         metrics.eval_fused(out['foreground'], out['prediction'], target_d, mask_d, 10, tables.SWEEP_THRESHOLDS, sync=False, break_table=break_table)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    # 768 MB: flushes L2 and keeps the device busy long enough for the host to have the call enqueued when the timed
+    # region opens (the number is the device time of the call, not the Python launch latency)
+    flush = torch.empty(768 << 20, dtype=torch.uint8, device=device)
     ece_ms = []
     for _ in range(10):
         flush.zero_()  # L2 flush between iterations

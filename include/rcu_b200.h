@@ -49,7 +49,8 @@ int rcu_device_check(int device);
 
 /* Workspace (bytes) the metric calls below need for `n_subjects` subjects per launch. */
 size_t rcu_metrics_workspace_bytes(int n_subjects);
-/* Must be called once on a fresh workspace (zeroes the per-subject tickets); stream-ordered. */
+/* Must be called once on a fresh workspace (zeroes the per-subject tickets); stream-ordered.  Pass the same
+ * workspace_bytes to every call that uses the workspace (the tickets live at its end). */
 int rcu_metrics_workspace_init(void* workspace, size_t workspace_bytes, void* stream);
 
 /* ECE reliability-bin tables.

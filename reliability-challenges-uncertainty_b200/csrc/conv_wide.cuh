@@ -43,6 +43,9 @@ struct WideParams {
   int coef_off;
   int relu;
   int tma_store;             // epilogue writes through swizzled smem staging + TMA tensor stores (see conv_halo.cuh)
+  __nv_bfloat16* pool_out;   // when set (TAPS == 9): MaxPool2d(2) of the output rides in the epilogue (unet.py:92-95)
+  long long pool_img_stride;
+  int pool_c;                // pixel stride of the pooled tensor in elements
 };
 
 template <int TAPS>   // 9: conv3x3, 4: one up-path phase per unit
@@ -267,6 +270,32 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             uint4* d4 = reinterpret_cast<uint4*>(dst + cb);
 #pragma unroll
             for (int i = 0; i < 4; ++i) d4[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+          }
+          if (TAPS == 9 && prm.pool_out != nullptr) {
+            // 2x2 max over the quad (y^1, x^1): row = y * 8 + x within the accumulator, a warp holds four y rows, so the
+            // partners are lanes ^1 and ^8.  h, w are even: out-of-image pixels only pair with out-of-image pixels.
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              __nv_bfloat162 m = *reinterpret_cast<__nv_bfloat162*>(&packed[i]);
+              uint32_t o = __shfl_xor_sync(0xffffffffu, packed[i], 1);
+              m = __hmax2(m, *reinterpret_cast<__nv_bfloat162*>(&o));
+              uint32_t mm = *reinterpret_cast<uint32_t*>(&m);
+              o = __shfl_xor_sync(0xffffffffu, mm, 8);
+              m = __hmax2(m, *reinterpret_cast<__nv_bfloat162*>(&o));
+              packed[i] = *reinterpret_cast<uint32_t*>(&m);
+            }
+            if (valid) {
+              // the four lanes of a quad hold the same maxima: each stores one 16-byte quarter of the 32 channels
+              const int part = ((y & 1) << 1) | (x & 1);
+              __nv_bfloat16* pd = prm.pool_out + (long long)img * prm.pool_img_stride +
+                                  ((long long)(y >> 1) * (prm.in_w >> 1) + (x >> 1)) * prm.pool_c + nt * kWideN + cb + part * 8;
+              uint4 v4;
+              v4.x = part == 0 ? packed[0] : part == 1 ? packed[4] : part == 2 ? packed[8] : packed[12];
+              v4.y = part == 0 ? packed[1] : part == 1 ? packed[5] : part == 2 ? packed[9] : packed[13];
+              v4.z = part == 0 ? packed[2] : part == 1 ? packed[6] : part == 2 ? packed[10] : packed[14];
+              v4.w = part == 0 ? packed[3] : part == 1 ? packed[7] : part == 2 ? packed[11] : packed[15];
+              *reinterpret_cast<uint4*>(pd) = v4;
+            }
           }
         }
       }

@@ -18,6 +18,8 @@ namespace rcu {
 
 constexpr int kHistThreads = 256;
 constexpr int kMaxBlocksPerSubject = 1024;
+constexpr int kFoldGroup = 16;                                        // blocks per first-level fold
+constexpr int kTicketsPerSubject = 1 + kMaxBlocksPerSubject / kFoldGroup;   // subject ticket + one per group
 constexpr int kPartialSlots = 3 * (RCU_MAX_BINS + 1) + 4 * RCU_MAX_UE_CLASSES + 1;
 constexpr int kMaxVoxelsPerThread = 60000;  // 16-bit private counters must not wrap
 constexpr int kBreakPad = 128;              // break table padded with +inf to a power of two
@@ -131,49 +133,72 @@ __device__ __forceinline__ void hist_block_finish(unsigned char* smem_raw, doubl
     my_partial[n_slots - 1] = tot;
   }
 
-  // ---- last block of the subject folds the partials in block order ----
+  // ---- two-level fold in fixed order: the last block of every group of kFoldGroup blocks sums the group (block order),
+  // the last group to finish sums the group results (group order).  One thread per slot, all loads of a level in
+  // flight together: a level costs about one L2 round trip.  (A single block folding ~300 partials, one slot per warp,
+  // used to take as long as the streaming pass itself: 35 us of a 79 us single-subject launch.) ----
   __threadfence();
   __syncthreads();
+  const int n_groups = (blocks_per_subject + kFoldGroup - 1) / kFoldGroup;
+  const int group = blockIdx.x / kFoldGroup;
+  const int g_first = group * kFoldGroup;
+  const int g_size = min(kFoldGroup, blocks_per_subject - g_first);
+  unsigned int* tk = tickets + (long long)subject * kTicketsPerSubject;
   if (tid == 0) {
-    const unsigned int t = atomicAdd(&tickets[subject], 1u);
-    s_is_last = (t == (unsigned int)blocks_per_subject - 1u);
+    const unsigned int t = atomicAdd(&tk[1 + group], 1u);
+    s_is_last = (t == (unsigned int)g_size - 1u);
   }
   __syncthreads();
   if (!s_is_last) return;
   __threadfence();
-  const unsigned long long* sp = partials + (long long)subject * blocks_per_subject * kPartialSlots;
-  for (int s = warp; s < n_slots; s += kHistThreads / 32) {
-    const bool is_conf = (s >= 2 * nb1 && s < 3 * nb1);
+  unsigned long long* sp = partials + (long long)subject * blocks_per_subject * kPartialSlots;
+  const bool is_conf = (tid >= 2 * nb1 && tid < 3 * nb1);
+  if (tid < n_slots) {
+    unsigned long long v[kFoldGroup];
+#pragma unroll
+    for (int u = 0; u < kFoldGroup; ++u) v[u] = u < g_size ? __ldcg(sp + (long long)(g_first + u) * kPartialSlots + tid) : 0ull;
     unsigned long long iacc = 0;
     double dacc = 0.0;
-    // same summation order as a plain loop (b = lane, lane + 32, ...), but eight L2 loads in flight per lane
-    for (int b0 = lane; b0 < blocks_per_subject; b0 += 32 * 8) {
-      unsigned long long v[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int b = b0 + 32 * u;
-        v[u] = b < blocks_per_subject ? __ldcg(sp + (long long)b * kPartialSlots + s) : 0ull;   // +0.0 / 0: neutral
-      }
+    for (int u = 0; u < kFoldGroup; ++u) {
+      if (is_conf) dacc += __longlong_as_double((long long)v[u]);      // +0.0 for the padding: neutral
+      else iacc += v[u];
+    }
+    // the group's result replaces the partial of its first block (only this block touches the group's partials now)
+    __stcg(sp + (long long)g_first * kPartialSlots + tid, is_conf ? (unsigned long long)__double_as_longlong(dacc) : iacc);
+  }
+  if (tid == 0) tk[1 + group] = 0u;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int t = atomicAdd(&tk[0], 1u);
+    s_is_last = (t == (unsigned int)n_groups - 1u);
+  }
+  __syncthreads();
+  if (!s_is_last) return;
+  __threadfence();
+  if (tid < n_slots) {
+    unsigned long long iacc = 0;
+    double dacc = 0.0;
+    for (int g0 = 0; g0 < n_groups; g0 += kFoldGroup) {
+      unsigned long long v[kFoldGroup];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < kFoldGroup; ++u)
+        v[u] = g0 + u < n_groups ? __ldcg(sp + (long long)(g0 + u) * kFoldGroup * kPartialSlots + tid) : 0ull;
+#pragma unroll
+      for (int u = 0; u < kFoldGroup; ++u) {
         if (is_conf) dacc += __longlong_as_double((long long)v[u]);
         else iacc += v[u];
       }
     }
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
-      iacc += __shfl_down_sync(0xffffffffu, iacc, o);
-      dacc += __shfl_down_sync(0xffffffffu, dacc, o);
-    }
-    if (lane == 0) {
-      if (s < nb1) out.count[(long long)subject * nb1 + s] = iacc;
-      else if (s < 2 * nb1) out.positives[(long long)subject * nb1 + (s - nb1)] = iacc;
-      else if (s < 3 * nb1) out.conf_sum[(long long)subject * nb1 + (s - 2 * nb1)] = dacc;
-      else if (s < n_slots - 1) out.ue_counts[(long long)subject * 4 * ncls + (s - 3 * nb1)] = iacc;
-      else if (out.invalid) out.invalid[subject] = iacc;
-    }
+    const int s = tid;
+    if (s < nb1) out.count[(long long)subject * nb1 + s] = iacc;
+    else if (s < 2 * nb1) out.positives[(long long)subject * nb1 + (s - nb1)] = iacc;
+    else if (s < 3 * nb1) out.conf_sum[(long long)subject * nb1 + (s - 2 * nb1)] = dacc;
+    else if (s < n_slots - 1) out.ue_counts[(long long)subject * 4 * ncls + (s - 3 * nb1)] = iacc;
+    else if (out.invalid) out.invalid[subject] = iacc;
   }
-  if (tid == 0) tickets[subject] = 0u;  // workspace is reusable by the next stream-ordered call
+  if (tid == 0) tk[0] = 0u;  // workspace is reusable by the next stream-ordered call
 }
 
 // VK: 0 = float32 p (or float32 uncertainty, same search), 2 = float64 uncertainty; -1 = no U-E part.
@@ -356,7 +381,10 @@ eval_hist_kernel(const float* __restrict__ p, const double* __restrict__ u64v, c
 // s = base[bucket] + (p >= break[bucket]), exact because p * NB is exact for a power-of-two NB — and the per-segment
 // table holds the counter offsets pre-multiplied, which leaves ~45 instructions per voxel.  Same private-column counters,
 // same reduction, bit-identical tables.
-template <bool HAS_MASK>
+// LUT4: the bucket entry carries its (at most three) in-bucket break points itself — {base, b0, b1, b2}, +inf padded —
+// so the segment is ONE 16-byte table read and three compares: no second dependent lookup and no data-dependent loop,
+// which lets the compiler interleave the 16 voxels of an iteration (the scan variant serialises them on its branch).
+template <bool HAS_MASK, bool LUT4>
 __global__ void __launch_bounds__(kHistThreads)
 eval_fused_lut_kernel(const float* __restrict__ p, const unsigned char* __restrict__ pred, const unsigned char* __restrict__ target,
                       const unsigned char* __restrict__ mask, long long voxels_per_subject, int blocks_per_subject,
@@ -376,6 +404,7 @@ eval_fused_lut_kernel(const float* __restrict__ p, const unsigned char* __restri
   float* s_joint = reinterpret_cast<float*>(smem_raw + tail_off);                           // [kBreakPad] merged list, +inf padded
   unsigned int* s_seg2 = reinterpret_cast<unsigned int*>(smem_raw + tail_off + kBreakPad * 4);   // [kBreakPad + 1] k*T | (j*T) << 16
   unsigned int* s_lut = reinterpret_cast<unsigned int*>(smem_raw + tail_off + kBreakPad * 4 + (kBreakPad + 8) * 4);   // [n_buckets] base | n_inside << 8
+  uint4* s_lut4 = reinterpret_cast<uint4*>(s_lut);                                                                   // LUT4: [n_buckets] {base, b0, b1, b2}
 
   for (int i = tid; i < nb1 * kHistThreads; i += kHistThreads) {
     s_conf[i] = 0.0;
@@ -396,7 +425,16 @@ eval_fused_lut_kernel(const float* __restrict__ p, const unsigned char* __restri
     // entries strictly inside (lo, hi): the break points of the float arithmetic cluster a few ulps apart around each
     // threshold, so a bucket may hold several; they are resolved by a short scan (most buckets hold none)
     const int upto = b + 1 < n_buckets ? count_breaks<float, false>(__uint_as_float(__float_as_uint(hi) - 1u), s_joint, up.joint_top) : up.joint_n;
-    s_lut[b] = (unsigned int)base | ((unsigned int)(upto - base) << 8);
+    if (LUT4) {
+      uint4 e;
+      e.x = (unsigned int)base;
+      e.y = __float_as_uint(base + 0 < upto ? s_joint[base + 0] : __int_as_float(0x7f800000));
+      e.z = __float_as_uint(base + 1 < upto ? s_joint[base + 1] : __int_as_float(0x7f800000));
+      e.w = __float_as_uint(base + 2 < upto ? s_joint[base + 2] : __int_as_float(0x7f800000));
+      s_lut4[b] = e;
+    } else {
+      s_lut[b] = (unsigned int)base | ((unsigned int)(upto - base) << 8);
+    }
   }
   __syncthreads();
 
@@ -419,10 +457,17 @@ eval_fused_lut_kernel(const float* __restrict__ p, const unsigned char* __restri
     const float pv_ = (PV);                                                                                             \
     const unsigned int t_ = (T), d_ = (D), m_ = (M);                                                                    \
     const int b_ = max(0, min(__float2int_rz(pv_ * nb_f), n_buckets - 1));                                              \
-    const unsigned int le_ = s_lut[b_];                                                                                 \
     const bool nonneg_ = pv_ >= 0.0f;                                 /* false for NaN */                               \
-    int s_ = (int)(le_ & 0xffu);                                                                                        \
-    for (int i_ = (int)(le_ & 0xffu), e_ = i_ + (int)(le_ >> 8); i_ < e_; ++i_) s_ += (pv_ >= s_joint[i_]) ? 1 : 0;    \
+    int s_;                                                                                                             \
+    if (LUT4) {                                                                                                         \
+      const uint4 le_ = s_lut4[b_];                                                                                     \
+      s_ = (int)le_.x + ((pv_ >= __uint_as_float(le_.y)) ? 1 : 0) + ((pv_ >= __uint_as_float(le_.z)) ? 1 : 0) +         \
+           ((pv_ >= __uint_as_float(le_.w)) ? 1 : 0);                                                                   \
+    } else {                                                                                                            \
+      const unsigned int le_ = s_lut[b_];                                                                               \
+      s_ = (int)(le_ & 0xffu);                                                                                          \
+      for (int i_ = (int)(le_ & 0xffu), e_ = i_ + (int)(le_ >> 8); i_ < e_; ++i_) s_ += (pv_ >= s_joint[i_]) ? 1 : 0;  \
+    }                                                                                                                   \
     s_ = nonneg_ ? s_ : 0;                                            /* the search counts 0 entries for p < 0 / NaN */ \
     const unsigned int sg_ = s_seg2[s_];                                                                                \
     const bool use_ = HAS_MASK ? (m_ != 0u) : true;                                                                     \
@@ -511,8 +556,14 @@ confusion_kernel(const unsigned char* __restrict__ pred, const unsigned char* __
   }
 }
 
-static size_t tickets_bytes(int n_subjects) { return ((size_t)n_subjects * sizeof(unsigned int) + 255) & ~size_t(255); }
+static size_t tickets_bytes(int n_subjects) { return ((size_t)n_subjects * kTicketsPerSubject * sizeof(unsigned int) + 255) & ~size_t(255); }
 static long long partial_blocks_cap(int n_subjects) { return n_subjects > 2048 ? n_subjects : 2048; }
+// Workspace layout: per-block partial tables grow from the front, the tickets sit at the very end.  Calls with different
+// n_subjects on the same workspace (same workspace_bytes) then never see each other's partials in their ticket words,
+// which must read zero at entry (every launch leaves the tickets it used at zero).
+static unsigned int* tickets_of(void* workspace, size_t workspace_bytes, int n_subjects) {
+  return reinterpret_cast<unsigned int*>(reinterpret_cast<unsigned char*>(workspace) + (workspace_bytes & ~size_t(255)) - tickets_bytes(n_subjects));
+}
 
 static size_t hist_smem_bytes(bool calib, int vk, int n_bins, int n_classes) {
   const int nb1 = calib ? n_bins + 1 : 0;
@@ -561,8 +612,8 @@ static int launch_hist(const float* p, const double* u64v, const uint8_t* pred, 
     RCU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (dev >= 0 && dev < 64) configured[dev] = smem;
   }
-  unsigned int* tickets = reinterpret_cast<unsigned int*>(workspace);
-  unsigned long long* partials = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(workspace) + tickets_bytes(n_subjects));
+  unsigned int* tickets = tickets_of(workspace, workspace_bytes, n_subjects);
+  unsigned long long* partials = reinterpret_cast<unsigned long long*>(workspace);
   dim3 grid((unsigned)bps, (unsigned)n_subjects);
   kern<<<grid, kHistThreads, smem, stream>>>(p, u64v, pred, target, mask, (long long)vps, (int)bps, cp, up, out, tickets, partials, vec_ok);
   RCU_LAUNCH_CHECK();
@@ -622,7 +673,8 @@ using namespace rcu;
 
 extern "C" size_t rcu_metrics_workspace_bytes(int n_subjects) {
   if (n_subjects < 1) n_subjects = 1;
-  return tickets_bytes(n_subjects) + (size_t)partial_blocks_cap(n_subjects) * kPartialSlots * sizeof(unsigned long long);
+  const size_t partial_bytes = (size_t)partial_blocks_cap(n_subjects) * kPartialSlots * sizeof(unsigned long long);
+  return ((partial_bytes + 255) & ~size_t(255)) + tickets_bytes(n_subjects) + 256;   // + slack for the round-down in tickets_of
 }
 
 extern "C" int rcu_metrics_workspace_init(void* workspace, size_t workspace_bytes, void* stream) {
@@ -725,22 +777,39 @@ extern "C" int rcu_eval_fused(const float* p, const uint8_t* prediction, const u
       RCU_CHECK_ARG(per_thread <= kMaxVoxelsPerThread, "subject of %lld voxels is too large for one launch (split it)", (long long)vps);
       RCU_CHECK_ARG(n_subjects <= 65535, "n_subjects %d exceeds grid.y limit", n_subjects);
       const int nb1 = n_bins + 1;
+      // in-bucket break points: the 16-byte table entry holds three; a denser cluster takes the scanning variant
+      int max_inside = 0;
+      {
+        int run = 0, run_bucket = -1;
+        for (int i = 0; i < up.joint_n; ++i) {
+          const float fb = up.joint[i] * (float)n_buckets;          // exact: power-of-two bucket count
+          int b = fb >= (float)n_buckets ? n_buckets - 1 : (int)fb;
+          if (b < 0) b = 0;
+          const bool on_edge = fb < (float)n_buckets && fb == (float)b;   // equal to the bucket's lower bound: part of `base`
+          if (on_edge) continue;
+          run = (b == run_bucket) ? run + 1 : 1;
+          run_bucket = b;
+          if (run > max_inside) max_inside = run;
+        }
+      }
+      static const bool allow_lut4 = [] { const char* e = std::getenv("RCU_HIST_LUT4"); return !(e && e[0] == '0'); }();
+      const bool lut4 = allow_lut4 && max_inside <= 3 && (n_buckets & (n_buckets - 1)) == 0;
       size_t smem = (size_t)nb1 * kHistThreads * 12 + (size_t)4 * n_classes * kHistThreads * 2;
-      smem = ((smem + 15) & ~size_t(15)) + kBreakPad * 4 + (kBreakPad + 8) * 4 + (size_t)n_buckets * 4 + 64;
-      unsigned int* tickets = reinterpret_cast<unsigned int*>(workspace);
-      unsigned long long* partials = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(workspace) + tickets_bytes(n_subjects));
+      smem = ((smem + 15) & ~size_t(15)) + kBreakPad * 4 + (kBreakPad + 8) * 4 + (size_t)n_buckets * (lut4 ? 16 : 4) + 64;
+      unsigned int* tickets = tickets_of(workspace, workspace_bytes, n_subjects);
+      unsigned long long* partials = reinterpret_cast<unsigned long long*>(workspace);
       dim3 grid((unsigned)bps, (unsigned)n_subjects);
-      static size_t configured[2][64] = {{0}};
+      static size_t configured[4][64] = {{0}};
       int dev = 0;
       RCU_CUDA(cudaGetDevice(&dev));
-      const int mi = mask ? 1 : 0;
+      const int mi = (mask ? 1 : 0) + (lut4 ? 2 : 0);
+      auto kern = mask ? (lut4 ? eval_fused_lut_kernel<true, true> : eval_fused_lut_kernel<true, false>)
+                       : (lut4 ? eval_fused_lut_kernel<false, true> : eval_fused_lut_kernel<false, false>);
       if (dev < 0 || dev >= 64 || smem > configured[mi][dev]) {
-        if (mask) RCU_CUDA(cudaFuncSetAttribute(eval_fused_lut_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else RCU_CUDA(cudaFuncSetAttribute(eval_fused_lut_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RCU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (dev >= 0 && dev < 64) configured[mi][dev] = smem;
       }
-      if (mask) eval_fused_lut_kernel<true><<<grid, kHistThreads, smem, st>>>(p, prediction, target, mask, (long long)vps, (int)bps, cp, up, n_buckets, out, tickets, partials);
-      else eval_fused_lut_kernel<false><<<grid, kHistThreads, smem, st>>>(p, prediction, target, nullptr, (long long)vps, (int)bps, cp, up, n_buckets, out, tickets, partials);
+      kern<<<grid, kHistThreads, smem, st>>>(p, prediction, target, mask, (long long)vps, (int)bps, cp, up, n_buckets, out, tickets, partials);
       RCU_LAUNCH_CHECK();
       return RCU_OK;
     }

@@ -920,7 +920,7 @@ extern "C" int rcu_unet_plan(rcu_unet* net, int height, int width, int max_image
   for (ConvLayer& L : net->convs) L.pool_dst = Act();
   int rc = push_conv(E[0], slice(CAT[0], sf, sf));
   if (rc) return rc;
-  net->convs[ci - 1].pool_dst = P[0];     // the pool that follows can ride in this conv's epilogue (halo kernel only)
+  net->convs[ci - 1].pool_dst = P[0];     // the pool that follows rides in this conv's epilogue (halo and wide kernels)
   for (int l = 1; l <= depth; ++l) {
     const int cp = sf << (l - 1), c = sf << l;
     push_pool(slice(CAT[l - 1], cp, cp), P[l - 1]);
@@ -1107,9 +1107,14 @@ extern "C" int rcu_unet_forward_ex(rcu_unet* net, const float* images, int64_t n
           }
           HaloOutMaps maps;
           for (int i = 0; i < L.wide.n_phases; ++i) maps.m[i] = L.map_out[i];
+          static const bool fuse_pool = [] { const char* e = std::getenv("RCU_WIDE_POOL"); return !(e && e[0] == '0'); }();
+          if (fuse_pool && L.wide.n_phases == 1 && L.pool_dst.base != nullptr) {
+            wp.pool_out = L.pool_dst.base; wp.pool_img_stride = L.pool_dst.img_stride; wp.pool_c = L.pool_dst.c_total;
+          }
           int rc = L.wide.n_phases == 4 ? launch_conv_wide<4>(L, wp, maps, st) : launch_conv_wide<9>(L, wp, maps, st);
           if (rc) return rc;
           ++launches;
+          pool_done = wp.pool_out != nullptr;
           continue;
         }
         ConvParams prm;

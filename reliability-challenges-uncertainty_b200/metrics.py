@@ -23,6 +23,8 @@ def _to_device(x, dtype, name):
     """Flat contiguous CUDA tensor of `dtype` for a numpy array / torch tensor (bool -> uint8)."""
     if x is None:
         return None
+    if torch.is_tensor(x) and x.is_cuda and x.dtype == dtype and x.is_contiguous():   # in-memory pipeline: nothing to do
+        return x if x.dim() == 1 else x.view(-1)
     if isinstance(x, np.ndarray):
         if x.dtype == np.bool_:
             x = x.view(np.uint8)
@@ -53,6 +55,31 @@ class _Workspace:
             _lib.check(_lib.lib().rcu_metrics_workspace_init(_lib.ptr(buf), buf.numel(), _lib.current_stream()))
             cls._cache[dev] = buf
         return buf
+
+
+_EDGES = {}
+_BREAKS = {}
+
+
+def _edges_for(n_bins):
+    """(float32 edge array, ctypes pointer) of the calibration bins, built once per n_bins."""
+    e = _EDGES.get(n_bins)
+    if e is None:
+        e = _EDGES[n_bins] = _f32_array(tables.calibration_edges_f32(n_bins))
+    return e
+
+
+def _breaks_for(breaks, seg):
+    """ctypes views of a break table, cached per table object (the hooks reuse one table for every subject)."""
+    key = (id(breaks), id(seg))
+    e = _BREAKS.get(key)
+    if e is None or e[0] is not breaks or e[1] is not seg:
+        if len(_BREAKS) > 64:
+            _BREAKS.clear()
+        b32, b32_p = _f32_array(breaks)
+        seg8 = np.ascontiguousarray(seg, dtype=np.uint8)
+        e = _BREAKS[key] = (breaks, seg, b32, b32_p, seg8, seg8.ctypes.data_as(_lib.c_uint8_p))
+    return e[3], e[5]
 
 
 def _f32_array(a):
@@ -173,23 +200,20 @@ def eval_fused(p, prediction, target, mask=None, n_bins=10, thresholds=tables.SW
     width = 3 * nb1 + 4 * n_classes + 1
     flat = (torch.empty if n > 0 else torch.zeros)((n_subjects * width,), dtype=torch.int64, device=dev)
     o1, o2, o3, o4 = n_subjects * nb1, 2 * n_subjects * nb1, 3 * n_subjects * nb1, 3 * n_subjects * nb1 + n_subjects * 4 * n_classes
-    count = flat[:o1].view(n_subjects, nb1)
-    positives = flat[o1:o2].view(n_subjects, nb1)
-    conf = flat[o2:o3].view(torch.float64).view(n_subjects, nb1)
-    table = flat[o3:o4].view(n_subjects, 4, n_classes)
-    invalid = flat[o4:]
     if n > 0:
-        edges, edges_p = _f32_array(tables.calibration_edges_f32(n_bins))
-        b32, b32_p = _f32_array(breaks)
-        seg = np.ascontiguousarray(seg, dtype=np.uint8)
+        _, edges_p = _edges_for(n_bins)
+        b32_p, seg_p = _breaks_for(breaks, seg)
         ws = _Workspace.get(n_subjects)
+        base = flat.data_ptr()
         _lib.check(_lib.lib().rcu_eval_fused(_lib.ptr(p_d), _lib.ptr(d_d), _lib.ptr(t_d), _lib.ptr(m_d), vps, n_subjects, edges_p, n_bins,
-                                             b32_p, len(breaks), seg.ctypes.data_as(_lib.c_uint8_p), n_classes, _lib.ptr(count),
-                                             _lib.ptr(positives), _lib.ptr(conf), _lib.ptr(table), _lib.ptr(invalid), _lib.ptr(ws),
-                                             ws.numel(), _lib.current_stream()))
+                                             b32_p, len(breaks), seg_p, n_classes, base, base + 8 * o1, base + 8 * o2, base + 8 * o3,
+                                             base + 8 * o4, _lib.ptr(ws), ws.numel(), _lib.current_stream()))
     if not sync:
-        return count, positives, conf, table, invalid, order
-    return (count.cpu().numpy(), positives.cpu().numpy(), conf.cpu().numpy(), table.cpu().numpy(), invalid.cpu().numpy(), order)
+        return (flat[:o1].view(n_subjects, nb1), flat[o1:o2].view(n_subjects, nb1), flat[o2:o3].view(torch.float64).view(n_subjects, nb1),
+                flat[o3:o4].view(n_subjects, 4, n_classes), flat[o4:], order)
+    host = flat.cpu().numpy()      # ONE device->host copy for all five tables
+    return (host[:o1].reshape(n_subjects, nb1), host[o1:o2].reshape(n_subjects, nb1),
+            host[o2:o3].view(np.float64).reshape(n_subjects, nb1), host[o3:o4].reshape(n_subjects, 4, n_classes), host[o4:], order)
 
 
 def philox_keep_scale_host(seed, p_drop, site_channels, slice_index0, n_slices, sample0, n_samples):
