@@ -1057,8 +1057,8 @@ extern "C" int rcu_unet_forward_ex(rcu_unet* net, const float* images, int64_t n
       pool_done = false;
       OpTimer timer(net, (int)op_index, st);
       if (op.kind == OP_FIRST) {
-        const int tiles = ((H + kFirstTile - 1) / kFirstTile) * ((W + kFirstTile - 1) / kFirstTile);
-        const size_t smem = ((size_t)net->in_channels * 9 * sf + (size_t)net->in_channels * 324) * sizeof(float);
+        const int tiles = ((H + kFirstTileH - 1) / kFirstTileH) * ((W + kFirstTileW - 1) / kFirstTileW);
+        const size_t smem = ((size_t)net->in_channels * 9 * sf + (size_t)net->in_channels * kFirstInPx) * sizeof(float);
         dim3 grid((unsigned)tiles, (unsigned)cs);
         if (sf == 32)
           first_conv_kernel<32><<<grid, 256, smem, st>>>(images, net->in_channels, H, W, (long long)s0, cs, n_samples, net->d_first_w,

@@ -61,7 +61,13 @@ __global__ void coef_kernel(CoefColumns cols, float2* __restrict__ coef, int n_i
 // lanes of a warp write 32 consecutive 16-byte pieces (8 x-adjacent pixels x 64 B): fully coalesced stores, and
 // only 8 coefficient pairs per thread and sample.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kFirstTile = 16;  // 16x16 pixels per block, 256 threads
+// 256 pixels per block of 256 threads as a wide, flat tile: every sample's store is kFirstTileH runs of
+// kFirstTileW * 64 bytes (4 KB with 32 output channels), long enough to stream into HBM pages
+#ifndef RCU_FIRST_TILE_W
+#define RCU_FIRST_TILE_W 64
+#endif
+constexpr int kFirstTileW = RCU_FIRST_TILE_W, kFirstTileH = 256 / kFirstTileW;
+constexpr int kFirstInW = kFirstTileW + 2, kFirstInH = kFirstTileH + 2, kFirstInPx = kFirstInW * kFirstInH;
 
 template <int C_OUT>
 __global__ void __launch_bounds__(256)
@@ -72,16 +78,16 @@ first_conv_kernel(const float* __restrict__ images, int c_in, int h, int w, long
   constexpr int PG = 256 / CG;       // pixel groups
   extern __shared__ float s_first[];
   float* s_w = s_first;                                  // [c_in*9][C_OUT]
-  float* s_in = s_first + c_in * 9 * C_OUT;              // [c_in][18][18]
-  const int tiles_x = (w + kFirstTile - 1) / kFirstTile;
+  float* s_in = s_first + c_in * 9 * C_OUT;              // [c_in][kFirstInH][kFirstInW]
+  const int tiles_x = (w + kFirstTileW - 1) / kFirstTileW;
   const int tile = blockIdx.x;
   const int sl = blockIdx.y;
-  const int ty0 = (tile / tiles_x) * kFirstTile, tx0 = (tile % tiles_x) * kFirstTile;
+  const int ty0 = (tile / tiles_x) * kFirstTileH, tx0 = (tile % tiles_x) * kFirstTileW;
   const float* img = images + (slice0 + sl) * (long long)c_in * h * w;
   for (int i = threadIdx.x; i < c_in * 9 * C_OUT; i += 256) s_w[i] = weight[i];
-  for (int i = threadIdx.x; i < c_in * 18 * 18; i += 256) {
-    const int c = i / 324, r = i - c * 324;
-    const int yy = ty0 + r / 18 - 1, xx = tx0 + r % 18 - 1;
+  for (int i = threadIdx.x; i < c_in * kFirstInPx; i += 256) {
+    const int c = i / kFirstInPx, r = i - c * kFirstInPx;
+    const int yy = ty0 + r / kFirstInW - 1, xx = tx0 + r % kFirstInW - 1;
     s_in[i] = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? img[((long long)c * h + yy) * w + xx] : 0.0f;
   }
   __syncthreads();
@@ -98,8 +104,8 @@ first_conv_kernel(const float* __restrict__ images, int c_in, int h, int w, long
       const float4 w1 = *reinterpret_cast<const float4*>(s_w + (ci * 9 + k) * C_OUT + cg * 8 + 4);
 #pragma unroll
       for (int j = 0; j < CG; ++j) {
-        const int p = pg + PG * j, ly = p >> 4, lx = p & 15;
-        const float v = s_in[ci * 324 + (ly + k / 3) * 18 + lx + k % 3];
+        const int p = pg + PG * j, ly = p / kFirstTileW, lx = p % kFirstTileW;
+        const float v = s_in[ci * kFirstInPx + (ly + k / 3) * kFirstInW + lx + k % 3];
         acc[j][0] = fmaf(v, w0.x, acc[j][0]); acc[j][1] = fmaf(v, w0.y, acc[j][1]);
         acc[j][2] = fmaf(v, w0.z, acc[j][2]); acc[j][3] = fmaf(v, w0.w, acc[j][3]);
         acc[j][4] = fmaf(v, w1.x, acc[j][4]); acc[j][5] = fmaf(v, w1.y, acc[j][5]);
@@ -114,7 +120,7 @@ first_conv_kernel(const float* __restrict__ images, int c_in, int h, int w, long
     for (int c = 0; c < 8; ++c) c8[c] = __ldg(cf + c);
 #pragma unroll
     for (int j = 0; j < CG; ++j) {
-      const int p = pg + PG * j, y = ty0 + (p >> 4), x = tx0 + (p & 15);
+      const int p = pg + PG * j, y = ty0 + p / kFirstTileW, x = tx0 + p % kFirstTileW;
       if (y >= h || x >= w) continue;
       uint32_t pk[4];
 #pragma unroll
