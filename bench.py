@@ -428,7 +428,7 @@ def run_gpu_arm(args):
     if os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f).get('dram_bytes_per_launch')
-    roofline = {'bound': 'tensor', 'kernel': 'conv_tc_kernel<BLOCK_N,KC> (all %d tcgen05 conv launches of a step, aggregated)' % (conv_launches // args.steps),
+    roofline = {'bound': 'tensor', 'kernel': 'conv_halo_kernel + conv_wide_kernel (all %d tcgen05 conv launches of a step, aggregated)' % (conv_launches // args.steps),
                 'achieved': achieved_tflops, 'peak': peaks['tflops_sustained'], 'unit': 'TFLOP/s',
                 'frac': achieved_tflops / peaks['tflops_sustained'], 'traffic': traffic,
                 'peak_source': '%s bf16_tflops_sustained (kernel timed inside a long step)' % peaks['source'],
