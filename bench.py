@@ -65,10 +65,14 @@ def synth_subject(seed):
     return images, blob.astype(np.uint8), brain.astype(np.uint8)
 
 
+DROPOUT = 0.05        # config/train_brats_baseline.yaml:6-12
+
+
 def make_state_dict(seed=20):
-    from oracle import restate as R  # weight SYNTHESIS only (seeded reference-style init); nothing measured here
-    cfg = R.UNetConfig(in_channels=CHANNELS)
-    return cfg, R.randomize_statistics(R.init_state_dict(cfg, seed), 7)
+    """Synthetic weights of the BraTS baseline net (rcu_b200.synth: seeded torch-default init, non-degenerate BN)."""
+    import rcu_b200  # noqa: F401
+    from rcu_b200 import synth
+    return synth.random_unet_state_dict(in_channels=CHANNELS, seed=seed)
 
 
 # ------------------------------------------------------------------------------------------------ clocks sampler
@@ -121,7 +125,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm (oracle port)
-def cpu_sample(n_slices, sd, cfg, images, target, mask, threads):
+def cpu_sample(n_slices, sd, images, target, mask, threads):
     """The reference's arithmetic for `n_slices` slices: McPredictStep(20) + MultiPredictionSummary on torch CPU, then
     AddBackgroundProbabilities/ToEntropy + EceBinaryNumpy(mask)+Dice+ConfusionMatrix + 11 x UncertaintyAndCorrectionEvalNumpy
     on numpy — the oracle restatement of those functions (oracle/restate.py).  Returns (seconds forward+summary, seconds metrics)."""
@@ -129,6 +133,7 @@ def cpu_sample(n_slices, sd, cfg, images, target, mask, threads):
     from oracle import restate as R
     torch.set_num_threads(threads)
     x = images[:n_slices]
+    cfg = R.UNetConfig(in_channels=CHANNELS, dropout=DROPOUT)
     sites = R.dropout_sites(cfg)
     g = torch.Generator().manual_seed(20)
     keep = [[(torch.rand((n_slices, c), generator=g) >= cfg.dropout).float() for (_, c) in sites] for _ in range(MC_STEPS)]
@@ -158,14 +163,14 @@ def run_reference_arm(args):
     import torch
     torch.set_grad_enabled(False)
     cores = os.cpu_count() or 1
-    cfg, sd = make_state_dict()
+    sd = make_state_dict()
     images, target, mask = synth_subject(1000)
     n_slices = args.cpu_slices
     for _ in range(args.warmup):
-        cpu_sample(1, sd, cfg, images, target, mask, cores)
+        cpu_sample(1, sd, images, target, mask, cores)
     times = []
     for _ in range(args.steps):
-        fwd, met = cpu_sample(n_slices, sd, cfg, images, target, mask, cores)
+        fwd, met = cpu_sample(n_slices, sd, images, target, mask, cores)
         times.append(fwd + met)
     ms = 1e3 * float(np.mean(times))
     value = n_slices * HEIGHT * WIDTH * MC_STEPS / (ms / 1e3)
@@ -215,8 +220,8 @@ def run_gpu_arm(args):
         sys.stderr.write('bench.py: --gpus %d but WORLD_SIZE=%d (launch N>1 with torch.distributed.run); using %d\n' % (args.gpus, world, world))
 
     peaks = measured_peaks()
-    cfg, sd = make_state_dict()
-    net = model.B200UNet(sd, in_channels=CHANNELS, dropout=cfg.dropout, device=device, seed=20)
+    sd = make_state_dict()
+    net = model.B200UNet(sd, in_channels=CHANNELS, dropout=DROPOUT, device=device, seed=20)
     images_h, target_h, mask_h = synth_subject(1000 + rank)
     images_pinned = images_h.pin_memory()
     images_d = images_h.to(device)
@@ -408,10 +413,10 @@ def run_gpu_arm(args):
 
     # ---------------- roofline of the dominant kernel family (tcgen05 convolutions)
     ops = net.op_table()
-    conv_ms = sum(float(op_ms[i]) for i, o in enumerate(ops) if o['kind'] == 'conv_tc')
-    conv_launches = int(sum(int(op_launches[i]) for i, o in enumerate(ops) if o['kind'] == 'conv_tc'))
+    conv_ms = sum(float(op_ms[i]) for i, o in enumerate(ops) if o['kind'] == 'conv')
+    conv_launches = int(sum(int(op_launches[i]) for i, o in enumerate(ops) if o['kind'] == 'conv'))
     images_per_step = SLICES * (MC_STEPS + 1)
-    conv_flop = 2.0 * sum(o['macs_per_image'] for o in ops if o['kind'] == 'conv_tc') * images_per_step * args.steps
+    conv_flop = 2.0 * sum(o['macs_per_image'] for o in ops if o['kind'] == 'conv') * images_per_step * args.steps
     achieved_tflops = conv_flop / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     per_layer = []
     for i, o in enumerate(ops):
@@ -451,8 +456,8 @@ def run_gpu_arm(args):
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        cpu_sample(1, sd, cfg, images_h, target_h, mask_h, cores)
-        fwd_s, met_s = cpu_sample(args.cpu_slices, sd, cfg, images_h, target_h, mask_h, cores)
+        cpu_sample(1, sd, images_h, target_h, mask_h, cores)
+        fwd_s, met_s = cpu_sample(args.cpu_slices, sd, images_h, target_h, mask_h, cores)
         cpu_baseline = {'value': args.cpu_slices * HEIGHT * WIDTH * MC_STEPS / (fwd_s + met_s), 'unit': UNIT, 'cores': cores, 'kind': 'port',
                         'sample': '%d of 155 slices (T=20 + weight-scaling pass) forward+summary %.2f s on %d torch threads, numpy metric set '
                                   '%.2f s on 1 thread; oracle port of the reference functions' % (args.cpu_slices, fwd_s, cores, met_s),
@@ -464,7 +469,7 @@ def run_gpu_arm(args):
         'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
         'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'l2_policy': 'inputs larger than L2 (143 MB images, 1.5 GB logits per step, 126 MB L2)',
-                   'weights': 'random init seed 20, BN statistics randomised (oracle.randomize_statistics)',
+                   'weights': 'random init seed 20, BN statistics randomised (rcu_b200.synth)',
                    'chunk_images': net.chunk_images, 'parallelism': 'subject-sharded x%d, no data-path collective' % world},
         'e2e': {'value': world * VOXELS * MC_STEPS / (e2e_ms * 1e-3), 'unit': UNIT, 'ms_per_step': e2e_ms,
                 'h2d_bytes_per_step': h2d['n'] // e2e_steps, 'd2h_bytes_per_step': d2h['n'] // e2e_steps,

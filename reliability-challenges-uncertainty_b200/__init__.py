@@ -16,12 +16,12 @@ The directory name follows the build contract (`reliability-challenges-uncertain
 from . import _lib  # noqa: F401
 from . import tables  # noqa: F401
 
-__all__ = ['_lib', 'tables', 'metrics', 'evaluation', 'model', 'steps', 'hooks', 'distributed', 'assembly']
+__all__ = ['_lib', 'tables', 'metrics', 'evaluation', 'model', 'steps', 'hooks', 'distributed', 'assembly', 'synth']
 
 
 def __getattr__(name):
     # torch-dependent submodules are imported on first use so that `import rcu_b200` stays cheap
-    if name in ('metrics', 'evaluation', 'model', 'steps', 'hooks', 'distributed', 'assembly'):
+    if name in ('metrics', 'evaluation', 'model', 'steps', 'hooks', 'distributed', 'assembly', 'synth'):
         import importlib
         return importlib.import_module('.' + name, __name__)
     raise AttributeError(name)

@@ -316,7 +316,7 @@ class B200UNet(nn.Module):
             macs = ctypes.c_int64()
             _lib.check(_lib.lib().rcu_unet_op_info(self._handle, i, ctypes.byref(kind), ctypes.byref(macs), ctypes.byref(ci),
                                                    ctypes.byref(co), ctypes.byref(h), ctypes.byref(w)))
-            out.append({'kind': ('first_conv', 'conv_tc', 'maxpool', 'coef')[kind.value], 'macs_per_image': int(macs.value),
+            out.append({'kind': ('first_conv', 'conv', 'maxpool', 'coef')[kind.value], 'macs_per_image': int(macs.value),
                         'c_in': ci.value, 'c_out': co.value, 'h': h.value, 'w': w.value})
         return out
 

@@ -243,7 +243,7 @@ def stage_halo_layers():
     ref.set_conv_impl(2)
     out_ref = ref.forward_samples(x, 2, dropout_mode=1, det_first=True, seed=5)
     ops = ref.op_table()
-    conv_ops = [i for i, o in enumerate(ops) if o['kind'] == 'conv_tc']
+    conv_ops = [i for i, o in enumerate(ops) if o['kind'] == 'conv']
     ok = True
     for ci, op_i in enumerate(conv_ops):
         o = ops[op_i]

@@ -10,8 +10,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import rcu_b200  # noqa: E402,F401
-from rcu_b200 import metrics, model  # noqa: E402
-from oracle import restate as R  # noqa: E402  (weights only: random-init state dicts)
+from rcu_b200 import metrics, model, synth  # noqa: E402
 
 torch.set_grad_enabled(False)
 dev = torch.device('cuda:0')
@@ -33,13 +32,12 @@ def timeit(fn, reps=7, warm=2):
 
 
 x = torch.randn(Z, 4, H, W, device=dev)
-cfg = R.UNetConfig(in_channels=4, sigma_out=True)
-sd = R.randomize_statistics(R.init_state_dict(cfg, 20), 7)
-net = model.B200UNet(sd, in_channels=4, dropout=cfg.dropout)
+sd = synth.random_unet_state_dict(in_channels=4, seed=20, sigma_out=True)
+net = model.B200UNet(sd, in_channels=4, dropout=0.05)
 base = timeit(lambda: net.forward_outputs(x, 1))
 with_sigma = timeit(lambda: net.forward_outputs(x, 1, sigma=True))
 print('deterministic forward, one subject: %.3f ms; with the sigma head: %.3f ms (+%.3f ms for conv_sigma.0 + 1x1)' % (base, with_sigma, with_sigma - base))
-post = model.B200PostNet(R.postnet_init_state_dict(32, 2, 3, 21))
+post = model.B200PostNet(synth.random_postnet_state_dict())
 fused = timeit(lambda: net.forward_outputs(x, 1, postnet=post))
 print('  + fused PostNet: %.3f ms (+%.3f ms; %.1f GFMA -> %.1f TFLOP/s fp32)' % (fused, fused - base, 3136 * vox / 1e9, 2 * 3136 * vox / (fused - base) / 1e9))
 feat = timeit(lambda: net.forward_outputs(x, 1, features=True))

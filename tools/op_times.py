@@ -7,14 +7,12 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import rcu_b200  # noqa: E402,F401
-from rcu_b200 import model  # noqa: E402
-from oracle import restate as R  # noqa: E402
+from rcu_b200 import model, synth  # noqa: E402
 
 torch.set_grad_enabled(False)
 n_slices = int(sys.argv[1]) if len(sys.argv) > 1 else 16
-cfg = R.UNetConfig(in_channels=4)
-sd = R.randomize_statistics(R.init_state_dict(cfg, 20), 7)
-net = model.B200UNet(sd, in_channels=4, dropout=cfg.dropout, device='cuda:0', seed=20)
+sd = synth.random_unet_state_dict(in_channels=4, seed=20)
+net = model.B200UNet(sd, in_channels=4, dropout=0.05, device='cuda:0', seed=20)
 x = torch.randn((n_slices, 4, 240, 240), generator=torch.Generator().manual_seed(1)).cuda()
 for _ in range(2):
     net.forward_samples(x, 21, dropout_mode=1, det_first=True)
