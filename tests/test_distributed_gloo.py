@@ -12,7 +12,7 @@ import torch.multiprocessing as mp
 from rcu_b200 import distributed as D
 from rcu_b200 import tables
 from oracle import restate as R
-from common import synth_metric_inputs
+from helpers import synth_metric_inputs
 
 
 def test_shard_bounds_cover_and_balance():

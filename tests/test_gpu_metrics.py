@@ -8,7 +8,7 @@ import torch
 from rcu_b200 import evaluation as ev
 from rcu_b200 import hooks, metrics, tables
 from oracle import restate as R
-from common import SWEEP, synth_metric_inputs, results_equal
+from helpers import SWEEP, synth_metric_inputs, results_equal
 
 pytestmark = pytest.mark.gpu
 CONF_RTOL = 1e-12

@@ -6,7 +6,7 @@ import torch
 
 from rcu_b200 import model, steps
 from oracle import restate as R
-from common import GOLDEN_CONFIGS
+from helpers import GOLDEN_CONFIGS
 
 pytestmark = pytest.mark.gpu
 torch.set_grad_enabled(False)

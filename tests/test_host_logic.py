@@ -8,7 +8,7 @@ import pytest
 import rcu_b200
 from rcu_b200 import tables
 from oracle import restate as R
-from common import SWEEP, synth_metric_inputs, results_equal
+from helpers import SWEEP, synth_metric_inputs, results_equal
 
 
 def test_calibration_edges_are_exact_float32_ceilings():

@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from oracle import restate as R
-from common import GOLDEN_CONFIGS, SWEEP, results_equal
+from helpers import GOLDEN_CONFIGS, SWEEP, results_equal
 
 torch.set_grad_enabled(False)
 

@@ -7,7 +7,7 @@ import pytest
 
 from rcu_b200 import tables
 from oracle import restate as R
-from common import SWEEP
+from helpers import SWEEP
 
 
 def cohort(n_subjects=5, shape=(6, 30, 40), seed=4):   # mirrors tests/golden/make_golden_tables.py
