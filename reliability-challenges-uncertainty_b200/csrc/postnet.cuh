@@ -24,7 +24,7 @@ struct PostNetWeights {
 // SRC_BF16: features are the bf16 NHWC tensor the U-Net forward left in its workspace (image order [sample][slice in
 // chunk], pixel stride `px_stride` elements); otherwise float32 NCHW [image][32][hw] as `UNet.features` holds them.
 template <int NC, bool SRC_BF16>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, SRC_BF16 ? 4 : 5)   // measured: 128 registers for the bf16 source, ~100 for the NCHW one (uncapped: 186 / 255 and up to 2x slower)
 postnet_kernel(const __grid_constant__ PostNetWeights wt, const void* __restrict__ src, int px_stride, long long img_stride, int hw,
                int n_img, int chunk_slices, long long slice0, long long n_slices_total, float* __restrict__ logits) {
   const long long total = (long long)n_img * hw;
