@@ -156,3 +156,26 @@ def test_host_philox_stream_matches_oracle():
     assert not np.array_equal(a, b)
     with pytest.raises(ValueError):
         metrics.philox_keep_scale_host(20, 1.5, sites, 0, 1, 0, 1)
+
+
+def test_synthetic_weights_have_the_reference_state_dict_layout():
+    """rcu_b200.synth (bench / smoke / profiling weights) must stay loadable wherever a reference state dict is: same keys,
+    shapes and dtypes as the oracle's restatement of the reference constructor (pinned to the reference in
+    tests/test_oracle_golden*.py), and a usable logit spread."""
+    import torch
+    from rcu_b200 import synth
+    for kw in (dict(in_channels=4), dict(in_channels=3), dict(in_channels=5), dict(in_channels=4, sigma_out=True)):
+        cfg = R.UNetConfig(**kw)
+        ref = R.init_state_dict(cfg, 20)
+        sd = synth.random_unet_state_dict(seed=20, **kw)
+        assert list(sd.keys()) != [] and set(sd) == set(ref)
+        for k, v in ref.items():
+            assert tuple(sd[k].shape) == tuple(v.shape) and sd[k].dtype == v.dtype, k
+        again = synth.random_unet_state_dict(seed=20, **kw)
+        assert all(torch.equal(sd[k], again[k]) for k in sd)
+    psd = synth.random_postnet_state_dict()
+    pref = R.postnet_init_state_dict(32, 2, 3, 21)
+    assert set(psd) == set(pref) and all(tuple(psd[k].shape) == tuple(pref[k].shape) for k in pref)
+    x = torch.randn(1, 4, 32, 32, generator=torch.Generator().manual_seed(0))
+    logits = R.unet_forward(synth.random_unet_state_dict(in_channels=4, seed=20), x, R.UNetConfig(in_channels=4))
+    assert torch.isfinite(logits).all() and logits.std() > 0.05
