@@ -90,3 +90,53 @@ def test_world_size_2_allreduce_paths(tmp_path):
     assert torch.allclose(mean, ref['probabilities'], rtol=0, atol=2e-7)
     assert torch.allclose(R.torch_entropy(mean, 1, True), ref['entropy'], rtol=0, atol=5e-7)
     assert [r['subject'] for r in got['rows']] == [0, 1, 2, 3, 4] and [r['rank'] for r in got['rows']] == [0, 0, 0, 1, 1]
+
+
+def _cohort(n_subjects=6, n=6000):
+    out = []
+    for s in range(n_subjects):
+        p, target, mask, pred, _ = synth_metric_inputs(n, 30 + s)
+        out.append((np.clip(p * (0.6 + 0.08 * s), 0, 1).astype(np.float32), target, mask, pred))
+    return out
+
+
+def _subject_row(s, p, target, mask, pred):
+    cnt, pos, conf = R.calibration_tables(p, target, mask=mask)
+    unc = R.normalized_entropy(R.add_background_probability(p))
+    return {'subject': s, 'count': cnt.astype(np.int64), 'positives': pos.astype(np.int64), 'conf': conf,
+            'ece': R.ece_binary(p, target, mask=mask)[0], 'dice': R.dice(pred, target),
+            'sweep': {th: R.uncertainty_and_correction(pred, target, unc, th) for th in tables.SWEEP_THRESHOLDS}}
+
+
+def _report_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        cohort = _cohort()
+        lo, hi = D.shard_bounds(len(cohort), world, rank)           # whole subjects per rank: no table all-reduce needed
+        rows = D.gather_rows([_subject_row(s, *cohort[s]) for s in range(lo, hi)])
+        if rank == 0:
+            torch.save(rows, os.path.join(out_dir, 'rows.pt'))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_subject_sharded_report_tables(tmp_path):
+    """Config-5 style sharding (whole subjects per rank): the gathered per-subject rows give the same
+    data-set level ECE and best-threshold table as one process over all subjects."""
+    world = 2
+    mp.spawn(_report_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    rows = torch.load(os.path.join(str(tmp_path), 'rows.pt'), weights_only=False)
+    assert [r['subject'] for r in rows] == list(range(6))
+    single = [_subject_row(s, *c) for s, c in enumerate(_cohort())]
+    got = tables.dataset_vs_mean_subject_ece(*(np.stack([r[k] for r in rows]) for k in ('count', 'positives', 'conf')))
+    exp = tables.dataset_vs_mean_subject_ece(*(np.stack([r[k] for r in single]) for k in ('count', 'positives', 'conf')))
+    assert got == exp and np.isclose(got['ece'], np.mean([r['ece'] for r in single]), rtol=1e-12)
+    # the pooled ECE equals the ECE of the concatenated voxels
+    cohort = _cohort()
+    pooled = R.ece_binary(np.concatenate([c[0] for c in cohort]), np.concatenate([c[1] for c in cohort]),
+                          mask=np.concatenate([c[2] for c in cohort]))[0]
+    assert np.isclose(got['ds_ece'], pooled, rtol=1e-12)
+    a = tables.best_threshold_summary([r['sweep'] for r in rows], [r['ece'] for r in rows], [r['dice'] for r in rows])
+    b = R.best_threshold_summary([r['sweep'] for r in single], [r['ece'] for r in single], [r['dice'] for r in single])
+    assert a == b
