@@ -204,7 +204,7 @@ def _as_bool_u8(x):
     return (np.asarray(x) != 0).view(np.uint8)
 
 
-def _sweep_table(to_evaluate, threshold, mask, mask_tag):
+def _sweep_table(to_evaluate, threshold, mask, mask_src):
     """Joint table for `threshold`, shared between strategies evaluated on the same `to_evaluate` dict.
 
     The uncertainty entry decides the route: float64 numpy (what ToEntropy produces) -> exact float64 comparison on
@@ -218,14 +218,15 @@ def _sweep_table(to_evaluate, threshold, mask, mask_tag):
     kind = 'u64' if is64 else 'u32'
     group = tables.SWEEP_THRESHOLDS if threshold in tables.SWEEP_THRESHOLDS else (threshold,)
     cache = to_evaluate.setdefault(_CACHE_KEY, {})
-    key = (kind, group, mask_tag, id(unc), id(prediction), id(target))
+    key = (kind, group, id(mask_src) if mask_src is not None else None, id(unc), id(prediction), id(target))
     if key not in cache:
         bkey = ('bool', id(prediction), id(target))
         if bkey not in cache:
-            cache[bkey] = (_as_bool_u8(prediction), _as_bool_u8(target))
+            # the entries keep the keyed arrays alive: an id() can then never be recycled for another array of this dict
+            cache[bkey] = (_as_bool_u8(prediction), _as_bool_u8(target), prediction, target)
         table, _, order = metrics.ue_tables(unc, cache[bkey][0], cache[bkey][1], group, mask, kind=kind)
-        cache[key] = (table[0], list(np.asarray(group)[order]))
-    table, sorted_ths = cache[key]
+        cache[key] = (table[0], list(np.asarray(group)[order]), unc, mask_src)
+    table, sorted_ths = cache[key][:2]
     return table, sorted_ths.index(threshold)
 
 
@@ -242,7 +243,7 @@ class UncertaintyErrorDiceNumpy(NumpyEvaluationStrategy):
         if self.with_mask:
             boarder = to_evaluate['target_boarder']
             mask = (~boarder) if torch.is_tensor(boarder) else ~np.asarray(boarder, dtype=bool)
-        table, k = _sweep_table(to_evaluate, self.uncertainty_threshold, mask, 'boarder' if self.with_mask else None)
+        table, k = _sweep_table(to_evaluate, self.uncertainty_threshold, mask, to_evaluate['target_boarder'] if self.with_mask else None)
         tp, tn, fp, fn, tpu, tnu, fpu, fnu = tables.counts_at_threshold(table, k)
         results['{}precision'.format(self.prefix)] = tables.error_precision(tpu, tnu, fpu, fnu)
         results['{}recall'.format(self.prefix)] = tables.error_recall(fp, fn, fpu, fnu)
