@@ -369,6 +369,98 @@ static void run_mma_rate(int sms) {
   cudaFree(dcyc);
 }
 
+// ------------------------------------------------------------------------------------------------ 3b: swapped operand roles
+// Next-round question ("what comes next"): with the WEIGHTS as the A operand (M = 64 or 128 rows, from
+// shared memory or resident in TMEM) and the PIXELS as the B operand (N = 128 / 256 row-shifted SWIZZLE_128B views of an
+// 8-pixel-wide halo tile), is the MMA rate bound by the B stream alone?  Timing only (operands are zeros / whatever TMEM holds).
+__device__ __forceinline__ void umma_bf16_tmem_a(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <int M, int N>
+__global__ void __launch_bounds__(128, 1) mma_rate_ws_kernel(int a_in_tmem, int iters, long long* cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t s_tmem;
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+  if (threadIdx.x < 32) { tmem_alloc(smem_u32(&s_tmem), 512); tmem_relinquish(); }
+  for (int i = threadIdx.x; i < 190 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem_raw + (base - smem_u32(smem_raw)))[i] = 0;
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  if (threadIdx.x < 32) {
+    const bool leader = elect_one() != 0;
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+    // B: pixels.  N / 8 groups of 8 x-adjacent pixels, one group per tile row of a 10-pixel-pitch halo (SBO = 10 rows)
+    const uint64_t b0 = make_desc(base, 16, 1280, 2, 0);
+    // A: weights [tap][M rows][64 channels] as 128-byte SWIZZLE_128B rows, behind the halo region (N/8 + 2 rows of 10 pixels)
+    const uint32_t a_base = base + 64 * 1024;
+    const uint64_t a0 = make_desc(a_base, 16, 1024, 2, 0);
+    const uint32_t tm_a = tmem + 256u;     // TMEM-resident A: one K = 16 slice is 8 columns; 9 taps x 4 slices = 288 columns
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const uint32_t boff = (uint32_t)(((tap / 3) * 10 + tap % 3) * 128) >> 4;
+        const uint32_t aoff = (uint32_t)(tap * M * 128) >> 4;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          if (leader) {
+            if (a_in_tmem) umma_bf16_tmem_a(tmem, tm_a + (uint32_t)((tap * 4 + ks) % 28) * 8u, b0 + boff + 2 * ks, idesc, 1u);
+            else umma_bf16(tmem, a0 + aoff + 2 * ks, b0 + boff + 2 * ks, idesc, 1u);
+          }
+        }
+      }
+    }
+    if (leader) umma_commit(smem_u32(&bar));
+    mbar_wait(smem_u32(&bar), 0);
+    const long long t1 = clock64();
+    if (leader) cycles[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc(tmem, 512);
+}
+
+template <int M, int N>
+static void run_ws_one(int sms, long long* dcyc) {
+  const int smem = 200 * 1024;
+  CK(cudaFuncSetAttribute(mma_rate_ws_kernel<M, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  for (int a_in_tmem = 0; a_in_tmem <= 1; ++a_in_tmem) {
+    const int iters = 200;
+    CK(cudaMemset(dcyc, 0, sms * sizeof(long long)));
+    mma_rate_ws_kernel<M, N><<<sms, 128, smem>>>(a_in_tmem, iters, dcyc);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("MMA_WS M=%d N=%d A=%s failed: %s\n", M, N, a_in_tmem ? "tmem" : "smem", cudaGetErrorString(e)); exit(3); }
+    std::vector<long long> h(sms);
+    CK(cudaMemcpy(h.data(), dcyc, sms * sizeof(long long), cudaMemcpyDeviceToHost));
+    long long mx = 0;
+    for (long long c : h) mx = c > mx ? c : mx;
+    const double cyc = (double)mx / (iters * 36.0);
+    printf("MMA_WS weights-as-A M=%3d (%s) pixels-as-B N=%3d: %.1f clk/MMA -> %.0f MAC/clk/SM; smem operand bytes/MMA %d -> %.0f B/clk\n", M,
+           a_in_tmem ? "TMEM" : "smem", N, cyc, (double)M * N * 16 / cyc, (a_in_tmem ? 0 : M * 32) + N * 32,
+           ((a_in_tmem ? 0 : M * 32) + N * 32) / cyc);
+  }
+}
+
+static void run_ws(int sms) {
+  long long* dcyc;
+  CK(cudaMalloc(&dcyc, sms * sizeof(long long)));
+  run_ws_one<64, 128>(sms, dcyc);
+  run_ws_one<64, 256>(sms, dcyc);
+  run_ws_one<128, 128>(sms, dcyc);
+  run_ws_one<128, 256>(sms, dcyc);
+  cudaFree(dcyc);
+}
+
 // ------------------------------------------------------------------------------------------------ 4: L2 -> smem bandwidth
 __global__ void __launch_bounds__(256, 1) cpasync_bw_kernel(const uint8_t* __restrict__ src, size_t bytes_per_cta, int rounds, long long* cycles) {
   extern __shared__ uint8_t smem_raw[];
@@ -615,6 +707,7 @@ int main(int argc, char** argv) {
   if (all || std::string(what) == "tma5d") run_tma5d();
   if (all || std::string(what) == "tmabox") run_tma_box(prop.multiProcessorCount);
   if (all || std::string(what) == "rate") run_mma_rate(prop.multiProcessorCount);
+  if (all || std::string(what) == "ws") run_ws(prop.multiProcessorCount);
   if (all || std::string(what) == "bw") run_bw(prop.multiProcessorCount);
   return 0;
 }
