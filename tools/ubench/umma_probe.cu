@@ -4,6 +4,8 @@
 //   2. the same with SWIZZLE_128B rows (one pixel = one 128-byte row) and the descriptor's base_offset field
 //   3. tcgen05.mma issue rate vs N for shared-memory operands (is N=32/64 shared-memory-read bound?)
 //   4. L2 -> shared memory bandwidth per SM with cp.async (16 B per thread) and with bulk copies
+//   next round (written, compiled, not yet run): `ws` — weights as the A operand (smem or TMEM) against pixel views as B;
+//   `coll` — A-operand collector reuse across MMAs that share an input view
 //
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I reliability-challenges-uncertainty_b200/csrc \
 //        tools/ubench/umma_probe.cu -o tools/ubench/umma_probe
@@ -461,6 +463,101 @@ static void run_ws(int sms) {
   cudaFree(dcyc);
 }
 
+// ------------------------------------------------------------------------------------------------ 3c: A-operand collector reuse
+// Up-path phases share input views: consecutive MMAs with the SAME A tile and different B (weights of another phase) can
+// keep A in the tensor pipe's collector (.collector::a::fill / ::use / ::lastuse -> SASS A_KEEP / A_REUSE).  Does a reused A
+// take the 32 clk of its shared-memory read off the MMA?  Timing only.
+template <int MODE>   // 0: plain, 1: fill, 2: use, 3: lastuse
+__device__ __forceinline__ void umma_bf16_coll(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
+  if (MODE == 0) { umma_bf16(tmem_d, desc_a, desc_b, idesc, 1u); return; }
+#define RCU_COLL_MMA(Q)                                                                                                   \
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\ttcgen05.mma.cta_group::1.kind::f16.collector::a::" Q        \
+               " [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc) : "memory")
+  if (MODE == 1) RCU_COLL_MMA("fill");
+  if (MODE == 2) RCU_COLL_MMA("use");
+  if (MODE == 3) RCU_COLL_MMA("lastuse");
+#undef RCU_COLL_MMA
+}
+
+template <int N, int GROUP>   // GROUP consecutive MMAs share one A tile
+__global__ void __launch_bounds__(128, 1) mma_rate_coll_kernel(int use_collector, int iters, long long* cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t s_tmem;
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+  if (threadIdx.x < 32) { tmem_alloc(smem_u32(&s_tmem), 512); tmem_relinquish(); }
+  for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem_raw + (base - smem_u32(smem_raw)))[i] = 0;
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  if (threadIdx.x < 32) {
+    const bool leader = elect_one() != 0;
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(N >> 3) << 17) | (uint32_t(128 >> 4) << 24);
+    const uint64_t a0 = make_desc(base, 16, 1280, 2, 0);
+    const uint64_t b0 = make_desc(base + 96 * 1024, 16, 1024, 2, 0);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int view = 0; view < 9; ++view) {
+        const uint32_t aoff = (uint32_t)(((view / 3) * 10 + view % 3) * 128) >> 4;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+          for (int g = 0; g < GROUP; ++g) {     // phase g: its own accumulator and its own weights, the same A tile
+            const uint32_t d = tmem + (uint32_t)(g * N);
+            const uint64_t b = b0 + ((uint32_t)(g * N * 128) >> 4) + 2 * ks;
+            if (leader) {
+              if (!use_collector || GROUP == 1) umma_bf16_coll<0>(d, a0 + aoff + 2 * ks, b, idesc);
+              else if (g == 0) umma_bf16_coll<1>(d, a0 + aoff + 2 * ks, b, idesc);
+              else if (g + 1 < GROUP) umma_bf16_coll<2>(d, a0 + aoff + 2 * ks, b, idesc);
+              else umma_bf16_coll<3>(d, a0 + aoff + 2 * ks, b, idesc);
+            }
+          }
+        }
+      }
+    }
+    if (leader) umma_commit(smem_u32(&bar));
+    mbar_wait(smem_u32(&bar), 0);
+    const long long t1 = clock64();
+    if (leader) cycles[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc(tmem, 512);
+}
+
+template <int N, int GROUP>
+static void run_coll_one(int sms, long long* dcyc) {
+  const int smem = 200 * 1024;
+  CK(cudaFuncSetAttribute(mma_rate_coll_kernel<N, GROUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  for (int use = 0; use <= 1; ++use) {
+    const int iters = 100;
+    CK(cudaMemset(dcyc, 0, sms * sizeof(long long)));
+    mma_rate_coll_kernel<N, GROUP><<<sms, 128, smem>>>(use, iters, dcyc);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("MMA_COLL N=%d group=%d failed: %s\n", N, GROUP, cudaGetErrorString(e)); exit(3); }
+    std::vector<long long> h(sms);
+    CK(cudaMemcpy(h.data(), dcyc, sms * sizeof(long long), cudaMemcpyDeviceToHost));
+    long long mx = 0;
+    for (long long c : h) mx = c > mx ? c : mx;
+    printf("MMA_COLL M=128 N=%3d, %d MMAs per A tile, collector %s: %.1f clk/MMA\n", N, GROUP, use ? "fill/use/lastuse" : "off             ",
+           (double)mx / (iters * 36.0 * GROUP));
+  }
+}
+
+static void run_coll(int sms) {
+  long long* dcyc;
+  CK(cudaMalloc(&dcyc, sms * sizeof(long long)));
+  run_coll_one<32, 2>(sms, dcyc);
+  run_coll_one<32, 4>(sms, dcyc);
+  run_coll_one<64, 2>(sms, dcyc);
+  run_coll_one<64, 4>(sms, dcyc);
+  cudaFree(dcyc);
+}
+
 // ------------------------------------------------------------------------------------------------ 4: L2 -> smem bandwidth
 __global__ void __launch_bounds__(256, 1) cpasync_bw_kernel(const uint8_t* __restrict__ src, size_t bytes_per_cta, int rounds, long long* cycles) {
   extern __shared__ uint8_t smem_raw[];
@@ -708,6 +805,7 @@ int main(int argc, char** argv) {
   if (all || std::string(what) == "tmabox") run_tma_box(prop.multiProcessorCount);
   if (all || std::string(what) == "rate") run_mma_rate(prop.multiProcessorCount);
   if (all || std::string(what) == "ws") run_ws(prop.multiProcessorCount);
+  if (all || std::string(what) == "coll") run_coll(prop.multiProcessorCount);
   if (all || std::string(what) == "bw") run_bw(prop.multiProcessorCount);
   return 0;
 }
