@@ -231,6 +231,8 @@ def correction_results(tp, tn, fp, fn, tpu, tnu, fpu, fnu, results=None):
     Correcting the thresholded-uncertain voxels to background moves tpu from tp to fn and fpu from fp to tn;
     correcting them to foreground moves fnu from fn to tp and tnu from tn to fp."""
     r = {} if results is None else results
+    # numpy integers like the reference's np.sum results: 0 / 0 and x / 0 give nan / inf (compared below), not an exception
+    tp, tn, fp, fn, tpu, tnu, fpu, fnu = (np.int64(v) for v in (tp, tn, fp, fn, tpu, tnu, fpu, fnu))
     r['tpu'], r['tnu'], r['fpu'], r['fnu'] = tpu, tnu, fpu, fnu
     r['tp'], r['tn'], r['fp'], r['fn'] = tp, tn, fp, fn
     with np.errstate(divide='ignore', invalid='ignore'):
