@@ -10,7 +10,7 @@ import pytest
 import torch
 
 from oracle import ref_shim
-from rcu_b200 import assembly, hooks as b200_hooks
+from rcu_b200 import assembly, hooks as b200_hooks, nifti
 
 pytestmark = pytest.mark.skipif(not ref_shim.available(), reason='reference tree not present on this box')
 
@@ -20,7 +20,7 @@ class IndexExpression:
         self.expression = expression
 
 
-def test_unmodified_loop_with_device_assembler():
+def test_unmodified_loop_with_device_assembler(tmp_path):
     ref_shim.load()
     import common.trainloop.loops as loops
     import common.trainloop.context as ctx
@@ -57,7 +57,8 @@ def test_unmodified_loop_with_device_assembler():
             return {'subject': subject}
 
     metrics_hook = MetricsProbe()
-    hook = ref_hooks.ReducedComposeTestLoopHook([Recorder(), metrics_hook])
+    file_hook = nifti.AsyncNiftiWriteHook(out_dir=str(tmp_path))
+    hook = ref_hooks.ReducedComposeTestLoopHook([Recorder(), metrics_hook, file_hook])
     test = loops.Test([PredictStep()], [SubjectStep()], assembly.DeviceSubjectAssembler(), entries=('probabilities',), convert_fn=None)
     samples = [(s, z) for s in sorted(volumes) for z in range(volumes[s].shape[0])]
     batch_size = 4
@@ -84,6 +85,14 @@ def test_unmodified_loop_with_device_assembler():
         assert torch.allclose(p, probs[:, 1], rtol=0, atol=1e-6) and p.is_contiguous()
         assert (prediction != (probs[:, 1] > probs[:, 0]).to(torch.uint8)).sum().item() <= 1
         assert np.array_equal(target, labels[subject])
+    # ... and the file hook wrote what WriteHook writes (bin-dl/brats_test_default.py:96-108), in the background
+    hook.on_test_end(task_context, None)
+    for subject in (0, 1):
+        p_file, _ = nifti.read_nifti(str(tmp_path / '{}_probabilities.nii.gz'.format(subject)))
+        d_file, _ = nifti.read_nifti(str(tmp_path / '{}_prediction.nii.gz'.format(subject)))
+        assert p_file.dtype == np.float32 and d_file.dtype == np.uint8
+        assert np.array_equal(p_file, [e for e in evaluated if e[0] == subject][0][1].numpy())
+        assert np.array_equal(d_file, [e for e in evaluated if e[0] == subject][0][2].numpy())
 
 
 def test_2d_assembler_in_the_unmodified_loop():
