@@ -5,7 +5,8 @@
 //   3. tcgen05.mma issue rate vs N for shared-memory operands (is N=32/64 shared-memory-read bound?)
 //   4. L2 -> shared memory bandwidth per SM with cp.async (16 B per thread) and with bulk copies
 //   next round (written, compiled, not yet run): `ws` — weights as the A operand (smem or TMEM) against pixel views as B;
-//   `coll` — A-operand collector reuse across MMAs that share an input view
+//   `coll` — A-operand collector reuse across MMAs that share an input view; `wst` — correctness of the swapped roles
+//   (weights M = 128 / 64 as A, 128 shifted pixels as B) incl. which TMEM lane holds which output channel
 //
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I reliability-challenges-uncertainty_b200/csrc \
 //        tools/ubench/umma_probe.cu -o tools/ubench/umma_probe
@@ -13,6 +14,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -463,6 +465,122 @@ static void run_ws(int sms) {
   cudaFree(dcyc);
 }
 
+// ------------------------------------------------------------------------------------------------ 3b': swapped roles, correctness
+// D[co][pixel] = sum_tap sum_ci W[tap][co][ci] * X[pixel + shift(tap)][ci] with the weights as the A operand (M rows = output
+// channels) and NP = 128 pixels (16 rows of 8, pitch-10 halo) as the B operand through row-shifted SWIZZLE_128B views.  The
+// kernel dumps all 128 TMEM lanes x NP columns; the host finds which lane holds which output channel (the M = 64
+// accumulator layout is not in the guides at hand) and checks the values.
+template <int M>
+__global__ void __launch_bounds__(128, 1) wst_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w, float* __restrict__ out) {
+  constexpr int C = 64, P = 10, NP = 128, RB = 128;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sp = smem_raw + (base - smem_u32(smem_raw));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t s_tmem;
+  const uint32_t sX = base, sW = base + 32 * 1024;        // halo 18 x 10 rows of 128 B = 23 KB; weights 9 x M x 128 B
+  for (int i = threadIdx.x; i < 18 * 10 * (C / 8); i += blockDim.x) {
+    const int g = i % (C / 8), px = (i / (C / 8)) % 10, py = i / (C / 8) / 10;
+    const uint4 v = *reinterpret_cast<const uint4*>(x + ((size_t)(py * 10 + px) * C + g * 8));
+    const uint32_t row = (uint32_t)(py * P + px) * RB;
+    *reinterpret_cast<uint4*>(sp + row + (uint32_t)((g ^ ((row >> 7) & 7u)) * 16)) = v;
+  }
+  for (int i = threadIdx.x; i < 9 * M * (C / 8); i += blockDim.x) {
+    const int g = i % (C / 8), co = (i / (C / 8)) % M, tap = i / (C / 8) / M;
+    const uint4 v = *reinterpret_cast<const uint4*>(w + ((size_t)(tap * M + co) * C + g * 8));
+    const uint32_t row = (uint32_t)tap * (M * RB) + (uint32_t)co * RB;
+    *reinterpret_cast<uint4*>(sp + (sW - base) + row + (uint32_t)((g ^ ((row >> 7) & 7u)) * 16)) = v;
+  }
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+  if (threadIdx.x < 32) { tmem_alloc(smem_u32(&s_tmem), 128); tmem_relinquish(); }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(NP >> 3) << 17) | (uint32_t(M >> 4) << 24);
+    int first = 1;
+    for (int tap = 0; tap < 9; ++tap) {
+      const int ty = tap / 3, tx = tap % 3;
+      for (int ks = 0; ks < C / 16; ++ks) {
+        const uint64_t da = make_desc(sW + (uint32_t)tap * (M * RB) + (uint32_t)ks * 32, 16, 8 * RB, 2, 0);          // weights: dense rows
+        const uint64_t db = make_desc(sX + (uint32_t)(ty * P + tx) * RB + (uint32_t)ks * 32, 16, P * RB, 2, 0);      // pixels: shifted view
+        umma_bf16(tmem, da, db, idesc, first ? 0u : 1u);
+        first = 0;
+      }
+    }
+    umma_commit(smem_u32(&bar));
+  }
+  mbar_wait(smem_u32(&bar), 0);
+  tc_fence_after();
+  const int warp = threadIdx.x >> 5;
+  for (int cb = 0; cb < NP; cb += 32) {
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb, v);
+    tmem_ld_wait();
+    for (int c = 0; c < 32; ++c) out[threadIdx.x * NP + cb + c] = __uint_as_float(v[c]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc(tmem, 128);
+}
+
+template <int M>
+static void run_wst() {
+  const int C = 64, NP = 128;
+  std::vector<__nv_bfloat16> hx(18 * 10 * C), hw(9 * M * C);
+  std::vector<float> fx(hx.size()), fw(hw.size());
+  srand(4321 + M);
+  for (size_t i = 0; i < hx.size(); ++i) { const float v = (float)(rand() % 17 - 8) / 8.0f; hx[i] = __float2bfloat16(v); fx[i] = __bfloat162float(hx[i]); }
+  for (size_t i = 0; i < hw.size(); ++i) { const float v = (float)(rand() % 13 - 6) / 16.0f; hw[i] = __float2bfloat16(v); fw[i] = __bfloat162float(hw[i]); }
+  __nv_bfloat16 *dx, *dw;
+  float* dout;
+  CK(cudaMalloc(&dx, hx.size() * 2)); CK(cudaMalloc(&dw, hw.size() * 2)); CK(cudaMalloc(&dout, 128 * NP * 4));
+  CK(cudaMemcpy(dx, hx.data(), hx.size() * 2, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dw, hw.data(), hw.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dout, 0xff, 128 * NP * 4));
+  const int smem = 160 * 1024;
+  CK(cudaFuncSetAttribute(wst_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  wst_kernel<M><<<1, 128, smem>>>(dx, dw, dout);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("WST M=%d: kernel failed: %s\n", M, cudaGetErrorString(e)); exit(2); }
+  std::vector<float> got(128 * NP);
+  CK(cudaMemcpy(got.data(), dout, got.size() * 4, cudaMemcpyDeviceToHost));
+  // reference D[co][pixel], pixel = y * 8 + x of the 16 x 8 tile inside the 18 x 10 halo
+  std::vector<float> ref((size_t)M * NP, 0.f);
+  for (int co = 0; co < M; ++co)
+    for (int p = 0; p < NP; ++p) {
+      const int y = p / 8, xq = p % 8;
+      float acc = 0.f;
+      for (int tap = 0; tap < 9; ++tap)
+        for (int ci = 0; ci < C; ++ci) acc += fw[((size_t)tap * M + co) * C + ci] * fx[((size_t)(y + tap / 3) * 10 + xq + tap % 3) * C + ci];
+      ref[(size_t)co * NP + p] = acc;
+    }
+  // which TMEM lane holds which output channel?
+  int mapped = 0, bad_values = 0;
+  printf("WST weights-as-A M=%d, 128 pixels as B: lane -> channel:", M);
+  for (int lane = 0; lane < 128; ++lane) {
+    int best = -1;
+    for (int co = 0; co < M && best < 0; ++co) {
+      int ok = 1;
+      for (int p = 0; p < NP && ok; ++p) ok = fabsf(got[(size_t)lane * NP + p] - ref[(size_t)co * NP + p]) <= 1e-2f * (1.f + fabsf(ref[(size_t)co * NP + p]));
+      if (ok) best = co;
+    }
+    if (best >= 0) { ++mapped; if (lane < 8 || lane % 16 == 0) printf(" %d->%d", lane, best); }
+  }
+  for (int co = 0; co < M; ++co) {   // every channel must be somewhere
+    int found = 0;
+    for (int lane = 0; lane < 128 && !found; ++lane) {
+      int ok = 1;
+      for (int p = 0; p < NP && ok; ++p) ok = fabsf(got[(size_t)lane * NP + p] - ref[(size_t)co * NP + p]) <= 1e-2f * (1.f + fabsf(ref[(size_t)co * NP + p]));
+      found = ok;
+    }
+    bad_values += !found;
+  }
+  printf("\nWST M=%d: %d lanes hold a channel, %d of %d channels not found -> %s\n", M, mapped, bad_values, M, bad_values == 0 ? "OK" : "WRONG");
+  cudaFree(dx); cudaFree(dw); cudaFree(dout);
+}
+
 // ------------------------------------------------------------------------------------------------ 3c: A-operand collector reuse
 // Up-path phases share input views: consecutive MMAs with the SAME A tile and different B (weights of another phase) can
 // keep A in the tensor pipe's collector (.collector::a::fill / ::use / ::lastuse -> SASS A_KEEP / A_REUSE).  Does a reused A
@@ -806,6 +924,7 @@ int main(int argc, char** argv) {
   if (all || std::string(what) == "rate") run_mma_rate(prop.multiProcessorCount);
   if (all || std::string(what) == "ws") run_ws(prop.multiProcessorCount);
   if (all || std::string(what) == "coll") run_coll(prop.multiProcessorCount);
+  if (all || std::string(what) == "wst") { run_wst<128>(); run_wst<64>(); }
   if (all || std::string(what) == "bw") run_bw(prop.multiProcessorCount);
   return 0;
 }
