@@ -203,7 +203,7 @@ def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
     import rcu_b200  # noqa: F401
-    from rcu_b200 import model, steps, metrics, hooks, tables, _lib
+    from rcu_b200 import model, steps, metrics, hooks, tables
 
     torch.set_grad_enabled(False)
     rank = int(os.environ.get('RANK', '0'))

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-import rcu_b200
+import rcu_b200  # noqa: F401  (registers the package directory under this name)
 from rcu_b200 import _lib
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -27,7 +27,7 @@ def _worker(rank, world, port, out_dir):
     sys.path.insert(0, root)
     sys.path.insert(0, os.path.join(root, 'tests'))
     import rcu_b200  # noqa: F401
-    from rcu_b200 import distributed as D, metrics, model, steps, tables
+    from rcu_b200 import distributed as D, metrics, model, steps
     from oracle import restate as R
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     torch.cuda.set_device(rank)

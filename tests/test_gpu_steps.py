@@ -1,6 +1,5 @@
 """GPU tests of the drop-in BatchSteps: same output keys / shapes / dtypes / devices as the reference steps, values
 within the stated bf16 tolerance of the reference golden outputs."""
-import numpy as np
 import pytest
 import torch
 

@@ -1,11 +1,10 @@
 """CPU tests of the product's host-side logic (no GPU, no kernels): parameter tables, table reductions, topology
 bookkeeping and the host Philox stream — each checked against the oracle / the golden fixtures."""
-import ctypes
 
 import numpy as np
 import pytest
 
-import rcu_b200
+import rcu_b200  # noqa: F401  (registers the package directory under this name)
 from rcu_b200 import tables
 from oracle import restate as R
 from helpers import SWEEP, synth_metric_inputs, results_equal

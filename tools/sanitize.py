@@ -10,7 +10,6 @@ fused histogram (single and batched), border mask, min / max, confidence prepara
 import os
 import sys
 
-import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
