@@ -284,7 +284,8 @@ int rcu_unet_total_dropout_channels(const rcu_unet* net);
 int rcu_unet_debug_activation(rcu_unet* net, int index, float* out, size_t out_elems, void* stream);
 /* Selects the convolution implementation: 0 = tcgen05/TMEM/TMA implicit GEMM (default, the product path: halo-tile
  * kernel for the thin high-resolution layers, per-tap kernel for the rest), 1 = straightforward CUDA-core
- * fp32-accumulate kernel over the same bf16 data (on-device cross-check only), 2 = tcgen05 per-tap kernel everywhere. */
+ * fp32-accumulate kernel over the same bf16 data (on-device cross-check only), 2 = tcgen05 per-tap kernel everywhere,
+ * 3 = as 0 but the c_out = 32 layers run the pixel-row halo kernel instead of the pixel-pair one (A/B and parity). */
 int rcu_unet_set_conv_impl(rcu_unet* net, int impl);
 /* Debug: bit i of `mask` lets conv i (execution order, the first conv excluded) use the halo-tile kernel when it is
  * eligible; cleared bits fall back to the per-tap kernel.  Default: all ones. */

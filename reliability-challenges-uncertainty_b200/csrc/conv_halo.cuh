@@ -30,7 +30,19 @@ constexpr int kHaloTileH = 16;
 constexpr int kHaloTileW = 8;
 constexpr int kHaloPitch = kHaloTileW + 2;   // window pixels per row
 constexpr int kHaloRows = kHaloTileH + 2;    // window rows
-enum HaloMode { HALO_CONV64 = 0, HALO_CONV32 = 1, HALO_UP64 = 2 };   // 3x3 conv over 64-ch chunks / a 32-ch source / one up-path phase
+// 3x3 conv over 64-ch chunks / a 32-ch source / one up-path phase / pixel-pair rows over a 32-ch / a 64-ch source
+enum HaloMode { HALO_CONV64 = 0, HALO_CONV32 = 1, HALO_UP64 = 2, HALO_PAIR32 = 3, HALO_PAIR64 = 4 };
+// Pixel-pair formulation (c_out = 32 layers).  An N = 32 tcgen05.mma reads 4 KB of A and 1 KB of B from shared memory
+// for 128 x 32 x 16 MACs: the 128 B/clk operand port, not the tensor array, bounds it (40 clk against a 16 clk floor,
+// profiles/r01_umma_probe.log).  A GEMM row that holds TWO x-adjacent pixels (the dense NHWC tensor viewed as
+// [h][w/2][2c]) doubles N for the same A bytes: output column (a_o, c_o) of pair i sums taps dx = 2*di + a_in - a_o over
+// the pairs di = -1, 0, +1, so
+//     di =  0 : every (a_in, a_o) combination is a tap of the 3x3 kernel   -> dense [64 x K] weight tile, N = 64
+//     di = -1 : only a_in = 1 -> a_o = 0 (dx = -1)                        -> N = 32 into columns  0..31, K = the a_in = 1 half
+//     di = +1 : only a_in = 0 -> a_o = 1 (dx = +1)                        -> N = 32 into columns 32..63, K = the a_in = 0 half
+// No zero blocks are multiplied (executed MACs = algorithmic MACs); per 256 output pixels and 3x3 x 32 channels the MMAs
+// read 3 x (4 x 6 KB + 4 x 5 KB) = 132 KB instead of 2 x 18 x 5 KB = 180 KB, and a 32-channel halo box has no padding.
+constexpr bool halo_is_pair(int mode) { return mode == HALO_PAIR32 || mode == HALO_PAIR64; }
 constexpr int kHaloSmemBudget = 225 * 1024;
 
 struct HaloParams {
@@ -120,6 +132,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   static_assert(PH == 1 || MODE == HALO_UP64, "several phases per tile only exist on the up path");
   static_assert(S::kTmemCols <= 512, "accumulator stages exceed TMEM");
   static_assert(N == 32 || N == 64, "halo kernel serves c_out = 32 / 64");
+  static_assert(!halo_is_pair(MODE) || (N == 64 && PH == 1), "pair rows carry two 32-channel output pixels");
+  constexpr bool PAIR = halo_is_pair(MODE);
   extern __shared__ uint8_t smem_dyn[];
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_dyn + (base - smem_u32(smem_dyn));
@@ -264,6 +278,42 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           }
           const uint32_t lo_a = (((smem_a + (uint32_t)stage * prm.chunk_stride) & 0x3FFFFu) >> 4) | (1u << 16);
           // every offset below is a compile-time constant: the loops unroll into back-to-back UTCHMMA with uniform adds
+          if constexpr (PAIR) {
+            // weight tiles [chunk][dy]{T0: [64][64] centre, S: [32][64] side} = 768 sixteen-byte units per (chunk, dy)
+            constexpr uint32_t idesc32 = make_idesc<32>();
+            auto pair_taps = [&](const int jj) {
+#pragma unroll
+              for (int dyi = 0; dyi < 3; ++dyi) {
+                const uint32_t a_row = lo_a + (uint32_t)(dyi * kHaloPitch * 8);
+                const uint32_t b_t0 = lo_b0 + (uint32_t)((jj * 3 + dyi) * 768);
+                const uint32_t b_s = b_t0 + 512u;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                  if (leader)
+                    umma_bf16(tmem_d, desc_from(a_row + 8u + 2 * ks, hi_a), desc_from(b_t0 + 2 * ks, hi_b), idesc,
+                              (jj > 0 || dyi > 0 || ks > 0) ? 1u : 0u);
+                if (MODE == HALO_PAIR32) {
+                  // one chunk holds both pixels of the pair: K 32..63 is a_in = 1 (left neighbour pair -> a_o = 0),
+                  // K 0..31 is a_in = 0 (right neighbour pair -> a_o = 1)
+#pragma unroll
+                  for (int ks = 2; ks < 4; ++ks)
+                    if (leader) umma_bf16(tmem_d, desc_from(a_row + 2 * ks, hi_a), desc_from(b_s + 2 * ks, hi_b), idesc32, 1u);
+#pragma unroll
+                  for (int ks = 0; ks < 2; ++ks)
+                    if (leader) umma_bf16(tmem_d + 32u, desc_from(a_row + 16u + 2 * ks, hi_a), desc_from(b_s + 2 * ks, hi_b), idesc32, 1u);
+                } else if (jj == 0) {   // chunk 0 = pixel a_in = 0: right neighbour pair -> a_o = 1
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks)
+                    if (leader) umma_bf16(tmem_d + 32u, desc_from(a_row + 16u + 2 * ks, hi_a), desc_from(b_s + 2 * ks, hi_b), idesc32, 1u);
+                } else {                // chunk 1 = pixel a_in = 1: left neighbour pair -> a_o = 0
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks)
+                    if (leader) umma_bf16(tmem_d, desc_from(a_row + 2 * ks, hi_a), desc_from(b_s + 2 * ks, hi_b), idesc32, 1u);
+                }
+              }
+            };
+            if (j == 0) pair_taps(0); else pair_taps(1);
+          } else {
 #pragma unroll
           for (int p = 0; p < PH; ++p) {
             const uint32_t lo_a0 = lo_a + (MODE == HALO_UP64 ? prm.up_base16[p] : 0u);
@@ -281,6 +331,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                   umma_bf16(tmem_d + (uint32_t)(p * N), desc_from(lo_a0 + a_off + 2 * ks, hi_a), desc_from(lo_bj + b_off + 2 * ks, hi_b), idesc, accumulate);
               }
             }
+          }
           }
           if (i + 1 == nt && j + 1 == prm.n_chunks && n_issuers == 2 && leader) mbar_arrive(bar_turn + 8 * (mw ^ 1));   // hand the turn over
           if (leader) umma_commit(bar_empty + 8 * stage);
@@ -318,7 +369,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
       if (img != cur_img) {   // group-uniform
         asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");   // everyone is done with the old coefficients
-        if (gt < N) coef[gt] = __ldg(prm.coef + (long long)img * prm.coef_stride + prm.coef_off + gt);
+        if (gt < N) coef[gt] = __ldg(prm.coef + (long long)img * prm.coef_stride + prm.coef_off + (PAIR ? (gt & 31) : gt));   // pair rows: both pixels share the 32 channel coefficients
         asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
         cur_img = img;
       }
@@ -328,6 +379,104 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
       const int y = ty * kHaloTileH + (row >> 3), x = tx * kHaloTileW + (row & 7);
       const bool valid = (y < prm.in_h) && (x < prm.in_w);
+      if constexpr (PAIR) {
+        // row = pixel pair (y, x): accumulator columns [0, 32) are output pixel 2x, [32, 64) pixel 2x + 1 (prm.in_w counts pairs)
+        if (prm.head != nullptr) {
+          float lg[4];
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(taddr0 + (uint32_t)(half * 32), v);
+            tmem_ld_wait();
+            if (half == 1) {
+              tc_fence_before();
+              mbar_arrive(bar_tempty + 8 * group);
+            }
+            float l0 = s_head[64], l1 = s_head[65];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const float2 cf = coef[c];
+              float a = fmaf(__uint_as_float(v[c]), cf.x, cf.y);
+              a = prm.relu ? fmaxf(a, 0.0f) : a;
+              l0 = fmaf(a, s_head[c], l0);
+              l1 = fmaf(a, s_head[32 + c], l1);
+            }
+            lg[2 * half] = l0;
+            lg[2 * half + 1] = l1;
+          }
+          if (valid) {
+            const int t = img / prm.chunk_slices, sl = img - t * prm.chunk_slices;
+            const long long gimg = (long long)t * prm.n_slices_total + prm.slice0 + sl;
+            float2* dst = reinterpret_cast<float2*>(prm.logits) + (gimg * prm.out_h + y) * prm.out_w + 2 * x;   // out_w is even: 16-byte aligned
+            *reinterpret_cast<float4*>(dst) = make_float4(lg[0], lg[1], lg[2], lg[3]);
+          }
+        } else {
+          uint32_t packed[2][16];
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(taddr0 + (uint32_t)(half * 32), v);
+            tmem_ld_wait();
+            if (half == 1) {
+              tc_fence_before();
+              mbar_arrive(bar_tempty + 8 * group);
+            }
+#pragma unroll
+            for (int c = 0; c < 32; c += 2) {
+              const float2 c0 = coef[c], c1 = coef[c + 1];
+              float a0 = fmaf(__uint_as_float(v[c]), c0.x, c0.y);
+              float a1 = fmaf(__uint_as_float(v[c + 1]), c1.x, c1.y);
+              if (prm.relu) { a0 = fmaxf(a0, 0.0f); a1 = fmaxf(a1, 0.0f); }
+              __nv_bfloat162 b = __floats2bfloat162_rn(a0, a1);
+              packed[half][c >> 1] = *reinterpret_cast<uint32_t*>(&b);
+            }
+            if (prm.tma_store) {
+              // the even / odd output pixels of the tile are two strided views of the destination (out_maps.m[half])
+              const uint32_t so = smem_out + (uint32_t)group * S::kOutSlot;
+              if (gt == 0) bulk_wait_group_read0();
+              asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
+              const uint32_t rowa = so + (uint32_t)row * 64u;
+              const uint32_t sw = (uint32_t)(row >> 1) & 3u;
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + (((uint32_t)i ^ sw) << 4)), "r"(packed[half][4 * i]),
+                             "r"(packed[half][4 * i + 1]), "r"(packed[half][4 * i + 2]), "r"(packed[half][4 * i + 3])
+                             : "memory");
+              fence_proxy_async();
+              asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
+              if (gt == 0) {
+                tma_store_4d(&out_maps.m[half], so, 0, tx * kHaloTileW, ty * kHaloTileH, img);
+                bulk_commit_group();
+              }
+            } else if (valid) {
+              uint4* d4 = reinterpret_cast<uint4*>(prm.out + (long long)img * prm.out_img_stride + ((long long)y * prm.out_w + 2 * x + half) * prm.out_c);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) d4[i] = make_uint4(packed[half][4 * i], packed[half][4 * i + 1], packed[half][4 * i + 2], packed[half][4 * i + 3]);
+            }
+          }
+          if (prm.pool_out != nullptr) {
+            // 2x2 max: the x neighbour is the other half of this row, the y neighbour is lane ^ 8 (lane = (y & 3) * 8 + x)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              __nv_bfloat162 m = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&packed[0][i]), *reinterpret_cast<__nv_bfloat162*>(&packed[1][i]));
+              uint32_t mm = *reinterpret_cast<uint32_t*>(&m);
+              uint32_t o = __shfl_xor_sync(0xffffffffu, mm, 8);
+              m = __hmax2(m, *reinterpret_cast<__nv_bfloat162*>(&o));
+              packed[0][i] = *reinterpret_cast<uint32_t*>(&m);
+            }
+            if (valid) {
+              // both lanes of a quad hold the 32 maxima: the even row stores channels 0..15, the odd row 16..31
+              const int part = y & 1;
+              uint4* pd = reinterpret_cast<uint4*>(prm.pool_out + (long long)img * prm.pool_img_stride +
+                                                   ((long long)(y >> 1) * prm.in_w + x) * 32 + part * 16);
+              pd[0] = part == 0 ? make_uint4(packed[0][0], packed[0][1], packed[0][2], packed[0][3])
+                                : make_uint4(packed[0][8], packed[0][9], packed[0][10], packed[0][11]);
+              pd[1] = part == 0 ? make_uint4(packed[0][4], packed[0][5], packed[0][6], packed[0][7])
+                                : make_uint4(packed[0][12], packed[0][13], packed[0][14], packed[0][15]);
+            }
+          }
+        }
+      } else {
 #pragma unroll 1
       for (int p = 0; p < PH; ++p) {
       const uint32_t taddr = taddr0 + (uint32_t)(p * N);
@@ -429,6 +578,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
       }
       }  // phases
+      }
       acc_phase ^= 1u;
     }
     if (prm.tma_store && gt == 0) bulk_wait_group_read0();   // shared memory must outlive the last store's read

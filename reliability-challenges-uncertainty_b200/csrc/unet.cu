@@ -61,6 +61,7 @@ struct HaloPack {                  // create-time description of a layer the hal
   uint8_t* d_wimg[kMaxPhases] = {nullptr, nullptr, nullptr, nullptr};   // per-phase views into one contiguous image
   uint32_t w_bytes = 0;            // bytes of ONE phase
   int phases_per_launch = 1;       // up path: 4, 2 or 1 phases share a launch (weights of all of them resident)
+  int pair_mode = 0;               // 1 / 2: pixel-pair rows over a 32- / 64-channel source (HALO_PAIR32 / HALO_PAIR64)
 };
 
 struct WidePack {                  // create-time description of a layer the wide kernel can run (c_out % 128 == 0)
@@ -81,6 +82,7 @@ struct ConvLayer {
   const float* d_head = nullptr;         // fused 1x1 head of this layer: [2][c_out] + [2]
   int out_slot = 0;                      // 0: class logits (conv_cls), 1: sigma logits (conv_sigma, unet.py:162-164)
   HaloPack halo;
+  HaloPack pairp;                        // pixel-pair variant of the same layer (c_out = 32, dense source), preferred when planned
   WidePack wide;
   // plan-time
   int in_h = 0, in_w = 0;
@@ -90,6 +92,11 @@ struct ConvLayer {
   CUtensorMap map_out[kMaxPhases];       // halo kernel: TMA-store views of the destination (one per up-path phase)
   bool tma_store = false;
   int halo_stages = 0;
+  bool use_pair = false;                 // plan-time: run the pixel-pair kernel
+  bool pair_tma_store = false;
+  int pair_stages = 0;
+  CUtensorMap map_halo_pair;             // source viewed as [h][w/2][2c]
+  CUtensorMap map_out_pair[2];           // even / odd output pixels of the destination
 };
 
 struct Op {
@@ -133,6 +140,7 @@ struct rcu_unet {
   std::vector<Op> ops;
   int conv_impl = 0;
   unsigned long long halo_mask = ~0ull;  // debug: bit i enables the halo kernel for conv i (execution order)
+  bool pair_enabled = true;              // debug: rcu_unet_set_conv_impl(net, 3) runs the pixel-row halo kernel where the pair kernel would
   long long last_launches = 0;
   int last_n_img = 0;
   // optional per-op timing
@@ -431,6 +439,38 @@ static int pack_halo_conv3x3(rcu_unet* net, const rcu_conv_unit& u, HaloPack& hp
   return RCU_OK;
 }
 
+// Pixel-pair rows (conv_halo.cuh, HALO_PAIR32 / HALO_PAIR64): GEMM row = the two pixels (2i, 2i+1) of a dense NHWC source
+// viewed as [h][w/2][2c]; output column n = a_o * 32 + c_o.  Per (chunk j, dy) the image holds
+//   T0 [64 n][64 k]  pair tap di = 0: element = W[dy][dx = a_in - a_o][c_o][c_i]   (every combination is inside the 3x3 kernel)
+//   S  [32 n][64 k]  the two side taps, n = c_o: a_in = 0 columns carry W[dy][+1] (right neighbour pair -> a_o = 1),
+//                    a_in = 1 columns carry W[dy][-1] (left neighbour pair -> a_o = 0)
+// with k = a_in * 32 + c_i for a 32-channel source (one chunk) and k = c_i, a_in = j for a 64-channel source (two chunks).
+static int pack_halo_pair(rcu_unet* net, const rcu_conv_unit& u, HaloPack& hp) {
+  const char* e = std::getenv("RCU_HALO_PAIR");
+  if ((e && e[0] == '0') || u.c_out != 32 || !(u.c_in == 32 || u.c_in == 64)) return RCU_OK;
+  const int nj = u.c_in / 32;
+  auto W = [&](int co, int ci, int dy, int dx) { return u.weight[((size_t)co * u.c_in + ci) * 9 + (dy + 1) * 3 + (dx + 1)]; };
+  std::vector<uint16_t> img((size_t)nj * 3 * 96 * 64, 0);
+  for (int j = 0; j < nj; ++j)
+    for (int dyi = 0; dyi < 3; ++dyi) {
+      uint16_t* t0 = img.data() + (size_t)(j * 3 + dyi) * 96 * 64;
+      uint16_t* sd = t0 + 64 * 64;
+      for (int k = 0; k < 64; ++k) {
+        const int a_in = nj == 1 ? (k >> 5) : j, ci = nj == 1 ? (k & 31) : k;
+        for (int n = 0; n < 64; ++n) t0[sw128_index(n, k)] = f32_to_bf16_rn(W(n & 31, ci, dyi - 1, a_in - (n >> 5)));
+        for (int n = 0; n < 32; ++n) sd[sw128_index(n, k)] = f32_to_bf16_rn(W(n, ci, dyi - 1, a_in == 0 ? 1 : -1));
+      }
+    }
+  hp.pair_mode = nj; hp.pair = false; hp.n_chunks = nj; hp.n_phases = 1;
+  hp.w_bytes = (uint32_t)(img.size() * 2);
+  uint16_t* d;
+  int rc = dev_upload(net, img, &d);
+  if (rc) return rc;
+  hp.d_wimg[0] = reinterpret_cast<uint8_t*>(d);
+  hp.ok = true;
+  return RCU_OK;
+}
+
 // nearest-x2 + conv3x3 as four 2x2-tap phase convolutions (see pack_upconv_phases): one weight image per phase
 constexpr int kHaloGroups = 4;   // TMEM accumulator stages = epilogue warp groups
 static size_t halo_chunk_stride_bytes() { return ((size_t)kHaloRows * kHaloPitch * 128 + 1023) & ~size_t(1023); }
@@ -713,6 +753,8 @@ extern "C" int rcu_unet_create(const rcu_unet_desc* d, int device, rcu_unet** ou
     L.d_weights = reinterpret_cast<__nv_bfloat16*>(dw);
     rc2 = pack_halo_conv3x3(net, cu, L.halo);
     if (rc2) return rc2;
+    rc2 = pack_halo_pair(net, cu, L.pairp);
+    if (rc2) return rc2;
     rc2 = pack_wide(net, cu, false, L.wide);
     if (rc2) return rc2;
     net->convs.push_back(L);
@@ -778,8 +820,9 @@ extern "C" int rcu_unet_total_dropout_channels(const rcu_unet* net) { return net
 extern "C" int64_t rcu_unet_last_launch_count(const rcu_unet* net) { return net ? net->last_launches : 0; }
 extern "C" int rcu_unet_set_conv_impl(rcu_unet* net, int impl) {
   RCU_CHECK_ARG(net != nullptr, "NULL handle");
-  RCU_CHECK_ARG(impl >= 0 && impl <= 2, "conv impl must be 0 (tcgen05), 1 (cross-check) or 2 (tcgen05, per-tap kernel only)");
-  net->conv_impl = impl;
+  RCU_CHECK_ARG(impl >= 0 && impl <= 3, "conv impl must be 0 (tcgen05), 1 (cross-check), 2 (tcgen05, per-tap kernel only) or 3 (tcgen05 without the pixel-pair kernel)");
+  net->pair_enabled = impl != 3;
+  net->conv_impl = impl == 3 ? 0 : impl;
   return RCU_OK;
 }
 
@@ -891,6 +934,27 @@ extern "C" int rcu_unet_plan(rcu_unet* net, int height, int width, int max_image
         }
       }
     }
+    L.use_pair = false;
+    if (L.pairp.ok && src.c == src.c_total && src.w % 2 == 0 && !src.padded && dst.w == src.w) {
+      static const bool allow_tma_store = [] { const char* e = std::getenv("RCU_HALO_TMA_STORE"); return !(e && e[0] == '0'); }();
+      const int nj = L.pairp.n_chunks;
+      const int with_out = halo_stage_count<64>(L.pairp.w_bytes, false, true);
+      L.pair_tma_store = allow_tma_store && !L.head && with_out >= 2 * nj + 1;
+      L.pair_stages = L.pair_tma_store ? with_out : halo_stage_count<64>(L.pairp.w_bytes, false);
+      if (L.pair_stages >= nj + 1) {
+        Act pv = src;                       // [h][w/2][2c]
+        pv.c = pv.c_total = 2 * src.c_total; pv.w = src.w / 2;
+        rc = make_halo_map(&L.map_halo_pair, pv, (int)N, 64);
+        if (rc) return rc;
+        for (int half = 0; half < 2 && L.pair_tma_store; ++half) {
+          Act dv = dst;                     // the even / odd pixels of the destination slice
+          dv.base = dst.base + (size_t)half * dst.c_total; dv.c_total = 2 * dst.c_total; dv.w = dst.w / 2;
+          rc = make_out_map(&L.map_out_pair[half], dv, (int)N, 1, 0, 0);
+          if (rc) return rc;
+        }
+        L.use_pair = true;
+      }
+    }
     if (L.wide.ok) {
       rc = make_wide_map(&L.map_wide, src, (int)N);
       if (rc) return rc;
@@ -1000,6 +1064,45 @@ static int run_conv_halo(rcu_unet* net, const ConvLayer& L, int n_img, int cs, l
   return RCU_OK;
 }
 
+static int run_conv_halo_pair(rcu_unet* net, const ConvLayer& L, int n_img, int cs, long long s0, long long n_slices, float* logits,
+                              cudaStream_t st, long long* launches) {
+  const HaloPack& hp = L.pairp;
+  HaloParams prm;
+  std::memset(&prm, 0, sizeof(prm));
+  prm.n_img = n_img;
+  prm.in_h = L.in_h; prm.in_w = L.in_w / 2;                      // GEMM pixel grid = pixel pairs
+  prm.tiles_x = (prm.in_w + kHaloTileW - 1) / kHaloTileW;
+  prm.tiles_y = (L.in_h + kHaloTileH - 1) / kHaloTileH;
+  prm.n_chunks = hp.n_chunks;
+  prm.chunk_bytes = (uint32_t)(kHaloRows * kHaloPitch * 128);
+  prm.chunk_stride = halo_chunk_stride(false);
+  prm.n_stages = L.pair_stages;
+  prm.tma_store = L.pair_tma_store ? 1 : 0;
+  prm.tiles_per_turn = 1;
+  HaloOutMaps maps;
+  maps.m[0] = L.map_out_pair[0]; maps.m[1] = L.map_out_pair[1];
+  prm.w_image = hp.d_wimg[0];
+  prm.w_bytes = hp.w_bytes;
+  prm.out_mul = 1;
+  prm.out_h = L.in_h; prm.out_w = L.in_w;                        // output addressing is in pixels
+  prm.out_c = L.dst.c_total;
+  prm.out_img_stride = L.dst.img_stride;
+  prm.out = L.dst.base;
+  prm.pool_out = L.pool_dst.base;
+  prm.pool_img_stride = L.pool_dst.img_stride;
+  prm.coef = net->d_coef; prm.coef_stride = net->n_cols; prm.coef_off = L.coef_off;
+  prm.relu = L.relu;
+  prm.head = L.head ? L.d_head : nullptr;
+  prm.logits = logits;
+  prm.chunk_slices = cs; prm.slice0 = s0; prm.n_slices_total = n_slices;
+  ConvLayer view = L;
+  view.map_halo = L.map_halo_pair;
+  int rc = hp.pair_mode == 1 ? launch_conv_halo<64, HALO_PAIR32>(view, prm, maps, st) : launch_conv_halo<64, HALO_PAIR64>(view, prm, maps, st);
+  if (rc) return rc;
+  ++*launches;
+  return RCU_OK;
+}
+
 }  // namespace rcu
 
 extern "C" int rcu_unet_forward(rcu_unet* net, const float* images, int64_t n_slices, int n_samples, int dropout_mode,
@@ -1082,6 +1185,12 @@ extern "C" int rcu_unet_forward_ex(rcu_unet* net, const float* images, int64_t n
         const ConvLayer& L = net->convs[op.conv];
         float* const head_out = L.out_slot ? sigma : logits;
         if (L.out_slot && sigma == nullptr) continue;   // nobody asked for the sigma branch
+        if (net->conv_impl == 0 && L.use_pair && net->pair_enabled && ((net->halo_mask >> op.conv) & 1ull)) {
+          int rc = run_conv_halo_pair(net, L, n_img, cs, (long long)s0, (long long)n_slices, head_out, st, &launches);
+          if (rc) return rc;
+          pool_done = L.pool_dst.base != nullptr;
+          continue;
+        }
         if (net->conv_impl == 0 && L.halo.ok && ((net->halo_mask >> op.conv) & 1ull)) {
           int rc = run_conv_halo(net, L, n_img, cs, (long long)s0, (long long)n_slices, head_out, st, &launches);
           if (rc) return rc;

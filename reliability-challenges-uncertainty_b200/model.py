@@ -209,7 +209,8 @@ class B200UNet(nn.Module):
         return int(sum(self.site_channels))
 
     def set_conv_impl(self, impl):
-        """0 = tcgen05 (product path), 1 = CUDA-core cross-check kernels (tests only), 2 = tcgen05 per-tap kernel only."""
+        """0 = tcgen05 (product path), 1 = CUDA-core cross-check kernels (tests only), 2 = tcgen05 per-tap kernel only,
+        3 = tcgen05 without the pixel-pair kernel (A/B)."""
         _lib.check(_lib.lib().rcu_unet_set_conv_impl(self._handle, int(impl)))
 
     def set_halo_mask(self, mask):
