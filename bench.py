@@ -3,16 +3,26 @@
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU under torchrun)
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU arithmetic (oracle port) on the host cores
+    python bench.py --config isic_mc | ensemble10 | brats50  # the other BASELINE.json configurations (builder / profile runs)
 
-One step = one synthetic BraTS subject (155 slices of 4x240x240) through
+Default workload `brats_mc` (BASELINE.json configs[2], the one the metric is quoted on).  One step = one synthetic BraTS
+subject (155 slices of 4x240x240) through
     McPredictStep(mc=20) [T stochastic forwards + the deterministic weight-scaling forward, folded into the batch]
-    -> MultiPredictionSummary [fused softmax / mean / entropy / argmax]
+    -> MultiPredictionSummary [fused softmax / mean / entropy / argmax, the weight-scaling softmax in the same launch]
     -> ECE reliability tables (T2>0-style mask) + Dice/confusion + the 11-threshold U-E sweep [one fused histogram pass].
 `value` = MC voxel-samples/s = voxels x T / step time with the subject's images already in HBM (the weight-scaling
 forward is executed but not counted).  `e2e` = the same metric through the drop-in steps / hook with
 HOST buffers: pinned images are copied in per batch of 32 slices (the reference loader's batch size), the
 'probabilities' entry is copied back like loops.py:214-220 does, and the metric tables come back to the host.
 Every rank works on its own subject (no data-path collective): "scaling": "weak".
+
+  isic_mc     160 synthetic 3x256x256 images per step, MC T=20, summary, per-image ECE / U-E tables (one launch for all images)
+  ensemble10  BASELINE config 4: 10 random-init members over one subject, members sharded over the ranks, the 71 MB
+              probability sums reduced and finished by rcu_aggregate_finish_peer (--exchange peer, NVLink peer memory),
+              the library's NCCL all-reduce (--exchange nccl) or torch.distributed (--exchange torch).  Strong scaling.
+  brats50     BASELINE config 5: 50 synthetic subjects, MC T=20 + the full metric set; the 7750 slices are split evenly over
+              the ranks (subjects may span ranks), ONE all-reduce of the per-subject count tables at the end.  Strong scaling;
+              a step is the whole 50-subject pass.
 """
 import argparse
 import json
@@ -37,6 +47,9 @@ METRIC = 'MC-dropout voxel-samples/sec (BraTS T=20 U-Net forward + mean/entropy 
 UNIT = 'voxel-samples/s'
 WORKLOAD = 'brats_baseline_mc: 1 synthetic subject/step/GPU = 155 slices 4x240x240, T=20 (+1 weight-scaling pass), ' \
            'fused mean/entropy/argmax, ECE(mask)+Dice+11-threshold U-E tables'
+ENSEMBLE_MEMBERS = 10      # config/test_brats_ensemble.yaml:4,9-18
+N_SUBJECTS_50 = 50
+ISIC_IMAGES, ISIC_SIZE = 160, 256
 
 
 def measured_peaks():
@@ -68,11 +81,41 @@ def synth_subject(seed):
 DROPOUT = 0.05        # config/train_brats_baseline.yaml:6-12
 
 
-def make_state_dict(seed=20):
-    """Synthetic weights of the BraTS baseline net (rcu_b200.synth: seeded torch-default init, non-degenerate BN)."""
+def make_state_dict(seed=20, in_channels=CHANNELS):
+    """Synthetic weights of the baseline net (rcu_b200.synth: seeded torch-default init, non-degenerate BN)."""
     import rcu_b200  # noqa: F401
     from rcu_b200 import synth
-    return synth.random_unet_state_dict(in_channels=CHANNELS, seed=seed)
+    return synth.random_unet_state_dict(in_channels=in_channels, seed=seed)
+
+
+def centre_head_bias(sd, net_factory, images, weight=None, spread=3.0):
+    """Random weights predict one class almost everywhere with p ~ 0.5 (Dice against any label is 0, all voxels share one or
+    two reliability bins).  One deterministic forward measures the logit difference l1 - l0 (inside `weight`, e.g. the brain
+    mask); the 1x1 head is then rescaled so that its spread is `spread` (logits with sigma ~ 3) and its
+    foreground bias shifted so that the median is 0 — about half of those voxels are predicted foreground and the
+    probabilities fill every reliability bin.  Pure data synthesis, done once before anything is timed."""
+    import torch
+    net = net_factory(sd)
+    n = min(images.shape[0], 16)
+    idx = torch.linspace(0, images.shape[0] - 1, n).long().to(images.device)
+    logits = net.forward_samples(images[idx], 1, dropout_mode=0)[0]
+    d = (logits[..., 1] - logits[..., 0])
+    if weight is not None:
+        d = d[weight[idx].bool()]
+    d = d.float()
+    gain = spread / max(float(d.std().item()), 1e-6)
+    shift = float(d.median().item()) * gain
+    del net
+    return shifted_head(sd, shift, gain), (shift, gain)
+
+
+def shifted_head(sd, shift, gain=1.0):
+    sd = dict(sd)
+    sd['conv_cls.1.weight'] = sd['conv_cls.1.weight'] * gain
+    b = sd['conv_cls.1.bias'] * gain
+    b[1] -= shift
+    sd['conv_cls.1.bias'] = b
+    return sd
 
 
 # ------------------------------------------------------------------------------------------------ clocks sampler
@@ -185,7 +228,7 @@ def run_reference_arm(args):
     return 0
 
 
-# ------------------------------------------------------------------------------------------------ GPU arm
+# ------------------------------------------------------------------------------------------------ GPU arm: shared plumbing
 class _BatchContext:  # same fields as common/trainloop/context.py:334-342
     def __init__(self, batch, batch_index):
         self.input, self.batch_index, self.output, self.metrics, self.score, self.more = batch, batch_index, {}, {}, None, {}
@@ -199,94 +242,192 @@ class _Context:
         return self._seed
 
 
-def run_gpu_arm(args):
-    import torch
-    import torch.distributed as dist
+class Rig:
+    """Process-wide set-up of the GPU arm: device, process group, timing helpers."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.args = torch, dist, args
+        torch.set_grad_enabled(False)
+        self.rank = int(os.environ.get('RANK', '0'))
+        self.world = int(os.environ.get('WORLD_SIZE', '1'))
+        self.local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+        if not torch.cuda.is_available():
+            raise SystemExit('bench.py: no CUDA device (the product path has no CPU fallback; use --impl reference for the CPU arm)')
+        torch.cuda.set_device(self.local_rank)
+        self.device = torch.device('cuda', self.local_rank)
+        if self.world > 1:
+            os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+            dist.init_process_group('nccl', device_id=self.device)
+        if args.gpus != self.world and self.rank == 0:
+            sys.stderr.write('bench.py: --gpus %d but WORLD_SIZE=%d (launch N>1 with torch.distributed.run); using %d\n' % (args.gpus, self.world, self.world))
+        self.peaks = measured_peaks()
+        self.stream = torch.cuda.current_stream()
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(self, fn, steps):
+        """K steps of `fn(i)` bracketed by barrier + synchronize on both sides, CUDA events on the launch stream, max over
+        ranks; nvidia-smi clocks are sampled during the region on rank 0.  Returns (ms per step, clocks, last result)."""
+        torch = self.torch
+        sampler = ClockSampler(self.local_rank)
+        if self.rank == 0:
+            sampler.start()
+            time.sleep(0.3)
+        self.barrier()
+        w0 = time.time()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.stream)
+        last = None
+        for i in range(steps):
+            last = fn(i)
+        e1.record(self.stream)
+        self.barrier()
+        w1 = time.time()
+        clocks = sampler.stop(w0, w1) if self.rank == 0 else None
+        return self.max_over_ranks(e0.elapsed_time(e1)) / steps, clocks, last
+
+    def finish(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def beta_maps(torch, device, n, seed=20):
+    """Metric-kernel test data of SURVEY.md §8d: U-shaped p in [0, 1] (Beta(0.3, 0.3)-like: most mass near 0 and 1, every
+    reliability bin and uncertainty interval populated), target ~ Bernoulli(p), 25 % mask, iid per voxel — the worst case
+    for data-dependent table reads and counter updates."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    a = 0.3
+    u = torch.rand(n, device=device, generator=g).pow_(1.0 / a)
+    v = torch.rand(n, device=device, generator=g).pow_(1.0 / a)
+    p = (u / (u + v + 1e-30)).clamp_(0, 1)
+    del u, v
+    target = (torch.rand(n, device=device, generator=g) < p).to(torch.uint8)
+    pred = (p > 0.5).to(torch.uint8)
+    mask = (torch.rand(n, device=device, generator=g) < 0.25).to(torch.uint8)
+    return p, pred, target, mask
+
+
+def time_device_call(torch, stream, fn, flush, reps=10):
+    """Median device time (ms) of one call with an L2 flush (a >L2 buffer rewritten) before every timed repetition."""
+    for _ in range(3):
+        fn()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        fn()
+        b.record(stream)
+        b.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts))
+
+
+# ------------------------------------------------------------------------------------------------ brats_mc / isic_mc
+def run_mc_config(args, rig, isic=False):
+    torch = rig.torch
     import rcu_b200  # noqa: F401
     from rcu_b200 import model, steps, metrics, hooks, tables
+    device, stream, rank, world = rig.device, rig.stream, rig.rank, rig.world
+    if isic:
+        n_items, ch, h, w = ISIC_IMAGES, 3, ISIC_SIZE, ISIC_SIZE
+        g = torch.Generator().manual_seed(1000 + rank)
+        images_h = torch.rand((n_items, ch, h, w), generator=g)            # RGB / 255 (config/test_isic_baseline.yaml:15-20)
+        yy, xx = np.mgrid[0:h, 0:w]
+        target_h = np.stack([(((yy - 128 - 3 * (i % 7)) / 60.0) ** 2 + ((xx - 120 + 2 * (i % 5)) / 45.0) ** 2 < 1.0) for i in range(n_items)]).astype(np.uint8)
+        mask_h = None
+        n_subjects = n_items                                               # ISIC: one image = one subject (bin-eval/eval_uncertainty.py:21,25)
+        workload = 'isic_baseline_mc: %d synthetic images 3x%dx%d per step/GPU, T=20 (+1 weight-scaling pass), fused ' \
+                   'mean/entropy/argmax, per-image ECE (no mask) + Dice + 11-threshold U-E tables in one launch' % (n_items, h, w)
+        flop_per_voxel_sample = 517952
+    else:
+        n_items, ch, h, w = SLICES, CHANNELS, HEIGHT, WIDTH
+        images_h, target_h, mask_h = synth_subject(1000 + rank)
+        n_subjects = 1
+        workload = WORKLOAD
+        flop_per_voxel_sample = FLOP_PER_VOXEL_SAMPLE
+    voxels = n_items * h * w
 
-    torch.set_grad_enabled(False)
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    if not torch.cuda.is_available():
-        raise SystemExit('bench.py: no CUDA device (the product path has no CPU fallback; use --impl reference for the CPU arm)')
-    torch.cuda.set_device(local_rank)
-    device = torch.device('cuda', local_rank)
-    if world > 1:
-        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=device)
-    if args.gpus != world and rank == 0:
-        sys.stderr.write('bench.py: --gpus %d but WORLD_SIZE=%d (launch N>1 with torch.distributed.run); using %d\n' % (args.gpus, world, world))
-
-    peaks = measured_peaks()
-    sd = make_state_dict()
-    net = model.B200UNet(sd, in_channels=CHANNELS, dropout=DROPOUT, device=device, seed=20)
-    images_h, target_h, mask_h = synth_subject(1000 + rank)
-    images_pinned = images_h.pin_memory()
+    def factory(sd_):
+        return model.B200UNet(sd_, in_channels=ch, dropout=DROPOUT, device=device, seed=20)
     images_d = images_h.to(device)
+    mask_d = None if mask_h is None else torch.from_numpy(mask_h).to(device)
+    sd, head_shift = centre_head_bias(make_state_dict(in_channels=ch), factory, images_d, mask_d)
+    net = factory(sd)
+    images_pinned = images_h.pin_memory()
     target_d = torch.from_numpy(target_h).to(device).view(-1)
-    mask_d = torch.from_numpy(mask_h).to(device).view(-1)
+    mask_flat = None if mask_d is None else mask_d.view(-1)
     break_table = tables.uncertainty_break_table(tables.SWEEP_THRESHOLDS)
-    stream = torch.cuda.current_stream()
     launches = {'n': 0}
 
     def device_step(step_index, ev=None):
-        """Hot path with the subject resident in HBM.  ev: optional list collecting stage-boundary events."""
+        """Hot path with the inputs resident in HBM.  ev: optional list collecting stage-boundary events."""
         def mark():
             if ev is not None:
                 e = torch.cuda.Event(enable_timing=True)
                 e.record(stream)
                 ev.append(e)
         mark()
-        logits = net.forward_samples(images_d, MC_STEPS + 1, dropout_mode=1, det_first=True, slice_index0=step_index * SLICES, sample0=0)
+        logits = net.forward_samples(images_d, MC_STEPS + 1, dropout_mode=1, det_first=True, slice_index0=step_index * n_items, sample0=0)
         launches['n'] += net.last_launch_count()
         mark()
-        ws = steps.softmax_planar(logits[0])
-        out = steps.summarize(steps.LazyMultiProbabilities(logits[1:]), emit_prediction=True, emit_foreground=True)
-        launches['n'] += 2
-        mark()
-        res = metrics.eval_fused(out['foreground'], out['prediction'], target_d, mask_d, 10, tables.SWEEP_THRESHOLDS, sync=False,
-                                 break_table=break_table)
+        out = steps.summarize(steps.LazyMultiProbabilities(logits[1:]), emit_prediction=True, emit_foreground=True, ws_logits=logits[0])
         launches['n'] += 1
         mark()
-        return ws, out, res
+        res = metrics.eval_fused(out['foreground'], out['prediction'], target_d, mask_flat, 10, tables.SWEEP_THRESHOLDS, n_subjects=n_subjects,
+                                 sync=False, break_table=break_table)
+        launches['n'] += 1
+        mark()
+        return out, res
 
     hook = hooks.DeviceMetricsHook()
     ctx = _Context(net, device)
-    h2d = {'n': 0}
-    d2h = {'n': 0}
-
-    prob_pinned = torch.empty((SLICES, HEIGHT, WIDTH, 2), dtype=torch.float32).pin_memory()
+    h2d, d2h = {'n': 0}, {'n': 0}
+    copy_ev = {'h2d': [], 'd2h': []}
+    prob_pinned = torch.empty((n_items, h, w, 2), dtype=torch.float32).pin_memory()
     target_pinned = torch.from_numpy(target_h).pin_memory()
-    mask_pinned = torch.from_numpy(mask_h).pin_memory()
-
+    mask_pinned = None if mask_h is None else torch.from_numpy(mask_h).pin_memory()
     copy_in = torch.cuda.Stream(device)     # host -> device prefetch of the next batch's images
     copy_out = torch.cuda.Stream(device)    # device -> host copy of the previous batch's probabilities
 
     def e2e_step(step_index):
         """The call sequence a user of the reference makes (loops.py:204-235) with host buffers on both sides: images come
-        from (pinned) host memory per 32-slice batch, the 'probabilities' entry goes back to the host channel-last like
-        loops.py:214-220 does (into a pinned subject buffer), the foreground / prediction maps stay in HBM for the in-memory
+        from (pinned) host memory per 32-item batch, the 'probabilities' entry goes back to the host channel-last like
+        loops.py:214-220 does (into a pinned buffer), the foreground / prediction maps stay in HBM for the in-memory
         metric hook, labels and mask come from the host, the metric tables go back.  All of it inside the timed region;
         the copies run on two side streams (double-buffered like a pin_memory loader) so that they overlap the forward of
         the neighbouring batch instead of serialising with it."""
         mc = steps.McPredictStep(MC_STEPS)
-        mc.slices_seen = step_index * SLICES
+        mc.slices_seen = step_index * n_items
         summary = steps.MultiPredictionSummary(emit_prediction=True, emit_foreground=True)
         fg, pred = [], []
 
         def fetch(b0):
             with torch.cuda.stream(copy_in):
+                a = torch.cuda.Event(enable_timing=True)
+                a.record(copy_in)
                 t = images_pinned[b0:b0 + BATCH].to(device, non_blocking=True)
-                ready = torch.cuda.Event()
+                ready = torch.cuda.Event(enable_timing=True)
                 ready.record(copy_in)
+            copy_ev['h2d'].append((a, ready))
             h2d['n'] += t.numel() * 4
             return t, ready
         nxt = fetch(0)
-        for b0 in range(0, SLICES, BATCH):
+        for b0 in range(0, n_items, BATCH):
             images_b, ready = nxt
-            if b0 + BATCH < SLICES:
+            if b0 + BATCH < n_items:
                 nxt = fetch(b0 + BATCH)
             stream.wait_event(ready)
             images_b.record_stream(stream)
@@ -299,59 +440,46 @@ def run_gpu_arm(args):
             done.record(stream)
             with torch.cuda.stream(copy_out):
                 copy_out.wait_event(done)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(copy_out)
                 prob_pinned[b0:b0 + n].copy_(probs.permute(0, 2, 3, 1), non_blocking=True)
+                b.record(copy_out)
+            copy_ev['d2h'].append((a, b))
             probs.record_stream(copy_out)
-            d2h['n'] += n * HEIGHT * WIDTH * 2 * 4
+            d2h['n'] += n * h * w * 2 * 4
             fg.append(bc.output['foreground'])
             pred.append(bc.output['prediction'])
         target_dev = target_pinned.to(device, non_blocking=True)
-        mask_dev = mask_pinned.to(device, non_blocking=True)
-        h2d['n'] += target_pinned.numel() + mask_pinned.numel()
-        row = hook.evaluate(step_index, torch.cat(fg), torch.cat(pred), target_dev, mask_dev)   # tables come back to the host inside
-        d2h['n'] += 8 * (3 * 11 + 4 * 12 + 1)
-        copy_out.synchronize()                      # the subject's probabilities are on the host now
+        mask_dev = None if mask_pinned is None else mask_pinned.to(device, non_blocking=True)
+        h2d['n'] += target_pinned.numel() + (0 if mask_pinned is None else mask_pinned.numel())
+        if n_subjects == 1:
+            row = hook.evaluate(step_index, torch.cat(fg), torch.cat(pred), target_dev, mask_dev)   # tables come back to the host inside
+        else:
+            res = metrics.eval_fused(torch.cat(fg), torch.cat(pred), target_dev.view(-1), None, 10, tables.SWEEP_THRESHOLDS, n_subjects=n_subjects,
+                                     break_table=break_table)                                         # sync=True: one D2H copy of all tables
+            row = {'dice': tables.dice_from_counts(res[3][:, 0].sum(), res[3][:, 2].sum(), res[3][:, 3].sum())}
+        d2h['n'] += 8 * (3 * 11 + 4 * 12 + 1) * n_subjects
+        copy_out.synchronize()                      # the probabilities are on the host now
         torch.cuda.current_stream().synchronize()
         return row
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
     # ---------------- warm-up (also builds the plan / workspaces)
+    warm = max(args.warmup, 3)
     keep = None
-    for i in range(max(args.warmup, 3)):
+    for i in range(warm):
         keep = device_step(i)   # hold the previous step's outputs like the timed loop does: the caching allocator reaches steady state
     torch.cuda.synchronize()
 
     # ---------------- timed region: K device-resident steps (no per-launch events: those belong to the second pass below)
     launches['n'] = 0
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
     stage_events = []
-    barrier()
-    w0 = time.time()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for i in range(args.steps):
+
+    def timed_step(i):
         ev = []
-        keep = device_step(100 + i, ev)
+        r = device_step(100 + i, ev)
         stage_events.append(ev)
-    e1.record(stream)
-    barrier()
-    w1 = time.time()
-    clocks = sampler.stop(w0, w1) if rank == 0 else None
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    ms_step = ms_total / args.steps
+        return r
+    ms_step, clocks, keep = rig.timed(timed_step, args.steps)
     n_launches = launches['n']
     stages = np.array([[ev[j].elapsed_time(ev[j + 1]) for j in range(3)] for ev in stage_events]).mean(0)
 
@@ -370,54 +498,58 @@ def run_gpu_arm(args):
     ms_step_op_events = p0.elapsed_time(p1) / args.steps
     op_ms, op_launches = net.read_timing()
     net.enable_timing(False)
-    launches['n'] = n_launches
 
     # results of the last step, on the host (sanity: the work was really done)
-    ws, out, res = keep
+    out, res = keep
     count, positives, conf, ue, invalid = [t.cpu().numpy() for t in res[:5]]
-    assert int(ue[0].sum()) == VOXELS and int(invalid[0]) == 0 and int(count[0].sum()) == int(mask_h.sum())
-    ece = tables.ece_from_tables(count[0, :10], positives[0, :10], conf[0, :10], n_dim=3)
+    assert int(ue.sum()) == voxels and int(invalid.sum()) == 0
+    assert mask_h is None or int(count[0].sum()) == int(mask_h.sum())
+    ece = float(np.mean([tables.ece_from_tables(count[s, :10], positives[s, :10], conf[s, :10], n_dim=3) for s in range(n_subjects)]))
     mean_entropy = float(out['entropy'].mean().item())
+    bin_occupancy = [round(float(x), 4) for x in (count[:, :10].sum(0) / max(1, count[:, :10].sum()))]
+    pred_pos = float(out['prediction'].float().mean().item())
 
-    # ---------------- e2e through the drop-in steps with host buffers
+    # ---------------- e2e through the drop-in steps with host buffers: all K steps
     e2e_step(0)
     torch.cuda.synchronize()
     h2d['n'] = d2h['n'] = 0
-    barrier()
-    e2e_steps = max(1, min(args.steps, 3))
+    copy_ev['h2d'], copy_ev['d2h'] = [], []
+    rig.barrier()
     t0 = time.perf_counter()
-    for i in range(e2e_steps):
+    for i in range(args.steps):
         row = e2e_step(200 + i)
-    barrier()
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
+    rig.barrier()
+    e2e_ms = rig.max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
+    h2d_busy = sum(a.elapsed_time(b) for a, b in copy_ev['h2d']) / args.steps
+    d2h_busy = sum(a.elapsed_time(b) for a, b in copy_ev['d2h']) / args.steps
 
-    # ---------------- ECE-eval ms (second half of BASELINE's metric): full metric set per subject, device resident
-    for _ in range(3):
-        metrics.eval_fused(out['foreground'], out['prediction'], target_d, mask_d, 10, tables.SWEEP_THRESHOLDS, sync=False, break_table=break_table)
-    # 768 MB: flushes L2 and keeps the device busy long enough for the host to have the call enqueued when the timed
+    # ---------------- ECE-eval ms (second half of BASELINE's metric): full metric set per subject, device resident.
+    # 768 MB flush: flushes L2 and keeps the device busy long enough for the host to have the call enqueued when the timed
     # region opens (the number is the device time of the call, not the Python launch latency)
     flush = torch.empty(768 << 20, dtype=torch.uint8, device=device)
-    ece_ms = []
-    for _ in range(10):
-        flush.zero_()  # L2 flush between iterations
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(stream)
-        metrics.eval_fused(out['foreground'], out['prediction'], target_d, mask_d, 10, tables.SWEEP_THRESHOLDS, sync=False, break_table=break_table)
-        b.record(stream)
-        b.synchronize()
-        ece_ms.append(a.elapsed_time(b))
-    ece_eval_ms = float(np.median(ece_ms))
-    agg_ms = []
-    lazy = None
-    del flush
+    ece_eval_ms = time_device_call(torch, stream, lambda: metrics.eval_fused(out['foreground'], out['prediction'], target_d, mask_flat, 10,
+                                                                             tables.SWEEP_THRESHOLDS, n_subjects=n_subjects, sync=False,
+                                                                             break_table=break_table), flush)
+    bp, bpred, btarget, bmask = beta_maps(torch, device, VOXELS)
+    ece_eval_beta_ms = time_device_call(torch, stream, lambda: metrics.eval_fused(bp, bpred, btarget, bmask, 10, tables.SWEEP_THRESHOLDS, sync=False,
+                                                                                  break_table=break_table), flush)
+    bres = metrics.eval_fused(bp, bpred, btarget, bmask, 10, tables.SWEEP_THRESHOLDS, break_table=break_table)
+    beta_occupancy = [round(float(x), 4) for x in (bres[0][0, :10] / max(1, bres[0][0, :10].sum()))]
+    del bp, bpred, btarget, bmask
+    bp, bpred, btarget, bmask = beta_maps(torch, device, 50 * VOXELS, seed=21)
+    ece_eval_beta50_ms = time_device_call(torch, stream, lambda: metrics.eval_fused(bp, bpred, btarget, bmask, 10, tables.SWEEP_THRESHOLDS,
+                                                                                    n_subjects=50, sync=False, break_table=break_table), flush, reps=5)
+    del bp, bpred, btarget, bmask, flush
 
     # ---------------- roofline of the dominant kernel family (tcgen05 convolutions)
     ops = net.op_table()
     conv_ms = sum(float(op_ms[i]) for i, o in enumerate(ops) if o['kind'] == 'conv')
     conv_launches = int(sum(int(op_launches[i]) for i, o in enumerate(ops) if o['kind'] == 'conv'))
-    images_per_step = SLICES * (MC_STEPS + 1)
+    images_per_step = n_items * (MC_STEPS + 1)
     conv_flop = 2.0 * sum(o['macs_per_image'] for o in ops if o['kind'] == 'conv') * images_per_step * args.steps
+    conv_flop_exec = 2.0 * sum(o['executed_macs_per_image'] for o in ops if o['kind'] == 'conv') * images_per_step * args.steps
     achieved_tflops = conv_flop / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    executed_tflops = conv_flop_exec / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     per_layer = []
     for i, o in enumerate(ops):
         if op_launches[i] == 0:
@@ -427,53 +559,78 @@ def run_gpu_arm(args):
                 'launches_per_step': int(op_launches[i]) // args.steps}
         if o['macs_per_image']:
             row_['tflops'] = round(2.0 * o['macs_per_image'] * images_per_step / (t * 1e-3) / 1e12, 1)
+            row_['tflops_executed'] = round(2.0 * o['executed_macs_per_image'] * images_per_step / (t * 1e-3) / 1e12, 1)
         per_layer.append(row_)
-    traffic = None
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, 'profiles', 'conv_traffic.json')
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and not isic:
         with open(tpath) as f:
-            traffic = json.load(f).get('dram_bytes_per_launch')
+            tj = json.load(f)
+        traffic, traffic_src = tj.get('dram_bytes_per_launch'), tj.get('source')
+    peaks = rig.peaks
     roofline = {'bound': 'tensor', 'kernel': 'conv_halo_kernel + conv_wide_kernel (all %d tcgen05 conv launches of a step, aggregated)' % (conv_launches // args.steps),
                 'achieved': achieved_tflops, 'peak': peaks['tflops_sustained'], 'unit': 'TFLOP/s',
-                'frac': achieved_tflops / peaks['tflops_sustained'], 'traffic': traffic,
+                'frac': achieved_tflops / peaks['tflops_sustained'],
+                'achieved_executed': executed_tflops, 'frac_executed': executed_tflops / peaks['tflops_sustained'],
+                'accounting': 'achieved = ALGORITHMIC conv FLOPs (3x3 convs at the output resolution, SURVEY.md §8a) / summed launch time; '
+                              'achieved_executed counts the four up-path convs as the 2x2-tap phase convolutions that actually run (2.25x fewer MACs)',
+                'traffic': traffic, 'traffic_source': traffic_src,
                 'peak_source': '%s bf16_tflops_sustained (kernel timed inside a long step)' % peaks['source'],
                 'share_of_step': conv_ms / args.steps / ms_step_op_events,
                 'timed_over': 'a second pass of the same %d steps with per-launch CUDA events (%.1f ms/step there)' % (args.steps, ms_step_op_events)}
-    agg_bytes = VOXELS * (8.0 * (MC_STEPS + 1) + 8 + 12 + 4 + 1 + 4)   # logits in (T+1 samples), ws probs, mean, entropy, prediction, foreground
+    agg_alg_bytes = voxels * (8.0 * MC_STEPS + 12)                            # T logit pairs in, mean + entropy out
+    agg_all_bytes = voxels * (8.0 * (MC_STEPS + 1) + 8 + 12 + 4 + 1)          # + the weight-scaling sample in / out, foreground, prediction
     hist_bytes = VOXELS * 7.0
+
+    def hbm(kernel, nbytes, ms, **extra):
+        d = {'kernel': kernel, 'bound': 'hbm', 'achieved': nbytes / (ms * 1e-3) / 1e9, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+             'frac': nbytes / (ms * 1e-3) / 1e9 / peaks['hbm_gbs'], 'ms': float(ms)}
+        d.update(extra)
+        return d
     roofline_hbm = [
-        {'kernel': 'aggregate (softmax+mean+entropy+argmax, 2 launches)', 'bound': 'hbm', 'achieved': agg_bytes / (stages[1] * 1e-3) / 1e9,
-         'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': agg_bytes / (stages[1] * 1e-3) / 1e9 / peaks['hbm_gbs'], 'ms': float(stages[1])},
-        {'kernel': 'eval_fused (ECE bins + U-E joint histogram, 7 B/voxel)', 'bound': 'hbm', 'achieved': hist_bytes / (ece_eval_ms * 1e-3) / 1e9,
-         'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': hist_bytes / (ece_eval_ms * 1e-3) / 1e9 / peaks['hbm_gbs'], 'ms': ece_eval_ms}]
+        hbm('aggregate (softmax + mean + entropy + argmax + the weight-scaling softmax, ONE launch), 8T+12 = 172 B/voxel algorithmic',
+            agg_alg_bytes, stages[1], achieved_all_bytes=agg_all_bytes / (stages[1] * 1e-3) / 1e9,
+            frac_all_bytes=agg_all_bytes / (stages[1] * 1e-3) / 1e9 / peaks['hbm_gbs'], bytes_per_voxel_moved=8 * (MC_STEPS + 1) + 25),
+        hbm('eval_fused (ECE bins + U-E joint histogram, 7 B/voxel), one subject of Beta(0.3,0.3)-shaped iid p, Bernoulli(p) target, 25% mask',
+            hist_bytes, ece_eval_beta_ms, bin_occupancy=beta_occupancy),
+        hbm('eval_fused, 50 such subjects per launch', 50 * hist_bytes, ece_eval_beta50_ms, ms_per_subject=ece_eval_beta50_ms / 50),
+        hbm('eval_fused on the maps this run produced (%d subject%s per launch)' % (n_subjects, '' if n_subjects == 1 else 's'),
+            voxels * (7.0 if mask_h is not None else 6.0), ece_eval_ms, bin_occupancy=bin_occupancy)]
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return 0
+        return None
 
     # ---------------- CPU baseline (rank 0, N=1 only): bounded sample of the same workload on the host cores
     cpu_baseline = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not isic:
         cores = os.cpu_count() or 1
-        cpu_sample(1, sd, images_h, target_h, mask_h, cores)
-        fwd_s, met_s = cpu_sample(args.cpu_slices, sd, images_h, target_h, mask_h, cores)
+        sd_cpu = {k: (v.cpu() if hasattr(v, 'cpu') else v) for k, v in sd.items()}
+        cpu_sample(1, sd_cpu, images_h, target_h, mask_h, cores)
+        fwd_s, met_s = cpu_sample(args.cpu_slices, sd_cpu, images_h, target_h, mask_h, cores)
         cpu_baseline = {'value': args.cpu_slices * HEIGHT * WIDTH * MC_STEPS / (fwd_s + met_s), 'unit': UNIT, 'cores': cores, 'kind': 'port',
                         'sample': '%d of 155 slices (T=20 + weight-scaling pass) forward+summary %.2f s on %d torch threads, numpy metric set '
                                   '%.2f s on 1 thread; oracle port of the reference functions' % (args.cpu_slices, fwd_s, cores, met_s),
                         'ece_eval_ms_per_subject_extrapolated': met_s * 1e3 * SLICES / args.cpu_slices}
 
-    value = world * VOXELS * MC_STEPS / (ms_step * 1e-3)
+    value = world * voxels * MC_STEPS / (ms_step * 1e-3)
     line = {
-        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+        'metric': METRIC if not isic else METRIC.replace('BraTS', 'ISIC 3x256x256'), 'value': value, 'unit': UNIT, 'n_gpus': world,
+        'steps': args.steps, 'warmup': warm,
         'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
         'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'l2_policy': 'inputs larger than L2 (143 MB images, 1.5 GB logits per step, 126 MB L2)',
-                   'weights': 'random init seed 20, BN statistics randomised (rcu_b200.synth)',
+        'config': {'workload': workload, 'name': 'isic_mc' if isic else 'brats_mc',
+                   'l2_policy': 'inputs larger than L2 (%d MB images, %.1f GB logits per step, 126 MB L2)' % (images_h.numel() * 4 >> 20, voxels * 8 * 21 / 1e9),
+                   'weights': 'random init seed 20, BN statistics randomised (rcu_b200.synth), foreground bias of the 1x1 head centred '
+                              'and rescaled (shift %.3f, gain %.3f: logit difference median 0, sigma 3 inside the mask)' % head_shift,
                    'chunk_images': net.chunk_images, 'parallelism': 'subject-sharded x%d, no data-path collective' % world},
-        'e2e': {'value': world * VOXELS * MC_STEPS / (e2e_ms * 1e-3), 'unit': UNIT, 'ms_per_step': e2e_ms,
-                'h2d_bytes_per_step': h2d['n'] // e2e_steps, 'd2h_bytes_per_step': d2h['n'] // e2e_steps,
-                'api': 'McPredictStep(20)+MultiPredictionSummary per 32-slice batch from pinned host images, probabilities to host, DeviceMetricsHook.evaluate on host maps'},
+        'e2e': {'value': world * voxels * MC_STEPS / (e2e_ms * 1e-3), 'unit': UNIT, 'ms_per_step': e2e_ms, 'steps': args.steps,
+                'h2d_bytes_per_step': h2d['n'] // args.steps, 'd2h_bytes_per_step': d2h['n'] // args.steps,
+                'copy_stream_busy_ms_per_step': {'h2d': h2d_busy, 'd2h': d2h_busy},
+                'exposed_ms_per_step': e2e_ms - ms_step,   # everything the host-buffer route adds to the device-resident step: the first
+                # batch's copy-in and the last batch's copy-out (nothing to hide behind), 32-slice batches (partial chunks), host syncs
+                'copy_hidden_fraction': max(0.0, min(1.0, 1.0 - (e2e_ms - ms_step) / max(1e-9, h2d_busy + d2h_busy))),
+                'api': 'McPredictStep(20)+MultiPredictionSummary per 32-item batch from pinned host images, probabilities to host, '
+                       'DeviceMetricsHook.evaluate / eval_fused on the device maps, labels and mask from the host, tables to the host'},
         'gpu_launches': n_launches,
         'clocks': clocks,
         'roofline': roofline,
@@ -481,15 +638,244 @@ def run_gpu_arm(args):
         'cpu_baseline': cpu_baseline,
         'ece_eval_ms': ece_eval_ms,
         'stages_ms': {'unet_forward': float(stages[0]), 'aggregate': float(stages[1]), 'metrics': float(stages[2])},
-        'fraction_of_tensor_roofline_whole_step': value / world * FLOP_PER_VOXEL_SAMPLE / 1e12 / peaks['tflops_sustained'],
-        'check': {'ece': float(ece), 'mean_entropy': mean_entropy, 'dice': float(row['dice'])},
+        'fraction_of_tensor_roofline_whole_step': value / world * flop_per_voxel_sample / 1e12 / peaks['tflops_sustained'],
+        'check': {'ece': float(ece), 'mean_entropy': mean_entropy, 'dice': float(row['dice']), 'prediction_positive_fraction': pred_pos,
+                  'bin_occupancy': bin_occupancy},
     }
-    print(json.dumps(line), flush=True)
     if args.layers:
         with open(args.layers, 'w') as f:
             json.dump({'ms_per_step': ms_step, 'layers': per_layer}, f, indent=1)
-    if world > 1:
-        dist.destroy_process_group()
+    return line
+
+
+# ------------------------------------------------------------------------------------------------ ensemble10 (config 4)
+def run_ensemble(args, rig):
+    """bin-dl/brats_test_ensemble.py:72-94 with the 10 members sharded over the ranks: every rank runs its members over the
+    whole subject, accumulates fp32 probability sums, ONE exchange, then mean / entropy / argmax and the metric tables."""
+    torch = rig.torch
+    import rcu_b200  # noqa: F401
+    from rcu_b200 import model, metrics, tables
+    from rcu_b200 import distributed as D
+    device, stream, rank, world = rig.device, rig.stream, rig.rank, rig.world
+    images_h, target_h, mask_h = synth_subject(1000)      # every rank sees the SAME subject
+    images_d = images_h.to(device)
+    target_d = torch.from_numpy(target_h).to(device).view(-1)
+    mask_d = torch.from_numpy(mask_h).to(device).view(-1)
+    lo, hi = D.shard_bounds(ENSEMBLE_MEMBERS, world, rank)
+    engines = [model.B200UNet(make_state_dict(seed=20 + k), in_channels=CHANNELS, dropout=DROPOUT, device=device, seed=20 + k, chunk_images=SLICES)
+               for k in range(lo, hi)]                    # seeds 20 + k mirror config/train_ensemble/*: seed: 20 + k
+    route = args.exchange if world > 1 else 'none'
+    exchange = D.PeerExchange(SLICES, HEIGHT, WIDTH) if route == 'peer' else None
+    comm = D.Comm() if route == 'nccl' else None
+    break_table = tables.uncertainty_break_table(tables.SWEEP_THRESHOLDS)
+    launches = {'n': 0}
+    ev_log = []
+
+    def step(i, log=False):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record(stream)
+        logits = torch.stack([e.forward_samples(images_d, 1, dropout_mode=0)[0] for e in engines]) if engines else None
+        launches['n'] += sum(e.last_launch_count() for e in engines)
+        target = exchange.sums if exchange is not None else None
+        if logits is not None:
+            sums = D.aggregate_partial(logits, out=target)
+            launches['n'] += 1
+        else:
+            sums = target.zero_() if target is not None else torch.zeros((SLICES, 2, HEIGHT, WIDTH), dtype=torch.float32, device=device)
+        ev[1].record(stream)
+        if world == 1:
+            out = D.aggregate_finish(sums, ENSEMBLE_MEMBERS, emit_prediction=True, emit_foreground=True)
+            launches['n'] += 1
+        else:
+            out = D._reduce_and_finish(sums, ENSEMBLE_MEMBERS, False, False, True, True, None, comm, exchange)
+            launches['n'] += 3 if exchange is not None else 1
+        ev[2].record(stream)
+        res = metrics.eval_fused(out['foreground'], out['prediction'], target_d, mask_d, 10, tables.SWEEP_THRESHOLDS, sync=False, break_table=break_table)
+        launches['n'] += 1
+        ev[3].record(stream)
+        if log:
+            ev_log.append(ev)
+        return out, res
+
+    keep = None
+    for i in range(max(args.warmup, 3)):
+        keep = step(i)
+    torch.cuda.synchronize()
+    launches['n'] = 0
+    ms_step, clocks, keep = rig.timed(lambda i: step(i, True), args.steps)
+    n_launches = launches['n']
+    st = np.array([[e[j].elapsed_time(e[j + 1]) for j in range(3)] for e in ev_log]).mean(0)
+    exch_ms = rig.max_over_ranks(float(st[1]))
+    exch_min_ms = -rig.max_over_ranks(-float(st[1]))      # the rank that arrives last waits for nobody: its figure is the exchange proper
+    out, res = keep
+    count, positives, conf, ue, invalid = [t.cpu().numpy() for t in res[:5]]
+    assert int(ue[0].sum()) == VOXELS and int(invalid[0]) == 0
+    ece = tables.ece_from_tables(count[0, :10], positives[0, :10], conf[0, :10], n_dim=3)
+    sums_bytes = VOXELS * 2 * 4
+    line = None
+    if rank == 0:
+        # bytes that must cross NVLink per rank: the peer route reads (N-1)/N of one rank's sums and writes (N-1)/N of the 17 B/voxel
+        # outputs; an all-reduce moves 2 (N-1)/N of the buffer
+        link_bytes = 0 if world == 1 else ((world - 1) / world * (sums_bytes + 17 * VOXELS) if route == 'peer' else 2 * (world - 1) / world * sums_bytes)
+        value = VOXELS * ENSEMBLE_MEMBERS / (ms_step * 1e-3)
+        line = {
+            'metric': 'ensemble voxel-members/sec (BraTS 10-member ensemble forward + probability-sum exchange + mean/entropy + ECE/U-E eval)',
+            'value': value, 'unit': 'voxel-members/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_step,
+            'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+            'config': {'workload': 'brats_ensemble10 (BASELINE config 4): one synthetic subject (155 slices 4x240x240), 10 random-init members '
+                                   '(seeds 20..29) sharded over the ranks (%s per rank), fp32 probability sums exchanged once, then '
+                                   'mean/entropy/argmax + ECE(mask)/Dice/U-E tables on every rank' % D.shard_sizes(ENSEMBLE_MEMBERS, world),
+                       'name': 'ensemble10', 'exchange': route, 'l2_policy': 'inputs larger than L2 (143 MB images, 71 MB sums per member set)'},
+            'e2e': None, 'gpu_launches': n_launches, 'clocks': clocks,
+            'stages_ms': {'members_forward_and_partial_sums': float(st[0]), 'exchange_and_finish': float(st[1]), 'metrics': float(st[2])},
+            'exchange': {'route': route, 'ms_slowest_rank': exch_ms, 'ms_last_arriving_rank': exch_min_ms, 'share_of_step': exch_ms / ms_step,
+                         'sums_bytes': sums_bytes, 'nvlink_bytes_per_rank': link_bytes,
+                         'nvlink_gbs_per_rank': link_bytes / (exch_min_ms * 1e-3) / 1e9 if world > 1 else None,
+                         'of_measured_peer_copy_770_gbs': link_bytes / (exch_min_ms * 1e-3) / 1e9 / 770.0 if world > 1 else None,
+                         'note': 'ms_slowest_rank includes the wait for the last rank to finish its members (member imbalance); '
+                                 'ms_last_arriving_rank is barrier + exchange + finish with nobody to wait for'},
+            'strong_scaling_ceiling': ENSEMBLE_MEMBERS / (world * max(D.shard_sizes(ENSEMBLE_MEMBERS, world))),
+            'check': {'ece': float(ece), 'mean_entropy': float(out['entropy'].mean().item()),
+                      'prediction_positive_fraction': float(out['prediction'].float().mean().item())},
+        }
+    if exchange is not None:
+        exchange.close()
+    if comm is not None:
+        comm.close()
+    return line
+
+
+# ------------------------------------------------------------------------------------------------ brats50 (config 5)
+def run_brats50(args, rig):
+    """bin-eval/eval_uncertainty.py:39-50 over a 50-subject test set produced by MC dropout T=20: the 50 x 155 slices are split
+    evenly over the ranks (a subject may span two ranks), every rank runs forward + summary + the fused histogram pass on its
+    slices, and ONE grouped all-reduce sums the per-subject count tables / confidence sums (exact for the integers)."""
+    torch = rig.torch
+    import rcu_b200  # noqa: F401
+    from rcu_b200 import model, steps, metrics, tables
+    from rcu_b200 import distributed as D
+    device, stream, rank, world = rig.device, rig.stream, rig.rank, rig.world
+    n_sub = args.subjects
+    total_slices = n_sub * SLICES
+    lo, hi = D.shard_bounds(total_slices, world, rank)
+    segments = []   # (subject, first slice, end slice) on this rank — at most two partial subjects
+    s = lo
+    while s < hi:
+        subj = s // SLICES
+        e = min(hi, (subj + 1) * SLICES)
+        segments.append((subj, s - subj * SLICES, e - subj * SLICES))
+        s = e
+    yy, xx = np.mgrid[0:HEIGHT, 0:WIDTH]
+    zz = np.arange(SLICES)[:, None, None]
+    brain = torch.from_numpy((((yy - 120) / 100.0) ** 2 + ((xx - 120) / 85.0) ** 2 + ((zz - 77) / 75.0) ** 2 < 1.0)).to(device)
+    blob = torch.from_numpy(((((yy - 100) / 30.0) ** 2 + ((xx - 140) / 25.0) ** 2 + ((zz - 70) / 20.0) ** 2) < 1.0)).to(device)
+    # the rank's slices, resident in HBM before anything is timed (generated on the device: 143 MB per subject)
+    data = []
+    for subj, a, b in segments:
+        g = torch.Generator(device=device).manual_seed(5000 + subj)
+        img = torch.randn((SLICES, CHANNELS, HEIGHT, WIDTH), device=device, generator=g)[a:b].clone()
+        img *= brain[a:b, None].float()
+        data.append((subj, a, b, img, blob[a:b].to(torch.uint8).reshape(-1).contiguous(), brain[a:b].to(torch.uint8).reshape(-1).contiguous()))
+
+    def factory(sd_):
+        return model.B200UNet(sd_, in_channels=CHANNELS, dropout=DROPOUT, device=device, seed=20)
+    gp = torch.Generator(device=device).manual_seed(1)
+    probe = torch.randn((16, CHANNELS, HEIGHT, WIDTH), device=device, generator=gp) * brain[70:86, None].float()
+    _, head_shift = centre_head_bias(make_state_dict(), factory, probe, brain[70:86])
+    if world > 1:   # identical weights everywhere: the shift / gain measured on rank 0
+        t = torch.tensor(list(head_shift), dtype=torch.float64, device=device)
+        rig.dist.broadcast(t, src=0)
+        head_shift = (float(t[0].item()), float(t[1].item()))
+    net = factory(shifted_head(make_state_dict(), *head_shift))
+    comm = D.Comm() if world > 1 and args.exchange != 'torch' else None
+    break_table = tables.uncertainty_break_table(tables.SWEEP_THRESHOLDS)
+    nb1, ncls = 11, len(tables.SWEEP_THRESHOLDS) + 1
+    width_i = 2 * nb1 + 4 * ncls + 1
+    launches = {'n': 0}
+    ev_log = []
+
+    def job(i, subset=None, log=False):
+        ints = torch.zeros((n_sub, width_i), dtype=torch.int64, device=device)
+        conf = torch.zeros((n_sub, nb1), dtype=torch.float64, device=device)
+        e0 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for (subj, a, b, img, tgt, msk) in (data if subset is None else data[:subset]):
+            logits = net.forward_samples(img, MC_STEPS + 1, dropout_mode=1, det_first=True, slice_index0=subj * SLICES + a, sample0=0)
+            launches['n'] += net.last_launch_count()
+            out = steps.summarize(steps.LazyMultiProbabilities(logits[1:]), emit_prediction=True, emit_foreground=True, ws_logits=logits[0])
+            cnt, pos, cf, ue, inv, _ = metrics.eval_fused(out['foreground'], out['prediction'], tgt, msk, 10, tables.SWEEP_THRESHOLDS, sync=False,
+                                                          break_table=break_table)
+            launches['n'] += 2
+            ints[subj] += torch.cat([cnt.reshape(-1), pos.reshape(-1), ue.reshape(-1), inv.reshape(-1)])
+            conf[subj] += cf.reshape(-1)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record(stream)
+        if world > 1:
+            if comm is not None:
+                comm.allreduce_metric_tables_(ints.view(-1), conf.view(-1))
+            else:
+                rig.dist.all_reduce(ints)
+                rig.dist.all_reduce(conf)
+        e2 = torch.cuda.Event(enable_timing=True)
+        e2.record(stream)
+        if log:
+            ev_log.append((e0, e1, e2))
+        return ints, conf
+
+    for i in range(max(args.warmup, 1)):
+        job(i, subset=min(len(data), 2))        # warm-up passes run the rank's first two segments (same kernels, same shapes)
+    torch.cuda.synchronize()
+    launches['n'] = 0
+    ms_step, clocks, keep = rig.timed(lambda i: job(i, log=True), args.steps)
+    n_launches = launches['n']
+    compute_ms = float(np.mean([a.elapsed_time(b) for a, b, _ in ev_log]))
+    reduce_ms = float(np.mean([b.elapsed_time(c) for _, b, c in ev_log]))
+    slowest_compute = rig.max_over_ranks(compute_ms)
+    fastest_reduce = -rig.max_over_ranks(-reduce_ms)
+    ints, conf = keep
+    ints_h, conf_h = ints.cpu().numpy(), conf.cpu().numpy()
+    line = None
+    if rank == 0:
+        cnt, pos, ue = ints_h[:, :nb1], ints_h[:, nb1:2 * nb1], ints_h[:, 2 * nb1:2 * nb1 + 4 * ncls].reshape(n_sub, 4, ncls)
+        assert int(ints_h[:, -1].sum()) == 0 and all(int(ue[s_].sum()) == VOXELS for s_ in range(n_sub)), 'count conservation over the all-reduce'
+        eces = [tables.ece_from_tables(cnt[s_, :10], pos[s_, :10], conf_h[s_, :10], n_dim=3) for s_ in range(n_sub)]
+        dices = [tables.dice_from_counts(ue[s_, 0].sum(), ue[s_, 2].sum(), ue[s_, 3].sum()) for s_ in range(n_sub)]
+        value = n_sub * VOXELS * MC_STEPS / (ms_step * 1e-3)
+        sizes = D.shard_sizes(total_slices, world)
+        line = {
+            'metric': METRIC + ' over a %d-subject test set' % n_sub, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 1), 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+            'dtype': 'bf16', 'data': 'synthetic',
+            'config': {'workload': 'brats50 (BASELINE config 5): %d synthetic subjects x 155 slices 4x240x240, MC T=20 (+1), fused summary, ECE(mask)+Dice+'
+                                   '11-threshold U-E tables per subject; slices split evenly over the ranks (%s), one grouped all-reduce of the '
+                                   'per-subject tables; a step is the whole pass' % (n_sub, sizes),
+                       'name': 'brats50', 'exchange': 'none' if world == 1 else ('rcu_allreduce_counts (NCCL)' if comm is not None else 'torch.distributed'),
+                       'l2_policy': 'inputs larger than L2', 'weights': 'random init seed 20, head centred and rescaled (shift %.3f, gain %.3f)' % head_shift},
+            'e2e': None, 'gpu_launches': n_launches, 'clocks': clocks,
+            'stages_ms': {'forward_summary_metrics_rank0': compute_ms, 'forward_summary_metrics_slowest_rank': slowest_compute,
+                          'table_allreduce_rank0_incl_wait': reduce_ms, 'table_allreduce_last_arriving_rank': fastest_reduce},
+            'exchange': {'bytes': int(ints.numel() * 8 + conf.numel() * 8), 'ms': fastest_reduce, 'share_of_step': fastest_reduce / ms_step},
+            'ms_per_subject': ms_step / n_sub,
+            'check': {'mean_ece': float(np.mean(eces)), 'mean_dice': float(np.mean(dices)), 'subjects': n_sub},
+        }
+    if comm is not None:
+        comm.close()
+    return line
+
+
+def run_gpu_arm(args):
+    rig = Rig(args)
+    if args.config == 'brats_mc':
+        line = run_mc_config(args, rig, isic=False)
+    elif args.config == 'isic_mc':
+        line = run_mc_config(args, rig, isic=True)
+    elif args.config == 'ensemble10':
+        line = run_ensemble(args, rig)
+    else:
+        line = run_brats50(args, rig)
+    if rig.rank == 0 and line is not None:
+        print(json.dumps(line), flush=True)
+    rig.finish()
     return 0
 
 
@@ -499,6 +885,9 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--config', default='brats_mc', choices=['brats_mc', 'isic_mc', 'ensemble10', 'brats50'])
+    ap.add_argument('--exchange', default='peer', choices=['peer', 'nccl', 'torch'], help='probability-sum exchange of the sharded configs')
+    ap.add_argument('--subjects', type=int, default=N_SUBJECTS_50, help='subjects of the brats50 config')
     ap.add_argument('--cpu-slices', type=int, default=2, help='slices per CPU-baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--layers', default=None, help='write the per-layer timing table (JSON) here')

@@ -11,7 +11,8 @@
  *   - all data pointers are DEVICE pointers owned by the caller unless marked "host"; small parameter
  *     tables (edges, thresholds, break tables) are host pointers read before the call returns;
  *   - every call is asynchronous and ordered on the given stream (a cudaStream_t passed as void*);
- *   - no hidden device allocation after rcu_unet_plan(); metric calls use a caller-provided workspace;
+ *   - the handle's only device allocations are its folded weights (rcu_unet_create); the activation workspace and the
+ *     metric workspace are caller-provided buffers;
  *   - one rcu_unet handle per (device, weight set); a handle is not thread-safe, distinct handles are.
  */
 #ifndef RCU_B200_H
@@ -31,7 +32,8 @@ typedef enum rcu_status {
   RCU_EINVAL = -1,   /* bad argument (the Python side turns these into the reference's ValueError) */
   RCU_ECUDA = -2,    /* CUDA runtime / driver error */
   RCU_ENOTSUP = -3,  /* configuration outside the supported hot path */
-  RCU_ENOMEM = -4    /* workspace too small */
+  RCU_ENOMEM = -4,   /* workspace too small */
+  RCU_ENCCL = -5     /* NCCL not loadable, or an NCCL call failed */
 } rcu_status;
 
 #define RCU_MAX_BINS 32        /* ECE reliability bins per call */
@@ -137,6 +139,13 @@ int rcu_aggregate(const float* input, int input_kind, int n_samples, int64_t n_i
                   float* entropy, float* mutual_info, float* variance, uint8_t* prediction, float* foreground,
                   float* multi_out, void* stream);
 
+/* McPredictStep + MultiPredictionSummary in ONE pass (rechun/dl/customsteps.py:23-25 and :50-71): as rcu_aggregate on the
+ * interleaved per-sample logits (input_kind 0), and in the same launch the deterministic weight-scaling sample
+ *   ws_logits float32[n_images][hw][2]  ->  ws_probabilities float32[n_images][2][hw] = softmax  (`ws_probabilities`). */
+int rcu_aggregate_ws(const float* logits, int n_samples, int64_t n_images, int64_t hw, const float* ws_logits,
+                     float* ws_probabilities, float* mean, float* entropy, float* mutual_info, float* variance,
+                     uint8_t* prediction, float* foreground, void* stream);
+
 /* Partial aggregation for sample-sharded runs: writes the raw fp32 sums so ranks can allreduce them.
  *   sums float32[n_images][K][hw] with K = 2 (sum p0, sum p1) [+1: sum_t H(p_t) if want_mi] [+2: sum p0^2, sum p1^2 if want_var]
  * and the finisher that turns allreduced sums into the same outputs as rcu_aggregate. */
@@ -228,9 +237,14 @@ typedef struct rcu_unet_desc {
 int rcu_unet_create(const rcu_unet_desc* desc, int device, rcu_unet** out);
 void rcu_unet_destroy(rcu_unet* net);
 
-/* Fixes the spatial size and the number of images (slices x samples) processed per internal chunk and
- * allocates the activation workspace (the only allocation the handle ever makes).  Returns bytes reserved. */
+/* Fixes the spatial size and the number of images (slices x samples) processed per internal chunk and reports the
+ * size of the activation workspace that configuration needs.  Nothing is allocated: the CALLER owns the workspace
+ *  and hands it over with rcu_unet_bind_workspace — a 1024-byte aligned device buffer of at least
+ * `workspace_bytes`, which may be shared by several handles of one device as long as their forwards are ordered on one
+ * stream (the M members of an ensemble then need one arena, not M).  Binding lays the activations out in the buffer and
+ * encodes the TMA descriptors, so re-bind after every rcu_unet_plan and whenever the buffer moves. */
 int rcu_unet_plan(rcu_unet* net, int height, int width, int max_images_per_chunk, size_t* workspace_bytes);
+int rcu_unet_bind_workspace(rcu_unet* net, void* workspace, size_t workspace_bytes);
 
 /* Runs `n_samples` forwards of each of `n_slices` input slices (the samples are folded into the batch, weights
  * are read once per tile) and writes pixel-interleaved logits float32[n_samples][n_slices][H*W][2].
@@ -299,9 +313,60 @@ int rcu_unet_num_ops(const rcu_unet* net);
 /* kind: 0 first conv (CUDA cores), 1 tcgen05 conv, 2 max-pool, 3 coefficient table.  macs_per_image: algorithmic
  * multiply-accumulates of the reference layer this op computes (0 for non-conv ops). */
 int rcu_unet_op_info(const rcu_unet* net, int op, int* kind, int64_t* macs_per_image, int* c_in, int* c_out, int* h, int* w);
+/* MACs the schedule actually EXECUTES for that op per image: equal to the algorithmic figure of rcu_unet_op_info except
+ * for the up-path convs, which run nearest-x2 + conv3x3 as four pre-summed 2x2-tap phase convolutions (2.25x fewer). */
+int rcu_unet_op_executed_macs(const rcu_unet* net, int op, int64_t* macs_per_image);
 int rcu_unet_read_timing(rcu_unet* net, float* ms, int64_t* launches, int n_ops);
 /* Number of kernel launches issued by the last rcu_unet_forward on this handle. */
 int64_t rcu_unet_last_launch_count(const rcu_unet* net);
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-GPU exchange steps (one process per GPU on one box).  The reference has none of this: its only
+ * multi-GPU mechanism is nn.DataParallel in training (common/trainloop/context.py:223-233).
+ * ------------------------------------------------------------------------------------------------ */
+#define RCU_COMM_ID_BYTES 128    /* sizeof(ncclUniqueId) */
+#define RCU_IPC_HANDLE_BYTES 64  /* sizeof(cudaIpcMemHandle_t) */
+
+typedef struct rcu_comm rcu_comm;   /* an NCCL communicator (NCCL is resolved at run time from the process's libnccl.so.2) */
+
+/* Rank 0 makes the id (host buffer of RCU_COMM_ID_BYTES), hands it to the other ranks by any means (the Python side uses
+ * torch.distributed), every rank then creates its communicator — collective, like ncclCommInitRank. */
+int rcu_comm_unique_id(void* id_out);
+int rcu_comm_create(const void* id, int n_ranks, int rank, int device, rcu_comm** out);
+void rcu_comm_destroy(rcu_comm* comm);
+
+/* In-place fp32 sum over ranks of the probability-sum planes rcu_aggregate_partial wrote (MC samples or ensemble
+ * members split over ranks, rechun/dl/customsteps.py:31-36 / bin-dl/brats_test_ensemble.py:78-94); follow it with
+ * rcu_aggregate_finish on every rank. */
+int rcu_allreduce_probsum(rcu_comm* comm, float* sums, int64_t n, void* stream);
+/* In-place sum over ranks of the per-subject metric tables of subjects whose slices span ranks: the uint64 count tables
+ * (count | positives | ue_counts | invalid, any concatenation) and the float64 confidence sums, as one grouped NCCL call. */
+int rcu_allreduce_counts(rcu_comm* comm, uint64_t* counts, int64_t n_counts, double* conf_sums, int64_t n_conf, void* stream);
+
+/* Fused "reduce, then finish" over NVLink peer memory — the product path of the probability-sum exchange.
+ * Every rank owns one exchange REGION (device memory, CUDA-IPC mapped into every other rank's process) laid out as
+ * rcu_peer_layout says: signal words, the partial sums [n_images][planes][hw] (where rcu_aggregate_partial writes), and the
+ * outputs.  rcu_aggregate_finish_peer(region_ptrs[n_ranks], ...) on rank r:
+ *   flag barrier (all partial sums complete)  ->  ONE kernel that reads pixel slice r of every rank's sums through the
+ *   peer mappings, adds them in rank order, applies MultiPredictionSummary's arithmetic (rechun/dl/customsteps.py:57-71)
+ *   and stores mean / entropy / [mutual_info] / [variance] / foreground / prediction into EVERY rank's region  ->  flag barrier.
+ * Afterwards each region holds the complete outputs, bit-identical on all ranks.  `epoch` must be non-zero and strictly
+ * increasing from call to call on a set of regions; the call is collective (every rank must make it). */
+typedef struct rcu_peer_layout_t {
+  int planes;            /* 2 [+1 if has_mi] [+2 if has_var] */
+  size_t off_sums, off_mean, off_entropy, off_mi, off_var, off_foreground, off_prediction;
+  size_t bytes;          /* size of one region */
+} rcu_peer_layout_t;
+int rcu_peer_layout(int64_t n_images, int64_t hw, int has_mi, int has_var, rcu_peer_layout_t* out);
+/* Allocates a zeroed region on `device` and exports its IPC handle (host buffer of RCU_IPC_HANDLE_BYTES); the other ranks
+ * map it with rcu_peer_region_open.  (Exchange regions are the one place the library allocates on the caller's behalf:
+ * cudaIpcGetMemHandle needs the base of a cudaMalloc allocation.) */
+int rcu_peer_region_alloc(size_t bytes, int device, void** ptr, void* ipc_handle_out);
+int rcu_peer_region_open(const void* ipc_handle, int device, void** ptr);
+int rcu_peer_region_close(void* ptr);
+int rcu_peer_region_free(void* ptr);
+int rcu_aggregate_finish_peer(void* const* region_ptrs, int n_ranks, int rank, uint32_t epoch, int total_samples,
+                              int64_t n_images, int64_t hw, int has_mi, int has_var, void* stream);
 
 #ifdef __cplusplus
 }

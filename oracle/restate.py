@@ -688,7 +688,8 @@ def best_threshold_summary(sweeps, ece, dice, thresholds=SWEEP_THRESHOLDS):
                 else:
                     with np.errstate(divide='ignore', invalid='ignore'):
                         vals.append((2 * (r['fnu'] + r['fpu'])) / np.float64(r['fn'] + r['fp'] + r['fnu'] + r['fpu'] + r['tnu'] + r['tpu']))
-            per_th.append(np.mean(vals))
+            vals = np.asarray(vals, dtype=np.float64)             # DataFrame.mean skips NaN subjects (0 / 0 U-E Dice)
+            per_th.append(np.nan if np.all(np.isnan(vals)) else np.nanmean(vals))
         per_th = np.array(per_th)
         k = int(np.nanargmax(per_th))                            # Series.idxmax: first maximum, NaN skipped
         table[name], table[name + '_threshold'] = per_th[k], float(thresholds[k])

@@ -10,7 +10,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'librcu_b200.so')
 LIB_PATH = os.environ.get('RCU_B200_LIB', LIB_PATH)   # developer override (A/B builds)
 
-RCU_OK, RCU_EINVAL, RCU_ECUDA, RCU_ENOTSUP, RCU_ENOMEM = 0, -1, -2, -3, -4
+RCU_OK, RCU_EINVAL, RCU_ECUDA, RCU_ENOTSUP, RCU_ENOMEM, RCU_ENCCL = 0, -1, -2, -3, -4, -5
+RCU_COMM_ID_BYTES, RCU_IPC_HANDLE_BYTES = 128, 64
 RCU_MAX_BINS, RCU_MAX_UE_CLASSES, RCU_MAX_BREAKS = 32, 32, 96
 
 c_void_p, c_int, c_int64, c_uint64, c_size_t, c_float = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_uint64,
@@ -38,6 +39,11 @@ class RcuUnetOutputs(ctypes.Structure):
                 ('postnet_logits', c_void_p)]
 
 
+class RcuPeerLayout(ctypes.Structure):
+    _fields_ = [('planes', c_int), ('off_sums', c_size_t), ('off_mean', c_size_t), ('off_entropy', c_size_t), ('off_mi', c_size_t),
+                ('off_var', c_size_t), ('off_foreground', c_size_t), ('off_prediction', c_size_t), ('bytes', c_size_t)]
+
+
 # name -> (restype, argtypes); mirrors include/rcu_b200.h one to one
 PROTOTYPES = {
     'rcu_abi_version': (c_int, []),
@@ -55,6 +61,8 @@ PROTOTYPES = {
     'rcu_confusion': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     'rcu_aggregate': (c_int, [c_void_p, c_int, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_void_p, c_void_p]),
+    'rcu_aggregate_ws': (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_void_p]),
     'rcu_aggregate_partial': (c_int, [c_void_p, c_int, c_int, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p]),
     'rcu_aggregate_finish': (c_int, [c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p]),
@@ -68,6 +76,7 @@ PROTOTYPES = {
     'rcu_unet_create': (c_int, [ctypes.POINTER(RcuUnetDesc), c_int, ctypes.POINTER(c_void_p)]),
     'rcu_unet_destroy': (None, [c_void_p]),
     'rcu_unet_plan': (c_int, [c_void_p, c_int, c_int, c_int, ctypes.POINTER(c_size_t)]),
+    'rcu_unet_bind_workspace': (c_int, [c_void_p, c_void_p, c_size_t]),
     'rcu_unet_forward': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_uint64, c_int64, c_int, c_void_p,
                                  c_void_p, c_void_p]),
     'rcu_unet_forward_ex': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_uint64, c_int64, c_int, c_void_p,
@@ -84,7 +93,20 @@ PROTOTYPES = {
     'rcu_unet_enable_timing': (c_int, [c_void_p, c_int]),
     'rcu_unet_num_ops': (c_int, [c_void_p]),
     'rcu_unet_op_info': (c_int, [c_void_p, c_int, c_int_p, ctypes.POINTER(c_int64), c_int_p, c_int_p, c_int_p, c_int_p]),
+    'rcu_unet_op_executed_macs': (c_int, [c_void_p, c_int, ctypes.POINTER(c_int64)]),
     'rcu_unet_read_timing': (c_int, [c_void_p, c_float_p, ctypes.POINTER(c_int64), c_int]),
+    'rcu_comm_unique_id': (c_int, [c_void_p]),
+    'rcu_comm_create': (c_int, [c_void_p, c_int, c_int, c_int, ctypes.POINTER(c_void_p)]),
+    'rcu_comm_destroy': (None, [c_void_p]),
+    'rcu_allreduce_probsum': (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    'rcu_allreduce_counts': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
+    'rcu_peer_layout': (c_int, [c_int64, c_int64, c_int, c_int, ctypes.POINTER(RcuPeerLayout)]),
+    'rcu_peer_region_alloc': (c_int, [c_size_t, c_int, ctypes.POINTER(c_void_p), c_void_p]),
+    'rcu_peer_region_open': (c_int, [c_void_p, c_int, ctypes.POINTER(c_void_p)]),
+    'rcu_peer_region_close': (c_int, [c_void_p]),
+    'rcu_peer_region_free': (c_int, [c_void_p]),
+    'rcu_aggregate_finish_peer': (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, ctypes.c_uint32, c_int, c_int64, c_int64, c_int, c_int,
+                                          c_void_p]),
 }
 
 _lib = None

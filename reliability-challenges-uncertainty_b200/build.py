@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_PATH = os.path.join(HERE, 'librcu_b200.so')
 STAMP_PATH = os.path.join(HERE, 'build', 'librcu_b200.stamp')
-SOURCES = ['error.cu', 'metrics.cu', 'aggregate.cu', 'masks.cu', 'prepare.cu', 'unet.cu']
+SOURCES = ['error.cu', 'metrics.cu', 'aggregate.cu', 'masks.cu', 'prepare.cu', 'collective.cu', 'unet.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '--use_fast_math=false',
               '-Xcompiler', '-fPIC', '-Xptxas', '-v', '--expt-relaxed-constexpr']
 
@@ -59,7 +59,7 @@ def build(force=False, verbose=False):
         with open(obj + '.ptxas.log', 'w') as f:
             f.write(res.stderr)
         objs.append(obj)
-    cmd = [_nvcc(), '-shared', '-o', LIB_PATH] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a']
+    cmd = [_nvcc(), '-shared', '-o', LIB_PATH] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a', '-ldl']
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

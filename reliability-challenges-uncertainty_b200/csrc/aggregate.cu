@@ -56,7 +56,8 @@ __global__ void __launch_bounds__(kAggThreads, P > 1 ? RCU_AGG_MINB : 1)
 aggregate_kernel(const float* __restrict__ in, int n_samples, long long n_images, long long hw, float inv_or_scale,
                  float* __restrict__ mean, float* __restrict__ entropy, float* __restrict__ mutual_info,
                  float* __restrict__ variance, unsigned char* __restrict__ prediction, float* __restrict__ foreground,
-                 float* __restrict__ multi_out, float* __restrict__ sums) {
+                 float* __restrict__ multi_out, float* __restrict__ sums, const float* __restrict__ ws_in,
+                 float* __restrict__ ws_out) {
   const long long pairs_per_image = hw >> 1;  // hw is even (checked on the host)
   const long long total_pairs = n_images * pairs_per_image;
   const long long sample_stride = n_images * hw * 2;
@@ -76,6 +77,25 @@ aggregate_kernel(const float* __restrict__ in, int n_samples, long long n_images
       img_k[k] = pr / pairs_per_image;
       px_k[k] = (pr - img_k[k] * pairs_per_image) * 2;
       src[k] = in + img_k[k] * hw * 2 + (KIND == 0 ? px_k[k] * 2 : px_k[k]);
+    }
+    if (ws_in != nullptr) {
+      // the deterministic weight-scaling pass of McPredictStep (rechun/dl/customsteps.py:23-25) rides in the same launch:
+      // one more interleaved-logits sample in, its planar softmax out
+      float4 q[P];
+#pragma unroll
+      for (int k = 0; k < P; ++k)
+        q[k] = on[k] ? ld_stream_f4(ws_in + img_k[k] * hw * 2 + px_k[k] * 2) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < P; ++k) {
+        float a0, a1, b0, b1;
+        softmax2(q[k].x, q[k].y, a0, a1);
+        softmax2(q[k].z, q[k].w, b0, b1);
+        if (on[k]) {
+          float* dst = ws_out + img_k[k] * hw * 2 + px_k[k];
+          *reinterpret_cast<float2*>(dst) = make_float2(a0, b0);
+          *reinterpret_cast<float2*>(dst + hw) = make_float2(a1, b1);
+        }
+      }
     }
 #pragma unroll kAggSampleUnroll
     for (int t = 0; t < n_samples; ++t) {
@@ -198,10 +218,12 @@ aggregate_finish_kernel(const float* __restrict__ sums, float total_samples, lon
       ++pl;
     }
     if (has_var && variance) {
-      // unbiased variance from raw moments: (sum p^2 - T * mean^2) / (T - 1), averaged over the two classes
-      const float q0 = s[pl * hw], q1 = s[(pl + 1) * hw];
-      const float dn = total_samples - 1.0f;
-      variance[i] = 0.5f * ((q0 - total_samples * m0 * m0) / dn + (q1 - total_samples * m1 * m1) / dn);
+      // unbiased variance from raw moments: (sum p^2 - (sum p)^2 / T) / (T - 1), averaged over the two classes.  The
+      // difference cancels badly in float for confident pixels (p ~ 1: sum p^2 ~ T), so it is taken in double and clamped
+      // at 0 like torch.var, which never goes negative
+      const double T = (double)total_samples, dn = T - 1.0;
+      const double q0 = s[pl * hw], q1 = s[(pl + 1) * hw], d0 = s0, d1 = s1;
+      variance[i] = (float)(0.5 * ((fmax(q0 - d0 * d0 / T, 0.0) + fmax(q1 - d1 * d1 / T, 0.0)) / dn));
     }
     if (prediction) prediction[i] = m1 > m0 ? 1 : 0;
     if (foreground) foreground[i] = m1;
@@ -211,7 +233,8 @@ aggregate_finish_kernel(const float* __restrict__ sums, float total_samples, lon
 template <int KIND, bool PARTIAL>
 static int launch_aggregate(bool mi, bool var, const float* in, int n_samples, int64_t n_images, int64_t hw, float denom,
                             float* mean, float* entropy, float* mutual_info, float* variance, uint8_t* prediction,
-                            float* foreground, float* multi_out, float* sums, cudaStream_t st) {
+                            float* foreground, float* multi_out, float* sums, cudaStream_t st, const float* ws_in = nullptr,
+                            float* ws_out = nullptr) {
   const long long total_pairs = n_images * (hw / 2);
   if (total_pairs == 0) return RCU_OK;
   // the plain summary (no MI / variance) runs four pairs per thread; the variants with more accumulators keep one
@@ -223,14 +246,14 @@ static int launch_aggregate(bool mi, bool var, const float* in, int n_samples, i
   if (wide) {
     aggregate_kernel<KIND, false, false, PARTIAL, RCU_AGG_P><<<(unsigned)blocks, kAggThreads, 0, st>>>(
         in, n_samples, (long long)n_images, (long long)hw, denom, mean, entropy, mutual_info, variance, prediction, foreground,
-        multi_out, sums);
+        multi_out, sums, ws_in, ws_out);
     RCU_LAUNCH_CHECK();
     return RCU_OK;
   }
 #define RCU_AGG_LAUNCH(MI_, VAR_)                                                                                    \
   aggregate_kernel<KIND, MI_, VAR_, PARTIAL, 1><<<(unsigned)blocks, kAggThreads, 0, st>>>(                            \
       in, n_samples, (long long)n_images, (long long)hw, denom, mean, entropy, mutual_info, variance, prediction,     \
-      foreground, multi_out, sums)
+      foreground, multi_out, sums, ws_in, ws_out)
   if (mi && var) RCU_AGG_LAUNCH(true, true);
   else if (mi) RCU_AGG_LAUNCH(true, false);
   else if (var) RCU_AGG_LAUNCH(false, true);
@@ -269,6 +292,19 @@ extern "C" int rcu_aggregate(const float* input, int input_kind, int n_samples, 
     case 1: return launch_aggregate<1, false>(mi, var, input, n_samples, n_images, hw, denom, mean, entropy, mutual_info, variance, prediction, foreground, multi_out, nullptr, st);
     default: return launch_aggregate<2, false>(mi, var, input, n_samples, n_images, hw, denom, mean, entropy, mutual_info, variance, prediction, foreground, multi_out, nullptr, st);
   }
+}
+
+extern "C" int rcu_aggregate_ws(const float* logits, int n_samples, int64_t n_images, int64_t hw, const float* ws_logits,
+                                float* ws_probabilities, float* mean, float* entropy, float* mutual_info, float* variance,
+                                uint8_t* prediction, float* foreground, void* stream) {
+  int rc = check_agg_common(logits, 0, n_samples, n_images, hw);
+  if (rc) return rc;
+  RCU_CHECK_ARG(mean != nullptr && ws_logits != nullptr && ws_probabilities != nullptr, "NULL pointer argument");
+  RCU_CHECK_ARG(reinterpret_cast<uintptr_t>(ws_logits) % 16 == 0, "ws_logits must be 16-byte aligned");
+  RCU_CHECK_ARG(variance == nullptr || n_samples >= 2, "variance needs at least two samples");
+  return launch_aggregate<0, false>(mutual_info != nullptr, variance != nullptr, logits, n_samples, n_images, hw, (float)n_samples, mean,
+                                    entropy, mutual_info, variance, prediction, foreground, nullptr, nullptr, (cudaStream_t)stream,
+                                    ws_logits, ws_probabilities);
 }
 
 extern "C" int rcu_aggregate_partial(const float* input, int input_kind, int n_samples, int64_t n_images, int64_t hw,

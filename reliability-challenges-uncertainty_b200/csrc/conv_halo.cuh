@@ -71,10 +71,13 @@ struct HaloParams {
   long long coef_stride;
   int coef_off;
   int relu;
-  const float* head;
+  const float* head;         // non-NULL: fused 1x1 head (conv_cls.1 / conv_sigma.1); the weights themselves travel in head_w
   float* logits;
   int chunk_slices;
   long long slice0, n_slices_total;
+  // [2][32] weights + [2] bias of the fused head, in the kernel's constant bank: every FFMA of the head takes its weight
+  // as a constant operand (the shared-memory copy cost three LDS per channel on the port the tensor pipe reads its operands from)
+  float head_w[66];
 };
 
 __device__ __forceinline__ uint32_t elect_one() {
@@ -143,7 +146,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const uint32_t smem_out = base + w_span + (uint32_t)prm.n_stages * prm.chunk_stride;   // 1024-aligned
   const uint32_t tail = w_span + (uint32_t)prm.n_stages * prm.chunk_stride + (prm.tma_store ? (uint32_t)S::kOutBytes : 0u);
   float2* s_coef = reinterpret_cast<float2*>(base_ptr + tail);
-  float* s_head = reinterpret_cast<float*>(base_ptr + tail + S::kCoefBytes);
   uint8_t* bar_ptr = base_ptr + tail + S::kCoefBytes + S::kHeadBytes;
   const uint32_t bar_full = smem_u32(bar_ptr);                      // [kMaxStages]
   const uint32_t bar_empty = bar_full + S::kMaxStages * 8;          // [kMaxStages]
@@ -178,7 +180,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     tmem_alloc(smem_u32(s_tmem), S::kTmemCols);
     tmem_relinquish();
   }
-  if (prm.head != nullptr && threadIdx.x >= 96 && threadIdx.x < 96 + 66) s_head[threadIdx.x - 96] = prm.head[threadIdx.x - 96];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -392,14 +393,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               tc_fence_before();
               mbar_arrive(bar_tempty + 8 * group);
             }
-            float l0 = s_head[64], l1 = s_head[65];
+            float l0 = prm.head_w[64], l1 = prm.head_w[65];
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
               const float2 cf = coef[c];
               float a = fmaf(__uint_as_float(v[c]), cf.x, cf.y);
               a = prm.relu ? fmaxf(a, 0.0f) : a;
-              l0 = fmaf(a, s_head[c], l0);
-              l1 = fmaf(a, s_head[32 + c], l1);
+              l0 = fmaf(a, prm.head_w[c], l0);
+              l1 = fmaf(a, prm.head_w[32 + c], l1);
             }
             lg[2 * half] = l0;
             lg[2 * half + 1] = l1;
@@ -488,14 +489,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(bar_tempty + 8 * group);   // accumulator is in registers: the MMA warp may reuse the stage
-        float l0 = s_head[64], l1 = s_head[65];
+        float l0 = prm.head_w[64], l1 = prm.head_w[65];
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
           const float2 cf = coef[c];
           float a = fmaf(__uint_as_float(v[c]), cf.x, cf.y);
           a = prm.relu ? fmaxf(a, 0.0f) : a;
-          l0 = fmaf(a, s_head[c], l0);
-          l1 = fmaf(a, s_head[32 + c], l1);
+          l0 = fmaf(a, prm.head_w[c], l0);
+          l1 = fmaf(a, prm.head_w[32 + c], l1);
         }
         if (valid) {
           const int t = img / prm.chunk_slices, sl = img - t * prm.chunk_slices;

@@ -80,6 +80,7 @@ struct ConvLayer {
   int block_n = 0, kc = 0;
   bool head = false;
   const float* d_head = nullptr;         // fused 1x1 head of this layer: [2][c_out] + [2]
+  float h_head[66] = {0};                // host copy (kernel parameter of the halo kernels)
   int out_slot = 0;                      // 0: class logits (conv_cls), 1: sigma logits (conv_sigma, unet.py:162-164)
   HaloPack halo;
   HaloPack pairp;                        // pixel-pair variant of the same layer (c_out = 32, dense source), preferred when planned
@@ -130,8 +131,9 @@ struct rcu_unet {
   int n_cols = 0;
   // plan
   int H = 0, W = 0, max_images = 0;
-  void* arena = nullptr;
+  void* arena = nullptr;                 // caller-owned activation workspace (rcu_unet_bind_workspace)
   size_t arena_bytes = 0;
+  size_t planned_bytes = 0;
   float2* d_coef = nullptr;
   Act first_out;
   Act head_feat;                         // features of conv_cls.0 for the cross-check path
@@ -723,16 +725,18 @@ extern "C" int rcu_unet_create(const rcu_unet_desc* d, int device, rcu_unet** ou
     net->first_coef_off = unit_off[0];
   }
   // ---- 1x1 heads ----
-  auto upload_head = [&](const rcu_conv_unit& h, float** out_ptr) -> int {
+  std::vector<float> host_head[2];
+  auto upload_head = [&](const rcu_conv_unit& h, float** out_ptr, int slot) -> int {
     if (!(h.weight && h.bias) || h.c_in != sf || h.c_out != 2) { set_error("head must be a 1x1 conv start_filters -> 2"); return RCU_EINVAL; }
     std::vector<float> hw((size_t)2 * sf + 2);
     for (int i = 0; i < 2 * sf; ++i) hw[i] = h.weight[i];
     hw[2 * sf] = h.bias[0];
     hw[2 * sf + 1] = h.bias[1];
+    host_head[slot] = hw;
     return dev_upload(net, hw, out_ptr);
   };
-  RCU_TRY(upload_head(d->head, &net->d_head));
-  if (has_sigma) RCU_TRY(upload_head(*d->sigma_head, &net->d_sigma_head));
+  RCU_TRY(upload_head(d->head, &net->d_head, 0));
+  if (has_sigma) RCU_TRY(upload_head(*d->sigma_head, &net->d_sigma_head, 1));
   // ---- tensor-core conv layers in execution order ----
   auto add_unit = [&](int u, int c0, int c1, bool head, int out_slot = 0) -> int {
     const rcu_conv_unit& cu = unit_at(u);
@@ -743,6 +747,7 @@ extern "C" int rcu_unet_create(const rcu_unet_desc* d, int device, rcu_unet** ou
     L.coef_off = unit_off[u];
     L.out_slot = out_slot;
     L.d_head = out_slot ? net->d_sigma_head : net->d_head;
+    if (head && sf == 32) std::memcpy(L.h_head, host_head[out_slot ? 1 : 0].data(), sizeof(float) * 66);
     int rc2 = pick_tiles(c1 > 0 ? (c0 < c1 ? c0 : c1) : c0, cu.c_out, &L.block_n, &L.kc);
     if (rc2) return rc2;
     if (head && (L.block_n != 32 || cu.c_out != 32)) { set_error("fused head needs start_filters == 32"); return RCU_ENOTSUP; }
@@ -812,7 +817,6 @@ extern "C" void rcu_unet_destroy(rcu_unet* net) {
   cudaSetDevice(net->device);
   for (auto& e : net->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   for (void* p : net->owned) cudaFree(p);
-  if (net->arena) cudaFree(net->arena);
   delete net;
 }
 
@@ -832,7 +836,30 @@ extern "C" int rcu_unet_set_halo_mask(rcu_unet* net, uint64_t mask) {
   return RCU_OK;
 }
 
+// Sizes the activation workspace (base == nullptr) or lays the tensors out inside the caller's buffer, encodes the TMA
+// descriptors (they embed addresses) and builds the schedule.
+static int plan_impl(rcu_unet* net, int height, int width, int max_images_per_chunk, uint8_t* base_in, size_t* workspace_bytes);
+
 extern "C" int rcu_unet_plan(rcu_unet* net, int height, int width, int max_images_per_chunk, size_t* workspace_bytes) {
+  RCU_CHECK_ARG(net != nullptr, "NULL handle");
+  size_t bytes = 0;
+  int rc = plan_impl(net, height, width, max_images_per_chunk, nullptr, &bytes);
+  if (rc) return rc;
+  net->planned_bytes = bytes;
+  if (workspace_bytes) *workspace_bytes = bytes;
+  return RCU_OK;
+}
+
+extern "C" int rcu_unet_bind_workspace(rcu_unet* net, void* workspace, size_t workspace_bytes) {
+  RCU_CHECK_ARG(net != nullptr, "NULL handle");
+  RCU_CHECK_ARG(net->planned_bytes > 0, "rcu_unet_plan has not been called");
+  RCU_CHECK_ARG(workspace != nullptr && reinterpret_cast<uintptr_t>(workspace) % 1024 == 0, "workspace must be a 1024-byte aligned device buffer");
+  RCU_CHECK_ARG(workspace_bytes >= net->planned_bytes, "workspace of %zu bytes is smaller than the planned %zu", workspace_bytes, net->planned_bytes);
+  size_t bytes = 0;
+  return plan_impl(net, net->H, net->W, net->max_images, reinterpret_cast<uint8_t*>(workspace), &bytes);
+}
+
+static int plan_impl(rcu_unet* net, int height, int width, int max_images_per_chunk, uint8_t* base_in, size_t* workspace_bytes) {
   RCU_CHECK_ARG(net != nullptr, "NULL handle");
   const int div = 1 << net->depth;
   if (height % div != 0 || width % div != 0 || height < div || width < div) {
@@ -841,7 +868,7 @@ extern "C" int rcu_unet_plan(rcu_unet* net, int height, int width, int max_image
   }
   RCU_CHECK_ARG(max_images_per_chunk >= 1, "max_images_per_chunk must be >= 1");
   RCU_CUDA(cudaSetDevice(net->device));
-  if (net->arena) { RCU_CUDA(cudaFree(net->arena)); net->arena = nullptr; }
+  net->arena = nullptr;   // the workspace belongs to the caller (rcu_unet_bind_workspace)
   net->ops.clear();
   net->H = height; net->W = width; net->max_images = max_images_per_chunk;
   const long long N = max_images_per_chunk;
@@ -854,7 +881,7 @@ extern "C" int rcu_unet_plan(rcu_unet* net, int height, int width, int max_image
   std::vector<Act> E(depth + 1), CAT(depth), P(depth), DA(depth), DB(depth);
   Act SB, HF, HF2;
   size_t off = 0;
-  uint8_t* base = nullptr;
+  uint8_t* base = base_in;
   auto tensor = [&](int c_total, int h, int w) {
     Act a;
     a.c = a.c_total = c_total; a.h = h; a.w = w;
@@ -874,7 +901,7 @@ extern "C" int rcu_unet_plan(rcu_unet* net, int height, int width, int max_image
     return a;
   };
   size_t o_coef = 0;
-  for (int pass = 0; pass < 2; ++pass) {
+  {
     off = 0;
     for (int l = 0; l <= depth; ++l) {
       const int h = height >> l, w = width >> l, c = sf << l;
@@ -892,13 +919,11 @@ extern "C" int rcu_unet_plan(rcu_unet* net, int height, int width, int max_image
     if (net->has_sigma) HF2 = tensor(sf, height, width);
     o_coef = off;
     off += ((size_t)N * net->n_cols * sizeof(float2) + 1023) & ~size_t(1023);
-    if (pass == 0) {
-      RCU_CUDA(cudaMalloc(&net->arena, off));
-      RCU_CUDA(cudaMemset(net->arena, 0, off));   // zero rows of the padded tensors are never written again
-      net->arena_bytes = off;
-      base = reinterpret_cast<uint8_t*>(net->arena);
-    }
   }
+  if (workspace_bytes) *workspace_bytes = off;
+  if (base == nullptr) return RCU_OK;   // sizing pass: nothing else depends on addresses
+  net->arena = base;
+  net->arena_bytes = off;
   net->d_coef = reinterpret_cast<float2*>(base + o_coef);
   net->first_out = E[0];
   net->head_feat = HF;
@@ -1003,7 +1028,6 @@ extern "C" int rcu_unet_plan(rcu_unet* net, int height, int width, int max_image
   net->features = cur;
   if ((rc = push_conv(cur, net->head_feat))) return rc;             // conv_cls.0 (+ fused head)
   if (net->has_sigma && (rc = push_conv(cur, net->sigma_feat))) return rc;   // conv_sigma.0 (+ fused head)
-  if (workspace_bytes) *workspace_bytes = off;
   return RCU_OK;
 }
 
@@ -1049,6 +1073,7 @@ static int run_conv_halo(rcu_unet* net, const ConvLayer& L, int n_img, int cs, l
     prm.coef = net->d_coef; prm.coef_stride = net->n_cols; prm.coef_off = L.coef_off;
     prm.relu = L.relu;
     prm.head = L.head ? L.d_head : nullptr;
+    if (L.head) std::memcpy(prm.head_w, L.h_head, sizeof(prm.head_w));
     prm.logits = logits;
     prm.chunk_slices = cs; prm.slice0 = s0; prm.n_slices_total = n_slices;
     int rc;
@@ -1093,6 +1118,7 @@ static int run_conv_halo_pair(rcu_unet* net, const ConvLayer& L, int n_img, int 
   prm.coef = net->d_coef; prm.coef_stride = net->n_cols; prm.coef_off = L.coef_off;
   prm.relu = L.relu;
   prm.head = L.head ? L.d_head : nullptr;
+  if (L.head) std::memcpy(prm.head_w, L.h_head, sizeof(prm.head_w));
   prm.logits = logits;
   prm.chunk_slices = cs; prm.slice0 = s0; prm.n_slices_total = n_slices;
   ConvLayer view = L;
@@ -1125,7 +1151,8 @@ extern "C" int rcu_unet_forward_ex(rcu_unet* net, const float* images, int64_t n
   RCU_CHECK_ARG(sigma == nullptr || net->has_sigma, "sigma output requested from a net without conv_sigma (sigma_out=False)");
   RCU_CHECK_ARG(post == nullptr || outputs->postnet_logits != nullptr, "postnet without postnet_logits");
   RCU_CHECK_ARG(post == nullptr || (post->device == net->device && net->start_filters == kPostC), "postnet does not match this net");
-  RCU_CHECK_ARG(!net->ops.empty(), "rcu_unet_plan has not been called");
+  RCU_CHECK_ARG(net->planned_bytes > 0, "rcu_unet_plan has not been called");
+  RCU_CHECK_ARG(!net->ops.empty() && net->arena != nullptr, "no workspace bound (rcu_unet_bind_workspace)");
   RCU_CHECK_ARG(n_slices >= 0 && n_samples >= 1, "bad sizes: n_slices=%lld n_samples=%d", (long long)n_slices, n_samples);
   RCU_CHECK_ARG(dropout_mode >= 0 && dropout_mode <= 2, "dropout_mode must be 0, 1 or 2");
   RCU_CHECK_ARG(dropout_mode != 2 || scale != nullptr || net->total_dropout_channels == 0, "dropout_mode 2 needs a scale table");
@@ -1392,6 +1419,25 @@ extern "C" int rcu_unet_op_info(const rcu_unet* net, int op, int* kind, int64_t*
   if (c_out) *c_out = co;
   if (h) *h = hh;
   if (w) *w = ww;
+  return RCU_OK;
+}
+
+extern "C" int rcu_unet_op_executed_macs(const rcu_unet* net, int op, int64_t* macs_per_image) {
+  RCU_CHECK_ARG(net != nullptr && macs_per_image != nullptr, "NULL argument");
+  RCU_CHECK_ARG(op >= 0 && op <= (int)net->ops.size(), "op index %d out of range", op);
+  int64_t macs = 0;
+  if (op < (int)net->ops.size()) {
+    const Op& o = net->ops[op];
+    if (o.kind == OP_FIRST) {
+      macs = (int64_t)net->H * net->W * 9 * net->in_channels * net->start_filters;
+    } else if (o.kind == OP_CONV) {
+      const ConvLayer& L = net->convs[o.conv];
+      // the up-path convs run as four 2x2-tap phase convolutions on the low-resolution input: 4 taps per OUTPUT pixel
+      const int taps = L.n_phases == 4 ? 4 : 9;
+      macs = (int64_t)o.h * o.w * taps * (L.c0 + L.c1) * L.c_out + (L.head ? (int64_t)o.h * o.w * L.c_out * 2 : 0);
+    }
+  }
+  *macs_per_image = macs;
   return RCU_OK;
 }
 

@@ -15,6 +15,11 @@ from . import tables
 def subject_outputs(probabilities, prediction=None):
     """(foreground p float32, argmax prediction uint8) of an assembled subject — the two volumes WriteHook stores
     (bin-dl/brats_test_default.py:96-98; np.argmax ties -> class 0).  numpy in -> numpy out, tensor in -> tensor out."""
+    # maps assembled from (N, 1, H, W) step outputs arrive channel-last with one channel
+    if prediction is not None and prediction.ndim > 1 and prediction.shape[-1] == 1 and prediction.ndim == probabilities.ndim:
+        prediction = prediction[..., 0]
+    if probabilities.ndim > 1 and probabilities.shape[-1] == 1 and prediction is not None and probabilities.ndim == prediction.ndim + 1:
+        probabilities = probabilities[..., 0]
     if torch.is_tensor(probabilities):
         if probabilities.shape[-1] == 2:
             return probabilities[..., 1].float().contiguous(), (probabilities[..., 1] > probabilities[..., 0]).to(torch.uint8)

@@ -62,6 +62,30 @@ def _f32(t):
     return np.ascontiguousarray(t.detach().to('cpu', torch.float32).numpy())
 
 
+_WORKSPACES = {}
+
+
+def shared_workspace(device, nbytes):
+    """The per-device activation workspace (a uint8 CUDA tensor of at least `nbytes`), shared by all engines of the device.
+    Sharing assumes what the reference's test loop does: one Python thread, forwards ordered on one stream."""
+    device = torch.device(device)
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    buf = _WORKSPACES.get(key)
+    if buf is None or buf.numel() < nbytes:
+        if buf is not None:
+            _WORKSPACES.pop(key)
+            del buf
+        buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        assert buf.data_ptr() % 1024 == 0
+        _WORKSPACES[key] = buf
+    return buf
+
+
+def release_workspaces():
+    """Drop the shared activation workspaces (engines re-acquire one on their next forward)."""
+    _WORKSPACES.clear()
+
+
 class B200UNet(nn.Module):
     """See module docstring.  Not trainable: there are no parameters, only a device handle."""
 
@@ -92,6 +116,7 @@ class B200UNet(nn.Module):
         self._next_slice = 0       # run-global slice counter for forward() calls
         self._handle = None
         self._plan = None
+        self._workspace = None
         self._device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
         units, upconvs = unit_layout(in_channels, depth, start_filters, dropout, dropout_center)
         self.site_channels = [co for (_, _, co, d) in units if d]
@@ -232,6 +257,18 @@ class B200UNet(nn.Module):
             ws = ctypes.c_size_t()
             _lib.check(_lib.lib().rcu_unet_plan(self._handle, int(h), int(w), int(need), ctypes.byref(ws)))
             self._plan = (h, w, need, int(ws.value))
+            self._workspace = None
+        # the activation workspace is ours, not the library's: one buffer per device, shared by every engine on it (their
+        # forwards are ordered on the current stream), grown on demand
+        arena = shared_workspace(self._device, self._plan[3])
+        if self._workspace is not arena:
+            with torch.cuda.device(self._device):
+                _lib.check(_lib.lib().rcu_unet_bind_workspace(self._handle, _lib.ptr(arena), arena.numel()))
+            self._workspace = arena
+
+    def workspace_bytes(self):
+        """Bytes of activation workspace the current plan needs (0 before the first forward)."""
+        return 0 if self._plan is None else self._plan[3]
 
     def forward_samples(self, images, n_samples=1, dropout_mode=0, det_first=False, seed=None, slice_index0=0, sample0=0,
                         scale=None):
@@ -317,8 +354,10 @@ class B200UNet(nn.Module):
             macs = ctypes.c_int64()
             _lib.check(_lib.lib().rcu_unet_op_info(self._handle, i, ctypes.byref(kind), ctypes.byref(macs), ctypes.byref(ci),
                                                    ctypes.byref(co), ctypes.byref(h), ctypes.byref(w)))
+            ex = ctypes.c_int64()
+            _lib.check(_lib.lib().rcu_unet_op_executed_macs(self._handle, i, ctypes.byref(ex)))
             out.append({'kind': ('first_conv', 'conv', 'maxpool', 'coef')[kind.value], 'macs_per_image': int(macs.value),
-                        'c_in': ci.value, 'c_out': co.value, 'h': h.value, 'w': w.value})
+                        'executed_macs_per_image': int(ex.value), 'c_in': ci.value, 'c_out': co.value, 'h': h.value, 'w': w.value})
         return out
 
     def read_timing(self):

@@ -14,6 +14,8 @@ fused pass over the logits.  `batch_context.output['multi_probabilities']` is a 
 summary consumes the logits behind it directly; anything else that touches it gets the real (T, N, C, H, W) tensor.
 """
 import abc
+import itertools
+import weakref
 
 import torch
 
@@ -50,20 +52,33 @@ def _check_context(context):
             context.__class__.__name__))
 
 
-_ENGINES = {}
+_ENGINES = weakref.WeakKeyDictionary()   # reference module -> (weight fingerprint, converted engine); dies with the module
+
+
+def _weights_fingerprint(module):
+    """Changes whenever a parameter or buffer of `module` is rebound or written in place (load_state_dict / an optimizer
+    step bump the tensors' version counters), so a cached conversion never outlives the weights it was folded from."""
+    return tuple((t.data_ptr(), t._version) for t in itertools.chain(module.parameters(), module.buffers()))
 
 
 def engine_for(model, device=None, seed=None):
-    """The B200UNet behind a model: the model itself, or a cached conversion of a reference UNet."""
+    """The B200UNet behind a model: the model itself, or a cached conversion of a reference UNet (rebuilt when the
+    module's weights change, e.g. context.load_from_checkpoint between two evaluations of one model object)."""
     if isinstance(model, B200UNet):
         return model
-    key = id(model)
-    eng = _ENGINES.get(key)
-    if eng is None or eng[0] is not model:
+    fp = _weights_fingerprint(model)
+    eng = _ENGINES.get(model)
+    if eng is None or eng[0] != fp:
         kw = {} if seed is None else {'seed': seed}
-        eng = (model, B200UNet.from_reference(model, device=device, **kw))
-        _ENGINES[key] = eng
+        eng = (fp, B200UNet.from_reference(model, device=device, **kw))
+        _ENGINES[model] = eng
     return eng[1]
+
+
+def release_engines():
+    """Drop every cached conversion (their device weights go with them; the shared activation workspace stays)."""
+    _ENGINES.clear()
+    _POSTNETS.clear()
 
 
 def softmax_planar(logits_interleaved):
@@ -75,7 +90,46 @@ def softmax_planar(logits_interleaved):
     return out
 
 
-class LazyMultiProbabilities:
+class _LazyTensor:
+    """A stand-in that turns into the real tensor the moment anything tensor-like touches it."""
+
+    _tensor = None
+
+    def materialize(self):
+        raise NotImplementedError
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        kwargs = kwargs or {}
+        args = tuple(a.materialize() if isinstance(a, _LazyTensor) else a for a in args)
+        return func(*args, **kwargs)
+
+    def __getattr__(self, name):  # anything tensor-like falls through to the real tensor
+        if name.startswith('__'):
+            raise AttributeError(name)
+        return getattr(self.materialize(), name)
+
+
+class LazyWsProbabilities(_LazyTensor):
+    """`ws_probabilities` of McPredictStep (rechun/dl/customsteps.py:23-25) before its softmax has run.  The fused
+    MultiPredictionSummary computes it in its own launch and puts the real tensor into `batch_context.output`; any other
+    consumer that touches it first gets it from a stand-alone softmax pass."""
+
+    def __init__(self, logits):
+        self.logits = logits  # (N, H, W, 2) interleaved, float32
+
+    @property
+    def shape(self):
+        n, h, w, c = self.logits.shape
+        return torch.Size((n, c, h, w))
+
+    def materialize(self):
+        if self._tensor is None:
+            self._tensor = softmax_planar(self.logits)
+        return self._tensor
+
+
+class LazyMultiProbabilities(_LazyTensor):
     """Stands in for the stacked per-sample probabilities (T, N, 2, H, W) without materialising them."""
 
     def __init__(self, logits):
@@ -96,17 +150,6 @@ class LazyMultiProbabilities:
                                                 None, _lib.ptr(multi), _lib.current_stream()))
             self._tensor = multi
         return self._tensor
-
-    @classmethod
-    def __torch_function__(cls, func, types, args=(), kwargs=None):
-        kwargs = kwargs or {}
-        args = tuple(a.materialize() if isinstance(a, LazyMultiProbabilities) else a for a in args)
-        return func(*args, **kwargs)
-
-    def __getattr__(self, name):  # anything tensor-like falls through to the real tensor
-        if name.startswith('__'):
-            raise AttributeError(name)
-        return getattr(self.materialize(), name)
 
 
 class SegmentationPredictStep(_BatchStepBase):
@@ -147,18 +190,18 @@ class AleatoricPredictStep(_BatchStepBase):
         batch_context.output['probabilities'] = softmax_planar(logits)
 
 
-_POSTNETS = {}
+_POSTNETS = weakref.WeakKeyDictionary()
 
 
 def postnet_for(model, device=None):
     """The B200PostNet behind an auxiliary model: the model itself, or a cached conversion of a reference PostNet."""
     if isinstance(model, B200PostNet):
         return model
-    key = id(model)
-    post = _POSTNETS.get(key)
-    if post is None or post[0] is not model:
-        post = (model, B200PostNet.from_reference(model, device=device))
-        _POSTNETS[key] = post
+    fp = _weights_fingerprint(model)
+    post = _POSTNETS.get(model)
+    if post is None or post[0] != fp:
+        post = (fp, B200PostNet.from_reference(model, device=device))
+        _POSTNETS[model] = post
     return post[1]
 
 
@@ -202,9 +245,10 @@ class AuxiliarySegmPredictStep(_BatchStepBase):
 class McPredictStep(_BatchStepBase):
     """T stochastic forwards + the deterministic weight-scaling forward, as ONE folded batch of (T+1)·N images."""
 
-    def __init__(self, mc_steps) -> None:
+    def __init__(self, mc_steps, defer_ws=True) -> None:
         super().__init__()
         self.mc_steps = mc_steps
+        self.defer_ws = defer_ws
         self.slices_seen = 0  # run-global slice index: the Philox stream does not depend on batching
 
     def __call__(self, batch_context, task_context, context) -> None:
@@ -216,7 +260,9 @@ class McPredictStep(_BatchStepBase):
         logits = engine.forward_samples(images, self.mc_steps + 1, dropout_mode=mode, det_first=True,
                                         slice_index0=self.slices_seen, sample0=0)
         self.slices_seen += images.shape[0]
-        batch_context.output['ws_probabilities'] = softmax_planar(logits[0])
+        # the weight-scaling softmax rides in the fused summary's launch when one follows (it does in every reference
+        # script, bin-dl/brats_test_default.py:46-48); anything else that touches the entry first computes it on the spot
+        batch_context.output['ws_probabilities'] = LazyWsProbabilities(logits[0]) if self.defer_ws else softmax_planar(logits[0])
         batch_context.output['multi_probabilities'] = LazyMultiProbabilities(logits[1:])
 
 
@@ -245,21 +291,32 @@ class MultiPredictionSummary(_BatchStepBase):
         self.do_mi = do_mi
         self.do_var = do_var
         self.remove_multi_probs = remove_multi_probs
-        self.emit_prediction = emit_prediction  # extra 'prediction' (N, H, W) uint8 output for the in-memory metric path
-        self.emit_foreground = emit_foreground  # extra 'foreground' (N, H, W) float32 = probabilities[:, 1], dense
+        self.emit_prediction = emit_prediction  # extra 'prediction' (N, 1, H, W) uint8 output for the in-memory metric path
+        self.emit_foreground = emit_foreground  # extra 'foreground' (N, 1, H, W) float32 = probabilities[:, 1], dense
 
     def __call__(self, batch_context, task_context, context) -> None:
         if self.remove_multi_probs:
             multi = batch_context.output.pop('multi_probabilities')
         else:
             multi = batch_context.output['multi_probabilities']
-        out = summarize(multi, self.do_mi, self.do_var, self.emit_prediction, self.emit_foreground)
+        ws = batch_context.output.get('ws_probabilities')
+        ws = ws if isinstance(ws, LazyWsProbabilities) and ws._tensor is None and isinstance(multi, LazyMultiProbabilities) else None
+        out = summarize(multi, self.do_mi, self.do_var, self.emit_prediction, self.emit_foreground, ws_logits=None if ws is None else ws.logits)
+        if ws is not None:
+            ws._tensor = out.pop('ws_probabilities')
+        if isinstance(batch_context.output.get('ws_probabilities'), LazyWsProbabilities):
+            batch_context.output['ws_probabilities'] = batch_context.output['ws_probabilities'].materialize()
         if not self.remove_multi_probs and isinstance(multi, LazyMultiProbabilities):
             batch_context.output['multi_probabilities'] = multi.materialize()
+        # like every reference output the extra maps carry a channel dimension, (N, 1, H, W): the unmodified test loop
+        # applies th.channel_to_end to whatever it assembles (common/trainloop/loops.py:210-216)
+        for key in ('prediction', 'foreground'):
+            if key in out:
+                out[key] = out[key].unsqueeze(1)
         batch_context.output.update(out)
 
 
-def summarize(multi, do_mi=False, do_var=False, emit_prediction=False, emit_foreground=False):
+def summarize(multi, do_mi=False, do_var=False, emit_prediction=False, emit_foreground=False, ws_logits=None):
     """mean / entropy / [mutual_info] / [variance] / [prediction] / [foreground = mean[:, 1], dense] of a LazyMultiProbabilities or a real
     (T, N, 2, H, W) probability tensor — one fused pass (rechun/dl/customsteps.py:57-71)."""
     if isinstance(multi, LazyMultiProbabilities):
@@ -279,10 +336,22 @@ def summarize(multi, do_mi=False, do_var=False, emit_prediction=False, emit_fore
     var = torch.empty((n, 1, h, w), dtype=torch.float32, device=dev) if do_var else None
     pred = torch.empty((n, h, w), dtype=torch.uint8, device=dev) if emit_prediction else None
     fg = torch.empty((n, h, w), dtype=torch.float32, device=dev) if emit_foreground else None
+    ws_out = None
     with torch.cuda.device(dev):
-        _lib.check(_lib.lib().rcu_aggregate(_lib.ptr(src), kind, t, n, h * w, _lib.ptr(mean), _lib.ptr(entropy), _lib.ptr(mi),
-                                            _lib.ptr(var), _lib.ptr(pred), _lib.ptr(fg), None, _lib.current_stream()))
+        if ws_logits is not None:
+            # interleaved logits (N, H, W, 2) of the deterministic weight-scaling pass: its softmax shares this launch
+            if kind != 0 or tuple(ws_logits.shape) != (n, h, w, 2):
+                raise ValueError('ws_logits must be interleaved logits of shape {}'.format((n, h, w, 2)))
+            ws_out = torch.empty((n, 2, h, w), dtype=torch.float32, device=dev)
+            _lib.check(_lib.lib().rcu_aggregate_ws(_lib.ptr(src), t, n, h * w, _lib.ptr(ws_logits.contiguous()), _lib.ptr(ws_out), _lib.ptr(mean),
+                                                   _lib.ptr(entropy), _lib.ptr(mi), _lib.ptr(var), _lib.ptr(pred), _lib.ptr(fg),
+                                                   _lib.current_stream()))
+        else:
+            _lib.check(_lib.lib().rcu_aggregate(_lib.ptr(src), kind, t, n, h * w, _lib.ptr(mean), _lib.ptr(entropy), _lib.ptr(mi),
+                                                _lib.ptr(var), _lib.ptr(pred), _lib.ptr(fg), None, _lib.current_stream()))
     out = {'probabilities': mean, 'entropy': entropy}
+    if ws_out is not None:
+        out['ws_probabilities'] = ws_out
     if do_mi:
         out['mutual_info'] = mi
     if do_var:

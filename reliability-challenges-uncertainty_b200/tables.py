@@ -11,6 +11,8 @@ Reference arithmetic these tables encode (path:line relative to the reference ro
 """
 import math
 
+import warnings
+
 import numpy as np
 
 SWEEP_THRESHOLDS = (0.05, 0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9, 0.95)  # bin-eval/eval_uncertainty.py:239
@@ -322,18 +324,22 @@ def best_threshold_summary(sweeps, ece, dice, thresholds=None):
     sweeps: per subject, {threshold: UncertaintyAndCorrectionEvalNumpy results} (what DeviceMetricsHook rows hold under
     'sweep'); ece / dice: per-subject values.  `benefit` = corrected_dice > dice, `error` = the U-E Dice (:56-59); for
     each of the two the threshold with the best subject-mean is chosen (`get_best_thresholds`, :132-143; first maximum
-    in threshold order, NaNs skipped) and the subject-mean at that threshold reported."""
+    in threshold order) and the subject-mean at that threshold reported.  Both means are pandas means: a subject whose U-E
+    Dice is 0 / 0 at a threshold (nothing wrong, nothing uncertain) is left out of that threshold's mean (skipna), it does
+    not make the threshold ineligible.  Pinned by tests/golden/best_golden.npz (the unmodified `get_best_thresholds`)."""
     if thresholds is None:
         thresholds = list(sweeps[0].keys())
     benefit = np.array([[float(s[th]['corrected_dice'] - s[th]['dice'] > 0) for s in sweeps] for th in thresholds])
     error = np.array([[ue_table_columns(s[th])['ue'] for s in sweeps] for th in thresholds], dtype=np.float64)
 
     def best(table):
-        means = table.mean(axis=1)           # per threshold over subjects (a NaN subject makes the threshold NaN)
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore', RuntimeWarning)      # all-NaN threshold -> NaN, like DataFrame.mean
+            means = np.nanmean(table, axis=1)                    # per threshold over subjects, NaN subjects skipped
         if np.all(np.isnan(means)):
             return float('nan'), float('nan')
-        k = int(np.nanargmax(means))
-        return means[k], float(thresholds[k])
+        k = int(np.nanargmax(means))                             # Series.idxmax: first maximum, NaN skipped
+        return float(means[k]), float(thresholds[k])
     b_mean, b_th = best(benefit)
     e_mean, e_th = best(error)
     return {'ece': float(np.mean(ece)), 'dice': float(np.mean(dice)), 'benefit': b_mean, 'benefit_threshold': b_th,

@@ -15,7 +15,7 @@ from test_oracle_golden_aux import aleatoric_state, auxfeat_state
 
 pytestmark = pytest.mark.gpu
 torch.set_grad_enabled(False)
-P_MAX, P_MEAN = 2.5e-2, 2e-3
+P_MAX, P_MEAN = 1.2e-2, 2e-3
 
 
 class Ctx:

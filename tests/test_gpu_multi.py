@@ -45,16 +45,34 @@ def _worker(rank, world, port, out_dir):
         ref = steps.summarize(steps.LazyMultiProbabilities(logits[1:]), do_mi=True, do_var=True, emit_prediction=True)
         res = {k: float((out[k].float() - ref[k].float()).abs().max().item()) for k in ('probabilities', 'entropy', 'mutual_info', 'variance')}
         res['pred_mismatch'] = float((out['prediction'] != ref['prediction']).float().mean().item())
+        # (1b) the same exchange through the library's own NCCL communicator (rcu_comm_* / rcu_allreduce_probsum) ...
+        comm = D.Comm()
+        out_c = D.mc_predict_sample_sharded(net, x, T, want_mi=True, want_var=True, emit_prediction=True, comm=comm)
+        res['comm_vs_torch'] = max(float((out_c[k].float() - out[k].float()).abs().max().item()) for k in ('probabilities', 'entropy', 'mutual_info', 'variance'))
+        # (1c) ... and through the fused peer-memory reduce + finish kernel (rcu_aggregate_finish_peer): twice, the regions are reused
+        ex = D.PeerExchange(x.shape[0], x.shape[2], x.shape[3], want_mi=True, want_var=True)
+        for rep in range(2):
+            out_p = D.mc_predict_sample_sharded(net, x, T, want_mi=True, want_var=True, emit_prediction=True, emit_foreground=True, exchange=ex)
+            res['peer_rep%d' % rep] = max(float((out_p[k].float() - ref[k].float()).abs().max().item()) for k in ('probabilities', 'entropy', 'mutual_info', 'variance'))
+        res['peer_pred_mismatch'] = float((out_p['prediction'] != ref['prediction']).float().mean().item())
+        res['peer_fg'] = float((out_p['foreground'] - out_p['probabilities'][:, 1]).abs().max().item())
+        # every rank must hold bit-identical outputs: gather rank 0's probabilities and compare
+        probe = out_p['probabilities'].clone()
+        dist.broadcast(probe, src=0)
+        res['peer_ranks_identical'] = float(torch.equal(probe, out_p['probabilities']))
         # (2) ensemble members sharded over ranks == all members on one GPU
         sds = [R.randomize_statistics(R.init_state_dict(cfg, 20 + k), 7 + k) for k in range(3)]
         lo, hi = D.shard_bounds(3, world, rank)
         local = [model.B200UNet(sds[k], in_channels=4, dropout=cfg.dropout, device='cuda:%d' % rank) for k in range(lo, hi)]
         ens = D.ensemble_member_sharded(local, 3, x)
+        ex2 = D.PeerExchange(x.shape[0], x.shape[2], x.shape[3])
+        ens_p = D.ensemble_member_sharded(local, 3, x, exchange=ex2)
         all_nets = [model.B200UNet(s, in_channels=4, dropout=cfg.dropout, device='cuda:%d' % rank) for s in sds]
         lg = torch.stack([n.forward_samples(x, 1, dropout_mode=0)[0] for n in all_nets])
         ens_ref = steps.summarize(steps.LazyMultiProbabilities(lg))
         res['ens_prob'] = float((ens['probabilities'] - ens_ref['probabilities']).abs().max().item())
         res['ens_entropy'] = float((ens['entropy'] - ens_ref['entropy']).abs().max().item())
+        res['ens_peer_prob'] = float((ens_p['probabilities'] - ens_ref['probabilities']).abs().max().item())
         # (3) a subject whose voxels span ranks: per-rank tables, exact integer all-reduce
         n = 200000
         rng = np.random.default_rng(5)
@@ -64,7 +82,13 @@ def _worker(rank, world, port, out_dir):
         mask = rng.random(n) < 0.5
         a, b = D.shard_bounds(n, world, rank)
         cnt, pos, conf, ue, inv, order = metrics.eval_fused(p[a:b], pred[a:b], target[a:b], mask[a:b], sync=False)
+        # (3b) the library's grouped NCCL call on copies of the same per-rank tables
+        ints = torch.cat([cnt.reshape(-1), pos.reshape(-1), ue.reshape(-1)]).contiguous()
+        conf_c = conf.clone()
+        comm.allreduce_metric_tables_(ints, conf_c)
         D.allreduce_metric_tables_(cnt, pos, conf, ue)
+        res['counts_comm_equal'] = float(torch.equal(ints, torch.cat([cnt.reshape(-1), pos.reshape(-1), ue.reshape(-1)])) and
+                                         torch.equal(conf_c, conf))
         full = metrics.eval_fused(p, pred, target, mask)
         res['tables_equal'] = float(np.array_equal(cnt.cpu().numpy(), full[0]) and np.array_equal(pos.cpu().numpy(), full[1]) and
                                     np.array_equal(ue.cpu().numpy(), full[3]))
@@ -85,7 +109,12 @@ def test_two_gpu_sharded_paths(tmp_path):
     for rank in range(world):
         r = dict(zip(keys, np.load(os.path.join(str(tmp_path), 'rank%d.npy' % rank))))
         # fp32 sums re-associated by the all-reduce: ulp-level differences only
-        assert r['probabilities'] <= 1e-6 and r['entropy'] <= 2e-6 and r['mutual_info'] <= 2e-6 and r['variance'] <= 2e-6, r
+        # variance: raw second moments (float32 sums, float64 difference) against the single-GPU Welford pass
+        assert r['probabilities'] <= 1e-6 and r['entropy'] <= 2e-6 and r['mutual_info'] <= 2e-6 and r['variance'] <= 5e-6, r
         assert r['pred_mismatch'] <= 1e-3, r
-        assert r['ens_prob'] <= 1e-6 and r['ens_entropy'] <= 2e-6, r
+        assert r['comm_vs_torch'] <= 5e-6, r
+        assert r['peer_rep0'] <= 5e-6 and r['peer_rep1'] <= 5e-6 and r['peer_pred_mismatch'] <= 1e-3 and r['peer_fg'] == 0.0, r
+        assert r['peer_ranks_identical'] == 1.0, r
+        assert r['ens_prob'] <= 1e-6 and r['ens_entropy'] <= 2e-6 and r['ens_peer_prob'] <= 1e-6, r
+        assert r['counts_comm_equal'] == 1.0, r
         assert r['tables_equal'] == 1.0 and r['conf_rel'] <= 1e-12, r

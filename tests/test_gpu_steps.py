@@ -9,7 +9,7 @@ from helpers import GOLDEN_CONFIGS
 
 pytestmark = pytest.mark.gpu
 torch.set_grad_enabled(False)
-P_MAX = 2.5e-2
+P_MAX = 1.2e-2
 
 
 class BatchContext:  # same fields as common/trainloop/context.py:334-342

@@ -2,8 +2,8 @@
 reference) and against the oracle restatement at BraTS / ISIC sizes.
 
 Stated tolerance (bf16 operands, fp32 accumulation, fp32 reference): for nets whose logits spread over several
-units (std ~1, |max| ~3-4) the foreground probability differs from the fp32 reference by at most 2.5e-2 and by
-less than 2e-3 on average; logits by at most 0.08.  Integer-exact properties (chunking / batching invariance,
+units (std ~1, |max| ~3-4) the foreground probability differs from the fp32 reference by at most 1.2e-2 (measured
+1e-3 ... 8e-3) and by less than 2e-3 on average; logits by at most 0.08.  Integer-exact properties (chunking / batching invariance,
 injected == generated masks, tcgen05 == cross-check up to one bf16 ulp) are asserted exactly.
 """
 import numpy as np
@@ -16,7 +16,7 @@ from helpers import GOLDEN_CONFIGS
 
 pytestmark = pytest.mark.gpu
 torch.set_grad_enabled(False)
-P_MAX, P_MEAN, LOGIT_MAX = 2.5e-2, 2e-3, 0.08
+P_MAX, P_MEAN, LOGIT_MAX = 1.2e-2, 2e-3, 0.08
 
 
 def _net(name_or_kw, seed=20, **extra):
@@ -192,3 +192,66 @@ def test_free_running_mc_is_statistically_equivalent_to_torch_dropout():
     for k in range(2):
         mu, sd_ = ref[:, k].mean(), ref[:, k].std(ddof=1)
         assert abs(mine[k] - mu) <= 4 * sd_ + 2e-3, (k, mine[k], mu, sd_)
+
+
+def test_brats_t20_injected_masks_match_oracle_at_full_resolution():
+    """BASELINE config 3 at its real shape: 4x240x240 slices, T = 20 stochastic samples + the weight-scaling pass, the Philox
+    keep masks injected into the oracle's restatement of McPredictStep (rechun/dl/customsteps.py:16-39) — every sample,
+    the summary and the argmax are compared, not just properties of the run."""
+    cfg, sd, net = _net('brats')
+    n, T = 2, 20
+    x = torch.randn(n, 4, 240, 240, generator=torch.Generator().manual_seed(240))
+    logits = net.forward_samples(x, T + 1, dropout_mode=1, det_first=True, seed=20, slice_index0=5, sample0=0)
+    scale = metrics.philox_keep_scale_host(20, cfg.dropout, net.site_channels, 5, n, 0, T)
+    keep, off = [], 0
+    spans = []
+    for c in net.site_channels:
+        spans.append((off, c))
+        off += c
+    for t in range(T):
+        keep.append([torch.from_numpy((scale[t, :, o:o + c] > 0).astype(np.float32)) for (o, c) in spans])
+    ref = R.predict_mc(sd, x, cfg, T, keep)
+    probs = torch.softmax(logits.permute(0, 1, 4, 2, 3), 2).cpu()
+    dp = (probs[1:] - ref['multi_probabilities']).abs()
+    assert dp.max().item() <= P_MAX and dp.mean().item() <= P_MEAN, (dp.max().item(), dp.mean().item())
+    assert (probs[0] - ref['ws_probabilities']).abs().max().item() <= P_MAX
+    from rcu_b200 import steps
+    out = steps.summarize(steps.LazyMultiProbabilities(logits[1:]), do_mi=True, do_var=True, emit_prediction=True, ws_logits=logits[0])
+    summ = R.summarize(ref['multi_probabilities'], do_mi=True, do_var=True)
+    assert (out['probabilities'].cpu() - summ['probabilities']).abs().max().item() <= P_MAX
+    assert (out['entropy'].cpu() - summ['entropy']).abs().max().item() <= 2e-2          # dH/dp <= ln((1-p)/p): flat near 0.5, steep in the tails
+    assert (out['mutual_info'].cpu() - summ['mutual_info']).abs().max().item() <= 1e-2
+    assert (out['variance'].cpu() - summ['variance']).abs().max().item() <= 2e-3
+    assert (out['ws_probabilities'].cpu() - ref['ws_probabilities']).abs().max().item() <= P_MAX
+    pm = summ['probabilities']
+    clear = (pm[:, 1] - pm[:, 0]).abs() > 4 * P_MAX                                        # argmax can only flip where the classes are within tolerance
+    assert torch.equal(out['prediction'].cpu()[clear], (pm[:, 1] > pm[:, 0]).to(torch.uint8)[clear])
+
+
+def test_free_running_mc_entropy_distribution_matches_nn_dropout2d():
+    """free-running MC with the engine's Philox stream against runs whose masks come from nn.Dropout2d itself
+    (torch's feature dropout on an all-ones (N, C, 1, 1) tensor: exactly the noise Dropout2d multiplies with).  The per-voxel
+    predictive-entropy distributions are compared with the two-sample Kolmogorov-Smirnov distance; voxels are spatially
+    correlated, so the yardstick is not a p-value but the KS distance between independent torch-seeded runs."""
+    from scipy.stats import ks_2samp
+    cfg, sd, net = _net(dict(in_channels=4, dropout=0.2))
+    x = torch.randn(2, 4, 64, 64, generator=torch.Generator().manual_seed(0))
+    T, runs = 20, 6
+    drop = torch.nn.Dropout2d(cfg.dropout).train()
+
+    def entropy_map(mean_p):
+        return R.torch_entropy(mean_p, 1).reshape(-1).numpy()
+    torch_runs = []
+    for seed in range(runs):
+        torch.manual_seed(300 + seed)
+        probs = []
+        for t in range(T):
+            keep = [(drop(torch.ones(2, c, 1, 1)) > 0).reshape(2, c).to(torch.uint8) for _, c in R.dropout_sites(cfg)]
+            probs.append(torch.softmax(R.unet_forward(sd, x, cfg, keep), 1))
+        torch_runs.append(entropy_map(torch.stack(probs).mean(0)))
+    ours = net.forward_samples(x, T, dropout_mode=1, seed=20)
+    mine = entropy_map(torch.softmax(ours.permute(0, 1, 4, 2, 3), 2).mean(0).cpu())
+    d_tt = np.array([ks_2samp(torch_runs[i], torch_runs[j]).statistic for i in range(runs) for j in range(i + 1, runs)])
+    d_ot = np.array([ks_2samp(mine, r).statistic for r in torch_runs])
+    assert d_ot.mean() <= d_tt.mean() + 3 * d_tt.std(ddof=1) + 0.01, (d_ot, d_tt)
+    assert d_ot.max() <= d_tt.max() + 3 * d_tt.std(ddof=1) + 0.02, (d_ot, d_tt)

@@ -178,3 +178,34 @@ def test_synthetic_weights_have_the_reference_state_dict_layout():
     x = torch.randn(1, 4, 32, 32, generator=torch.Generator().manual_seed(0))
     logits = R.unet_forward(synth.random_unet_state_dict(in_channels=4, seed=20), x, R.UNetConfig(in_channels=4))
     assert torch.isfinite(logits).all() and logits.std() > 0.05
+
+
+def test_engine_cache_follows_the_weights_and_dies_with_the_module(monkeypatch):
+    """steps.engine_for caches the converted engine per reference module; the entry must be rebuilt when the module's weights
+    change (context.load_from_checkpoint / load_state_dict into the same object between two evaluations) and must not keep
+    the module — or the engine and its device buffers — alive."""
+    import gc
+    import torch
+    from rcu_b200 import steps
+    built = []
+
+    class FakeEngine:
+        pass
+
+    def fake_from_reference(cls, module, device=None, **kw):
+        built.append(FakeEngine())
+        return built[-1]
+    monkeypatch.setattr(steps.B200UNet, 'from_reference', classmethod(fake_from_reference))
+    module = torch.nn.Sequential(torch.nn.Conv2d(2, 2, 3), torch.nn.BatchNorm2d(2))
+    e1 = steps.engine_for(module)
+    assert steps.engine_for(module) is e1 and len(built) == 1
+    module.load_state_dict({k: v + 1 for k, v in module.state_dict().items()})          # same object, new weights
+    e2 = steps.engine_for(module)
+    assert e2 is not e1 and len(built) == 2 and steps.engine_for(module) is e2
+    with torch.no_grad():
+        module[1].running_mean.add_(0.5)                                                 # a buffer written in place counts too
+    assert steps.engine_for(module) is not e2 and len(built) == 3
+    n_before = len(steps._ENGINES)
+    del module
+    gc.collect()
+    assert len(steps._ENGINES) == n_before - 1

@@ -119,3 +119,26 @@ def test_degenerate_empty_prediction(golden_metrics):
     r = R.uncertainty_and_correction(z, z, unc, 0.5)
     for k in [k for k in golden_metrics.files if k.startswith('degenerate_empty/0.5/')]:
         results_equal(r[k.split('/')[-1]], golden_metrics[k], k)
+
+
+def test_restated_pymia_metrics_agree_with_an_independent_implementation():
+    """pymia 0.2.1 (`ConfusionMatrix`, `DiceCoefficient`, `Accuracy`: numpyfunctions.py:128-151) is not installable here and is
+    restated in oracle/ref_shim.py from its published semantics; the golden `dice_cm/*` entries therefore pin the
+    restatement against itself.  scikit-learn IS installed: its confusion_matrix / f1_score / accuracy_score are an
+    independent implementation of the same definitions (binary Dice == F1 of the positive class)."""
+    from sklearn.metrics import accuracy_score, confusion_matrix, f1_score
+    from oracle import ref_shim
+    rng = np.random.default_rng(17)
+    cases = [(rng.random(5000) < 0.3, rng.random(5000) < 0.25), (rng.random(777) < 0.9, rng.random(777) < 0.5),
+             (np.zeros(64, bool), rng.random(64) < 0.5), (rng.random(64) < 0.5, np.zeros(64, bool)), (np.ones(10, bool), np.ones(10, bool))]
+    for pred, target in cases:
+        pred8, tgt8 = pred.astype(np.uint8), target.astype(np.uint8)
+        tn, fp, fn, tp = confusion_matrix(tgt8, pred8, labels=[0, 1]).ravel()
+        assert tuple(int(v) for v in R.confusion(pred8, tgt8)) == (tp, tn, fp, fn, pred.size)
+        shim = ref_shim.ConfusionMatrix(pred8, tgt8)
+        assert (int(shim.tp), int(shim.tn), int(shim.fp), int(shim.fn), shim.n) == (tp, tn, fp, fn, pred.size)
+        assert np.isclose(R.dice(pred8, tgt8), f1_score(tgt8, pred8, zero_division=1.0), rtol=1e-15, atol=0)
+        assert np.isclose(R.accuracy(pred8, tgt8), accuracy_score(tgt8, pred8), rtol=1e-15, atol=0)
+    # the one convention sklearn cannot arbitrate: nothing predicted, nothing to find -> pymia's Dice is 1.0 (zero_division above)
+    z = np.zeros(32, np.uint8)
+    assert R.dice(z, z) == 1.0 and R.accuracy(z, z) == 1.0

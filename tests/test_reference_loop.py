@@ -121,3 +121,63 @@ def test_2d_assembler_in_the_unmodified_loop():
     assert sorted(seen) == [0, 1, 2, 3, 4]
     for i in range(5):
         assert torch.allclose(seen[i], torch.softmax(images[i:i + 1, :2], 1)[0].permute(1, 2, 0), rtol=0, atol=1e-6)
+
+
+def test_all_entries_with_the_extra_maps_on_non_square_slices():
+    """`entries=None` (bin-dl/brats_test_ensemble.py:63, isic_test_default.py:54-55): the unmodified loop applies
+    th.channel_to_end to EVERY output it assembles (loops.py:210-216), so the extra 'prediction' / 'foreground' maps of
+    the fused summary must carry a channel dimension like all reference outputs — (N, 1, H, W), the shape
+    steps.MultiPredictionSummary emits.  Non-square slices: a missing channel dimension would transpose or fail."""
+    ref_shim.load()
+    import common.trainloop.loops as loops
+    import common.trainloop.context as ctx
+    import common.trainloop.hooks as ref_hooks
+    import common.trainloop.steps as ref_steps
+
+    g = torch.Generator().manual_seed(9)
+    volume = torch.randn(6, 4, 8, 6, generator=g)
+    weight = torch.randn(2, 4, generator=g)
+    labels = (torch.rand(6, 8, 6, generator=g) < 0.3).numpy().astype(np.uint8)
+
+    class SummaryLikeStep(ref_steps.BatchStep):          # the output protocol of McPredictStep + MultiPredictionSummary(emit_*=True)
+        def __call__(self, batch_context, task_context, context):
+            probs = torch.softmax(torch.einsum('kc,nchw->nkhw', weight, batch_context.input['images'].float()), 1)
+            batch_context.output['probabilities'] = probs
+            batch_context.output['entropy'] = -(probs * probs.log()).sum(1, keepdim=True)
+            batch_context.output['prediction'] = (probs[:, 1] > probs[:, 0]).to(torch.uint8).unsqueeze(1)
+            batch_context.output['foreground'] = probs[:, 1].unsqueeze(1).contiguous()
+
+    class SubjectStep(ref_steps.SubjectStep):
+        def __call__(self, subject_context, task_context, context):
+            subject_context.subject_data['labels'] = labels
+
+    evaluated = []
+
+    class MetricsProbe(b200_hooks.DeviceMetricsHook):
+        def evaluate(self, subject, p, prediction, target, mask=None):
+            evaluated.append((p, prediction))
+            return {'subject': subject}
+
+    seen = {}
+
+    class Recorder(ref_hooks.TestLoopHook):
+        def on_test_subject_end(self, subject_context, task_context, context):
+            seen.update(subject_context.subject_data)
+
+    hook = ref_hooks.ReducedComposeTestLoopHook([Recorder(), MetricsProbe(probability_entry='foreground')])
+    test = loops.Test([SummaryLikeStep()], [SubjectStep()], assembly.DeviceSubjectAssembler(), entries=None, convert_fn=None)
+    task_context = ctx.TaskContext(0, types.SimpleNamespace(nb_batches=2), None)
+    for b, sl in enumerate((slice(0, 4), slice(4, 6))):
+        n = sl.stop - sl.start
+        batch = {'images': volume[sl], 'subject_index': [0] * n,
+                 'index_expr': [pickle.dumps(IndexExpression((z,))) for z in range(sl.start, sl.stop)], 'shape': [(6, 8, 6)] * n}
+        test._test_batch(ctx.BatchContext(batch, b), task_context, None, hook)
+    probs = torch.softmax(torch.einsum('kc,nchw->nkhw', weight, volume), 1)
+    assert tuple(seen['probabilities'].shape) == (6, 8, 6, 2) and tuple(seen['entropy'].shape) == (6, 8, 6, 1)
+    assert tuple(seen['prediction'].shape) == (6, 8, 6, 1) and tuple(seen['foreground'].shape) == (6, 8, 6, 1)
+    assert torch.allclose(seen['foreground'][..., 0], probs[:, 1], rtol=0, atol=1e-6)
+    # the metrics hook squeezes the channel: what it evaluates is the (Z, H, W) foreground map and the emitted argmax
+    (p, prediction), = evaluated
+    assert tuple(p.shape) == (6, 8, 6) and tuple(prediction.shape) == (6, 8, 6)
+    assert torch.allclose(p, probs[:, 1], rtol=0, atol=1e-6)
+    assert (prediction != (probs[:, 1] > probs[:, 0]).to(torch.uint8)).sum().item() <= 1

@@ -92,7 +92,7 @@ def test_host_reductions_follow_the_oracle(golden_tables):
     assert np.isclose(ds['ds_ece'], golden_tables['ds_ece/ds_ece'], rtol=1e-12, atol=0)
     with pytest.raises(ValueError):
         tables.dataset_vs_mean_subject_ece(tabs[0][0], tabs[0][1], tabs[0][2])
-    # best-threshold table against the restatement (unpinned, see oracle/restate.py header)
+    # best-threshold table against the restatement (itself pinned by test_best_threshold_reduction_matches_the_unmodified_reference_function)
     ece = [c['ece'] for c in calib]
     dice = [s[SWEEP[0]]['dice'] for s in sweeps]
     got = tables.best_threshold_summary(sweeps, ece, dice)
@@ -135,3 +135,24 @@ def test_device_hook_rows_become_the_reference_csv(golden_tables):
     _, sweeps = _oracle_results()
     exp = R.best_threshold_summary(sweeps, [r['ece'] for r in rows], [r['dice'] for r in rows])
     assert summary == exp
+
+
+def test_best_threshold_reduction_matches_the_unmodified_reference_function():
+    """tests/golden/best_golden.npz: `get_best_thresholds` (bin-analysis/table_ece_ue_bnf_dice.py:132-143), exec'd unmodified on
+    a numeric frame, followed by the script's own merges and groupby('test_id').mean() — including a subject whose U-E
+    Dice is 0 / 0 at two thresholds (pandas skips it; it must not disqualify those thresholds)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'best_golden.npz'))
+    cols = [str(c) for c in g['columns']]
+    ths = [float(t) for t in g['thresholds']]
+    for ti in range(len(g['test_ids'])):
+        d = g['data'][ti]                                   # [threshold][subject][column]
+        sweeps = [{th: {c: (d[ki, s, ci] if c in ('corrected_dice', 'dice') else int(d[ki, s, ci])) for ci, c in enumerate(cols) if c != 'ece'}
+                   for ki, th in enumerate(ths)} for s in range(d.shape[1])]
+        ece, dice = d[0, :, cols.index('ece')], d[0, :, cols.index('dice')]
+        exp = dict(zip([str(c) for c in g['result_columns']], g['result'][ti]))
+        for impl in (tables.best_threshold_summary, R.best_threshold_summary):
+            got = impl(sweeps, ece, dice, thresholds=ths)
+            for k, v in exp.items():
+                assert np.isclose(got[k], v, rtol=1e-12, atol=0), (impl.__module__, ti, k, got[k], v)
+    assert np.isnan(g['data'][0, 1, 2, cols.index('fp')]) == False and 'groupby' in str(g['function_source'])

@@ -43,3 +43,16 @@ T = 20
 logits = torch.randn((T + 1, 155, 240, 240, 2), device=dev)
 ms = timeit(lambda: steps.summarize(steps.LazyMultiProbabilities(logits[1:]), emit_prediction=True, emit_foreground=True))
 print('aggregate T=20 one subject: %.4f ms (%.0f GB/s of %d B/voxel)' % (ms, (8 * T + 12 + 4 + 1 + 4) * vps / ms / 1e6, 8 * T + 21))
+ms = timeit(lambda: steps.summarize(steps.LazyMultiProbabilities(logits[1:]), emit_prediction=True, emit_foreground=True, ws_logits=logits[0]))
+print('aggregate T=20 + weight-scaling softmax in the same launch: %.4f ms (%.0f GB/s of %d B/voxel; %.0f GB/s on the 8T+12 = 172 B/voxel accounting)'
+      % (ms, (8 * T + 37) * vps / ms / 1e6, 8 * T + 37, (8 * T + 12) * vps / ms / 1e6))
+for S in (1, 50):   # Beta(0.3, 0.3) maps, target ~ Bernoulli(p), 25 % mask: the data-dependent table reads see a spread
+    n = S * vps
+    bd = torch.distributions.Beta(torch.tensor(0.3, device=dev), torch.tensor(0.3, device=dev))
+    p = bd.sample((n,)).float().clamp_(0, 1)
+    target = (torch.rand(n, device=dev) < p).to(torch.uint8)
+    pred = (p > 0.5).to(torch.uint8)
+    mask = (torch.rand(n, device=dev) < 0.25).to(torch.uint8)
+    ms = timeit(lambda: metrics.eval_fused(p, pred, target, mask, 10, tables.SWEEP_THRESHOLDS, n_subjects=S, sync=False, break_table=bt))
+    print('eval_fused Beta(0.3,0.3) S=%2d: %.4f ms  (%.1f us/subject, %.0f GB/s of 7 B/voxel)' % (S, ms, ms * 1e3 / S, 7.0 * n / ms / 1e6))
+    del p, target, pred, mask
