@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define RCU_ABI_VERSION 1
+#define RCU_ABI_VERSION 2
 
 typedef enum rcu_status {
   RCU_OK = 0,
@@ -231,6 +231,11 @@ typedef struct rcu_unet_desc {
    * same features as conv_cls.0) and `conv_sigma.1` (1x1 -> 2).  Both NULL for sigma_out=False. */
   const rcu_conv_unit* sigma_unit;
   const rcu_conv_unit* sigma_head;
+  /* residual=True nets (ConvResidualBlock, unet.py:42-60): the 2 * depth + 1 `residual` 1x1 convolutions (weight [c_out][c_in],
+   * bias; bn_* NULL) in forward order — down_convs.0 ... down_convs.{depth-1}, bottom_convs, up_convs.0 ... — each added onto
+   * its block's output, whose last Conv2dBnRelu then has no ReLU.  NULL / 0 for residual=False. */
+  const rcu_conv_unit* residuals;
+  int n_residuals;
 } rcu_unet_desc;
 
 /* Folds BN into per-channel scale/shift, converts weights to the device layout, uploads them. */

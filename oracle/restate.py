@@ -46,8 +46,9 @@ class UNetConfig:
     """Constructor arguments of the reference UNet that the hot path supports."""
 
     def __init__(self, nb_classes=2, in_channels=4, depth=4, start_filters=32, dropout=0.05, dropout_center=None,
-                 sigma_out=False):
+                 sigma_out=False, residual=False):
         self.sigma_out = sigma_out
+        self.residual = residual      # ConvResidualBlock instead of ConvBlock (unet.py:42-60, 133)
         self.nb_classes = nb_classes
         self.in_channels = in_channels
         self.depth = depth
@@ -99,6 +100,15 @@ def conv_sites(cfg):
 SIGMA_PREFIX = 'conv_sigma.0.conv2d_batch_relu'
 
 
+def residual_prefix(cfg, block):
+    """state_dict prefix of the `residual` 1x1 conv of block number `block` in forward order (down 0.., bottom, up 0..)."""
+    if block < cfg.depth:
+        return 'down_convs.%d.block.residual' % block
+    if block == cfg.depth:
+        return 'bottom_convs.residual'
+    return 'up_convs.%d.block.residual' % (block - cfg.depth - 1)
+
+
 def dropout_sites(cfg):
     """[(prefix, channels)] of the units that own a Dropout2d, in forward order (conv_sigma.0 of a sigma_out net
     runs after conv_cls, unet.py:181-185)."""
@@ -140,13 +150,17 @@ def init_state_dict(cfg, seed):
 
     sites = conv_sites(cfg)
     n_down = 2 * cfg.depth + 2
-    for (p, ci, co, _) in sites[:n_down]:
+    for i, (p, ci, co, _) in enumerate(sites[:n_down]):
         unit(p, ci, co)
+        if cfg.residual and i % 2 == 1:   # ConvResidualBlock.__init__ creates `residual` after the block's convs (unet.py:54-55)
+            conv(residual_prefix(cfg, i // 2), co, sites[i - 1][1], 1)
     k = n_down
     for j in range(cfg.depth):
         (p0, ci0, co0, _), (p1, ci1, co1, _) = sites[k], sites[k + 1]
         unit(p0, ci0, co0)
         unit(p1, ci1, co1)
+        if cfg.residual:
+            conv(residual_prefix(cfg, cfg.depth + 1 + j), co1, ci0, 1)
         conv('up_convs.%d.upconv.1' % j, co0, 2 * co0, 3)
         k += 2
     p, ci, co, _ = sites[k]
@@ -188,7 +202,7 @@ def randomize_statistics(sd, seed, logit_gain=24.0):
 # ------------------------------------------------------------------------------------------------
 # U-Net forward (common/model/unet.py:166-186) with optional injected Dropout2d keep-masks
 # ------------------------------------------------------------------------------------------------
-def _unit(x, sd, prefix, p_drop, keep):
+def _unit(x, sd, prefix, p_drop, keep, activation=True):
     y = F.conv2d(x, sd[prefix + '.conv.weight'], sd[prefix + '.conv.bias'], padding=1)
     if keep is not None:
         # nn.Dropout2d in train mode: per-(n, c) Bernoulli(1-p) noise divided by (1-p), multiplied in.
@@ -196,7 +210,7 @@ def _unit(x, sd, prefix, p_drop, keep):
         y = y * noise[:, :, None, None]
     y = F.batch_norm(y, sd[prefix + '.bn.running_mean'], sd[prefix + '.bn.running_var'],
                      sd[prefix + '.bn.weight'], sd[prefix + '.bn.bias'], False, 0.0, BN_EPS)
-    return F.relu(y)
+    return F.relu(y) if activation else y
 
 
 def unet_forward(sd, x, cfg, keep_masks=None, return_all=False):
@@ -210,21 +224,28 @@ def unet_forward(sd, x, cfg, keep_masks=None, return_all=False):
     sites = conv_sites(cfg)
     masks = iter(keep_masks) if keep_masks is not None else None
 
-    def run(x, idx):
+    def run(x, idx, activation=True):
         prefix, _, _, has_do = sites[idx]
         keep = next(masks) if (masks is not None and has_do) else None
-        return _unit(x, sd, prefix, cfg.dropout, keep)
+        return _unit(x, sd, prefix, cfg.dropout, keep, activation)
+
+    def block(x, idx, number):
+        """ConvBlock (unet.py:26-39) or ConvResidualBlock (:42-60): the last unit without ReLU, plus residual(x)."""
+        y = run(x, idx)
+        if not cfg.residual:
+            return run(y, idx + 1)
+        y = run(y, idx + 1, activation=False)
+        rp = residual_prefix(cfg, number)
+        return y + F.conv2d(x, sd[rp + '.weight'], sd[rp + '.bias'])
 
     skips = []
     idx = 0
-    for _ in range(cfg.depth):
-        x = run(x, idx)
-        x = run(x, idx + 1)
+    for lvl in range(cfg.depth):
+        x = block(x, idx, lvl)
         idx += 2
         skips.append(x)
         x = F.max_pool2d(x, 2)
-    x = run(x, idx)
-    x = run(x, idx + 1)
+    x = block(x, idx, cfg.depth)
     idx += 2
     for j in range(cfg.depth):
         skip = skips[-(j + 1)]
@@ -235,8 +256,7 @@ def unet_forward(sd, x, cfg, keep_masks=None, return_all=False):
             dx = skip.shape[-1] - up.shape[-1]
             up = F.pad(up, (dx // 2, dx // 2 + dx % 2, dy // 2, dy // 2 + dy % 2))
         x = torch.cat((up, skip), 1)
-        x = run(x, idx)
-        x = run(x, idx + 1)
+        x = block(x, idx, cfg.depth + 1 + j)
         idx += 2
     features = x
     x = run(features, idx)

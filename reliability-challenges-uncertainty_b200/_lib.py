@@ -10,6 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'librcu_b200.so')
 LIB_PATH = os.environ.get('RCU_B200_LIB', LIB_PATH)   # developer override (A/B builds)
 
+RCU_ABI_VERSION = 2
 RCU_OK, RCU_EINVAL, RCU_ECUDA, RCU_ENOTSUP, RCU_ENOMEM, RCU_ENCCL = 0, -1, -2, -3, -4, -5
 RCU_COMM_ID_BYTES, RCU_IPC_HANDLE_BYTES = 128, 64
 RCU_MAX_BINS, RCU_MAX_UE_CLASSES, RCU_MAX_BREAKS = 32, 32, 96
@@ -31,7 +32,8 @@ class RcuUnetDesc(ctypes.Structure):
     _fields_ = [('in_channels', c_int), ('depth', c_int), ('start_filters', c_int), ('nb_classes', c_int),
                 ('p_drop', c_float), ('bn_eps', c_float), ('units', ctypes.POINTER(RcuConvUnit)), ('n_units', c_int),
                 ('upconvs', ctypes.POINTER(RcuConvUnit)), ('n_upconvs', c_int), ('head', RcuConvUnit),
-                ('sigma_unit', ctypes.POINTER(RcuConvUnit)), ('sigma_head', ctypes.POINTER(RcuConvUnit))]
+                ('sigma_unit', ctypes.POINTER(RcuConvUnit)), ('sigma_head', ctypes.POINTER(RcuConvUnit)),
+                ('residuals', ctypes.POINTER(RcuConvUnit)), ('n_residuals', c_int)]
 
 
 class RcuUnetOutputs(ctypes.Structure):
@@ -128,8 +130,8 @@ def lib():
             fn = getattr(handle, name)  # AttributeError here = header/library drift
             fn.restype = restype
             fn.argtypes = argtypes
-        if handle.rcu_abi_version() != 1:
-            raise RcuError('librcu_b200.so ABI version {} != 1'.format(handle.rcu_abi_version()))
+        if handle.rcu_abi_version() != RCU_ABI_VERSION:
+            raise RcuError('librcu_b200.so ABI version {} != {} (rebuild: python __graft_entry__.py)'.format(handle.rcu_abi_version(), RCU_ABI_VERSION))
         _lib = handle
     return _lib
 

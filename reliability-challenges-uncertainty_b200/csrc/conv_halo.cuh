@@ -169,7 +169,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     for (int s = 0; s < G; ++s) {
       mbar_init(bar_tfull + 8 * s, 1);
-      mbar_init(bar_tempty + 8 * s, 128);
+      mbar_init(bar_tempty + 8 * s, 4);   // one arrival per epilogue warp (mbar_arrive_warp)
     }
     mbar_init(bar_w, 1);
     mbar_init(bar_turn, 1);
@@ -391,7 +391,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             tmem_ld_wait();
             if (half == 1) {
               tc_fence_before();
-              mbar_arrive(bar_tempty + 8 * group);
+              mbar_arrive_warp(bar_tempty + 8 * group);
             }
             float l0 = prm.head_w[64], l1 = prm.head_w[65];
 #pragma unroll
@@ -420,7 +420,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             tmem_ld_wait();
             if (half == 1) {
               tc_fence_before();
-              mbar_arrive(bar_tempty + 8 * group);
+              mbar_arrive_warp(bar_tempty + 8 * group);
             }
 #pragma unroll
             for (int c = 0; c < 32; c += 2) {
@@ -488,7 +488,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         tmem_ld_32x32b_x32(taddr, v);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(bar_tempty + 8 * group);   // accumulator is in registers: the MMA warp may reuse the stage
+        mbar_arrive_warp(bar_tempty + 8 * group);   // accumulator is in registers: the MMA warp may reuse the stage
         float l0 = prm.head_w[64], l1 = prm.head_w[65];
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
@@ -513,7 +513,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           tmem_ld_wait();
           if (cb + 32 == N && p + 1 == PH) {
             tc_fence_before();
-            mbar_arrive(bar_tempty + 8 * group);
+            mbar_arrive_warp(bar_tempty + 8 * group);
           }
           uint32_t packed[16];
 #pragma unroll

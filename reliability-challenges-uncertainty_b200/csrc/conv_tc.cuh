@@ -55,6 +55,9 @@ struct ConvParams {
   float* logits;
   int chunk_slices;          // images are ordered [sample][slice-in-chunk]
   long long slice0, n_slices_total;
+  // residual branch of a ConvResidualBlock (common/model/unet.py:57-59): out = bf16(float(out) + acc * scale + shift),
+  // i.e. the 1x1 convolution of the block input is added onto the block output already in `out`
+  int accumulate;
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -70,6 +73,13 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// One arrival for the whole (converged) warp: every lane has finished its TMEM reads (tcgen05.wait::ld is warp-collective and
+// each lane has issued tcgen05.fence::before_thread_sync), lane 0 signals.  A per-thread arrive is 32 serialised shared-memory
+// atomics on one word per warp and tile — on the data pipe the tensor cores read their operands from.
+__device__ __forceinline__ void mbar_arrive_warp(uint32_t bar) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -345,11 +355,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           tmem_ld_32x32b_x32(taddr + (uint32_t)cb, v);
           tmem_ld_wait();
           uint32_t packed[16];
+          if (prm.accumulate && valid) {
+            const uint4* s4 = reinterpret_cast<const uint4*>(dst + cb);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint4 q = s4[i];
+              packed[4 * i] = q.x; packed[4 * i + 1] = q.y; packed[4 * i + 2] = q.z; packed[4 * i + 3] = q.w;
+            }
+          }
 #pragma unroll
           for (int c = 0; c < 32; c += 2) {
             const float2 c0 = coef[cb + c], c1 = coef[cb + c + 1];
             float a0 = fmaf(__uint_as_float(v[c]), c0.x, c0.y);
             float a1 = fmaf(__uint_as_float(v[c + 1]), c1.x, c1.y);
+            if (prm.accumulate) {
+              const float2 old = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&packed[c >> 1]));
+              a0 += old.x;
+              a1 += old.y;
+            }
             if (prm.relu) { a0 = fmaxf(a0, 0.0f); a1 = fmaxf(a1, 0.0f); }
             __nv_bfloat162 b = __floats2bfloat162_rn(a0, a1);
             packed[c >> 1] = *reinterpret_cast<uint32_t*>(&b);

@@ -97,7 +97,7 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     tma_prefetch_desc(&map_a);
     for (int s = 0; s < C::kAStages; ++s) { mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, 1); }
     for (int s = 0; s < C::kWStages; ++s) { mbar_init(bar_wfull + 8 * s, 1); mbar_init(bar_wempty + 8 * s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, 128); }
+    for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, 4); }   // tempty: one arrival per epilogue warp (mbar_arrive_warp)
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -237,7 +237,7 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           tmem_ld_wait();
           if (s == 1 && cb + 32 == kWideN) {
             tc_fence_before();
-            mbar_arrive(bar_tempty + 8 * group);   // both accumulators are in registers / stored: release the stage
+            mbar_arrive_warp(bar_tempty + 8 * group);   // both accumulators are in registers / stored: release the stage
           }
           uint32_t packed[16];
 #pragma unroll

@@ -1016,8 +1016,11 @@ extern "C" int rcu_eval_fused(const float* p, const uint8_t* prediction, const u
                  reinterpret_cast<unsigned long long*>(ue_counts), reinterpret_cast<unsigned long long*>(invalid)};
   cudaStream_t st = (cudaStream_t)stream;
   {
-    // joint-cell kernel (default): aligned float32 p, few enough segments for the private cell columns
-    static const bool allow_cell = [] { const char* e = std::getenv("RCU_HIST_CELL"); return !(e && e[0] == '0'); }();
+    // joint-cell kernel: OPT-IN (RCU_HIST_CELL=1).  Measured on B200 (profiles/r02_hist_kernels_ncu.md) it is not faster than
+    // the bucket-table kernel below: both execute ~21 M warp instructions per 8.9 M-voxel subject (the duplicate resolution
+    // and the 64-bit selects eat what the single counter update saves) and its 152 KB of private counters allow only one
+    // block of 8 warps per SM, so the dependent shared-memory chains are hidden even less (issue slots 34 % busy against 46 %)
+    static const bool allow_cell = [] { const char* e = std::getenv("RCU_HIST_CELL"); return e && e[0] == '1'; }();
     static const int cell_buckets = [] { const char* e = std::getenv("RCU_HIST_CELL_BUCKETS"); return e ? std::atoi(e) : 512; }();
     static const int cell_bpsm = [] { const char* e = std::getenv("RCU_HIST_CELL_BPSM"); return e ? std::atoi(e) : 1; }();
     const bool aligned_c = reinterpret_cast<uintptr_t>(p) % 16 == 0 && reinterpret_cast<uintptr_t>(target) % 4 == 0 &&
@@ -1102,12 +1105,16 @@ extern "C" int rcu_eval_fused(const float* p, const uint8_t* prediction, const u
     static const bool allow_lut = [] { const char* e = std::getenv("RCU_HIST_LUT"); return !(e && e[0] == '0'); }();
     const bool aligned = reinterpret_cast<uintptr_t>(p) % 16 == 0 && reinterpret_cast<uintptr_t>(target) % 4 == 0 &&
                          reinterpret_cast<uintptr_t>(prediction) % 4 == 0 && (mask == nullptr || reinterpret_cast<uintptr_t>(mask) % 4 == 0);
-    static const int lut_buckets = [] { const char* e = std::getenv("RCU_HIST_BUCKETS"); return e ? std::atoi(e) : 1024; }();
+    // measured (gpurun sweep, r02): 3 blocks / SM with a 512-entry table for a few subjects per launch (48 us per 8.9 M-voxel
+    // subject), 6 blocks / SM with a 256-entry table when many subjects share the launch (31 us per subject at 50)
+    static const int lut_buckets_env = [] { const char* e = std::getenv("RCU_HIST_BUCKETS"); return e ? std::atoi(e) : 0; }();
+    const int lut_buckets = lut_buckets_env > 0 ? lut_buckets_env : (n_subjects >= 8 ? 256 : 512);
     const int n_buckets = (allow_lut && aligned && (n_subjects == 1 || vps % 4 == 0)) ? lut_buckets : 0;
     if (n_buckets > 0) {
       RCU_CHECK_ARG(workspace_bytes >= rcu_metrics_workspace_bytes(n_subjects), "metrics workspace too small");
       const int sms = sm_count();
-      static const int lut_bpsm = [] { const char* e = std::getenv("RCU_HIST_BPSM"); return e ? std::atoi(e) : 2; }();
+      static const int lut_bpsm_env = [] { const char* e = std::getenv("RCU_HIST_BPSM"); return e ? std::atoi(e) : 0; }();
+      const int lut_bpsm = lut_bpsm_env > 0 ? lut_bpsm_env : (n_subjects >= 8 ? 6 : 3);
       long long bps = ((long long)sms * lut_bpsm + n_subjects - 1) / n_subjects;
       const long long groups = (vps + 3) / 4;
       if (bps * 256 > groups) bps = groups / 256;

@@ -39,7 +39,7 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-enum OpKind { OP_FIRST = 0, OP_CONV = 1, OP_POOL = 2 };
+enum OpKind { OP_FIRST = 0, OP_CONV = 1, OP_POOL = 2, OP_RES_FIRST = 3 };
 
 // A channel slice of a bf16 NHWC tensor inside the arena.  Producers write slices of the concat buffers directly
 // (torch.cat((up, skip), 1), common/model/unet.py:118, is never materialised by a copy).  `padded` tensors carry one
@@ -79,6 +79,7 @@ struct ConvLayer {
   int coef_off = 0;
   int block_n = 0, kc = 0;
   bool head = false;
+  bool accumulate = false;               // residual branch: a 1x1 conv of the block input added onto the block output (per-tap kernel)
   const float* d_head = nullptr;         // fused 1x1 head of this layer: [2][c_out] + [2]
   float h_head[66] = {0};                // host copy (kernel parameter of the halo kernels)
   int out_slot = 0;                      // 0: class logits (conv_cls), 1: sigma logits (conv_sigma, unet.py:162-164)
@@ -125,6 +126,10 @@ struct rcu_unet {
   float* d_head = nullptr;               // conv_cls.1:   [2][sf] + [2]
   float* d_sigma_head = nullptr;         // conv_sigma.1: [2][sf] + [2] (sigma_out nets only)
   bool has_sigma = false;
+  bool residual = false;                 // residual=True nets (ConvResidualBlock, common/model/unet.py:42-60)
+  float* d_res0_w = nullptr;             // first block's residual 1x1 conv on the float32 input: [sf][c_in], and its bias [sf]
+  float* d_res0_b = nullptr;
+  Act res0_dst;
   std::vector<ConvLayer> convs;          // execution order
   CoefColumns cols{};
   std::vector<void*> owned;              // device allocations freed in destroy
@@ -671,6 +676,9 @@ extern "C" int rcu_unet_create(const rcu_unet_desc* d, int device, rcu_unet** ou
   std::vector<int> site, chin, scol;
   // sigma_out nets (unet.py:162-164) carry one more Conv2dBnRelu + 1x1 head on the same features; its unit (and its
   // Dropout2d site) come after conv_cls.0, the order the reference's forward visits them in (unet.py:181-185)
+  const bool residual = d->residuals != nullptr;
+  if (residual && d->n_residuals != 2 * d->depth + 1) { set_error("expected %d residual convs for depth %d, got %d", 2 * d->depth + 1, d->depth, d->n_residuals); delete net; return RCU_EINVAL; }
+  net->residual = residual;
   const bool has_sigma = d->sigma_unit != nullptr;
   if (has_sigma && d->sigma_head == nullptr) { set_error("sigma_unit without sigma_head"); rcu_unet_destroy(net); return RCU_EINVAL; }
   net->has_sigma = has_sigma;
@@ -702,6 +710,14 @@ extern "C" int rcu_unet_create(const rcu_unet_desc* d, int device, rcu_unet** ou
     up_off[u] = (int)fa.size();
     fold_unit(d->upconvs[u], d->bn_eps, fa, fba, fd);
     for (int c = 0; c < d->upconvs[u].c_out; ++c) { site.push_back(-1); chin.push_back(c); scol.push_back(0); }
+  }
+  std::vector<int> res_off(residual ? d->n_residuals : 0);
+  for (int r = 0; r < (int)res_off.size(); ++r) {   // bias-only columns, like the upconvs
+    const rcu_conv_unit& ru = d->residuals[r];
+    if (!(ru.weight && ru.bias)) { set_error("residual %d: NULL weight / bias", r); rcu_unet_destroy(net); return RCU_EINVAL; }
+    res_off[r] = (int)fa.size();
+    fold_unit(ru, d->bn_eps, fa, fba, fd);
+    for (int c = 0; c < ru.c_out; ++c) { site.push_back(-1); chin.push_back(c); scol.push_back(0); }
   }
   net->n_sites = n_sites;
   net->total_dropout_channels = drop_cols;
@@ -738,11 +754,11 @@ extern "C" int rcu_unet_create(const rcu_unet_desc* d, int device, rcu_unet** ou
   RCU_TRY(upload_head(d->head, &net->d_head, 0));
   if (has_sigma) RCU_TRY(upload_head(*d->sigma_head, &net->d_sigma_head, 1));
   // ---- tensor-core conv layers in execution order ----
-  auto add_unit = [&](int u, int c0, int c1, bool head, int out_slot = 0) -> int {
+  auto add_unit = [&](int u, int c0, int c1, bool head, int out_slot = 0, int relu = 1) -> int {
     const rcu_conv_unit& cu = unit_at(u);
     if (cu.c_in != c0 + c1) { set_error("unit %d: c_in=%d does not match the topology (%d)", u, cu.c_in, c0 + c1); return RCU_EINVAL; }
     ConvLayer L;
-    L.c0 = c0; L.c1 = c1; L.c_out = cu.c_out; L.n_taps = 9; L.n_phases = 1; L.out_mul = 1; L.relu = 1; L.head = head;
+    L.c0 = c0; L.c1 = c1; L.c_out = cu.c_out; L.n_taps = 9; L.n_phases = 1; L.out_mul = 1; L.relu = relu; L.head = head;
     for (int t = 0; t < 9; ++t) { L.dy[0][t] = (signed char)(t / 3 - 1); L.dx[0][t] = (signed char)(t % 3 - 1); }
     L.coef_off = unit_off[u];
     L.out_slot = out_slot;
@@ -785,23 +801,55 @@ extern "C" int rcu_unet_create(const rcu_unet_desc* d, int device, rcu_unet** ou
     net->convs.push_back(L);
     return RCU_OK;
   };
+  // residual branch of block r (forward order: down 0.., bottom, up 0..): block output += conv1x1(block input) + bias,
+  // and the block's last Conv2dBnRelu has no activation (unet.py:52-53)
+  auto add_residual = [&](int r, int c_in, int c_out) -> int {
+    const rcu_conv_unit& ru = d->residuals[r];
+    if (ru.c_in != c_in || ru.c_out != c_out) { set_error("residual %d: %d -> %d channels, topology says %d -> %d", r, ru.c_in, ru.c_out, c_in, c_out); return RCU_EINVAL; }
+    if (r == 0) {   // the block input is the float32 image: CUDA-core kernel (first_residual_kernel)
+      std::vector<float> w(ru.weight, ru.weight + (size_t)c_out * c_in), b(ru.bias, ru.bias + c_out);
+      int rc2 = dev_upload(net, w, &net->d_res0_w);
+      if (rc2) return rc2;
+      return dev_upload(net, b, &net->d_res0_b);
+    }
+    ConvLayer L;
+    L.c0 = c_in; L.c1 = 0; L.c_out = c_out; L.n_taps = 1; L.n_phases = 1; L.out_mul = 1; L.relu = 0; L.accumulate = true;
+    L.dy[0][0] = 0; L.dx[0][0] = 0;
+    L.coef_off = res_off[r];
+    int rc2 = pick_tiles(c_in, c_out, &L.block_n, &L.kc);
+    if (rc2) return rc2;
+    std::vector<uint16_t> w((size_t)c_out * c_in);
+    for (size_t i = 0; i < w.size(); ++i) w[i] = f32_to_bf16_rn(ru.weight[i]);   // [1 tap][c_out][c_in]
+    uint16_t* dw;
+    rc2 = dev_upload(net, w, &dw);
+    if (rc2) return rc2;
+    L.d_weights = reinterpret_cast<__nv_bfloat16*>(dw);
+    net->convs.push_back(L);
+    return RCU_OK;
+  };
   {
     int u = 1;  // unit 0 is the first conv
+    int r = 0;
     int c = sf;
-    RCU_TRY(add_unit(u++, c, 0, false));                 // down 0, second conv
+    const int last_relu = residual ? 0 : 1;
+    RCU_TRY(add_unit(u++, c, 0, false, 0, last_relu));   // down 0, second conv
+    if (residual) RCU_TRY(add_residual(r++, d->in_channels, c));
     for (int l = 1; l < d->depth; ++l) {
       RCU_TRY(add_unit(u++, c, 0, false));               // c -> 2c
       c *= 2;
-      RCU_TRY(add_unit(u++, c, 0, false));
+      RCU_TRY(add_unit(u++, c, 0, false, 0, last_relu));
+      if (residual) RCU_TRY(add_residual(r++, c / 2, c));
     }
     RCU_TRY(add_unit(u++, c, 0, false));                 // bottom
     c *= 2;
-    RCU_TRY(add_unit(u++, c, 0, false));
+    RCU_TRY(add_unit(u++, c, 0, false, 0, last_relu));
+    if (residual) RCU_TRY(add_residual(r++, c / 2, c));
     for (int j = 0; j < d->depth; ++j) {
       RCU_TRY(add_upconv(j, c, c / 2));
       c /= 2;
       RCU_TRY(add_unit(u++, 2 * c, 0, false));           // cat((up, skip), 1): one 2c-channel concat buffer
-      RCU_TRY(add_unit(u++, c, 0, false));
+      RCU_TRY(add_unit(u++, c, 0, false, 0, last_relu));
+      if (residual) RCU_TRY(add_residual(r++, 2 * c, c));
     }
     const bool fuse_head = (sf == 32);
     RCU_TRY(add_unit(u++, c, 0, fuse_head));             // conv_cls.0
@@ -1007,15 +1055,25 @@ static int plan_impl(rcu_unet* net, int height, int width, int max_images_per_ch
     net->ops.push_back(first);
   }
   for (ConvLayer& L : net->convs) L.pool_dst = Act();
+  const bool res = net->residual;
   int rc = push_conv(E[0], slice(CAT[0], sf, sf));
   if (rc) return rc;
-  net->convs[ci - 1].pool_dst = P[0];     // the pool that follows rides in this conv's epilogue (halo and wide kernels)
+  // the pool that follows rides in this conv's epilogue (halo and wide kernels) — unless a residual branch is still to be added
+  if (!res) net->convs[ci - 1].pool_dst = P[0];
+  if (res) {
+    net->res0_dst = slice(CAT[0], sf, sf);
+    Op op;
+    op.kind = OP_RES_FIRST; op.out = net->res0_dst; op.h = height; op.w = width; op.c = sf;
+    net->ops.push_back(op);
+  }
   for (int l = 1; l <= depth; ++l) {
     const int cp = sf << (l - 1), c = sf << l;
     push_pool(slice(CAT[l - 1], cp, cp), P[l - 1]);
+    const Act block_out = l < depth ? slice(CAT[l], c, c) : SB;
     if ((rc = push_conv(P[l - 1], E[l]))) return rc;
-    if ((rc = push_conv(E[l], l < depth ? slice(CAT[l], c, c) : SB))) return rc;
-    if (l < depth) net->convs[ci - 1].pool_dst = P[l];
+    if ((rc = push_conv(E[l], block_out))) return rc;
+    if (l < depth && !res) net->convs[ci - 1].pool_dst = P[l];
+    if (res && (rc = push_conv(P[l - 1], block_out))) return rc;   // + residual(block input)
   }
   Act cur = SB;
   for (int l = depth - 1; l >= 0; --l) {
@@ -1023,6 +1081,7 @@ static int plan_impl(rcu_unet* net, int height, int width, int max_images_per_ch
     if ((rc = push_conv(cur, slice(CAT[l], 0, c)))) return rc;     // upconv phases: low-res in, high-res up half of the concat
     if ((rc = push_conv(CAT[l], DA[l]))) return rc;                 // conv over cat((up, skip), 1)
     if ((rc = push_conv(DA[l], DB[l]))) return rc;
+    if (res && (rc = push_conv(CAT[l], DB[l]))) return rc;          // + residual(cat((up, skip), 1))
     cur = DB[l];
   }
   net->features = cur;
@@ -1200,6 +1259,15 @@ extern "C" int rcu_unet_forward_ex(rcu_unet* net, const float* images, int64_t n
                                                          net->first_out.img_stride);
         RCU_LAUNCH_CHECK();
         ++launches;
+      } else if (op.kind == OP_RES_FIRST) {
+        const long long total = (long long)cs * H * W * (sf / 8);
+        long long blocks = (total + 255) / 256;
+        if (blocks > (long long)sm_count() * 16) blocks = (long long)sm_count() * 16;
+        first_residual_kernel<<<(unsigned)blocks, 256, 0, st>>>(images, net->in_channels, H * W, (long long)s0, cs, n_samples, net->d_res0_w,
+                                                                net->d_res0_b, sf, net->res0_dst.base, net->res0_dst.c_total,
+                                                                net->res0_dst.img_stride);
+        RCU_LAUNCH_CHECK();
+        ++launches;
       } else if (op.kind == OP_POOL) {
         const long long total = (long long)n_img * op.h * op.w * (op.c / 8);
         long long blocks = (total + 255) / 256;
@@ -1271,6 +1339,7 @@ extern "C" int rcu_unet_forward_ex(rcu_unet* net, const float* images, int64_t n
         prm.out = L.dst.base;
         prm.coef = net->d_coef; prm.coef_stride = net->n_cols; prm.coef_off = L.coef_off;
         prm.relu = L.relu;
+        prm.accumulate = L.accumulate ? 1 : 0;
         prm.head = nullptr; prm.logits = head_out;
         prm.chunk_slices = cs; prm.slice0 = s0; prm.n_slices_total = n_slices;
         if (net->conv_impl != 1) {
@@ -1405,12 +1474,15 @@ extern "C" int rcu_unet_op_info(const rcu_unet* net, int op, int* kind, int64_t*
       macs = (int64_t)net->H * net->W * 9 * net->in_channels * net->start_filters;
     } else if (o.kind == OP_POOL) {
       k = 2; ci = o.c;
+    } else if (o.kind == OP_RES_FIRST) {
+      k = 0; ci = net->in_channels;
+      macs = (int64_t)o.h * o.w * ci * o.c;
     } else {
       const ConvLayer& L = net->convs[o.conv];
       k = 1; ci = L.c0 + L.c1;
       // algorithmic MACs of the reference layer: a 3x3 conv at the OUTPUT resolution (for the up-path conv that is
-      // the conv after nearest-x2, common/model/unet.py:105), plus the fused 1x1 head
-      macs = (int64_t)o.h * o.w * 9 * ci * L.c_out + (L.head ? (int64_t)o.h * o.w * L.c_out * 2 : 0);
+      // the conv after nearest-x2, common/model/unet.py:105; 1x1 for a residual branch), plus the fused 1x1 head
+      macs = (int64_t)o.h * o.w * (L.accumulate ? 1 : 9) * ci * L.c_out + (L.head ? (int64_t)o.h * o.w * L.c_out * 2 : 0);
     }
   }
   if (kind) *kind = k;
@@ -1430,10 +1502,12 @@ extern "C" int rcu_unet_op_executed_macs(const rcu_unet* net, int op, int64_t* m
     const Op& o = net->ops[op];
     if (o.kind == OP_FIRST) {
       macs = (int64_t)net->H * net->W * 9 * net->in_channels * net->start_filters;
+    } else if (o.kind == OP_RES_FIRST) {
+      macs = (int64_t)net->H * net->W * net->in_channels * net->start_filters;
     } else if (o.kind == OP_CONV) {
       const ConvLayer& L = net->convs[o.conv];
       // the up-path convs run as four 2x2-tap phase convolutions on the low-resolution input: 4 taps per OUTPUT pixel
-      const int taps = L.n_phases == 4 ? 4 : 9;
+      const int taps = L.accumulate ? 1 : (L.n_phases == 4 ? 4 : 9);
       macs = (int64_t)o.h * o.w * taps * (L.c0 + L.c1) * L.c_out + (L.head ? (int64_t)o.h * o.w * L.c_out * 2 : 0);
     }
   }

@@ -148,6 +148,46 @@ __device__ __forceinline__ uint4 bf16x8_max(uint4 a, uint4 b) {
   return r;
 }
 
+// Residual branch of the FIRST block of a residual=True net (ConvResidualBlock.residual, common/model/unet.py:57-59): a 1x1
+// convolution of the float32 input slices (c_in <= 8 channels) added onto the block output already in `out`.  The
+// branch does not depend on the MC sample, so it is computed once per slice pixel and added to every sample's image.
+// One thread = one pixel x 8 output channels.
+__global__ void __launch_bounds__(256)
+first_residual_kernel(const float* __restrict__ images, int c_in, int hw, long long slice0, int chunk_slices, int n_samples,
+                      const float* __restrict__ weight /* [c_out][c_in] */, const float* __restrict__ bias, int c_out,
+                      __nv_bfloat16* __restrict__ out, int out_c, long long out_img_stride) {
+  const int groups = c_out / 8;
+  const long long total = (long long)chunk_slices * hw * groups;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int g = (int)(i % groups);
+    const long long px_all = i / groups;
+    const int sl = (int)(px_all / hw);
+    const int px = (int)(px_all - (long long)sl * hw);
+    const float* img = images + (slice0 + sl) * (long long)c_in * hw + px;
+    float r[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) r[c] = __ldg(bias + g * 8 + c);
+    for (int ci = 0; ci < c_in; ++ci) {
+      const float v = __ldg(img + (long long)ci * hw);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) r[c] = fmaf(v, __ldg(weight + (g * 8 + c) * c_in + ci), r[c]);
+    }
+    for (int t = 0; t < n_samples; ++t) {
+      uint4* dst = reinterpret_cast<uint4*>(out + (long long)(t * chunk_slices + sl) * out_img_stride + (long long)px * out_c + g * 8);
+      uint4 q = *dst;
+      uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float2 old = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[c]));
+        __nv_bfloat162 b = __floats2bfloat162_rn(old.x + r[2 * c], old.y + r[2 * c + 1]);
+        w4[c] = *reinterpret_cast<uint32_t*>(&b);
+      }
+      *dst = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+    }
+  }
+}
+
+
 __global__ void __launch_bounds__(256)
 maxpool2_kernel(const __nv_bfloat16* __restrict__ in, int in_px_stride, long long in_img_stride, __nv_bfloat16* __restrict__ out,
                 long long out_img_stride, long long n_img, int h, int w, int c) {
@@ -193,9 +233,11 @@ conv_check_kernel(const __nv_bfloat16* __restrict__ src, int c_in, int src_px_st
     }
     const float2 cf = prm.coef[(long long)img * prm.coef_stride + prm.coef_off + co];
     float v = fmaf(acc, cf.x, cf.y);
-    if (prm.relu) v = fmaxf(v, 0.0f);
     const int oy = prm.out_mul * y + (ph >> 1), ox = prm.out_mul * x + (ph & 1);
-    prm.out[(long long)img * prm.out_img_stride + ((long long)oy * prm.out_w + ox) * prm.out_c + co] = __float2bfloat16_rn(v);
+    __nv_bfloat16* o = prm.out + (long long)img * prm.out_img_stride + ((long long)oy * prm.out_w + ox) * prm.out_c + co;
+    if (prm.accumulate) v += __bfloat162float(*o);
+    if (prm.relu) v = fmaxf(v, 0.0f);
+    *o = __float2bfloat16_rn(v);
   }
 }
 

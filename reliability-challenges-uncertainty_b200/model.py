@@ -97,8 +97,8 @@ class B200UNet(nn.Module):
         if nb_classes != 2:
             raise NotImplementedError('the B200 hot path is binary (nb_classes == 2)')
         state_dict = {(k[len('module.'):] if k.startswith('module.') else k): v for k, v in state_dict.items()}
-        if any('.residual.' in k for k in state_dict):
-            raise NotImplementedError('residual=True nets are outside the B200 hot path')
+        # residual=True (unet.py:42-60, 144-148): every block adds a 1x1 convolution of its input and its last conv has no ReLU
+        self.residual = any(k.endswith('.residual.weight') for k in state_dict)
         has_sigma_weights = any(k.startswith('conv_sigma.') for k in state_dict)
         # sigma_out=True (unet.py:162-164): a second head on the same features, forward returns (logits, sigma)
         self.sigma_out = has_sigma_weights if sigma_out is None else bool(sigma_out)
@@ -199,6 +199,17 @@ class B200UNet(nn.Module):
         desc.units, desc.n_units = unit_arr, len(units)
         desc.upconvs, desc.n_upconvs = up_arr, len(upconvs)
         desc.head = unit_struct('conv_cls.1', self.start_filters, self.nb_classes, False, bn=False, conv_key='')
+        if self.residual:
+            names = (['down_convs.%d.block.residual' % l for l in range(self.depth)] + ['bottom_convs.residual'] +
+                     ['up_convs.%d.block.residual' % j for j in range(self.depth)])
+            res = []
+            for name in names:
+                w = sd[name + '.weight'] if name + '.weight' in sd else None
+                if w is None:
+                    raise ValueError('state_dict is missing "{}.weight" (residual=True nets carry one per block)'.format(name))
+                res.append(unit_struct(name, int(w.shape[1]), int(w.shape[0]), False, bn=False, conv_key=''))
+            res_arr = (_lib.RcuConvUnit * len(res))(*res)
+            desc.residuals, desc.n_residuals = res_arr, len(res)
         if self.sigma_out:
             sf = self.start_filters
             sigma_unit = unit_struct('conv_sigma.0.conv2d_batch_relu', sf, sf, self.dropout is not None)

@@ -155,8 +155,8 @@ def test_unsupported_configurations_fail_loudly():
         model.B200UNet(bad)
     bad = dict(sd)
     bad['down_convs.0.block.residual.weight'] = torch.zeros(32, 4, 1, 1)
-    with pytest.raises(NotImplementedError):
-        model.B200UNet(bad)                                    # residual=True blocks (no shipped config uses them)
+    with pytest.raises(ValueError):
+        model.B200UNet(bad)                                    # a residual=True net with the other blocks' residual convs missing
     with pytest.raises(ValueError):
         net.forward_outputs(torch.randn(1, 4, 32, 32), sigma=True)   # sigma requested from a sigma_out=False net
     missing = {k: v for k, v in sd.items() if 'bottom_convs.block.1' not in k}
@@ -255,3 +255,32 @@ def test_free_running_mc_entropy_distribution_matches_nn_dropout2d():
     d_ot = np.array([ks_2samp(mine, r).statistic for r in torch_runs])
     assert d_ot.mean() <= d_tt.mean() + 3 * d_tt.std(ddof=1) + 0.01, (d_ot, d_tt)
     assert d_ot.max() <= d_tt.max() + 3 * d_tt.std(ddof=1) + 0.02, (d_ot, d_tt)
+
+
+def test_residual_net_matches_reference_golden_and_oracle():
+    """residual=True nets (ConvResidualBlock, common/model/unet.py:42-60): block output = conv - [dropout] - bn of the second
+    unit WITHOUT ReLU plus a 1x1 convolution of the block input.  Against the unmodified reference's outputs
+    (tests/golden/residual_golden.npz: deterministic logits, `UNet.features`, one stochastic pass with injected masks), and
+    layer by layer against the CUDA-core cross-check path."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'residual_golden.npz'))
+    cfg = R.UNetConfig(in_channels=4, residual=True)
+    sd = R.randomize_statistics(R.init_state_dict(cfg, 20), 7)
+    net = model.B200UNet(sd, in_channels=4, dropout=cfg.dropout, provide_features=True)
+    assert net.residual
+    x = torch.from_numpy(g['input'])
+    _close(net(x.cuda()), torch.from_numpy(g['logits']))
+    feat = net.features.cpu()
+    ref_feat = torch.from_numpy(g['features'])
+    assert (feat - ref_feat).abs().max().item() <= 0.05 * max(1.0, ref_feat.abs().max().item())
+    mc = net.forward_samples(x, 1, dropout_mode=1, seed=20, slice_index0=0, sample0=0)[0].permute(0, 3, 1, 2)
+    _close(mc, torch.from_numpy(g['mc_logits']))
+    # tcgen05 path against the CUDA-core kernels over the same bf16 data
+    ck = model.B200UNet(sd, in_channels=4, dropout=cfg.dropout)
+    ck.set_conv_impl(1)
+    a = net.forward_samples(x, 2, dropout_mode=1, det_first=True, seed=5)
+    b = ck.forward_samples(x, 2, dropout_mode=1, det_first=True, seed=5)
+    assert (a - b).abs().max().item() <= 0.05
+    # a residual=False state dict of the same topology still takes the plain path
+    plain = model.B200UNet(R.randomize_statistics(R.init_state_dict(R.UNetConfig(in_channels=4), 20), 7), in_channels=4, dropout=cfg.dropout)
+    assert not plain.residual

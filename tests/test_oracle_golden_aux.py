@@ -80,3 +80,28 @@ def test_confidence_preparations(golden_aux):
         R.uncertainty_to_foreground_probabilities(u, pred)          # not rescaled: values > 1
     with pytest.raises(ValueError):
         R.uncertainty_to_foreground_probabilities(resc, pred[:2])
+
+
+def test_residual_net_restatement_matches_the_unmodified_reference():
+    """residual=True (ConvResidualBlock, common/model/unet.py:42-60): parameter creation order (so a seeded init is reproduced
+    bit for bit), state_dict key order, the deterministic forward, `UNet.features` and a stochastic forward with injected
+    Dropout2d masks — against tests/golden/residual_golden.npz, written by the unmodified reference UNet."""
+    import os
+    import torch
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'residual_golden.npz'))
+    cfg = R.UNetConfig(in_channels=4, residual=True)
+    sd = R.init_state_dict(cfg, 20)
+    assert [str(k) for k in g['keys']] == list(sd.keys())
+    assert np.float64(sum(v.double().sum().item() for v in sd.values())) == g['param_sum']
+    assert np.float64(sum(v.double().abs().sum().item() for v in sd.values())) == g['param_abs_sum']
+    assert np.array_equal(sd['down_convs.0.block.residual.weight'].numpy(), g['residual0_weight'])
+    assert np.array_equal(sd['up_convs.3.block.residual.bias'].numpy(), g['residual_last_bias'])
+    sd = R.randomize_statistics(sd, 7)
+    x = torch.from_numpy(g['input'])
+    with torch.no_grad():
+        out = R.unet_forward(sd, x, cfg, return_all=True)
+        mc = R.unet_forward(sd, x, cfg, R.philox_keep_masks(cfg, 20, 0, 0, x.shape[0]))
+    assert np.allclose(out['logits'].numpy(), g['logits'], rtol=0, atol=2e-5)
+    assert np.allclose(out['features'].numpy(), g['features'], rtol=0, atol=2e-5)
+    assert np.allclose(mc.numpy(), g['mc_logits'], rtol=0, atol=2e-5)
+    assert np.abs(g['mc_logits'] - g['logits']).max() > 1e-2          # the masks do something

@@ -10,6 +10,15 @@ import sys
 COLS = [
     ('gpu__time_duration.sum', 'dur_us', 1e-3),
     ('sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed', 'tensor_pipe_pct', 1),
+    # the tcgen05 (UTCHMMA) work itself: executed bf16 tensor math ops (2 per MAC), the HMMA-subpipe busy fraction, the
+    # warp-level tensor instructions and the shared-memory operand wavefronts the MMAs read
+    ('sm__ops_path_tensor_op_hmma_src_bf16_dst_fp32.sum', 'tensor_ops_G', 1e-9),
+    ('sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed', 'hmma_subpipe_pct', 1),
+    ('sm__inst_executed_pipe_tensor_subpipe_hmma.sum', 'utchmma_inst', 1),
+    ('l1tex__data_pipe_tc_wavefronts_mem_shared_op_utcmma_matrix_a.sum', 'smem_wf_A_M', 1e-6),
+    ('l1tex__data_pipe_tc_wavefronts_mem_shared_op_utcmma_matrix_b_scope_1cta.sum', 'smem_wf_B_M', 1e-6),
+    ('l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'smem_wf_lsu_M', 1e-6),
+    ('sm__cycles_elapsed.max', 'sm_cycles', 1),
     ('sm__throughput.avg.pct_of_peak_sustained_elapsed', 'sm_pct', 1),
     ('dram__bytes_read.sum', 'dram_rd_MB', 1e-6),
     ('dram__bytes_write.sum', 'dram_wr_MB', 1e-6),
