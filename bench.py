@@ -339,7 +339,7 @@ def time_device_call(torch, stream, fn, flush, reps=10):
 def run_mc_config(args, rig, isic=False):
     torch = rig.torch
     import rcu_b200  # noqa: F401
-    from rcu_b200 import model, steps, metrics, hooks, tables
+    from rcu_b200 import model, steps, metrics, tables
     device, stream, rank, world = rig.device, rig.stream, rig.rank, rig.world
     if isic:
         n_items, ch, h, w = ISIC_IMAGES, 3, ISIC_SIZE, ISIC_SIZE
@@ -392,7 +392,6 @@ def run_mc_config(args, rig, isic=False):
         mark()
         return out, res
 
-    hook = hooks.DeviceMetricsHook()
     ctx = _Context(net, device)
     h2d, d2h = {'n': 0}, {'n': 0}
     copy_ev = {'h2d': [], 'd2h': []}
@@ -402,33 +401,46 @@ def run_mc_config(args, rig, isic=False):
     copy_in = torch.cuda.Stream(device)     # host -> device prefetch of the next batch's images
     copy_out = torch.cuda.Stream(device)    # device -> host copy of the previous batch's probabilities
 
-    def e2e_step(step_index):
-        """The call sequence a user of the reference makes (loops.py:204-235) with host buffers on both sides: images come
-        from (pinned) host memory per 32-item batch, the 'probabilities' entry goes back to the host channel-last like
-        loops.py:214-220 does (into a pinned buffer), the foreground / prediction maps stay in HBM for the in-memory
-        metric hook, labels and mask come from the host, the metric tables go back.  All of it inside the timed region;
-        the copies run on two side streams (double-buffered like a pin_memory loader) so that they overlap the forward of
-        the neighbouring batch instead of serialising with it."""
-        mc = steps.McPredictStep(MC_STEPS)
-        mc.slices_seen = step_index * n_items
-        summary = steps.MultiPredictionSummary(emit_prediction=True, emit_foreground=True)
-        fg, pred = [], []
+    n_tab = (3 * 11 + 4 * 12 + 1) * n_subjects
+    tables_pinned = [torch.empty(n_tab, dtype=torch.int64).pin_memory() for _ in range(2)]
+    prob_pinned2 = [prob_pinned, torch.empty_like(prob_pinned).pin_memory()]
 
-        def fetch(b0):
+    def e2e_run(n_steps, first_index):
+        """The call sequence a user of the reference makes (loops.py:204-235) with host buffers on both sides, for `n_steps`
+        subjects back to back: images come from (pinned) host memory per 32-item batch, the 'probabilities' entry goes back
+        to the host channel-last like loops.py:214-220 does (into a pinned buffer), the foreground / prediction maps stay in
+        HBM for the in-memory metric pass, labels and mask come from the host, the metric tables go back.  All of it inside
+        the timed region.  The copies run on two side streams and the NEXT batch — of this subject or of the next one, the
+        way a pin_memory DataLoader runs ahead — is in flight while the current one is computed; nothing on the host waits
+        for the device until the end of the run, where the tables of every step are turned into rows."""
+        batches = [(st_, b0) for st_ in range(n_steps) for b0 in range(0, n_items, BATCH)]
+        summary = steps.MultiPredictionSummary(emit_prediction=True, emit_foreground=True)
+
+        def fetch(k):
+            st_, b0 = batches[k]
             with torch.cuda.stream(copy_in):
                 a = torch.cuda.Event(enable_timing=True)
                 a.record(copy_in)
                 t = images_pinned[b0:b0 + BATCH].to(device, non_blocking=True)
+                extra = None
+                if b0 + BATCH >= n_items:   # last batch of a subject: its labels / mask travel with it
+                    extra = (target_pinned.to(device, non_blocking=True), None if mask_pinned is None else mask_pinned.to(device, non_blocking=True))
+                    h2d['n'] += target_pinned.numel() + (0 if mask_pinned is None else mask_pinned.numel())
                 ready = torch.cuda.Event(enable_timing=True)
                 ready.record(copy_in)
             copy_ev['h2d'].append((a, ready))
             h2d['n'] += t.numel() * 4
-            return t, ready
+            return t, extra, ready
         nxt = fetch(0)
-        for b0 in range(0, n_items, BATCH):
-            images_b, ready = nxt
-            if b0 + BATCH < n_items:
-                nxt = fetch(b0 + BATCH)
+        mc, fg, pred = None, [], []
+        for k, (st_, b0) in enumerate(batches):
+            if b0 == 0:
+                mc = steps.McPredictStep(MC_STEPS)
+                mc.slices_seen = (first_index + st_) * n_items
+                fg, pred = [], []
+            images_b, extra, ready = nxt
+            if k + 1 < len(batches):
+                nxt = fetch(k + 1)
             stream.wait_event(ready)
             images_b.record_stream(stream)
             bc = _BatchContext({'images': images_b}, b0 // BATCH)
@@ -436,32 +448,41 @@ def run_mc_config(args, rig, isic=False):
             summary(bc, None, ctx)
             n = images_b.shape[0]
             probs = bc.output['probabilities']
+            fg.append(bc.output['foreground'])
+            pred.append(bc.output['prediction'])
+            flat = None
+            if extra is not None:        # subject complete: the fused metric pass on the maps in HBM
+                target_dev, mask_dev = extra
+                target_dev.record_stream(stream)
+                if mask_dev is not None:
+                    mask_dev.record_stream(stream)
+                res = metrics.eval_fused(torch.cat(fg), torch.cat(pred), target_dev.view(-1), None if mask_dev is None else mask_dev.view(-1), 10,
+                                         tables.SWEEP_THRESHOLDS, n_subjects=n_subjects, sync=False, break_table=break_table)
+                flat = torch.cat([res[0].reshape(-1), res[1].reshape(-1), res[2].view(torch.int64).reshape(-1), res[3].reshape(-1), res[4].reshape(-1)])
             done = torch.cuda.Event()
             done.record(stream)
             with torch.cuda.stream(copy_out):
                 copy_out.wait_event(done)
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record(copy_out)
-                prob_pinned[b0:b0 + n].copy_(probs.permute(0, 2, 3, 1), non_blocking=True)
+                prob_pinned2[st_ & 1][b0:b0 + n].copy_(probs.permute(0, 2, 3, 1), non_blocking=True)
+                if flat is not None:
+                    tables_pinned[st_ & 1].copy_(flat, non_blocking=True)
+                    flat.record_stream(copy_out)
+                    d2h['n'] += 8 * n_tab
                 b.record(copy_out)
             copy_ev['d2h'].append((a, b))
             probs.record_stream(copy_out)
             d2h['n'] += n * h * w * 2 * 4
-            fg.append(bc.output['foreground'])
-            pred.append(bc.output['prediction'])
-        target_dev = target_pinned.to(device, non_blocking=True)
-        mask_dev = None if mask_pinned is None else mask_pinned.to(device, non_blocking=True)
-        h2d['n'] += target_pinned.numel() + (0 if mask_pinned is None else mask_pinned.numel())
-        if n_subjects == 1:
-            row = hook.evaluate(step_index, torch.cat(fg), torch.cat(pred), target_dev, mask_dev)   # tables come back to the host inside
-        else:
-            res = metrics.eval_fused(torch.cat(fg), torch.cat(pred), target_dev.view(-1), None, 10, tables.SWEEP_THRESHOLDS, n_subjects=n_subjects,
-                                     break_table=break_table)                                         # sync=True: one D2H copy of all tables
-            row = {'dice': tables.dice_from_counts(res[3][:, 0].sum(), res[3][:, 2].sum(), res[3][:, 3].sum())}
-        d2h['n'] += 8 * (3 * 11 + 4 * 12 + 1) * n_subjects
-        copy_out.synchronize()                      # the probabilities are on the host now
+        copy_out.synchronize()                      # probabilities and tables of the last subject are on the host now
         torch.cuda.current_stream().synchronize()
-        return row
+        t = tables_pinned[(n_steps - 1) & 1].numpy()
+        nb1 = 11
+        cnt, pos = t[:n_subjects * nb1].reshape(n_subjects, nb1), t[n_subjects * nb1:2 * n_subjects * nb1].reshape(n_subjects, nb1)
+        conf_ = t[2 * n_subjects * nb1:3 * n_subjects * nb1].view(np.float64).reshape(n_subjects, nb1)
+        ue_ = t[3 * n_subjects * nb1:3 * n_subjects * nb1 + n_subjects * 48].reshape(n_subjects, 4, 12)
+        return {'ece': float(np.mean([tables.ece_from_tables(cnt[s_, :10], pos[s_, :10], conf_[s_, :10], n_dim=3) for s_ in range(n_subjects)])),
+                'dice': tables.dice_from_counts(ue_[:, 0].sum(), ue_[:, 2].sum(), ue_[:, 3].sum())}
 
     # ---------------- warm-up (also builds the plan / workspaces)
     warm = max(args.warmup, 3)
@@ -509,15 +530,14 @@ def run_mc_config(args, rig, isic=False):
     bin_occupancy = [round(float(x), 4) for x in (count[:, :10].sum(0) / max(1, count[:, :10].sum()))]
     pred_pos = float(out['prediction'].float().mean().item())
 
-    # ---------------- e2e through the drop-in steps with host buffers: all K steps
-    e2e_step(0)
+    # ---------------- e2e through the drop-in steps with host buffers: all K steps, one continuous pipeline
+    e2e_run(1, 0)
     torch.cuda.synchronize()
     h2d['n'] = d2h['n'] = 0
     copy_ev['h2d'], copy_ev['d2h'] = [], []
     rig.barrier()
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        row = e2e_step(200 + i)
+    row = e2e_run(args.steps, 200)
     rig.barrier()
     e2e_ms = rig.max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
     h2d_busy = sum(a.elapsed_time(b) for a, b in copy_ev['h2d']) / args.steps
@@ -629,8 +649,9 @@ def run_mc_config(args, rig, isic=False):
                 'exposed_ms_per_step': e2e_ms - ms_step,   # everything the host-buffer route adds to the device-resident step: the first
                 # batch's copy-in and the last batch's copy-out (nothing to hide behind), 32-slice batches (partial chunks), host syncs
                 'copy_hidden_fraction': max(0.0, min(1.0, 1.0 - (e2e_ms - ms_step) / max(1e-9, h2d_busy + d2h_busy))),
-                'api': 'McPredictStep(20)+MultiPredictionSummary per 32-item batch from pinned host images, probabilities to host, '
-                       'DeviceMetricsHook.evaluate / eval_fused on the device maps, labels and mask from the host, tables to the host'},
+                'api': 'McPredictStep(20)+MultiPredictionSummary per 32-item batch from pinned host images (next batch prefetched, also across '
+                       'subjects), probabilities to pinned host memory, metrics.eval_fused on the device maps with labels and mask from the '
+                       'host, tables to the host; one host synchronisation at the end of the K steps'},
         'gpu_launches': n_launches,
         'clocks': clocks,
         'roofline': roofline,

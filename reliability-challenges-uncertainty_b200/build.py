@@ -69,5 +69,45 @@ def build(force=False, verbose=False):
     return LIB_PATH
 
 
+TORCH_EXT_PATH = os.path.join(HERE, 'librcu_b200_torch.so')
+TORCH_EXT_STAMP = os.path.join(HERE, 'build', 'librcu_b200_torch.stamp')
+
+
+def build_torch_extension(force=False, verbose=False):
+    """Compile csrc/torch_binding.cpp (the torch.ops.rcu_b200.* operators over the C-ABI) in-tree with g++ against the
+    installed PyTorch and link it to librcu_b200.so next to it.  Returns the path (load it with torch.ops.load_library)."""
+    import torch
+    from torch.utils import cpp_extension
+    src = os.path.join(CSRC, 'torch_binding.cpp')
+    h = hashlib.sha256()
+    for path in (src, os.path.join(HERE, '..', 'include', 'rcu_b200.h')):
+        with open(path, 'rb') as f:
+            h.update(f.read())
+    h.update(torch.__version__.encode())
+    fp = h.hexdigest()
+    if not force and os.path.exists(TORCH_EXT_PATH) and os.path.exists(TORCH_EXT_STAMP):
+        with open(TORCH_EXT_STAMP) as f:
+            if f.read().strip() == fp:
+                return TORCH_EXT_PATH
+    build(force=False, verbose=verbose)          # the library it links against
+    torch_lib = os.path.join(os.path.dirname(torch.__file__), 'lib')
+    cuda_inc = os.path.join(os.environ.get('CUDA_HOME', '/usr/local/cuda'), 'include')
+    cmd = ['g++', '-O2', '-std=c++17', '-fPIC', '-shared', src, '-o', TORCH_EXT_PATH,
+           '-D_GLIBCXX_USE_CXX11_ABI=%d' % int(torch._C._GLIBCXX_USE_CXX11_ABI)]
+    cmd += ['-I' + p for p in cpp_extension.include_paths()] + ['-I' + cuda_inc]
+    cmd += ['-L' + torch_lib, '-ltorch', '-ltorch_cpu', '-lc10', '-ltorch_cuda', '-lc10_cuda', '-L' + HERE, '-l:librcu_b200.so',
+            '-Wl,-rpath,$ORIGIN', '-Wl,-rpath,' + torch_lib, '-Wl,--no-as-needed']
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        sys.stderr.write(' '.join(cmd) + '\n' + res.stdout + res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError('g++ failed on torch_binding.cpp')
+    os.makedirs(os.path.dirname(TORCH_EXT_STAMP), exist_ok=True)
+    with open(TORCH_EXT_STAMP, 'w') as f:
+        f.write(fp)
+    return TORCH_EXT_PATH
+
+
 if __name__ == '__main__':
     print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    print(build_torch_extension(force='--force' in sys.argv, verbose='-v' in sys.argv))

@@ -10,6 +10,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from . import _torch_ext
 from . import tables
 
 
@@ -19,7 +20,17 @@ def _device():
     return torch.device('cuda', torch.cuda.current_device())
 
 
-def _to_device(x, dtype, name):
+def _pick_device(*xs):
+    """The device the call runs on: that of the first CUDA tensor among the inputs, else the current CUDA device (numpy inputs
+    are copied there).  Every C call below is made under torch.cuda.device(that device), so tensors on cuda:1 work while
+    cuda:0 is current, and the per-device workspace matches the data."""
+    for x in xs:
+        if torch.is_tensor(x) and x.is_cuda:
+            return x.device
+    return _device()
+
+
+def _to_device(x, dtype, name, device=None):
     """Flat contiguous CUDA tensor of `dtype` for a numpy array / torch tensor (bool -> uint8)."""
     if x is None:
         return None
@@ -37,7 +48,7 @@ def _to_device(x, dtype, name):
         raise ValueError("object of type '{}' must be '{}'".format(type(x).__name__, np.ndarray.__name__))
     if t.dtype != dtype:
         t = t.to(dtype)
-    t = t.to(_device(), non_blocking=True).contiguous().view(-1)
+    t = t.to(device if device is not None else _device(), non_blocking=True).contiguous().view(-1)
     return t
 
 
@@ -47,7 +58,7 @@ class _Workspace:
 
     @classmethod
     def get(cls, n_subjects):
-        dev = torch.cuda.current_device()
+        dev = torch.cuda.current_device()     # callers switch to the tensors' device first (torch.cuda.device(...))
         need = int(_lib.lib().rcu_metrics_workspace_bytes(int(n_subjects)))
         buf = cls._cache.get(dev)
         if buf is None or buf.numel() < need:
@@ -82,6 +93,22 @@ def _breaks_for(breaks, seg):
     return e[3], e[5]
 
 
+_HOST_TABLES = {}
+
+
+def _host_tables(n_bins, breaks, seg):
+    """Host torch tensors (edges float32, breaks float32, seg uint8) for the torch-extension operators, cached like _breaks_for."""
+    key = (n_bins, id(breaks), id(seg))
+    e = _HOST_TABLES.get(key)
+    if e is None or e[0] is not breaks or e[1] is not seg:
+        if len(_HOST_TABLES) > 64:
+            _HOST_TABLES.clear()
+        e = _HOST_TABLES[key] = (breaks, seg, torch.from_numpy(np.ascontiguousarray(tables.calibration_edges_f32(n_bins), dtype=np.float32).copy()),
+                                 torch.from_numpy(np.ascontiguousarray(breaks, dtype=np.float32).copy()),
+                                 torch.from_numpy(np.ascontiguousarray(seg, dtype=np.uint8).copy()))
+    return e[2], e[3], e[4]
+
+
 def _f32_array(a):
     a = np.ascontiguousarray(a, dtype=np.float32)
     return a, a.ctypes.data_as(_lib.c_float_p)
@@ -101,23 +128,24 @@ def calibration_tables(p, target, mask=None, n_bins=10, threshold_range=None, n_
     Returns (count int64[S, n_bins+1], positives int64[S, n_bins+1], conf_sum float64[S, n_bins+1]); the last
     slot counts values outside every bin (p < 0, p >= 1+1e-8, NaN).  With sync=False CUDA tensors are returned.
     """
-    p_d = _to_device(p, torch.float32, 'probabilities')
-    t_d = _to_device(target, torch.uint8, 'target')
-    m_d = _to_device(mask, torch.uint8, 'mask')
+    dev = _pick_device(p, target, mask)
+    p_d = _to_device(p, torch.float32, 'probabilities', dev)
+    t_d = _to_device(target, torch.uint8, 'target', dev)
+    m_d = _to_device(mask, torch.uint8, 'mask', dev)
     n = p_d.numel()
     vps = n // max(n_subjects, 1)
     _check_lengths(n, vps, n_subjects, target=t_d, mask=m_d)
-    dev = p_d.device
     count = torch.zeros((n_subjects, n_bins + 1), dtype=torch.int64, device=dev)
     positives = torch.zeros_like(count)
     conf = torch.zeros((n_subjects, n_bins + 1), dtype=torch.float64, device=dev)
     if n > 0:
         edges, edges_p = _f32_array(tables.calibration_edges_f32(n_bins))
         lo, hi = (float('nan'), float('nan')) if threshold_range is None else (float(threshold_range[0]), float(threshold_range[1]))
-        ws = _Workspace.get(n_subjects)
-        _lib.check(_lib.lib().rcu_calib_hist(_lib.ptr(p_d), _lib.ptr(t_d), _lib.ptr(m_d), vps, n_subjects, edges_p, n_bins, lo, hi,
-                                             _lib.ptr(count), _lib.ptr(positives), _lib.ptr(conf), _lib.ptr(ws), ws.numel(),
-                                             _lib.current_stream()))
+        with torch.cuda.device(dev):
+            ws = _Workspace.get(n_subjects)
+            _lib.check(_lib.lib().rcu_calib_hist(_lib.ptr(p_d), _lib.ptr(t_d), _lib.ptr(m_d), vps, n_subjects, edges_p, n_bins, lo, hi,
+                                                 _lib.ptr(count), _lib.ptr(positives), _lib.ptr(conf), _lib.ptr(ws), ws.numel(),
+                                                 _lib.current_stream()))
     if not sync:
         return count, positives, conf
     return count.cpu().numpy(), positives.cpu().numpy(), conf.cpu().numpy()
@@ -148,20 +176,19 @@ def ue_tables(values, prediction, target, thresholds=tables.SWEEP_THRESHOLDS, ma
         raise ValueError('unknown kind "{}"'.format(kind))
     breaks, seg, order = break_table if break_table is not None else _ue_tables_for(kind, thresholds)
     n_classes = len(order) + 1
-    v_d = _to_device(values, torch.float64 if kind == 'u64' else torch.float32, 'values')
-    d_d = _to_device(prediction, torch.uint8, 'prediction')
-    t_d = _to_device(target, torch.uint8, 'target')
-    m_d = _to_device(mask, torch.uint8, 'mask')
+    dev = _pick_device(values, prediction, target, mask)
+    v_d = _to_device(values, torch.float64 if kind == 'u64' else torch.float32, 'values', dev)
+    d_d = _to_device(prediction, torch.uint8, 'prediction', dev)
+    t_d = _to_device(target, torch.uint8, 'target', dev)
+    m_d = _to_device(mask, torch.uint8, 'mask', dev)
     n = v_d.numel()
     vps = n // max(n_subjects, 1)
     _check_lengths(n, vps, n_subjects, prediction=d_d, target=t_d, mask=m_d)
-    dev = v_d.device
     table = torch.zeros((n_subjects, 4, n_classes), dtype=torch.int64, device=dev)
     invalid = torch.zeros((n_subjects,), dtype=torch.int64, device=dev)
     if n > 0:
         seg = np.ascontiguousarray(seg, dtype=np.uint8)
         seg_p = seg.ctypes.data_as(_lib.c_uint8_p)
-        ws = _Workspace.get(n_subjects)
         if kind == 'u64':
             b64 = np.ascontiguousarray(breaks, dtype=np.float64)
             b32_p, b64_p = None, b64.ctypes.data_as(_lib.c_double_p)
@@ -170,9 +197,11 @@ def ue_tables(values, prediction, target, thresholds=tables.SWEEP_THRESHOLDS, ma
             b32, b32_p = _f32_array(breaks)
             b64_p = None
             vk = 0 if kind == 'p' else 1
-        _lib.check(_lib.lib().rcu_ue_hist(_lib.ptr(v_d), vk, _lib.ptr(d_d), _lib.ptr(t_d), _lib.ptr(m_d), vps, n_subjects, b32_p, b64_p,
-                                          len(breaks), seg_p, n_classes, _lib.ptr(table), _lib.ptr(invalid), _lib.ptr(ws), ws.numel(),
-                                          _lib.current_stream()))
+        with torch.cuda.device(dev):
+            ws = _Workspace.get(n_subjects)
+            _lib.check(_lib.lib().rcu_ue_hist(_lib.ptr(v_d), vk, _lib.ptr(d_d), _lib.ptr(t_d), _lib.ptr(m_d), vps, n_subjects, b32_p, b64_p,
+                                              len(breaks), seg_p, n_classes, _lib.ptr(table), _lib.ptr(invalid), _lib.ptr(ws), ws.numel(),
+                                              _lib.current_stream()))
     if not sync:
         return table, invalid, order
     return table.cpu().numpy(), invalid.cpu().numpy(), order
@@ -186,28 +215,37 @@ def eval_fused(p, prediction, target, mask=None, n_bins=10, thresholds=tables.SW
     """
     breaks, seg, order = break_table if break_table is not None else tables.uncertainty_break_table(thresholds)
     n_classes = len(order) + 1
-    p_d = _to_device(p, torch.float32, 'probabilities')
-    d_d = _to_device(prediction, torch.uint8, 'prediction')
-    t_d = _to_device(target, torch.uint8, 'target')
-    m_d = _to_device(mask, torch.uint8, 'mask')
+    dev = _pick_device(p, prediction, target, mask)
+    p_d = _to_device(p, torch.float32, 'probabilities', dev)
+    d_d = _to_device(prediction, torch.uint8, 'prediction', dev)
+    t_d = _to_device(target, torch.uint8, 'target', dev)
+    m_d = _to_device(mask, torch.uint8, 'mask', dev)
     n = p_d.numel()
     vps = n // max(n_subjects, 1)
     _check_lengths(n, vps, n_subjects, prediction=d_d, target=t_d, mask=m_d)
-    dev = p_d.device
     # one allocation for all five result tables (the kernel's last block writes every slot, nothing needs zeroing):
     # the single-subject call is otherwise bound by five tiny memset launches
     nb1 = n_bins + 1
     width = 3 * nb1 + 4 * n_classes + 1
-    flat = (torch.empty if n > 0 else torch.zeros)((n_subjects * width,), dtype=torch.int64, device=dev)
     o1, o2, o3, o4 = n_subjects * nb1, 2 * n_subjects * nb1, 3 * n_subjects * nb1, 3 * n_subjects * nb1 + n_subjects * 4 * n_classes
-    if n > 0:
+    ext = _torch_ext.ops() if n > 0 else None
+    if ext is not None:
+        # torch-extension binding: one registered operator call (tensors in, the flat table out, current stream inside)
+        with torch.cuda.device(dev):
+            ws = _Workspace.get(n_subjects)
+            edges_t, breaks_t, seg_t = _host_tables(n_bins, breaks, seg)
+            flat = ext.eval_fused(p_d, d_d, t_d, m_d, edges_t, breaks_t, seg_t, n_subjects, n_classes, ws)
+    else:
+        flat = (torch.empty if n > 0 else torch.zeros)((n_subjects * width,), dtype=torch.int64, device=dev)
+    if n > 0 and ext is None:
         _, edges_p = _edges_for(n_bins)
         b32_p, seg_p = _breaks_for(breaks, seg)
-        ws = _Workspace.get(n_subjects)
-        base = flat.data_ptr()
-        _lib.check(_lib.lib().rcu_eval_fused(_lib.ptr(p_d), _lib.ptr(d_d), _lib.ptr(t_d), _lib.ptr(m_d), vps, n_subjects, edges_p, n_bins,
-                                             b32_p, len(breaks), seg_p, n_classes, base, base + 8 * o1, base + 8 * o2, base + 8 * o3,
-                                             base + 8 * o4, _lib.ptr(ws), ws.numel(), _lib.current_stream()))
+        with torch.cuda.device(dev):
+            ws = _Workspace.get(n_subjects)
+            base = flat.data_ptr()
+            _lib.check(_lib.lib().rcu_eval_fused(_lib.ptr(p_d), _lib.ptr(d_d), _lib.ptr(t_d), _lib.ptr(m_d), vps, n_subjects, edges_p, n_bins,
+                                                 b32_p, len(breaks), seg_p, n_classes, base, base + 8 * o1, base + 8 * o2, base + 8 * o3,
+                                                 base + 8 * o4, _lib.ptr(ws), ws.numel(), _lib.current_stream()))
     if not sync:
         return (flat[:o1].view(n_subjects, nb1), flat[o1:o2].view(n_subjects, nb1), flat[o2:o3].view(torch.float64).view(n_subjects, nb1),
                 flat[o3:o4].view(n_subjects, 4, n_classes), flat[o4:], order)
@@ -236,13 +274,15 @@ def philox_keep_scale(seed, p_drop, site_channels, slice_index0, n_slices, sampl
 
 def confusion_counts(prediction, target, n_subjects=1, sync=True):
     """tp, tn, fp, fn per subject with pymia's ConfusionMatrix semantics (== 1 / == 0 comparisons)."""
-    d_d = _to_device(prediction, torch.uint8, 'prediction')
-    t_d = _to_device(target, torch.uint8, 'target')
+    dev = _pick_device(prediction, target)
+    d_d = _to_device(prediction, torch.uint8, 'prediction', dev)
+    t_d = _to_device(target, torch.uint8, 'target', dev)
     n = d_d.numel()
     vps = n // max(n_subjects, 1)
     _check_lengths(n, vps, n_subjects, target=t_d)
-    out = torch.zeros((n_subjects, 4), dtype=torch.int64, device=d_d.device)
-    _lib.check(_lib.lib().rcu_confusion(_lib.ptr(d_d), _lib.ptr(t_d), vps, n_subjects, _lib.ptr(out), _lib.current_stream()))
+    out = torch.zeros((n_subjects, 4), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().rcu_confusion(_lib.ptr(d_d), _lib.ptr(t_d), vps, n_subjects, _lib.ptr(out), _lib.current_stream()))
     return out.cpu().numpy() if sync else out
 
 

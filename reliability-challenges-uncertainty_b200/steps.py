@@ -20,6 +20,7 @@ import weakref
 import torch
 
 from . import _lib
+from . import _torch_ext
 from .model import B200UNet, B200PostNet
 
 try:  # inside the reference tree the real protocol classes are used, so isinstance checks keep working
@@ -330,6 +331,25 @@ def summarize(multi, do_mi=False, do_var=False, emit_prediction=False, emit_fore
         if not src.is_cuda:
             raise _lib.RcuError('multi_probabilities must live on the GPU (there is no CPU fallback)')
     dev = src.device
+    ext = _torch_ext.ops() if kind == 0 else None
+    if ext is not None:
+        # torch-extension binding: one registered operator (outputs allocated inside, PyTorch's current stream)
+        if ws_logits is not None and tuple(ws_logits.shape) != (n, h, w, 2):
+            raise ValueError('ws_logits must be interleaved logits of shape {}'.format((n, h, w, 2)))
+        mean, entropy, mi, var, pred, fg, ws_out = ext.aggregate(src.contiguous(), None if ws_logits is None else ws_logits.contiguous(), bool(do_mi),
+                                                                  bool(do_var), bool(emit_prediction), bool(emit_foreground))
+        out = {'probabilities': mean, 'entropy': entropy}
+        if ws_logits is not None:
+            out['ws_probabilities'] = ws_out
+        if do_mi:
+            out['mutual_info'] = mi
+        if do_var:
+            out['variance'] = var
+        if emit_prediction:
+            out['prediction'] = pred
+        if emit_foreground:
+            out['foreground'] = fg
+        return out
     mean = torch.empty((n, 2, h, w), dtype=torch.float32, device=dev)
     entropy = torch.empty((n, 1, h, w), dtype=torch.float32, device=dev)
     mi = torch.empty((n, 1, h, w), dtype=torch.float32, device=dev) if do_mi else None

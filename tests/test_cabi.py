@@ -88,3 +88,20 @@ def test_product_package_does_not_import_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), f
                 assert '/root/reference' not in src, f
+
+
+def test_torch_extension_registers_the_operators_and_validates_like_the_abi():
+    """librcu_b200_torch.so (csrc/torch_binding.cpp): torch.ops.rcu_b200.* over the same C-ABI.  On a CPU-only box the
+    operators must load, report the ABI version and refuse host tensors with the reference's exception type."""
+    from rcu_b200 import _torch_ext
+    ops = _torch_ext.ops()
+    if ops is None:
+        pytest.skip('torch extension not built (python __graft_entry__.py builds it)')
+    assert int(ops.abi_version()) == _lib.RCU_ABI_VERSION
+    for name in ('eval_fused', 'aggregate', 'unet_forward'):
+        assert hasattr(ops, name)
+    z8 = torch.zeros(4, dtype=torch.uint8)
+    with pytest.raises(ValueError):
+        ops.eval_fused(torch.zeros(4), z8, z8, None, torch.linspace(0, 1, 11), torch.zeros(2), torch.zeros(3, dtype=torch.uint8), 1, 3, torch.zeros(8, dtype=torch.uint8))
+    with pytest.raises(ValueError):
+        ops.aggregate(torch.zeros(2, 1, 4, 4, 2), None, False, False, False, False)
