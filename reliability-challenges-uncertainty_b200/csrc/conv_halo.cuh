@@ -395,12 +395,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
             float l0 = prm.head_w[64], l1 = prm.head_w[65];
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              const float2 cf = coef[c];
-              float a = fmaf(__uint_as_float(v[c]), cf.x, cf.y);
-              a = prm.relu ? fmaxf(a, 0.0f) : a;
-              l0 = fmaf(a, prm.head_w[c], l0);
-              l1 = fmaf(a, prm.head_w[32 + c], l1);
+            for (int c = 0; c < 32; c += 2) {
+              const float4 cc = *reinterpret_cast<const float4*>(&coef[c]);   // two channels per 16-byte broadcast read
+              float a0 = fmaf(__uint_as_float(v[c]), cc.x, cc.y), a1 = fmaf(__uint_as_float(v[c + 1]), cc.z, cc.w);
+              if (prm.relu) { a0 = fmaxf(a0, 0.0f); a1 = fmaxf(a1, 0.0f); }
+              l0 = fmaf(a0, prm.head_w[c], l0);
+              l1 = fmaf(a0, prm.head_w[32 + c], l1);
+              l0 = fmaf(a1, prm.head_w[c + 1], l0);
+              l1 = fmaf(a1, prm.head_w[33 + c], l1);
             }
             lg[2 * half] = l0;
             lg[2 * half + 1] = l1;
@@ -424,7 +426,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
 #pragma unroll
             for (int c = 0; c < 32; c += 2) {
-              const float2 c0 = coef[c], c1 = coef[c + 1];
+              const float4 cc = *reinterpret_cast<const float4*>(&coef[c]);   // two channels per 16-byte broadcast read
+            const float2 c0 = make_float2(cc.x, cc.y), c1 = make_float2(cc.z, cc.w);
               float a0 = fmaf(__uint_as_float(v[c]), c0.x, c0.y);
               float a1 = fmaf(__uint_as_float(v[c + 1]), c1.x, c1.y);
               if (prm.relu) { a0 = fmaxf(a0, 0.0f); a1 = fmaxf(a1, 0.0f); }
@@ -491,12 +494,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         mbar_arrive_warp(bar_tempty + 8 * group);   // accumulator is in registers: the MMA warp may reuse the stage
         float l0 = prm.head_w[64], l1 = prm.head_w[65];
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const float2 cf = coef[c];
-          float a = fmaf(__uint_as_float(v[c]), cf.x, cf.y);
-          a = prm.relu ? fmaxf(a, 0.0f) : a;
-          l0 = fmaf(a, prm.head_w[c], l0);
-          l1 = fmaf(a, prm.head_w[32 + c], l1);
+        for (int c = 0; c < 32; c += 2) {
+          const float4 cc = *reinterpret_cast<const float4*>(&coef[c]);
+          float a0 = fmaf(__uint_as_float(v[c]), cc.x, cc.y), a1 = fmaf(__uint_as_float(v[c + 1]), cc.z, cc.w);
+          if (prm.relu) { a0 = fmaxf(a0, 0.0f); a1 = fmaxf(a1, 0.0f); }
+          l0 = fmaf(a0, prm.head_w[c], l0);
+          l1 = fmaf(a0, prm.head_w[32 + c], l1);
+          l0 = fmaf(a1, prm.head_w[c + 1], l0);
+          l1 = fmaf(a1, prm.head_w[33 + c], l1);
         }
         if (valid) {
           const int t = img / prm.chunk_slices, sl = img - t * prm.chunk_slices;
@@ -518,7 +523,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           uint32_t packed[16];
 #pragma unroll
           for (int c = 0; c < 32; c += 2) {
-            const float2 c0 = coef[cb + c], c1 = coef[cb + c + 1];
+            const float4 cc = *reinterpret_cast<const float4*>(&coef[cb + c]);   // two channels per 16-byte broadcast read
+            const float2 c0 = make_float2(cc.x, cc.y), c1 = make_float2(cc.z, cc.w);
             float a0 = fmaf(__uint_as_float(v[c]), c0.x, c0.y);
             float a1 = fmaf(__uint_as_float(v[c + 1]), c1.x, c1.y);
             if (prm.relu) { a0 = fmaxf(a0, 0.0f); a1 = fmaxf(a1, 0.0f); }

@@ -242,7 +242,8 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           uint32_t packed[16];
 #pragma unroll
           for (int c = 0; c < 32; c += 2) {
-            const float2 c0 = coef[cb + c], c1 = coef[cb + c + 1];
+            const float4 cc = *reinterpret_cast<const float4*>(&coef[cb + c]);   // two channels per 16-byte broadcast read
+            const float2 c0 = make_float2(cc.x, cc.y), c1 = make_float2(cc.z, cc.w);
             float a0 = fmaf(__uint_as_float(v[c]), c0.x, c0.y);
             float a1 = fmaf(__uint_as_float(v[c + 1]), c1.x, c1.y);
             if (prm.relu) { a0 = fmaxf(a0, 0.0f); a1 = fmaxf(a1, 0.0f); }
