@@ -69,6 +69,30 @@ def build(force=False, verbose=False):
     return LIB_PATH
 
 
+def build_variant(name, defines):
+    """A/B build of the library with extra -D switches (e.g. RCU_ARRIVE_PER_THREAD=1): build/variants/librcu_b200_<name>.so.
+    Select it at run time with RCU_B200_LIB=<path> RCU_B200_BINDING=ctypes (the torch extension links the default library)."""
+    out_dir = os.path.join(HERE, 'build', 'variants')
+    os.makedirs(out_dir, exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f not in ('--use_fast_math=false', '-v', '-Xptxas')] + ['-D' + d for d in defines]
+    objs = []
+    for src in SOURCES:
+        obj = os.path.join(out_dir, '%s_%s' % (name, src.replace('.cu', '.o')))
+        res = subprocess.run([_nvcc()] + flags + ['-c', os.path.join(CSRC, src), '-o', obj], capture_output=True, text=True)
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+            raise RuntimeError('nvcc failed on {} ({})'.format(src, name))
+        objs.append(obj)
+    lib = os.path.join(out_dir, 'librcu_b200_%s.so' % name)
+    res = subprocess.run([_nvcc(), '-shared', '-o', lib] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a', '-ldl'], capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError('link failed')
+    for o in objs:
+        os.remove(o)
+    return lib
+
+
 TORCH_EXT_PATH = os.path.join(HERE, 'librcu_b200_torch.so')
 TORCH_EXT_STAMP = os.path.join(HERE, 'build', 'librcu_b200_torch.stamp')
 

@@ -42,6 +42,9 @@ enum HaloMode { HALO_CONV64 = 0, HALO_CONV32 = 1, HALO_UP64 = 2, HALO_PAIR32 = 3
 //     di = +1 : only a_in = 0 -> a_o = 1 (dx = +1)                        -> N = 32 into columns 32..63, K = the a_in = 0 half
 // No zero blocks are multiplied (executed MACs = algorithmic MACs); per 256 output pixels and 3x3 x 32 channels the MMAs
 // read 3 x (4 x 6 KB + 4 x 5 KB) = 132 KB instead of 2 x 18 x 5 KB = 180 KB, and a 32-channel halo box has no padding.
+#ifndef RCU_UP_PAIRED
+#define RCU_UP_PAIRED 1      // A/B switch: 0 runs the up-path phases one by one (and packs their weights per phase)
+#endif
 constexpr bool halo_is_pair(int mode) { return mode == HALO_PAIR32 || mode == HALO_PAIR64; }
 constexpr int kHaloSmemBudget = 225 * 1024;
 
@@ -169,7 +172,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     for (int s = 0; s < G; ++s) {
       mbar_init(bar_tfull + 8 * s, 1);
-      mbar_init(bar_tempty + 8 * s, 4);   // one arrival per epilogue warp (mbar_arrive_warp)
+      mbar_init(bar_tempty + 8 * s, kEpilogueArrivals);   // one arrival per epilogue warp (mbar_arrive_warp)
     }
     mbar_init(bar_w, 1);
     mbar_init(bar_turn, 1);
@@ -314,6 +317,35 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               }
             };
             if (j == 0) pair_taps(0); else pair_taps(1);
+          } else if constexpr (MODE == HALO_UP64 && PH >= 2 && RCU_UP_PAIRED) {
+            // Up-path phases in x-PAIRS: the phases (a, 0) and (a, 1) read window columns {0, 1} and {1, 2} of the same
+            // rows, and their accumulators are adjacent TMEM columns.  Column 1 therefore feeds ONE N' = 2N MMA with both
+            // phases' weights stacked, columns 0 and 2 one N MMA each into their phase's accumulator: 6 MMAs per K step and
+            // row pair instead of 8, 20 % (N = 32) / 17 % (N = 64) fewer operand wavefronts.  Weight image per
+            // (phase pair, chunk, window row i2): [2N][64] both | [N][64] column 0 -> b = 0 | [N][64] column 2 -> b = 1.
+            constexpr uint32_t idesc2 = make_idesc<2 * N>();
+#pragma unroll
+            for (int pp = 0; pp < PH / 2; ++pp) {
+              const uint32_t base_a = lo_a + prm.up_base16[2 * pp];                      // phase (a, 0): window row a, column 0
+              const uint32_t wpp = lo_b0 + (uint32_t)((pp * prm.n_chunks + j) * 2) * (4u * kTile16);
+#pragma unroll
+              for (int i2 = 0; i2 < 2; ++i2) {
+                const uint32_t a_row = base_a + (uint32_t)(i2 * kHaloPitch * 8);
+                const uint32_t wt = wpp + (uint32_t)i2 * (4u * kTile16);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                  if (leader)
+                    umma_bf16(tmem_d + (uint32_t)(2 * pp * N), desc_from(a_row + 8u + 2 * ks, hi_a), desc_from(wt + 2 * ks, hi_b), idesc2,
+                              (j > 0 || i2 > 0 || ks > 0) ? 1u : 0u);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                  if (leader) umma_bf16(tmem_d + (uint32_t)(2 * pp * N), desc_from(a_row + 2 * ks, hi_a), desc_from(wt + 2u * kTile16 + 2 * ks, hi_b), idesc, 1u);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                  if (leader)
+                    umma_bf16(tmem_d + (uint32_t)((2 * pp + 1) * N), desc_from(a_row + 16u + 2 * ks, hi_a), desc_from(wt + 3u * kTile16 + 2 * ks, hi_b), idesc, 1u);
+              }
+            }
           } else {
 #pragma unroll
           for (int p = 0; p < PH; ++p) {
@@ -426,8 +458,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
 #pragma unroll
             for (int c = 0; c < 32; c += 2) {
-              const float4 cc = *reinterpret_cast<const float4*>(&coef[c]);   // two channels per 16-byte broadcast read
-            const float2 c0 = make_float2(cc.x, cc.y), c1 = make_float2(cc.z, cc.w);
+              RCU_COEF2(c);
               float a0 = fmaf(__uint_as_float(v[c]), c0.x, c0.y);
               float a1 = fmaf(__uint_as_float(v[c + 1]), c1.x, c1.y);
               if (prm.relu) { a0 = fmaxf(a0, 0.0f); a1 = fmaxf(a1, 0.0f); }
@@ -523,8 +554,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           uint32_t packed[16];
 #pragma unroll
           for (int c = 0; c < 32; c += 2) {
-            const float4 cc = *reinterpret_cast<const float4*>(&coef[cb + c]);   // two channels per 16-byte broadcast read
-            const float2 c0 = make_float2(cc.x, cc.y), c1 = make_float2(cc.z, cc.w);
+            RCU_COEF2(cb + c);
             float a0 = fmaf(__uint_as_float(v[c]), c0.x, c0.y);
             float a1 = fmaf(__uint_as_float(v[c + 1]), c1.x, c1.y);
             if (prm.relu) { a0 = fmaxf(a0, 0.0f); a1 = fmaxf(a1, 0.0f); }

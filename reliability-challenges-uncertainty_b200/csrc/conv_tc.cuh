@@ -77,9 +77,17 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // One arrival for the whole (converged) warp: every lane has finished its TMEM reads (tcgen05.wait::ld is warp-collective and
 // each lane has issued tcgen05.fence::before_thread_sync), lane 0 signals.  A per-thread arrive is 32 serialised shared-memory
 // atomics on one word per warp and tile — on the data pipe the tensor cores read their operands from.
+#ifndef RCU_ARRIVE_PER_THREAD
+#define RCU_ARRIVE_PER_THREAD 0      // A/B switch (tools/ab_variants.sh): 1 restores one arrival per epilogue thread
+#endif
+constexpr uint32_t kEpilogueArrivals = RCU_ARRIVE_PER_THREAD ? 128u : 4u;   // arrival count of the accumulator-free barriers
 __device__ __forceinline__ void mbar_arrive_warp(uint32_t bar) {
+#if RCU_ARRIVE_PER_THREAD
+  mbar_arrive(bar);
+#else
   __syncwarp();
   if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+#endif
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -155,6 +163,19 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Epilogue coefficients of two adjacent channels: one 16-byte broadcast read (the 8-byte reads the compiler emits for two
+// float2 loads cost twice the shared-memory wavefronts).  RCU_COEF_LDS64=1 restores the separate loads (A/B).
+#ifndef RCU_COEF_LDS64
+#define RCU_COEF_LDS64 0
+#endif
+#if RCU_COEF_LDS64
+#define RCU_COEF2(IDX) const float2 c0 = coef[(IDX)], c1 = coef[(IDX) + 1]
+#else
+#define RCU_COEF2(IDX)                                                      \
+  const float4 cc_ = *reinterpret_cast<const float4*>(&coef[(IDX)]);        \
+  const float2 c0 = make_float2(cc_.x, cc_.y), c1 = make_float2(cc_.z, cc_.w)
+#endif
 
 // K-major operand tile descriptor (PTX "matrix descriptor"; field layout as in cute::UMMA::SmemDescriptor):
 //   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled K-major) |

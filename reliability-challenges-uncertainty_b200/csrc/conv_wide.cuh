@@ -97,7 +97,7 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     tma_prefetch_desc(&map_a);
     for (int s = 0; s < C::kAStages; ++s) { mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, 1); }
     for (int s = 0; s < C::kWStages; ++s) { mbar_init(bar_wfull + 8 * s, 1); mbar_init(bar_wempty + 8 * s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, 4); }   // tempty: one arrival per epilogue warp (mbar_arrive_warp)
+    for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, kEpilogueArrivals); }   // tempty: one arrival per epilogue warp (mbar_arrive_warp)
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -242,8 +242,7 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           uint32_t packed[16];
 #pragma unroll
           for (int c = 0; c < 32; c += 2) {
-            const float4 cc = *reinterpret_cast<const float4*>(&coef[cb + c]);   // two channels per 16-byte broadcast read
-            const float2 c0 = make_float2(cc.x, cc.y), c1 = make_float2(cc.z, cc.w);
+            RCU_COEF2(cb + c);
             float a0 = fmaf(__uint_as_float(v[c]), c0.x, c0.y);
             float a1 = fmaf(__uint_as_float(v[c + 1]), c1.x, c1.y);
             if (prm.relu) { a0 = fmaxf(a0, 0.0f); a1 = fmaxf(a1, 0.0f); }

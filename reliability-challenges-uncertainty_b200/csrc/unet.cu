@@ -493,6 +493,41 @@ static int pack_halo_upconv(rcu_unet* net, const rcu_conv_unit& u, HaloPack& hp)
   for (int phs = 4; phs >= 2; phs >>= 1)
     if (kHaloGroups * phs * N <= 512 && (size_t)phs * hp.w_bytes + 3 * halo_chunk_stride_bytes() + 4096 <= (size_t)kHaloSmemBudget) { hp.phases_per_launch = phs; break; }
   std::vector<uint16_t> all((size_t)4 * hp.n_chunks * 4 * N * 64, 0);
+  // tap (i2, j2) of phase (a, b) reads window row a + i2, column b + j2; its weight is the sum of the 3x3 taps that
+  // nearest-x2 folds onto that low-resolution pixel (see pack_upconv_phases)
+  auto phase_weight = [&](int a, int b, int i2, int j2, int n, int ci) {
+    int ky0, ky1, kx0, kx1;
+    if (a == 0) { ky0 = i2 == 0 ? 0 : 1; ky1 = i2 == 0 ? 0 : 2; } else { ky0 = i2 == 0 ? 0 : 2; ky1 = i2 == 0 ? 1 : 2; }
+    if (b == 0) { kx0 = j2 == 0 ? 0 : 1; kx1 = j2 == 0 ? 0 : 2; } else { kx0 = j2 == 0 ? 0 : 2; kx1 = j2 == 0 ? 1 : 2; }
+    float sum = 0.0f;
+    for (int ky = ky0; ky <= ky1; ++ky)
+      for (int kx = kx0; kx <= kx1; ++kx) sum += u.weight[((size_t)n * u.c_in + ci) * 9 + ky * 3 + kx];
+    return f32_to_bf16_rn(sum);
+  };
+  if (hp.phases_per_launch >= 2 && RCU_UP_PAIRED) {
+    // x-paired layout (conv_halo.cuh, HALO_UP64 with PH >= 2): per (a, chunk, i2) a [2N][64] tile for window column 1
+    // (rows 0..N-1: phase (a, 0) tap j2 = 1, rows N..2N-1: phase (a, 1) tap j2 = 0), then [N][64] for column 0 (phase (a, 0),
+    // j2 = 0) and [N][64] for column 2 (phase (a, 1), j2 = 1).  Same bytes as the per-phase layout: 4N rows per (a, chunk, i2).
+    for (int a = 0; a < 2; ++a)
+      for (int j = 0; j < hp.n_chunks; ++j)
+        for (int i2 = 0; i2 < 2; ++i2) {
+          uint16_t* blk = all.data() + ((size_t)((a * hp.n_chunks + j) * 2 + i2)) * 4 * N * 64;
+          for (int k = 0; k < 64; ++k) {
+            const int ci = j * 64 + k;
+            for (int n = 0; n < 2 * N; ++n) blk[sw128_index(n, k)] = phase_weight(a, n / N, i2, n < N ? 1 : 0, n % N, ci);
+            for (int n = 0; n < N; ++n) {
+              blk[(size_t)2 * N * 64 + sw128_index(n, k)] = phase_weight(a, 0, i2, 0, n, ci);
+              blk[(size_t)3 * N * 64 + sw128_index(n, k)] = phase_weight(a, 1, i2, 1, n, ci);
+            }
+          }
+        }
+    uint16_t* dp;
+    int rcp = dev_upload(net, all, &dp);
+    if (rcp) return rcp;
+    for (int ph = 0; ph < 4; ++ph) hp.d_wimg[ph] = reinterpret_cast<uint8_t*>(dp) + (size_t)ph * hp.w_bytes;
+    hp.ok = true;
+    return RCU_OK;
+  }
   for (int a = 0; a < 2; ++a)
     for (int b = 0; b < 2; ++b) {
       const int ph = a * 2 + b;

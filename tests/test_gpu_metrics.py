@@ -231,3 +231,42 @@ def test_device_metrics_hook_rows():
             results_equal(row['sweep'][th][k], v, k)
         assert row['sweep'][th]['ue'] == R.ue_table_row(exp)['ue']
     assert row['dice'] == R.dice(pred, target.reshape(shape))
+
+
+def test_opt_in_joint_cell_kernel_gives_the_same_tables():
+    """RCU_HIST_CELL=1 routes rcu_eval_fused through the joint-cell kernel (one counter update per voxel; opt-in because it is
+    not faster).  The switch is read once per process, so the comparison runs in a subprocess: adversarial
+    values at every bin edge and break point, ragged size, with and without mask — tables must be identical, the float64
+    confidence sums equal to 1e-12."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import rcu_b200
+from rcu_b200 import metrics, tables
+from helpers import synth_metric_inputs
+bt = tables.uncertainty_break_table(tables.SWEEP_THRESHOLDS)
+p, target, mask, pred, _ = synth_metric_inputs(240007, 3, with_break_neighbours=bt[0])
+p[100000:100008] = [np.nan, -0.5, 1.5, np.inf, -0.0, 1.0, 0.0, np.float32(1) - np.float32(2) ** -24]
+out = []
+for m in (mask, None):
+    for n in (p.size, p.size - 3, 4 * 50000):
+        r = metrics.eval_fused(p[:n], pred[:n], target[:n], None if m is None else m[:n], n_subjects=4 if n == 200000 else 1, break_table=bt)
+        out.append(np.concatenate([r[0].ravel(), r[1].ravel(), r[3].ravel(), r[4].ravel()]).astype(np.float64))
+        out.append(np.nan_to_num(r[2].ravel(), nan=-1.0))
+np.save(sys.argv[1], np.concatenate(out))
+''' % (root, os.path.join(root, 'tests'))
+    import tempfile
+    res = {}
+    with tempfile.TemporaryDirectory() as d:
+        for name, flag in (('lut', '0'), ('cell', '1')):
+            path = os.path.join(d, name + '.npy')
+            env = dict(os.environ, RCU_HIST_CELL=flag)
+            r = subprocess.run([sys.executable, '-c', code, path], env=env, capture_output=True, text=True, timeout=600)
+            assert r.returncode == 0, r.stderr[-2000:]
+            res[name] = np.load(path)
+    assert res['lut'].shape == res['cell'].shape
+    assert np.allclose(res['lut'], res['cell'], rtol=1e-12, atol=0)
