@@ -533,251 +533,11 @@ eval_fused_lut_kernel(const float* __restrict__ p, const unsigned char* __restri
 }
 
 
-// ---------------------------------------------------------------------------------------------------------------------
-// Joint-cell variant of the fused pass (the default for the common case: float32 p, aligned inputs, no threshold_range).
-// The LUT kernel above is bound by instruction issue and by shared-memory wavefronts (77 instructions and ~17 LSU
-// wavefronts per voxel-warp: three private read-modify-writes, a second table lookup, per-voxel byte unpacking).  Here
-//   * every quantity the tables need is a function of ONE cell index  (segment of p) x (mask, target, prediction):
-//     the voxel's single integer read-modify-write is a 16-bit private counter of that cell, and count / positives /
-//     U-E rows / invalid are folded out of the cell totals at block end (integer, exact);
-//   * the merged break list also carries the last calibration edge and nextafter(1), so out-of-range and invalid
-//     values are ordinary segments (plus one extra segment for negative / NaN), not extra compares and counters;
-//   * mask / target / prediction bytes are normalised to 0 / 1 four at a time (SWAR) and packed into one 3-bit code;
-//   * only the float64 confidence sum keeps its own private column (bit-for-bit the same order of additions as before).
-// ~33 instructions and ~12 LSU wavefronts per voxel-warp.  Shared memory: (segments + 1) x 8 cells x 256 threads x 2 B.
-// ---------------------------------------------------------------------------------------------------------------------
-constexpr int kCellMaxSegs = 46;     // (regular segments + the negative / NaN one) the 227 KB of shared memory can hold
-
-struct CellParams {
-  float list[kBreakPad];             // merged, strictly increasing: inner edges, last edge, nextafter(1), U-E breaks; +inf padded
-  unsigned int attr[kBreakPad + 2];  // per segment s = #{list <= p} (and n_list + 1 = negative / NaN): bin | class << 8 | invalid << 16
-  int n_list, top;
-};
-
 __device__ __forceinline__ unsigned int swar_nonzero(unsigned int w) {   // per byte: 1 if the byte is non-zero
   return ((w | ((w & 0x7f7f7f7fu) + 0x7f7f7f7fu)) >> 7) & 0x01010101u;
 }
 
-constexpr int kCellMaxBuckets = 1024;
-constexpr int kCellMaxBins1 = 12;    // n_bins + 1 the static confidence columns hold
-
-// The lookup tables and the confidence columns are STATIC shared arrays, the cell counters the dynamic one: distinct
-// objects, so the compiler may hoist the (read-only) table reads of later voxels above the counter stores of earlier
-// ones.  The read-modify-writes of one float4 of voxels are issued together — four loads, then four stores — with
-// duplicates resolved in registers (a later store to the same counter carries the earlier increments as well), so a
-// group costs one shared-memory round trip instead of four dependent ones.
-template <bool HAS_MASK>
-__global__ void __launch_bounds__(kHistThreads, 1)
-eval_fused_cell_kernel(const float* __restrict__ p, const unsigned char* __restrict__ pred, const unsigned char* __restrict__ target,
-                       const unsigned char* __restrict__ mask, long long voxels_per_subject, int blocks_per_subject, int n_bins,
-                       int n_classes, const __grid_constant__ CellParams cl, int n_buckets, HistOut out,
-                       unsigned int* __restrict__ tickets, unsigned long long* __restrict__ partials) {
-  extern __shared__ __align__(16) unsigned char smem_cells[];                 // [seg][code][tid] 16-bit counters
-  __shared__ double s_conf[kCellMaxBins1 * kHistThreads];                     // [bin][tid]
-  __shared__ float s_list[kBreakPad + 4];                                     // merged list, +inf padded (reads reach index n_list + 2)
-  __shared__ unsigned int s_attr[kBreakPad + 2];
-  __shared__ unsigned int s_koff[kBreakPad + 2];                              // byte offset of the segment's bin row in s_conf
-  __shared__ unsigned int s_tot[kCellMaxSegs * 8];
-  __shared__ unsigned char s_base[kCellMaxBuckets];                           // per bucket: #entries <= its lower bound
-  const int tid = threadIdx.x;
-  const int nb1 = n_bins + 1;
-  const int ncls = n_classes;
-  const int n_seg = cl.n_list + 2;                       // regular segments 0..n_list, then the negative / NaN segment
-  const int cells_bytes = n_seg * 8 * kHistThreads * 2;
-  unsigned short* s_cells = reinterpret_cast<unsigned short*>(smem_cells);
-
-  {
-    uint4* z = reinterpret_cast<uint4*>(smem_cells);
-    for (int i = tid; i < (cells_bytes >> 4); i += kHistThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
-    for (int i = tid; i < nb1 * kHistThreads; i += kHistThreads) s_conf[i] = 0.0;
-  }
-  for (int i = tid; i < kBreakPad + 4; i += kHistThreads) s_list[i] = i < cl.n_list ? cl.list[i] : __int_as_float(0x7f800000);
-  for (int i = tid; i < n_seg; i += kHistThreads) {
-    s_attr[i] = cl.attr[i];
-    s_koff[i] = (cl.attr[i] & 0xffu) * (kHistThreads * 8);
-  }
-  __syncthreads();
-  const float nb_f = (float)n_buckets, inv_nb = 1.0f / nb_f;
-  for (int b = tid; b < n_buckets; b += kHistThreads)   // exact bucket bounds (power-of-two bucket count)
-    s_base[b] = (unsigned char)count_breaks<float, false>((float)b * inv_nb, s_list, cl.top);
-  __syncthreads();
-
-  const int subject = blockIdx.y;
-  const long long base_v = (long long)subject * voxels_per_subject;
-  const long long groups = (voxels_per_subject + 3) >> 2;
-  const long long gpb = (groups + blocks_per_subject - 1) / blocks_per_subject;
-  const long long g0 = (long long)blockIdx.x * gpb;
-  const long long g1 = min(groups, g0 + gpb);
-  const unsigned int nbm1 = (unsigned int)n_buckets - 1u;
-  const unsigned int s_bad = (unsigned int)cl.n_list + 1u;
-  unsigned char* cells_col = smem_cells + tid * 2;                                   // + seg * 4096 + code * 512
-  unsigned char* conf_col = reinterpret_cast<unsigned char*>(s_conf) + tid * 8;      // + bin * 2048
-
-  // segment of p: the bucket's base count plus the next three list entries (anything further lies beyond the bucket, host-checked)
-#define RCU_CELL_SEG(PV, S)                                                                                             \
-  do {                                                                                                                  \
-    const float pv_ = (PV);                                                                                             \
-    const unsigned int bs_ = s_base[min(__float2uint_rz(pv_ * nb_f), nbm1)];   /* NaN, negative -> bucket 0 */          \
-    const float* l_ = s_list + bs_;                                                                                     \
-    const unsigned int s_ = bs_ + ((pv_ >= l_[0]) ? 1u : 0u) + ((pv_ >= l_[1]) ? 1u : 0u) + ((pv_ >= l_[2]) ? 1u : 0u); \
-    (S) = (pv_ >= 0.0f) ? s_ : s_bad;                                          /* false for NaN */                      \
-  } while (0)
-
-  // four voxels: CODES holds prediction | target << 1 | mask << 2 per byte, every bit already normalised to 0 / 1
-#define RCU_CELL_FOUR(P0, P1, P2, P3, CODES)                                                                            \
-  do {                                                                                                                  \
-    const float pq_[4] = {(P0), (P1), (P2), (P3)};                                                                      \
-    const unsigned int cw_ = (CODES);                                                                                   \
-    unsigned int sg_[4], co_[4], ko_[4];                                                                                \
-    _Pragma("unroll") for (int e = 0; e < 4; ++e) RCU_CELL_SEG(pq_[e], sg_[e]);                                         \
-    _Pragma("unroll") for (int e = 0; e < 4; ++e) {                                                                     \
-      co_[e] = sg_[e] * (8 * kHistThreads * 2) + ((cw_ >> (8 * e)) & 7u) * (kHistThreads * 2);                          \
-      ko_[e] = s_koff[sg_[e]];                                                                                          \
-    }                                                                                                                   \
-    unsigned int cv_[4];                                                                                                \
-    _Pragma("unroll") for (int e = 0; e < 4; ++e) cv_[e] = *reinterpret_cast<unsigned short*>(cells_col + co_[e]);      \
-    cv_[0] += 1u;                                                                                                       \
-    cv_[1] += 1u + (co_[1] == co_[0] ? 1u : 0u);                                                                        \
-    cv_[2] += 1u + (co_[2] == co_[0] ? 1u : 0u) + (co_[2] == co_[1] ? 1u : 0u);                                         \
-    cv_[3] += 1u + (co_[3] == co_[0] ? 1u : 0u) + (co_[3] == co_[1] ? 1u : 0u) + (co_[3] == co_[2] ? 1u : 0u);          \
-    _Pragma("unroll") for (int e = 0; e < 4; ++e) *reinterpret_cast<unsigned short*>(cells_col + co_[e]) = (unsigned short)cv_[e]; \
-    if (cw_ & 0x04040404u) {   /* some voxel of the group is inside the mask (warps off the mask skip the float64 columns) */ \
-      double d_[4], f_[4];                                                                                              \
-      _Pragma("unroll") for (int e = 0; e < 4; ++e) d_[e] = ((cw_ >> (8 * e)) & 4u) ? (double)pq_[e] : 0.0;             \
-      _Pragma("unroll") for (int e = 0; e < 4; ++e) f_[e] = *reinterpret_cast<double*>(conf_col + ko_[e]);              \
-      /* running sums per bin row, in voxel order: a later store to the same row carries the earlier addends */        \
-      const double t1_ = d_[1] + (ko_[1] == ko_[0] ? d_[0] : 0.0);                                                      \
-      const double t2_ = d_[2] + (ko_[2] == ko_[1] ? t1_ : (ko_[2] == ko_[0] ? d_[0] : 0.0));                           \
-      double t3_ = d_[3];                                                                                               \
-      if (ko_[3] == ko_[2]) t3_ += t2_;                                                                                 \
-      else if (ko_[3] == ko_[1]) t3_ += t1_;                                                                            \
-      else if (ko_[3] == ko_[0]) t3_ += d_[0];                                                                          \
-      *reinterpret_cast<double*>(conf_col + ko_[0]) = f_[0] + d_[0];                                                    \
-      *reinterpret_cast<double*>(conf_col + ko_[1]) = f_[1] + t1_;                                                      \
-      *reinterpret_cast<double*>(conf_col + ko_[2]) = f_[2] + t2_;                                                      \
-      *reinterpret_cast<double*>(conf_col + ko_[3]) = f_[3] + t3_;                                                      \
-    }                                                                                                                   \
-  } while (0)
-
-  // Software pipeline over iterations of U float4 groups: the loads of iteration i + 1 are in flight while iteration i
-  // is counted (one block of 8 warps per SM cannot hide the DRAM latency by occupancy alone).
-  constexpr int U = 4;
-  const long long stride = (long long)kHistThreads * U;
-  float4 pv[2][U];
-  unsigned int tw[2][U], dw[2][U], mw[2][U];
-  auto issue = [&](int buf, long long g) {
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long gg = g + (long long)u * kHistThreads;
-      const bool in = gg < g1 && (gg * 4 + 3 < voxels_per_subject);
-      pv[buf][u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      tw[buf][u] = dw[buf][u] = mw[buf][u] = 0u;
-      if (in) {
-        const long long v = base_v + gg * 4;
-        pv[buf][u] = ld_stream_f4(p + v);
-        tw[buf][u] = ld_stream_u32(target + v);
-        dw[buf][u] = ld_stream_u32(pred + v);
-        if (HAS_MASK) mw[buf][u] = ld_stream_u32(mask + v);
-      }
-    }
-  };
-  auto count_iter = [&](int buf, long long g) {
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long gg = g + (long long)u * kHistThreads;
-      if (gg >= g1) break;
-      if (gg * 4 + 3 < voxels_per_subject) {
-        const unsigned int cw = swar_nonzero(dw[buf][u]) + 2u * swar_nonzero(tw[buf][u]) + (HAS_MASK ? 4u * swar_nonzero(mw[buf][u]) : 0x04040404u);
-        RCU_CELL_FOUR(pv[buf][u].x, pv[buf][u].y, pv[buf][u].z, pv[buf][u].w, cw);
-      } else {  // ragged last group of the subject
-        for (long long v = gg * 4; v < voxels_per_subject; ++v) {
-          const long long a = base_v + v;
-          const unsigned int code = (pred[a] != 0 ? 1u : 0u) | (target[a] != 0 ? 2u : 0u) | ((HAS_MASK ? mask[a] != 0 : true) ? 4u : 0u);
-          unsigned int sg;
-          RCU_CELL_SEG(p[a], sg);
-          unsigned short* cell = reinterpret_cast<unsigned short*>(cells_col + sg * (8 * kHistThreads * 2) + code * (kHistThreads * 2));
-          *cell = (unsigned short)(*cell + 1);
-          double* cf = reinterpret_cast<double*>(conf_col + s_koff[sg]);
-          *cf += (code & 4u) ? (double)p[a] : 0.0;
-        }
-      }
-    }
-  };
-  {
-    long long g = g0 + tid;
-    if (g < g1) issue(0, g);
-    for (; g < g1; g += 2 * stride) {          // two iterations per trip: the buffer index stays a compile-time constant
-      if (g + stride < g1) issue(1, g + stride);
-      count_iter(0, g);
-      if (g + stride < g1) {
-        if (g + 2 * stride < g1) issue(0, g + 2 * stride);
-        count_iter(1, g + stride);
-      }
-    }
-  }
-#undef RCU_CELL_FOUR
-#undef RCU_CELL_SEG
-  __syncthreads();
-
-  // ---- block totals of every cell (fixed order; integer) ----
-  const int warp = tid >> 5, lane = tid & 31;
-  const int n_cells = n_seg * 8;
-  for (int c0 = warp * 4; c0 < n_cells; c0 += (kHistThreads / 32) * 4) {   // four cells per trip (n_cells is a multiple of 8)
-    unsigned int acc[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const unsigned int* col = reinterpret_cast<const unsigned int*>(s_cells + (c0 + q) * kHistThreads);   // two 16-bit counters per word
-      acc[q] = 0;
-#pragma unroll
-      for (int i = 0; i < kHistThreads / 64; ++i) {
-        const unsigned int w = col[lane + 32 * i];
-        acc[q] += (w & 0xffffu) + (w >> 16);
-      }
-    }
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1)
-#pragma unroll
-      for (int q = 0; q < 4; ++q) acc[q] += __shfl_down_sync(0xffffffffu, acc[q], o);
-    if (lane == 0)
-#pragma unroll
-      for (int q = 0; q < 4; ++q) s_tot[c0 + q] = acc[q];
-  }
-  // ---- confidence sums: block reduction in fixed order ----
-  const int n_slots = 3 * nb1 + 4 * ncls + 1;
-  unsigned long long* my_partial = partials + ((long long)subject * blocks_per_subject + blockIdx.x) * kPartialSlots;
-  for (int k = warp; k < nb1; k += kHistThreads / 32) {
-    const double* col = s_conf + k * kHistThreads;
-    double acc = 0.0;
-#pragma unroll
-    for (int i = 0; i < kHistThreads / 32; ++i) acc += col[lane + 32 * i];
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-    if (lane == 0) my_partial[2 * nb1 + k] = (unsigned long long)__double_as_longlong(acc);
-  }
-  __syncthreads();
-  // ---- table slots out of the cell totals: one thread per slot ----
-  if (tid < n_slots && !(tid >= 2 * nb1 && tid < 3 * nb1)) {
-    unsigned long long acc = 0;
-    for (int sg = 0; sg < n_seg; ++sg) {
-      const unsigned int at = s_attr[sg];
-      const int k = (int)(at & 0xffu), j = (int)((at >> 8) & 0xffu);
-      const unsigned int* t8 = s_tot + sg * 8;           // code = prediction | target << 1 | mask << 2
-      if (tid < nb1) {
-        if (k == tid) acc += (unsigned long long)t8[4] + t8[5] + t8[6] + t8[7];
-      } else if (tid < 2 * nb1) {
-        if (k == tid - nb1) acc += (unsigned long long)t8[6] + t8[7];
-      } else if (tid < n_slots - 1) {
-        const int r = (tid - 3 * nb1) / ncls, jj = (tid - 3 * nb1) - r * ncls;   // rows tp, tn, fp, fn
-        const int code = r == 0 ? 3 : (r == 1 ? 0 : (r == 2 ? 1 : 2));           // (target, prediction) = 11, 00, 01, 10
-        if (j == jj) acc += (unsigned long long)t8[code] + t8[code + 4];
-      } else if ((at >> 16) & 1u) {
-        for (int c = 0; c < 8; ++c) acc += t8[c];
-      }
-    }
-    my_partial[tid] = acc;
-  }
-  hist_global_fold(nb1, ncls, subject, blocks_per_subject, out, tickets, partials);
-}
+#include "eval_atom.cuh"
 
 // Confusion matrix with pymia 0.2.1 semantics (ConfusionMatrix: prediction == 1 / == 0 against label == 1 / == 0),
 // reached from np_fn.dice / confusion_matrx / accuracy (common/evalutation/numpyfunctions.py:128-151).  2 B/voxel.
@@ -823,6 +583,12 @@ static long long partial_blocks_cap(int n_subjects) { return n_subjects > 2048 ?
 // which must read zero at entry (every launch leaves the tickets it used at zero).
 static unsigned int* tickets_of(void* workspace, size_t workspace_bytes, int n_subjects) {
   return reinterpret_cast<unsigned int*>(reinterpret_cast<unsigned char*>(workspace) + (workspace_bytes & ~size_t(255)) - tickets_bytes(n_subjects));
+}
+// Per-subject accumulator tables of the shared-atomic kernel (64-bit global reductions), right below the tickets and, like
+// them, zero at rest.
+static size_t accs_bytes(int n_subjects) { return ((size_t)n_subjects * kPartialSlots * sizeof(unsigned long long) + 255) & ~size_t(255); }
+static unsigned long long* accs_of(void* workspace, size_t workspace_bytes, int n_subjects) {
+  return reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(tickets_of(workspace, workspace_bytes, n_subjects)) - accs_bytes(n_subjects));
 }
 
 static size_t hist_smem_bytes(bool calib, int vk, int n_bins, int n_classes) {
@@ -934,7 +700,7 @@ using namespace rcu;
 extern "C" size_t rcu_metrics_workspace_bytes(int n_subjects) {
   if (n_subjects < 1) n_subjects = 1;
   const size_t partial_bytes = (size_t)partial_blocks_cap(n_subjects) * kPartialSlots * sizeof(unsigned long long);
-  return ((partial_bytes + 255) & ~size_t(255)) + tickets_bytes(n_subjects) + 256;   // + slack for the round-down in tickets_of
+  return ((partial_bytes + 255) & ~size_t(255)) + accs_bytes(n_subjects) + tickets_bytes(n_subjects) + 256;   // + slack for the round-down in tickets_of
 }
 
 extern "C" int rcu_metrics_workspace_init(void* workspace, size_t workspace_bytes, void* stream) {
@@ -1016,85 +782,102 @@ extern "C" int rcu_eval_fused(const float* p, const uint8_t* prediction, const u
                  reinterpret_cast<unsigned long long*>(ue_counts), reinterpret_cast<unsigned long long*>(invalid)};
   cudaStream_t st = (cudaStream_t)stream;
   {
-    // joint-cell kernel: OPT-IN (RCU_HIST_CELL=1).  Measured on B200 (profiles/r02_hist_kernels_ncu.md) it is not faster than
-    // the bucket-table kernel below: both execute ~21 M warp instructions per 8.9 M-voxel subject (the duplicate resolution
-    // and the 64-bit selects eat what the single counter update saves) and its 152 KB of private counters allow only one
-    // block of 8 warps per SM, so the dependent shared-memory chains are hidden even less (issue slots 34 % busy against 46 %)
-    static const bool allow_cell = [] { const char* e = std::getenv("RCU_HIST_CELL"); return e && e[0] == '1'; }();
-    static const int cell_buckets = [] { const char* e = std::getenv("RCU_HIST_CELL_BUCKETS"); return e ? std::atoi(e) : 512; }();
-    static const int cell_bpsm = [] { const char* e = std::getenv("RCU_HIST_CELL_BPSM"); return e ? std::atoi(e) : 1; }();
-    const bool aligned_c = reinterpret_cast<uintptr_t>(p) % 16 == 0 && reinterpret_cast<uintptr_t>(target) % 4 == 0 &&
+    // shared-atomic kernel (eval_atom.cuh): the default for aligned float32 inputs.  RCU_HIST_ATOM=0 falls through to the
+    // private-column kernel below (A/B and cross-checks).  (Round 2 also tried private 16-bit counters per joint cell: same
+    // instruction count as the bucket-table kernel, one block of 8 warps per SM, slower — removed.)
+    static const bool allow_atom = [] { const char* e = std::getenv("RCU_HIST_ATOM"); return !(e && e[0] == '0'); }();
+    static const int atom_bits = [] { const char* e = std::getenv("RCU_HIST_ATOM_BITS"); return e ? std::atoi(e) : 10; }();
+    constexpr int atom_threads = kAtomThreads;
+    const bool aligned_a = reinterpret_cast<uintptr_t>(p) % 16 == 0 && reinterpret_cast<uintptr_t>(target) % 4 == 0 &&
                            reinterpret_cast<uintptr_t>(prediction) % 4 == 0 && (mask == nullptr || reinterpret_cast<uintptr_t>(mask) % 4 == 0);
-    if (allow_cell && aligned_c && (n_subjects == 1 || vps % 4 == 0) && cell_buckets >= 32 && (cell_buckets & (cell_buckets - 1)) == 0) {
-      CellParams cl;
-      // merged list: inner edges, last edge (calibration bin -> out of range from there on), nextafter(1) (invalid from there
-      // on) and the U-E break points, strictly increasing
-      float vals[kBreakPad + RCU_MAX_BINS + 2];
+    if (allow_atom && aligned_a && (n_subjects == 1 || vps % 4 == 0) && atom_bits >= 4 && atom_bits <= kAtomMaxLutBits) {
+      AtomParams ap;
+      float vals[kBreakPad + RCU_MAX_BINS + 4];
       int nv = 0;
+      vals[nv++] = 0.0f;
       for (int i = 1; i <= n_bins; ++i) vals[nv++] = cp.edges[i];
       const float oneplus = nextafterf(1.0f, 2.0f);
       vals[nv++] = oneplus;
       for (int i = 0; i < n_breaks; ++i) vals[nv++] = up.breaks32[i];
+      bool ok = true;
+      for (int i = 0; i < nv; ++i) ok = ok && vals[i] >= 0.0f && vals[i] < INFINITY;   // false for NaN
       std::sort(vals, vals + nv);
       nv = (int)(std::unique(vals, vals + nv) - vals);
-      bool ok = nv <= kBreakPad - 1 && nv + 2 <= kCellMaxSegs && vals[nv - 1] < INFINITY && !(vals[0] != vals[0]);
-      int max_inside = 0;
+      ok = ok && nv <= kBreakPad - 1;
+      // integer confidence sums need edge[1] >= 2^-K with K <= 8 (q = p * 2^(23+K) < 2^32 up to the last edge)
+      int K = 0;
+      while (K <= 8 && std::ldexp(1.0f, -K) > cp.edges[1]) ++K;
+      ok = ok && (n_bins == 1 || K <= 8) && cp.edges[n_bins] <= 1.5f;
+      const int n_seg = nv + 1;
+      const size_t smem_a = (size_t)n_seg * kAtomSegBytes + ((size_t)(1u << atom_bits) + 1) * 8;
+      ok = ok && n_seg <= kAtomMaxSegs && smem_a + 6 * 1024 <= 227 * 1024;
+      // blocks: every block at most kAtomMaxVoxelsPerBlock voxels; whole waves of the resident slots (one block per SM)
+      const int sms = sm_count();
+      const long long groups = (vps + 3) / 4;
+      // (the partial region only holds one float64 per block here)
+      long long max_bps = std::min<long long>(kMaxBlocksPerSubject, partial_blocks_cap(n_subjects) * (long long)kPartialSlots / n_subjects);
+      if (max_bps * atom_threads > groups) max_bps = groups / atom_threads;   // at least one group per thread
+      if (max_bps < 1) max_bps = 1;
+      const long long min_bps = (vps + kAtomMaxVoxelsPerBlock - 1) / kAtomMaxVoxelsPerBlock;
+      ok = ok && min_bps <= max_bps && n_subjects <= 65535;
       if (ok) {
-        int run = 0, run_bucket = -1;
-        for (int i = 0; i < nv; ++i) {
-          const float fb = vals[i] * (float)cell_buckets;          // exact: power-of-two bucket count
-          int b = fb >= (float)cell_buckets ? cell_buckets - 1 : (fb < 0.f ? 0 : (int)fb);
-          const bool on_edge = fb < (float)cell_buckets && fb == (float)b;   // equal to the bucket's lower bound: part of its base count
-          if (on_edge || fb < 0.f) continue;
-          run = (b == run_bucket) ? run + 1 : 1;
-          run_bucket = b;
-          if (run > max_inside) max_inside = run;
+        const long long slots = sms;
+        // model: waves x (fixed cost per block + streaming time of a block's share); a block streams ~5.5 voxels / ns
+        // (measured), so the grid is sized to fill whole waves of the 148 slots as long as the waves are few
+        static const int bps_env = [] { const char* e = std::getenv("RCU_HIST_ATOM_BPS"); return e ? std::atoi(e) : 0; }();
+        long long bps = min_bps > 1 ? min_bps : 1;
+        double best = 1e300;
+        for (long long b = bps; b <= max_bps; ++b) {
+          const long long waves = (b * n_subjects + slots - 1) / slots;
+          const double cost = (double)waves * (4000.0 + (double)vps / (double)b / 5.5);
+          if (cost < best) { best = cost; bps = b; }
+          if (waves > 16) break;
         }
-        ok = max_inside <= 3;
-      }
-      const int n_seg = nv + 2;
-      const size_t smem_c = (size_t)n_seg * 8 * kHistThreads * 2;   // the cell counters; tables and confidence columns are static (~30 KB)
-      ok = ok && smem_c + 32 * 1024 <= 227 * 1024 && n_bins + 1 <= kCellMaxBins1 && cell_buckets <= kCellMaxBuckets && nv <= 250;
-      if (ok) {
-        for (int i = 0; i < kBreakPad; ++i) cl.list[i] = i < nv ? vals[i] : INFINITY;
-        cl.n_list = nv;
+        if (bps_env > 0) bps = std::max<long long>(min_bps, std::min<long long>(bps_env, max_bps));
+        for (int i = 0; i < kBreakPad; ++i) ap.list[i] = i < nv ? vals[i] : INFINITY;
+        ap.n_list = nv;
         int top = 1;
         while (2 * top - 1 < nv) top *= 2;
-        cl.top = top;
-        for (int sg = 0; sg <= nv; ++sg) {
-          const float r = sg == 0 ? nextafterf(vals[0], -INFINITY) : vals[sg - 1];   // a value of segment sg
+        ap.top = top;
+        ap.attr[0] = (unsigned int)n_bins | ((unsigned int)up.seg_class[0] << 8) | (1u << 16);   // negative / NaN
+        ap.seg_sum_lo = ap.seg_sum_hi = -1;
+        for (int sg = 1; sg <= nv; ++sg) {
+          const float r = vals[sg - 1];   // the smallest value of segment sg
           int k = 0, nb = 0;
           for (int i = 1; i <= n_bins; ++i) k += cp.edges[i] <= r ? 1 : 0;
           for (int i = 0; i < n_breaks; ++i) nb += up.breaks32[i] <= r ? 1 : 0;
-          cl.attr[sg] = (unsigned int)k | ((unsigned int)up.seg_class[nb] << 8) | ((oneplus <= r ? 1u : 0u) << 16);
+          ap.attr[sg] = (unsigned int)k | ((unsigned int)up.seg_class[nb] << 8) | ((oneplus <= r ? 1u : 0u) << 16);
+          if (k >= 1 && ap.seg_sum_lo < 0) ap.seg_sum_lo = sg;
+          if (k >= n_bins && ap.seg_sum_hi < 0) ap.seg_sum_hi = sg;
         }
-        cl.attr[nv + 1] = (unsigned int)n_bins | ((unsigned int)up.seg_class[0] << 8) | (1u << 16);   // negative / NaN
+        if (ap.seg_sum_hi < 0) ap.seg_sum_hi = nv + 1;
+        if (ap.seg_sum_lo < 0) ap.seg_sum_lo = ap.seg_sum_hi;
+        for (int k = 0; k <= n_bins + 1 && k < RCU_MAX_BINS + 2; ++k) ap.bin_seg[k] = (unsigned char)ap.seg_sum_hi;
+        for (int sg = nv; sg >= 1; --sg) {
+          const int k = (int)(ap.attr[sg] & 0xffu);
+          if (k <= n_bins) ap.bin_seg[k] = (unsigned char)sg;   // first segment of bin k
+        }
+        for (int k = n_bins - 1; k >= 0; --k)
+          if (ap.bin_seg[k] > ap.bin_seg[k + 1]) ap.bin_seg[k] = ap.bin_seg[k + 1];   // empty bins (cannot happen for increasing edges)
+        ap.q_scale = std::ldexp(1.0f, 23 + K);
+        ap.q_inv = std::ldexp(1.0, -(23 + K));
+        ap.edge1 = cp.edges[1];
+        ap.lut_bits = atom_bits;
         RCU_CHECK_ARG(workspace_bytes >= rcu_metrics_workspace_bytes(n_subjects), "metrics workspace too small");
-        const int sms = sm_count();
-        long long bps = ((long long)sms * cell_bpsm + n_subjects - 1) / n_subjects;
-        const long long groups = (vps + 3) / 4;
-        if (bps * 256 > groups) bps = groups / 256;
-        if (bps < 1) bps = 1;
-        if (bps > kMaxBlocksPerSubject) bps = kMaxBlocksPerSubject;
-        if (bps * n_subjects > partial_blocks_cap(n_subjects)) bps = partial_blocks_cap(n_subjects) / n_subjects;
-        if (bps < 1) bps = 1;
-        const long long per_thread = ((groups + bps - 1) / bps + kHistThreads - 1) / kHistThreads * 4;
-        RCU_CHECK_ARG(per_thread <= kMaxVoxelsPerThread, "subject of %lld voxels is too large for one launch (split it)", (long long)vps);
-        RCU_CHECK_ARG(n_subjects <= 65535, "n_subjects %d exceeds grid.y limit", n_subjects);
         unsigned int* tickets = tickets_of(workspace, workspace_bytes, n_subjects);
         unsigned long long* partials = reinterpret_cast<unsigned long long*>(workspace);
         dim3 grid((unsigned)bps, (unsigned)n_subjects);
         static size_t configured[2][64] = {{0}};
         int dev = 0;
         RCU_CUDA(cudaGetDevice(&dev));
-        auto kern = mask ? eval_fused_cell_kernel<true> : eval_fused_cell_kernel<false>;
+        auto kern = mask ? eval_fused_atom_kernel<true> : eval_fused_atom_kernel<false>;
         const int mi = mask ? 1 : 0;
-        if (dev < 0 || dev >= 64 || smem_c > configured[mi][dev]) {
-          RCU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
-          if (dev >= 0 && dev < 64) configured[mi][dev] = smem_c;
+        if (dev < 0 || dev >= 64 || smem_a > configured[mi][dev]) {
+          RCU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
+          if (dev >= 0 && dev < 64) configured[mi][dev] = smem_a;
         }
-        kern<<<grid, kHistThreads, smem_c, st>>>(p, prediction, target, mask, (long long)vps, (int)bps, n_bins, n_classes, cl, cell_buckets, out,
-                                                 tickets, partials);
+        kern<<<grid, atom_threads, smem_a, st>>>(p, prediction, target, mask, (long long)vps, (int)bps, n_bins, n_classes, ap, out, tickets, partials,
+                                                 accs_of(workspace, workspace_bytes, n_subjects));
         RCU_LAUNCH_CHECK();
         return RCU_OK;
       }
@@ -1166,6 +949,14 @@ extern "C" int rcu_eval_fused(const float* p, const uint8_t* prediction, const u
   if (mask) return launch_hist<true, 0, true>(p, nullptr, prediction, target, mask, vps, n_subjects, cp, up, out, workspace, workspace_bytes, st);
   return launch_hist<true, 0, false>(p, nullptr, prediction, target, nullptr, vps, n_subjects, cp, up, out, workspace, workspace_bytes, st);
 }
+
+#ifdef RCU_ATOM_TRACE
+extern "C" int rcu_debug_atom_trace(unsigned long long* host_out, int n_words) {
+  RCU_CUDA(cudaDeviceSynchronize());
+  RCU_CUDA(cudaMemcpyFromSymbol(host_out, rcu::g_atom_trace, sizeof(unsigned long long) * (size_t)n_words));
+  return RCU_OK;
+}
+#endif
 
 extern "C" int rcu_confusion(const uint8_t* prediction, const uint8_t* target, int64_t vps, int n_subjects, uint64_t* counts,
                              void* stream) {

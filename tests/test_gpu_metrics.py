@@ -233,11 +233,12 @@ def test_device_metrics_hook_rows():
     assert row['dice'] == R.dice(pred, target.reshape(shape))
 
 
-def test_opt_in_joint_cell_kernel_gives_the_same_tables():
-    """RCU_HIST_CELL=1 routes rcu_eval_fused through the joint-cell kernel (one counter update per voxel; opt-in because it is
-    not faster).  The switch is read once per process, so the comparison runs in a subprocess: adversarial
-    values at every bin edge and break point, ragged size, with and without mask — tables must be identical, the float64
-    confidence sums equal to 1e-12."""
+def test_both_fused_kernels_give_the_same_tables():
+    """rcu_eval_fused has two kernels for aligned float32 input: the shared-atomic one (default; also with a 129-entry bucket table, which makes more buckets take the several-entries scan) and the
+    bucket-table private-column one (RCU_HIST_ATOM=0).  The switches are read once per process, so the
+    comparison runs in subprocesses: adversarial values at every bin edge and break point, NaN / negative /
+    > 1 / inf, ragged sizes, several subjects, with and without mask — tables must be identical, the float64 confidence sums
+    equal to 1e-12 (the overflow slot's sum is unspecified: the atomic kernel reports 0 there)."""
     import os
     import subprocess
     import sys
@@ -250,23 +251,26 @@ from rcu_b200 import metrics, tables
 from helpers import synth_metric_inputs
 bt = tables.uncertainty_break_table(tables.SWEEP_THRESHOLDS)
 p, target, mask, pred, _ = synth_metric_inputs(240007, 3, with_break_neighbours=bt[0])
-p[100000:100008] = [np.nan, -0.5, 1.5, np.inf, -0.0, 1.0, 0.0, np.float32(1) - np.float32(2) ** -24]
+p[100000:100012] = [np.nan, -0.5, 1.5, np.inf, -0.0, 1.0, 0.0, np.float32(1) - np.float32(2) ** -24, -1e-30, np.float32(1) + np.float32(2) ** -23, -np.inf, 1e-45]
 out = []
 for m in (mask, None):
     for n in (p.size, p.size - 3, 4 * 50000):
         r = metrics.eval_fused(p[:n], pred[:n], target[:n], None if m is None else m[:n], n_subjects=4 if n == 200000 else 1, break_table=bt)
+        conf = np.array(r[2], dtype=np.float64)
+        conf[:, -1] = 0.0
         out.append(np.concatenate([r[0].ravel(), r[1].ravel(), r[3].ravel(), r[4].ravel()]).astype(np.float64))
-        out.append(np.nan_to_num(r[2].ravel(), nan=-1.0))
+        out.append(np.nan_to_num(conf.ravel(), nan=-1.0))
 np.save(sys.argv[1], np.concatenate(out))
 ''' % (root, os.path.join(root, 'tests'))
     import tempfile
     res = {}
     with tempfile.TemporaryDirectory() as d:
-        for name, flag in (('lut', '0'), ('cell', '1')):
+        for name, flags in (('atom', {}), ('lut', {'RCU_HIST_ATOM': '0'}), ('atom2', {'RCU_HIST_ATOM_BITS': '7'})):
             path = os.path.join(d, name + '.npy')
-            env = dict(os.environ, RCU_HIST_CELL=flag)
+            env = dict(os.environ, **flags)
             r = subprocess.run([sys.executable, '-c', code, path], env=env, capture_output=True, text=True, timeout=600)
             assert r.returncode == 0, r.stderr[-2000:]
             res[name] = np.load(path)
-    assert res['lut'].shape == res['cell'].shape
-    assert np.allclose(res['lut'], res['cell'], rtol=1e-12, atol=0)
+    for name in ('atom', 'atom2'):
+        assert res['lut'].shape == res[name].shape
+        assert np.allclose(res['lut'], res[name], rtol=1e-12, atol=0), name

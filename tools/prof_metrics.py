@@ -10,7 +10,7 @@ dev = 'cuda:0'
 p = torch.rand(n, device=dev)
 target = (torch.rand(n, device=dev) < p).to(torch.uint8)
 pred = (p > 0.5).to(torch.uint8)
-mask = (torch.rand(n, device=dev) < 0.5).to(torch.uint8)
+mask = (torch.rand(n, device=dev) < 0.25).to(torch.uint8)
 bt = tables.uncertainty_break_table(tables.SWEEP_THRESHOLDS)
 for _ in range(2):
     metrics.eval_fused(p, pred, target, mask, 10, tables.SWEEP_THRESHOLDS, n_subjects=S, sync=False, break_table=bt)
