@@ -35,7 +35,7 @@
 #pragma once
 
 constexpr int kAtomThreads = 1024;                        // one block of 32 warps per SM
-constexpr int kAtomMaxLutBits = 12;
+constexpr int kAtomMaxLutBits = 10;                      // at most 1025 buckets: two per thread
 constexpr int kAtomSegBytes = 3072;                       // [word: count, W, H][code][lane] x 4 B
 constexpr int kAtomMaxSegs = 68;
 constexpr long long kAtomMaxVoxelsPerBlock = 1ll << 20;   // < 65536 values per (cell, lane) column with margin
@@ -59,9 +59,11 @@ __device__ __forceinline__ unsigned long long atom_now() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-#define ATOM_TRACE(I) do { if (threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.x < 2048) g_atom_trace[blockIdx.x * 8 + (I)] = atom_now(); } while (0)
+#define ATOM_TRACE(I) do { if (threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.x < 2040) g_atom_trace[blockIdx.x * 8 + (I)] = atom_now(); } while (0)
+#define ATOM_CLK(I) do { if (threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.x == 0) g_atom_trace[2040 * 8 + (I)] = (unsigned long long)clock64(); } while (0)
 #else
 #define ATOM_TRACE(I) do { } while (0)
+#define ATOM_CLK(I) do { } while (0)
 #endif
 
 __device__ __forceinline__ unsigned int atom_bucket(float p_sat, int sh) {
@@ -82,9 +84,11 @@ eval_fused_atom_kernel(const float* __restrict__ p, const unsigned char* __restr
   __shared__ unsigned int s_slot[kPartialSlots];                 // this block's integer table slots
   __shared__ unsigned long long s_segq[kAtomMaxSegs];            // this block's sum(q) per segment (masked-in codes)
   __shared__ double s_red[32];
+  __shared__ int s_binseg[RCU_MAX_BINS + 2];
   __shared__ int s_is_last;
   const int tid = threadIdx.x;
   ATOM_TRACE(0);
+  ATOM_CLK(0);
   const int warp = tid >> 5, lane = tid & 31;
   const int nb1 = n_bins + 1;
   const int ncls = n_classes;
@@ -125,16 +129,27 @@ eval_fused_atom_kernel(const float* __restrict__ p, const unsigned char* __restr
   };
   load(0, pa, ta, da, ma);
   load(1, pb, tb, db, mb);
+  ATOM_CLK(1);
 
   {
     uint4* z = reinterpret_cast<uint4*>(smem_atom);
     for (int i = tid; i < n_seg * (kAtomSegBytes / 16); i += kAtomThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
   }
-  for (int i = tid; i < kBreakPad + 4; i += kAtomThreads) s_list[i] = i < ap.n_list ? ap.list[i] : __int_as_float(0x7f800000);
-  for (int i = tid; i < kBreakPad; i += kAtomThreads) s_bidx[i] = i < ap.n_list ? atom_bucket(__saturatef(ap.list[i]), sh) : 0xffffffffu;
-  for (int i = tid; i < n_seg; i += kAtomThreads) s_attr[i] = ap.attr[i];
+  // the tables out of the kernel parameters: per-thread indices into the constant bank serialise (32 replays per warp),
+  // so three single threads in three different warps copy them with uniform reads while the other warps clear the cells
+  for (int i = ap.n_list + tid; i < kBreakPad + 4; i += kAtomThreads) s_list[i] = __int_as_float(0x7f800000);
+  for (int i = ap.n_list + tid; i < kBreakPad; i += kAtomThreads) s_bidx[i] = 0xffffffffu;
+  if (tid == 32) {
+    for (int i = 0; i < ap.n_list; ++i) { const float v = ap.list[i]; s_list[i] = v; s_bidx[i] = atom_bucket(__saturatef(v), sh); }
+  } else if (tid == 64) {
+    for (int i = 0; i < n_seg; ++i) s_attr[i] = ap.attr[i];
+  } else if (tid == 96) {
+    for (int i = 0; i < n_bins + 2; ++i) s_binseg[i] = ap.bin_seg[i];
+  }
   for (int i = tid; i < kPartialSlots; i += kAtomThreads) s_slot[i] = 0u;
+  ATOM_CLK(2);
   __syncthreads();
+  ATOM_CLK(3);
   // bucket table: entries in lower buckets are <= every p of the bucket, entries of higher buckets above every p (the
   // bucket map is monotone), so a bucket needs #{entries below it} and its own entries.  One entry: {cell base, the entry};
   // several: {cell base | count, index of the first} — the flagged path scans them
@@ -149,8 +164,10 @@ eval_fused_atom_kernel(const float* __restrict__ p, const unsigned char* __restr
     s_lut[b] = inside >= 2 ? make_uint2((unsigned int)lo * (unsigned int)kAtomSegBytes | (unsigned int)min(inside, 1023), (unsigned int)lo)
                            : make_uint2((unsigned int)lo * (unsigned int)kAtomSegBytes, inside == 1 ? __float_as_uint(s_list[lo]) : 0x7f800000u);
   }
+  ATOM_CLK(4);
   __syncthreads();
   ATOM_TRACE(1);
+  ATOM_CLK(5);
 
   const unsigned int cells_a = (unsigned int)__cvta_generic_to_shared(smem_atom) + lane * 4;   // + seg * 3072 + word * 1024 + code * 128
   const unsigned int lut_a = (unsigned int)__cvta_generic_to_shared(s_lut) - ((0x3f800000u >> sh) << 3);
@@ -229,8 +246,10 @@ eval_fused_atom_kernel(const float* __restrict__ p, const unsigned char* __restr
       add_one(pv, __saturatef(pv), off, code * 128u, code, 4u);
     }
   }
+  ATOM_CLK(6);
   __syncthreads();
   ATOM_TRACE(2);
+  ATOM_CLK(7);
 
   // ---- block totals, one thread per cell: the 32 lane columns are read rotated by the thread index (bank == lane stays
   // conflict-free), every cell's count goes to the table slots it belongs to, the masked-in cells' exact sum(q) to their segment ----
@@ -266,6 +285,7 @@ eval_fused_atom_kernel(const float* __restrict__ p, const unsigned char* __restr
       atomicAdd(&s_slot[3 * nb1 + r * ncls + j], cnt);
       if ((at >> 16) & 1u) atomicAdd(&s_slot[n_slots - 1], cnt);
     }
+    ATOM_CLK(8);
     sumq += __shfl_xor_sync(0xffffffffu, sumq, 1);    // codes 4..7 of a segment are four adjacent lanes
     sumq += __shfl_xor_sync(0xffffffffu, sumq, 2);
     if (valid && code == 4) s_segq[sg] = sumq;       // 0 outside the summed segments
@@ -276,7 +296,9 @@ eval_fused_atom_kernel(const float* __restrict__ p, const unsigned char* __restr
     for (int o = 16; o >= 1; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
     if (lane == 0) s_red[warp] = v;
   }
+  ATOM_CLK(9);
   __syncthreads();
+  ATOM_CLK(10);
   unsigned long long* acc = accs + (long long)subject * kPartialSlots;
   double* bin0_partials = reinterpret_cast<double*>(partials) + (long long)subject * blocks_per_subject;
   if (tid < n_slots) {
@@ -284,7 +306,7 @@ eval_fused_atom_kernel(const float* __restrict__ p, const unsigned char* __restr
       const int k = tid - 2 * nb1;
       if (k >= 1 && k < n_bins) {
         unsigned long long tot = 0ull;
-        for (int sg = ap.bin_seg[k]; sg < (int)ap.bin_seg[k + 1]; ++sg) tot += s_segq[sg];
+        for (int sg = s_binseg[k]; sg < s_binseg[k + 1]; ++sg) tot += s_segq[sg];
         if (tot != 0ull) atomicAdd(&acc[tid], tot);
       }
     } else if (s_slot[tid] != 0u) {
@@ -298,15 +320,19 @@ eval_fused_atom_kernel(const float* __restrict__ p, const unsigned char* __restr
     if (lane == 0) bin0_partials[blockIdx.x] = v;
   }
   ATOM_TRACE(3);
-  __threadfence();
+  ATOM_CLK(11);
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");   // release: reductions and the partial before the ticket (everything read back goes through L2)
+  ATOM_CLK(12);
   __syncthreads();
   ATOM_TRACE(4);
+  ATOM_CLK(13);
   unsigned int* tk = tickets + (long long)subject * kTicketsPerSubject;
   if (tid == 0) s_is_last = (atomicAdd(tk, 1u) == (unsigned int)blocks_per_subject - 1u);
   __syncthreads();
   ATOM_TRACE(5);
+  ATOM_CLK(14);
   if (!s_is_last) return;
-  __threadfence();
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
   if (tid < n_slots) {
     const unsigned long long v = __ldcg(&acc[tid]);
     __stcg(&acc[tid], 0ull);   // zero at rest for the next stream-ordered call
@@ -320,7 +346,13 @@ eval_fused_atom_kernel(const float* __restrict__ p, const unsigned char* __restr
   }
   if (warp == kWarps - 1) {   // bin 0: the per-block float64 sums in block order (lane-strided runs, then a fixed tree)
     double v = 0.0;
-    for (int b = lane; b < blocks_per_subject; b += 32) v += __ldcg(&bin0_partials[b]);
+    for (int b0 = 0; b0 < blocks_per_subject; b0 += 256) {   // eight independent loads per lane and trip
+      double x[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) x[u] = b0 + 32 * u + lane < blocks_per_subject ? __ldcg(&bin0_partials[b0 + 32 * u + lane]) : 0.0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v += x[u];
+    }
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
     if (lane == 0) out.conf_sum[(long long)subject * nb1] = v;
