@@ -559,7 +559,21 @@ def run_mc_config(args, rig, isic=False):
     bp, bpred, btarget, bmask = beta_maps(torch, device, 50 * VOXELS, seed=21)
     ece_eval_beta50_ms = time_device_call(torch, stream, lambda: metrics.eval_fused(bp, bpred, btarget, bmask, 10, tables.SWEEP_THRESHOLDS,
                                                                                     n_subjects=50, sync=False, break_table=break_table), flush, reps=5)
-    del bp, bpred, btarget, bmask, flush
+    del bp, bpred, btarget, bmask
+    # the run's own maps again (after the synthetic ones: same clocks / power state as those), and with the voxel order shuffled
+    ece_eval_again_ms = time_device_call(torch, stream, lambda: metrics.eval_fused(out['foreground'], out['prediction'], target_d, mask_flat, 10,
+                                                                                   tables.SWEEP_THRESHOLDS, n_subjects=n_subjects, sync=False,
+                                                                                   break_table=break_table), flush)
+    ece_eval_shuffled_ms = None
+    if n_subjects == 1:
+        perm = torch.randperm(out['foreground'].numel(), device=device)
+        sp, sd_, st_ = out['foreground'].reshape(-1)[perm].contiguous(), out['prediction'].reshape(-1)[perm].contiguous(), target_d[perm].contiguous()
+        sm_ = None if mask_flat is None else mask_flat[perm].contiguous()
+        del perm
+        ece_eval_shuffled_ms = time_device_call(torch, stream, lambda: metrics.eval_fused(sp, sd_, st_, sm_, 10, tables.SWEEP_THRESHOLDS, sync=False,
+                                                                                          break_table=break_table), flush)
+        del sp, sd_, st_, sm_
+    del flush
 
     # ---------------- roofline of the dominant kernel family (tcgen05 convolutions)
     ops = net.op_table()
@@ -615,7 +629,8 @@ def run_mc_config(args, rig, isic=False):
             hist_bytes, ece_eval_beta_ms, bin_occupancy=beta_occupancy),
         hbm('eval_fused, 50 such subjects per launch', 50 * hist_bytes, ece_eval_beta50_ms, ms_per_subject=ece_eval_beta50_ms / 50),
         hbm('eval_fused on the maps this run produced (%d subject%s per launch)' % (n_subjects, '' if n_subjects == 1 else 's'),
-            voxels * (7.0 if mask_h is not None else 6.0), ece_eval_ms, bin_occupancy=bin_occupancy)]
+            voxels * (7.0 if mask_h is not None else 6.0), ece_eval_ms, bin_occupancy=bin_occupancy, ms_measured_again_after_the_synthetic_maps=ece_eval_again_ms,
+            ms_same_values_voxel_order_shuffled=ece_eval_shuffled_ms)]
 
     if rank != 0:
         return None

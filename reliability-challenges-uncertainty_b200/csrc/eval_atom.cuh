@@ -49,6 +49,7 @@ struct AtomParams {
   float q_scale;                     // 2^(23 + K)
   double q_inv;                      // 2^-(23 + K)
   float edge1;                       // upper edge of bin 0
+  unsigned int span_ulps;            // widest (last - first entry, in float32 ulps) + 1 over the buckets holding several entries
   int lut_bits;
 };
 
@@ -173,6 +174,7 @@ eval_fused_atom_kernel(const float* __restrict__ p, const unsigned char* __restr
   const unsigned int lut_a = (unsigned int)__cvta_generic_to_shared(s_lut) - ((0x3f800000u >> sh) << 3);
   const int sh3 = sh - 3;
   const float q_scale = ap.q_scale, edge1 = ap.edge1;
+  const unsigned int span_ulps = ap.span_ulps;
   double acc0 = 0.0;
 
   // one voxel whose cell offset is known: three atomics on the cell, bin 0 into the register accumulator.  `mbit` selects
@@ -204,13 +206,22 @@ eval_fused_atom_kernel(const float* __restrict__ p, const unsigned char* __restr
       const unsigned int la = lut_a + ((__float_as_uint(ps[e] + 1.0f) >> sh3) & 0xfffffff8u);
       asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(off[e]), "=r"(brk[e]) : "r"(la));
     }
-    if ((off[0] | off[1] | off[2] | off[3]) & 1023u) {   // some bucket holds several entries: scan them (rare)
+    if ((off[0] | off[1] | off[2] | off[3]) & 1023u) {   // some bucket holds several entries
+      // The entries of such a bucket are a cluster a few ulps wide (the float32 u(p) arithmetic is not monotone right at a
+      // threshold): a value below the cluster or at / above its end skips all of it at once; only a value INSIDE the
+      // cluster's span (span_ulps: the widest one, from the host) is compared with every entry.
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const unsigned int cnt = off[e] & 1023u;
         if (cnt) {
+          const float first = s_list[brk[e]];
           off[e] -= cnt;
-          for (unsigned int i = 0; i < cnt; ++i) off[e] += (pq[e] >= s_list[brk[e] + i]) ? (unsigned int)kAtomSegBytes : 0u;
+          const float pz = pq[e] > 0.0f ? pq[e] : 0.0f;   // -0, negative values and NaN sit at the bottom of bucket 0: always compared exactly
+          if (__float_as_uint(pz) - __float_as_uint(first) < span_ulps) {
+            for (unsigned int i = 0; i < cnt; ++i) off[e] += (pq[e] >= s_list[brk[e] + i]) ? (unsigned int)kAtomSegBytes : 0u;
+          } else if (pq[e] >= first) {
+            off[e] += cnt * (unsigned int)kAtomSegBytes;
+          }
           brk[e] = 0x7f800000u;
         }
       }

@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -863,6 +864,25 @@ extern "C" int rcu_eval_fused(const float* p, const uint8_t* prediction, const u
         ap.q_inv = std::ldexp(1.0, -(23 + K));
         ap.edge1 = cp.edges[1];
         ap.lut_bits = atom_bits;
+        {
+          // the device's bucket map, on the host (same IEEE arithmetic): widest span of a bucket that holds several entries
+          auto bucket_of = [&](float v) {
+            const float sat = v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v);
+            const float t = sat + 1.0f;
+            uint32_t bits;
+            std::memcpy(&bits, &t, 4);
+            return (bits - 0x3f800000u) >> (23 - atom_bits);
+          };
+          auto bits_of = [](float v) { uint32_t b; std::memcpy(&b, &v, 4); return b; };
+          uint32_t span = 0;
+          for (int i = 0; i < nv;) {
+            int j = i;
+            while (j + 1 < nv && bucket_of(vals[j + 1]) == bucket_of(vals[i])) ++j;
+            if (j > i) span = std::max(span, bits_of(vals[j]) - bits_of(vals[i]));
+            i = j + 1;
+          }
+          ap.span_ulps = span + 1u;
+        }
         RCU_CHECK_ARG(workspace_bytes >= rcu_metrics_workspace_bytes(n_subjects), "metrics workspace too small");
         unsigned int* tickets = tickets_of(workspace, workspace_bytes, n_subjects);
         unsigned long long* partials = reinterpret_cast<unsigned long long*>(workspace);
