@@ -380,10 +380,11 @@ def run_mc_config(args, rig, isic=False):
                 e.record(stream)
                 ev.append(e)
         mark()
-        logits = net.forward_samples(images_d, MC_STEPS + 1, dropout_mode=1, det_first=True, slice_index0=step_index * n_items, sample0=0)
+        # the head writes logit differences l0 - l1 (all a two-class softmax needs): what McPredictStep asks for as well
+        logits = net.forward_samples(images_d, MC_STEPS + 1, dropout_mode=1, det_first=True, slice_index0=step_index * n_items, sample0=0, diff=True)
         launches['n'] += net.last_launch_count()
         mark()
-        out = steps.summarize(steps.LazyMultiProbabilities(logits[1:]), emit_prediction=True, emit_foreground=True, ws_logits=logits[0])
+        out = steps.summarize(steps.LazyMultiProbabilities(logits[1:], diff=True), emit_prediction=True, emit_foreground=True, ws_logits=logits[0])
         launches['n'] += 1
         mark()
         res = metrics.eval_fused(out['foreground'], out['prediction'], target_d, mask_flat, 10, tables.SWEEP_THRESHOLDS, n_subjects=n_subjects,
@@ -500,9 +501,11 @@ def run_mc_config(args, rig, isic=False):
         r = device_step(100 + i, ev)
         stage_events.append(ev)
         return r
+    keep = None   # the timed loop holds one previous result like the warm-up did: no new block has to be cudaMalloc'ed inside it
     ms_step, clocks, keep = rig.timed(timed_step, args.steps)
     n_launches = launches['n']
-    stages = np.array([[ev[j].elapsed_time(ev[j + 1]) for j in range(3)] for ev in stage_events]).mean(0)
+    stages_all = np.array([[ev[j].elapsed_time(ev[j + 1]) for j in range(3)] for ev in stage_events])
+    stages = stages_all.mean(0)
 
     # ---------------- the same K steps again with every kernel launch of the U-Net bracketed by CUDA events on the launch
     # stream (rcu_unet_enable_timing): per-kernel durations for the roofline.  Kept out of the region above because ~1300
@@ -613,7 +616,7 @@ def run_mc_config(args, rig, isic=False):
                 'share_of_step': conv_ms / args.steps / ms_step_op_events,
                 'timed_over': 'a second pass of the same %d steps with per-launch CUDA events (%.1f ms/step there)' % (args.steps, ms_step_op_events)}
     agg_alg_bytes = voxels * (8.0 * MC_STEPS + 12)                            # T logit pairs in, mean + entropy out
-    agg_all_bytes = voxels * (8.0 * (MC_STEPS + 1) + 8 + 12 + 4 + 1)          # + the weight-scaling sample in / out, foreground, prediction
+    agg_all_bytes = voxels * (4.0 * (MC_STEPS + 1) + 8 + 12 + 4 + 1)          # what it moves: logit DIFFERENCES in (4 B per voxel-sample incl. the weight-scaling one), its softmax, mean, entropy, foreground, prediction out
     hist_bytes = VOXELS * 7.0
 
     def hbm(kernel, nbytes, ms, **extra):
@@ -622,9 +625,11 @@ def run_mc_config(args, rig, isic=False):
         d.update(extra)
         return d
     roofline_hbm = [
-        hbm('aggregate (softmax + mean + entropy + argmax + the weight-scaling softmax, ONE launch), 8T+12 = 172 B/voxel algorithmic',
+        hbm('aggregate (softmax + mean + entropy + argmax + the weight-scaling softmax, ONE launch) on the 8T+12 = 172 B/voxel algorithmic '
+            'accounting of SURVEY.md (T logit pairs in, mean + entropy out); the head hands over logit differences, so the launch moves '
+            '4(T+1)+25 = 109 B/voxel',
             agg_alg_bytes, stages[1], achieved_all_bytes=agg_all_bytes / (stages[1] * 1e-3) / 1e9,
-            frac_all_bytes=agg_all_bytes / (stages[1] * 1e-3) / 1e9 / peaks['hbm_gbs'], bytes_per_voxel_moved=8 * (MC_STEPS + 1) + 25),
+            frac_all_bytes=agg_all_bytes / (stages[1] * 1e-3) / 1e9 / peaks['hbm_gbs'], bytes_per_voxel_moved=4 * (MC_STEPS + 1) + 25),
         hbm('eval_fused (ECE bins + U-E joint histogram, 7 B/voxel), one subject of Beta(0.3,0.3)-shaped iid p, Bernoulli(p) target, 25% mask',
             hist_bytes, ece_eval_beta_ms, bin_occupancy=beta_occupancy),
         hbm('eval_fused, 50 such subjects per launch', 50 * hist_bytes, ece_eval_beta50_ms, ms_per_subject=ece_eval_beta50_ms / 50),
@@ -654,7 +659,7 @@ def run_mc_config(args, rig, isic=False):
         'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
         'data': 'synthetic',
         'config': {'workload': workload, 'name': 'isic_mc' if isic else 'brats_mc',
-                   'l2_policy': 'inputs larger than L2 (%d MB images, %.1f GB logits per step, 126 MB L2)' % (images_h.numel() * 4 >> 20, voxels * 8 * 21 / 1e9),
+                   'l2_policy': 'inputs larger than L2 (%d MB images, %.2f GB logit differences per step, 126 MB L2)' % (images_h.numel() * 4 >> 20, voxels * 4 * 21 / 1e9),
                    'weights': 'random init seed 20, BN statistics randomised (rcu_b200.synth), foreground bias of the 1x1 head centred '
                               'and rescaled (shift %.3f, gain %.3f: logit difference median 0, sigma 3 inside the mask)' % head_shift,
                    'chunk_images': net.chunk_images, 'parallelism': 'subject-sharded x%d, no data-path collective' % world},
@@ -674,6 +679,7 @@ def run_mc_config(args, rig, isic=False):
         'cpu_baseline': cpu_baseline,
         'ece_eval_ms': ece_eval_ms,
         'stages_ms': {'unet_forward': float(stages[0]), 'aggregate': float(stages[1]), 'metrics': float(stages[2])},
+        'stages_ms_per_step': [[round(float(x), 3) for x in row] for row in stages_all],
         'fraction_of_tensor_roofline_whole_step': value / world * flop_per_voxel_sample / 1e12 / peaks['tflops_sustained'],
         'check': {'ece': float(ece), 'mean_entropy': mean_entropy, 'dice': float(row['dice']), 'prediction_positive_fraction': pred_pos,
                   'bin_occupancy': bin_occupancy},
@@ -836,9 +842,9 @@ def run_brats50(args, rig):
         e0 = torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for (subj, a, b, img, tgt, msk) in (data if subset is None else data[:subset]):
-            logits = net.forward_samples(img, MC_STEPS + 1, dropout_mode=1, det_first=True, slice_index0=subj * SLICES + a, sample0=0)
+            logits = net.forward_samples(img, MC_STEPS + 1, dropout_mode=1, det_first=True, slice_index0=subj * SLICES + a, sample0=0, diff=True)
             launches['n'] += net.last_launch_count()
-            out = steps.summarize(steps.LazyMultiProbabilities(logits[1:]), emit_prediction=True, emit_foreground=True, ws_logits=logits[0])
+            out = steps.summarize(steps.LazyMultiProbabilities(logits[1:], diff=True), emit_prediction=True, emit_foreground=True, ws_logits=logits[0])
             cnt, pos, cf, ue, inv, _ = metrics.eval_fused(out['foreground'], out['prediction'], tgt, msk, 10, tables.SWEEP_THRESHOLDS, sync=False,
                                                           break_table=break_table)
             launches['n'] += 2

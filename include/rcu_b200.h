@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define RCU_ABI_VERSION 2
+#define RCU_ABI_VERSION 3
 
 typedef enum rcu_status {
   RCU_OK = 0,
@@ -124,6 +124,8 @@ int rcu_confusion(const uint8_t* prediction, const uint8_t* target, int64_t voxe
  *   input_kind 1: probabilities, planar      float32[n_samples][n_images][2][hw]   (a reference-made
  *                 `multi_probabilities` tensor; no softmax applied)
  *   input_kind 2: logits, planar             float32[n_samples][n_images][2][hw]
+ *   input_kind 3: logit differences l0 - l1  float32[n_samples][n_images][hw]      (rcu_unet_outputs.logit_diff; the softmax
+ *                 of two classes is a function of the difference alone: same outputs as kind 0, half the bytes)
  * Outputs (any may be NULL except mean):
  *   mean       float32[n_images][2][hw]   sum_t p_t / n_samples  (sequential fp32 sum in t, like torch)
  *   entropy    float32[n_images][hw]      -sum_c where(p>0, p ln p, 0) of the mean
@@ -145,6 +147,13 @@ int rcu_aggregate(const float* input, int input_kind, int n_samples, int64_t n_i
 int rcu_aggregate_ws(const float* logits, int n_samples, int64_t n_images, int64_t hw, const float* ws_logits,
                      float* ws_probabilities, float* mean, float* entropy, float* mutual_info, float* variance,
                      uint8_t* prediction, float* foreground, void* stream);
+/* The same on logit DIFFERENCES l0 - l1 (input_kind 3 of rcu_aggregate; what rcu_unet_outputs.logit_diff holds):
+ *   logit_diff float32[n_samples][n_images][hw], ws_logit_diff float32[n_images][hw].
+ * F.softmax over two classes (customsteps.py:33) depends on the difference alone — p_max = 1 / (1 + exp(-|d|)) — so every
+ * output is bit-identical to rcu_aggregate_ws on the logit pairs, for half the bytes read (4 instead of 8 per voxel-sample). */
+int rcu_aggregate_ws_diff(const float* logit_diff, int n_samples, int64_t n_images, int64_t hw, const float* ws_logit_diff,
+                          float* ws_probabilities, float* mean, float* entropy, float* mutual_info, float* variance,
+                          uint8_t* prediction, float* foreground, void* stream);
 
 /* Partial aggregation for sample-sharded runs: writes the raw fp32 sums so ranks can allreduce them.
  *   sums float32[n_images][K][hw] with K = 2 (sum p0, sum p1) [+1: sum_t H(p_t) if want_mi] [+2: sum p0^2, sum p1^2 if want_var]
@@ -292,6 +301,10 @@ typedef struct rcu_unet_outputs {
   float* features;
   const rcu_postnet* postnet;
   float* postnet_logits;
+  float* logit_diff;   /* alternative to `logits` (exactly one of the two is non-NULL): float32[n_samples][n_slices][H][W],
+                        * l0 - l1 of the class head.  The stochastic-inference steps only ever take the softmax of the pair,
+                        * which is a function of the difference: the head then writes 4 instead of 8 bytes per voxel-sample
+                        * and rcu_aggregate (input_kind 3) / rcu_aggregate_ws_diff read half as much */
 } rcu_unet_outputs;
 int rcu_unet_forward_ex(rcu_unet* net, const float* images, int64_t n_slices, int n_samples, int dropout_mode,
                         int det_first, uint64_t seed, int64_t slice_index0, int sample0, const float* scale,

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'librcu_b200.so')
 LIB_PATH = os.environ.get('RCU_B200_LIB', LIB_PATH)   # developer override (A/B builds)
 
-RCU_ABI_VERSION = 2
+RCU_ABI_VERSION = 3
 RCU_OK, RCU_EINVAL, RCU_ECUDA, RCU_ENOTSUP, RCU_ENOMEM, RCU_ENCCL = 0, -1, -2, -3, -4, -5
 RCU_COMM_ID_BYTES, RCU_IPC_HANDLE_BYTES = 128, 64
 RCU_MAX_BINS, RCU_MAX_UE_CLASSES, RCU_MAX_BREAKS = 32, 32, 96
@@ -38,7 +38,7 @@ class RcuUnetDesc(ctypes.Structure):
 
 class RcuUnetOutputs(ctypes.Structure):
     _fields_ = [('logits', c_void_p), ('sigma', c_void_p), ('features', c_void_p), ('postnet', c_void_p),
-                ('postnet_logits', c_void_p)]
+                ('postnet_logits', c_void_p), ('logit_diff', c_void_p)]
 
 
 class RcuPeerLayout(ctypes.Structure):
@@ -65,6 +65,8 @@ PROTOTYPES = {
                               c_void_p, c_void_p, c_void_p]),
     'rcu_aggregate_ws': (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p]),
+    'rcu_aggregate_ws_diff': (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_void_p]),
     'rcu_aggregate_partial': (c_int, [c_void_p, c_int, c_int, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p]),
     'rcu_aggregate_finish': (c_int, [c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p]),

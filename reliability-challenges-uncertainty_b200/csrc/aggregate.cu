@@ -18,6 +18,15 @@
 #ifndef RCU_AGG_MINB
 #define RCU_AGG_MINB 4
 #endif
+#ifndef RCU_AGG_FAST_MATH
+#define RCU_AGG_FAST_MATH 1
+#endif
+#ifndef RCU_AGG_DIFF_P        // pairs per thread on logit-difference input (a multiple of two: 16-byte loads cover two pairs)
+#define RCU_AGG_DIFF_P 4
+#endif
+#ifndef RCU_AGG_DIFF_MINB
+#define RCU_AGG_DIFF_MINB 4
+#endif
 
 namespace rcu {
 
@@ -26,11 +35,18 @@ constexpr int kAggSampleUnroll = RCU_AGG_TU;
 
 __device__ __forceinline__ void softmax2(float l0, float l1, float& p0, float& p1) {
   // torch's formulation, exp(l - max) / sum, for two classes: the larger logit contributes exp(0) = 1 exactly, the
-  // other e = exp(-|l0 - l1|); p_max = 1 / (1 + e) is the correctly rounded quotient torch computes, p_min = e * p_max
-  // differs from e / (1 + e) by at most one ulp.  One expf and one reciprocal per pixel-sample instead of two each.
+  // other e = exp(-|l0 - l1|); p_max = 1 / (1 + e), p_min = e * p_max.  One exponential and one reciprocal per
+  // pixel-sample instead of two each.  RCU_AGG_FAST_MATH (default): ex2.approx / rcp.approx (2 + 1 ulp: below 2e-7
+  // absolute on a probability, against the 1e-6 the parity tests allow) — with logit differences as input the pass is
+  // bound by instruction issue, not by HBM, and the IEEE-rounded expf / reciprocal are two thirds of its instructions.
   const float d = l0 - l1;
+#if RCU_AGG_FAST_MATH
+  const float e = __expf(-fabsf(d));
+  const float r = __fdividef(1.0f, 1.0f + e);
+#else
   const float e = expf(-fabsf(d));
   const float r = __frcp_rn(1.0f + e);
+#endif
   const float q = e * r;
   const bool first = d >= 0.0f;      // NaN logits give NaN probabilities either way
   p0 = first ? r : q;
@@ -50,9 +66,12 @@ struct AggAcc {
 // Pair (thread, k) = warp_base + k * 32 + lane: every load instruction of a warp reads 512 contiguous bytes of one
 // sample, and with P = 4 the P loads of a sample are issued back to back, so a warp walks 2 KB runs of each of the
 // n_samples streams (long DRAM bursts; deeper unrolling over samples instead opens more streams at once and is slower).
-// KIND 0: interleaved logits [t][n][hw][2];  1: planar probabilities [t][n][2][hw];  2: planar logits.
+// KIND 0: interleaved logits [t][n][hw][2];  1: planar probabilities [t][n][2][hw];  2: planar logits;
+// 3: logit differences l0 - l1 [t][n][hw] (what the fused head writes in rcu_unet_outputs.logit_diff mode: softmax2 only ever
+//    uses the difference, so the outputs are bit-identical to KIND 0 at half the bytes).  A lane then owns two ADJACENT
+//    pixel pairs per 16-byte load: pair (thread, k) = warp_base + (k / 2) * 64 + lane * 2 + (k & 1).
 template <int KIND, bool MI, bool VAR, bool PARTIAL, int P>
-__global__ void __launch_bounds__(kAggThreads, P > 1 ? RCU_AGG_MINB : 1)
+__global__ void __launch_bounds__(kAggThreads, KIND == 3 && P > 1 ? RCU_AGG_DIFF_MINB : (P > 1 ? RCU_AGG_MINB : 1))
 aggregate_kernel(const float* __restrict__ in, int n_samples, long long n_images, long long hw, float inv_or_scale,
                  float* __restrict__ mean, float* __restrict__ entropy, float* __restrict__ mutual_info,
                  float* __restrict__ variance, unsigned char* __restrict__ prediction, float* __restrict__ foreground,
@@ -60,7 +79,8 @@ aggregate_kernel(const float* __restrict__ in, int n_samples, long long n_images
                  float* __restrict__ ws_out) {
   const long long pairs_per_image = hw >> 1;  // hw is even (checked on the host)
   const long long total_pairs = n_images * pairs_per_image;
-  const long long sample_stride = n_images * hw * 2;
+  const long long sample_stride = n_images * hw * (KIND == 3 ? 1 : 2);
+  static_assert(KIND != 3 || P % 2 == 0 || P == 1, "difference input reads two adjacent pairs per 16-byte load");
   const int lane = threadIdx.x & 31;
   const long long warp_id = ((long long)blockIdx.x * kAggThreads + threadIdx.x) >> 5;
   const long long n_warps = ((long long)gridDim.x * kAggThreads) >> 5;
@@ -71,20 +91,26 @@ aggregate_kernel(const float* __restrict__ in, int n_samples, long long n_images
     bool on[P];
 #pragma unroll
     for (int k = 0; k < P; ++k) {
-      const long long pair = wbase + k * 32 + lane;
+      const long long pair = (KIND == 3 && P > 1) ? wbase + (k >> 1) * 64 + lane * 2 + (k & 1) : wbase + k * 32 + lane;
       on[k] = pair < total_pairs;
       const long long pr = on[k] ? pair : 0;
       img_k[k] = pr / pairs_per_image;
       px_k[k] = (pr - img_k[k] * pairs_per_image) * 2;
-      src[k] = in + img_k[k] * hw * 2 + (KIND == 0 ? px_k[k] * 2 : px_k[k]);
+      src[k] = KIND == 3 ? in + img_k[k] * hw + px_k[k] : in + img_k[k] * hw * 2 + (KIND == 0 ? px_k[k] * 2 : px_k[k]);
     }
     if (ws_in != nullptr) {
       // the deterministic weight-scaling pass of McPredictStep (rechun/dl/customsteps.py:23-25) rides in the same launch:
       // one more interleaved-logits sample in, its planar softmax out
       float4 q[P];
 #pragma unroll
-      for (int k = 0; k < P; ++k)
-        q[k] = on[k] ? ld_stream_f4(ws_in + img_k[k] * hw * 2 + px_k[k] * 2) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < P; ++k) {
+        if (KIND == 3) {   // the weight-scaling sample as differences as well: (d, 0) is the same pair of logits to softmax2
+          const float2 d2 = on[k] ? ld_stream_f2(ws_in + img_k[k] * hw + px_k[k]) : make_float2(0.f, 0.f);
+          q[k] = make_float4(d2.x, 0.f, d2.y, 0.f);
+        } else {
+          q[k] = on[k] ? ld_stream_f4(ws_in + img_k[k] * hw * 2 + px_k[k] * 2) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
 #pragma unroll
       for (int k = 0; k < P; ++k) {
         float a0, a1, b0, b1;
@@ -106,6 +132,17 @@ aggregate_kernel(const float* __restrict__ in, int n_samples, long long n_images
         if (KIND == 0) {
           const float4 q = ld_stream_f4(src[k] + (long long)t * sample_stride);
           v[k][0] = q.x; v[k][1] = q.y; v[k][2] = q.z; v[k][3] = q.w;
+        } else if (KIND == 3) {
+          if (P > 1) {
+            if ((k & 1) == 0) {   // one 16-byte load serves this pair and the next (both on or both off: pairs_per_image is even there)
+              const float4 q = ld_stream_f4(src[k] + (long long)t * sample_stride);
+              v[k][0] = q.x; v[k][1] = 0.f; v[k][2] = q.y; v[k][3] = 0.f;
+              if (k + 1 < P) { v[k + 1][0] = q.z; v[k + 1][1] = 0.f; v[k + 1][2] = q.w; v[k + 1][3] = 0.f; }
+            }
+          } else {
+            const float2 q = ld_stream_f2(src[k] + (long long)t * sample_stride);
+            v[k][0] = q.x; v[k][1] = 0.f; v[k][2] = q.y; v[k][3] = 0.f;
+          }
         } else {
           const float2 c0 = ld_stream_f2(src[k] + (long long)t * sample_stride);
           const float2 c1 = ld_stream_f2(src[k] + (long long)t * sample_stride + hw);
@@ -122,7 +159,7 @@ aggregate_kernel(const float* __restrict__ in, int n_samples, long long n_images
           softmax2(v[k][2], v[k][3], p[1][0], p[1][1]);
         }
         if (multi_out != nullptr && on[k]) {
-          float* dst = multi_out + (long long)t * sample_stride + img_k[k] * hw * 2 + px_k[k];
+          float* dst = multi_out + (long long)t * n_images * hw * 2 + img_k[k] * hw * 2 + px_k[k];
           *reinterpret_cast<float2*>(dst) = make_float2(p[0][0], p[1][0]);
           *reinterpret_cast<float2*>(dst + hw) = make_float2(p[0][1], p[1][1]);
         }
@@ -238,13 +275,15 @@ static int launch_aggregate(bool mi, bool var, const float* in, int n_samples, i
   const long long total_pairs = n_images * (hw / 2);
   if (total_pairs == 0) return RCU_OK;
   // the plain summary (no MI / variance) runs four pairs per thread; the variants with more accumulators keep one
-  const bool wide = !mi && !var && total_pairs >= (long long)sm_count() * kAggThreads * 8;
-  const int per_thread = wide ? RCU_AGG_P : 1;
+  const bool wide = !mi && !var && total_pairs >= (long long)sm_count() * kAggThreads * 8 && (KIND != 3 || hw % 4 == 0);
+  // (difference input: eight pairs, so that a warp still walks 2 KB runs of every sample stream with 16-byte loads)
+  constexpr int kWideP = KIND == 3 ? RCU_AGG_DIFF_P : RCU_AGG_P;
+  const int per_thread = wide ? kWideP : 1;
   long long blocks = (total_pairs + (long long)kAggThreads * per_thread - 1) / ((long long)kAggThreads * per_thread);
   const long long cap = (long long)sm_count() * 16;
   if (blocks > cap) blocks = cap;
   if (wide) {
-    aggregate_kernel<KIND, false, false, PARTIAL, RCU_AGG_P><<<(unsigned)blocks, kAggThreads, 0, st>>>(
+    aggregate_kernel<KIND, false, false, PARTIAL, kWideP><<<(unsigned)blocks, kAggThreads, 0, st>>>(
         in, n_samples, (long long)n_images, (long long)hw, denom, mean, entropy, mutual_info, variance, prediction, foreground,
         multi_out, sums, ws_in, ws_out);
     RCU_LAUNCH_CHECK();
@@ -265,7 +304,7 @@ static int launch_aggregate(bool mi, bool var, const float* in, int n_samples, i
 
 static int check_agg_common(const float* input, int input_kind, int n_samples, int64_t n_images, int64_t hw) {
   RCU_CHECK_ARG(input != nullptr, "input is NULL");
-  RCU_CHECK_ARG(input_kind >= 0 && input_kind <= 2, "input_kind must be 0, 1 or 2");
+  RCU_CHECK_ARG(input_kind >= 0 && input_kind <= 3, "input_kind must be 0, 1, 2 or 3");
   RCU_CHECK_ARG(n_samples >= 1 && n_images >= 0 && hw >= 0, "bad sizes: n_samples=%d n_images=%lld hw=%lld", n_samples,
                 (long long)n_images, (long long)hw);
   RCU_CHECK_ARG(hw % 2 == 0, "hw=%lld must be even (pixel pairs are processed together)", (long long)hw);
@@ -290,6 +329,7 @@ extern "C" int rcu_aggregate(const float* input, int input_kind, int n_samples, 
   switch (input_kind) {
     case 0: return launch_aggregate<0, false>(mi, var, input, n_samples, n_images, hw, denom, mean, entropy, mutual_info, variance, prediction, foreground, multi_out, nullptr, st);
     case 1: return launch_aggregate<1, false>(mi, var, input, n_samples, n_images, hw, denom, mean, entropy, mutual_info, variance, prediction, foreground, multi_out, nullptr, st);
+    case 3: return launch_aggregate<3, false>(mi, var, input, n_samples, n_images, hw, denom, mean, entropy, mutual_info, variance, prediction, foreground, multi_out, nullptr, st);
     default: return launch_aggregate<2, false>(mi, var, input, n_samples, n_images, hw, denom, mean, entropy, mutual_info, variance, prediction, foreground, multi_out, nullptr, st);
   }
 }
@@ -307,6 +347,19 @@ extern "C" int rcu_aggregate_ws(const float* logits, int n_samples, int64_t n_im
                                     ws_logits, ws_probabilities);
 }
 
+extern "C" int rcu_aggregate_ws_diff(const float* logit_diff, int n_samples, int64_t n_images, int64_t hw, const float* ws_logit_diff,
+                                     float* ws_probabilities, float* mean, float* entropy, float* mutual_info, float* variance,
+                                     uint8_t* prediction, float* foreground, void* stream) {
+  int rc = check_agg_common(logit_diff, 3, n_samples, n_images, hw);
+  if (rc) return rc;
+  RCU_CHECK_ARG(mean != nullptr && ws_logit_diff != nullptr && ws_probabilities != nullptr, "NULL pointer argument");
+  RCU_CHECK_ARG(reinterpret_cast<uintptr_t>(ws_logit_diff) % 8 == 0, "ws_logit_diff must be 8-byte aligned");
+  RCU_CHECK_ARG(variance == nullptr || n_samples >= 2, "variance needs at least two samples");
+  return launch_aggregate<3, false>(mutual_info != nullptr, variance != nullptr, logit_diff, n_samples, n_images, hw, (float)n_samples, mean,
+                                    entropy, mutual_info, variance, prediction, foreground, nullptr, nullptr, (cudaStream_t)stream,
+                                    ws_logit_diff, ws_probabilities);
+}
+
 extern "C" int rcu_aggregate_partial(const float* input, int input_kind, int n_samples, int64_t n_images, int64_t hw,
                                      int want_mi, int want_var, float* sums, void* stream) {
   int rc = check_agg_common(input, input_kind, n_samples, n_images, hw);
@@ -316,6 +369,7 @@ extern "C" int rcu_aggregate_partial(const float* input, int input_kind, int n_s
   switch (input_kind) {
     case 0: return launch_aggregate<0, true>(want_mi != 0, want_var != 0, input, n_samples, n_images, hw, 1.f, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, sums, st);
     case 1: return launch_aggregate<1, true>(want_mi != 0, want_var != 0, input, n_samples, n_images, hw, 1.f, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, sums, st);
+    case 3: return launch_aggregate<3, true>(want_mi != 0, want_var != 0, input, n_samples, n_images, hw, 1.f, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, sums, st);
     default: return launch_aggregate<2, true>(want_mi != 0, want_var != 0, input, n_samples, n_images, hw, 1.f, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, sums, st);
   }
 }

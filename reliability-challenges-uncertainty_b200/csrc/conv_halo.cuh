@@ -76,6 +76,7 @@ struct HaloParams {
   int relu;
   const float* head;         // non-NULL: fused 1x1 head (conv_cls.1 / conv_sigma.1); the weights themselves travel in head_w
   float* logits;
+  int head_diff;             // 1: the head stores l0 - l1 (float32 per pixel, softmax is a function of the difference alone) instead of the logit pair
   int chunk_slices;
   long long slice0, n_slices_total;
   // [2][32] weights + [2] bias of the fused head, in the kernel's constant bank: every FFMA of the head takes its weight
@@ -442,8 +443,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           if (valid) {
             const int t = img / prm.chunk_slices, sl = img - t * prm.chunk_slices;
             const long long gimg = (long long)t * prm.n_slices_total + prm.slice0 + sl;
-            float2* dst = reinterpret_cast<float2*>(prm.logits) + (gimg * prm.out_h + y) * prm.out_w + 2 * x;   // out_w is even: 16-byte aligned
-            *reinterpret_cast<float4*>(dst) = make_float4(lg[0], lg[1], lg[2], lg[3]);
+            if (prm.head_diff) {
+              float* dst = prm.logits + (gimg * prm.out_h + y) * prm.out_w + 2 * x;
+              *reinterpret_cast<float2*>(dst) = make_float2(lg[0] - lg[1], lg[2] - lg[3]);
+            } else {
+              float2* dst = reinterpret_cast<float2*>(prm.logits) + (gimg * prm.out_h + y) * prm.out_w + 2 * x;   // out_w is even: 16-byte aligned
+              *reinterpret_cast<float4*>(dst) = make_float4(lg[0], lg[1], lg[2], lg[3]);
+            }
           }
         } else {
           uint32_t packed[2][16];
@@ -537,8 +543,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (valid) {
           const int t = img / prm.chunk_slices, sl = img - t * prm.chunk_slices;
           const long long gimg = (long long)t * prm.n_slices_total + prm.slice0 + sl;
-          float2* dst = reinterpret_cast<float2*>(prm.logits) + (gimg * prm.out_h + oy) * prm.out_w + ox;
-          *dst = make_float2(l0, l1);
+          if (prm.head_diff) {
+            prm.logits[(gimg * prm.out_h + oy) * prm.out_w + ox] = l0 - l1;
+          } else {
+            float2* dst = reinterpret_cast<float2*>(prm.logits) + (gimg * prm.out_h + oy) * prm.out_w + ox;
+            *dst = make_float2(l0, l1);
+          }
         }
       } else {
         __nv_bfloat16* dst = prm.out + (long long)img * prm.out_img_stride + ((long long)oy * prm.out_w + ox) * prm.out_c;

@@ -53,6 +53,7 @@ struct ConvParams {
   // fused 1x1 head (only when BLOCK_N == c_out == 32): logits[img_global][pixel][2]
   const float* head;         // [2][32] weights then [2] bias, fp32; NULL when not fused
   float* logits;
+  int head_diff;             // 1: the fused head stores l0 - l1 per pixel instead of the logit pair
   int chunk_slices;          // images are ordered [sample][slice-in-chunk]
   long long slice0, n_slices_total;
   // residual branch of a ConvResidualBlock (common/model/unet.py:57-59): out = bf16(float(out) + acc * scale + shift),
@@ -365,8 +366,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         if (valid) {
           const int t = img / prm.chunk_slices, sl = img - t * prm.chunk_slices;
           const long long gimg = (long long)t * prm.n_slices_total + prm.slice0 + sl;
-          float2* dst = reinterpret_cast<float2*>(prm.logits) + (gimg * prm.out_h + oy) * prm.out_w + ox;
-          *dst = make_float2(l0, l1);
+          if (prm.head_diff) {
+            prm.logits[(gimg * prm.out_h + oy) * prm.out_w + ox] = l0 - l1;
+          } else {
+            float2* dst = reinterpret_cast<float2*>(prm.logits) + (gimg * prm.out_h + oy) * prm.out_w + ox;
+            *dst = make_float2(l0, l1);
+          }
         }
       } else {
         __nv_bfloat16* dst = prm.out + (long long)img * prm.out_img_stride + ((long long)oy * prm.out_w + ox) * prm.out_c + nt * BLOCK_N;

@@ -91,6 +91,34 @@ std::vector<at::Tensor> aggregate(const at::Tensor& logits, const std::optional<
   return {mean, entropy, mi, var, pred, fg, ws};
 }
 
+// The same on logit differences l0 - l1: (T, N, H, W) [+ the weight-scaling sample (N, H, W)] (rcu_aggregate_ws_diff / input_kind 3).
+std::vector<at::Tensor> aggregate_diff(const at::Tensor& diff, const std::optional<at::Tensor>& ws_diff, bool want_mi, bool want_var,
+                                       bool emit_prediction, bool emit_foreground) {
+  need_cuda(diff, at::kFloat, "logit_diff");
+  TORCH_CHECK_VALUE(diff.dim() == 4, "logit_diff must have shape (T, N, H, W)");
+  const int64_t t = diff.size(0), n = diff.size(1), h = diff.size(2), w = diff.size(3);
+  c10::cuda::CUDAGuard guard(diff.device());
+  auto f32 = diff.options();
+  at::Tensor none = at::empty({0}, f32);
+  at::Tensor mean = at::empty({n, 2, h, w}, f32), entropy = at::empty({n, 1, h, w}, f32);
+  at::Tensor mi = want_mi ? at::empty({n, 1, h, w}, f32) : none, var = want_var ? at::empty({n, 1, h, w}, f32) : none;
+  at::Tensor pred = emit_prediction ? at::empty({n, h, w}, f32.dtype(at::kByte)) : at::empty({0}, f32.dtype(at::kByte));
+  at::Tensor fg = emit_foreground ? at::empty({n, h, w}, f32) : none;
+  at::Tensor ws = none;
+  auto opt = [](const at::Tensor& x) -> float* { return x.numel() ? x.data_ptr<float>() : nullptr; };
+  if (ws_diff) {
+    need_cuda(*ws_diff, at::kFloat, "ws_logit_diff");
+    TORCH_CHECK_VALUE(ws_diff->dim() == 3 && ws_diff->size(0) == n && ws_diff->size(1) == h && ws_diff->size(2) == w, "ws_logit_diff must have shape (N, H, W)");
+    ws = at::empty({n, 2, h, w}, f32);
+    check(rcu_aggregate_ws_diff(diff.data_ptr<float>(), (int)t, n, h * w, ws_diff->data_ptr<float>(), ws.data_ptr<float>(), mean.data_ptr<float>(),
+                                entropy.data_ptr<float>(), opt(mi), opt(var), pred.numel() ? pred.data_ptr<uint8_t>() : nullptr, opt(fg), stream_of(diff)));
+  } else {
+    check(rcu_aggregate(diff.data_ptr<float>(), 3, (int)t, n, h * w, mean.data_ptr<float>(), entropy.data_ptr<float>(), opt(mi), opt(var),
+                        pred.numel() ? pred.data_ptr<uint8_t>() : nullptr, opt(fg), nullptr, stream_of(diff)));
+  }
+  return {mean, entropy, mi, var, pred, fg, ws};
+}
+
 // rcu_unet_forward on an engine handle (the integer value of the rcu_unet* the Python side owns; its workspace is bound).
 at::Tensor unet_forward(int64_t handle, const at::Tensor& images, int64_t n_samples, int64_t dropout_mode, bool det_first, int64_t seed,
                         int64_t slice_index0, int64_t sample0, const std::optional<at::Tensor>& scale) {
@@ -114,6 +142,8 @@ TORCH_LIBRARY(rcu_b200, m) {
   m.def("eval_fused(Tensor p, Tensor prediction, Tensor target, Tensor? mask, Tensor edges_f32, Tensor breaks_f32, Tensor seg_class, "
         "int n_subjects, int n_classes, Tensor(a!) workspace) -> Tensor", &eval_fused);
   m.def("aggregate(Tensor logits, Tensor? ws_logits, bool want_mi, bool want_var, bool emit_prediction, bool emit_foreground) -> Tensor[]", &aggregate);
+  m.def("aggregate_diff(Tensor logit_diff, Tensor? ws_logit_diff, bool want_mi, bool want_var, bool emit_prediction, bool emit_foreground) -> Tensor[]",
+        &aggregate_diff);
   m.def("unet_forward(int handle, Tensor images, int n_samples, int dropout_mode, bool det_first, int seed, int slice_index0, int sample0, "
         "Tensor? scale) -> Tensor", &unet_forward);
 }

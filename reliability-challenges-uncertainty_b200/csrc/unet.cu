@@ -1127,7 +1127,7 @@ static int plan_impl(rcu_unet* net, int height, int width, int max_images_per_ch
 
 namespace rcu {
 
-static int run_conv_halo(rcu_unet* net, const ConvLayer& L, int n_img, int cs, long long s0, long long n_slices, float* logits,
+static int run_conv_halo(rcu_unet* net, const ConvLayer& L, int n_img, int cs, long long s0, long long n_slices, float* logits, int head_diff,
                          cudaStream_t st, long long* launches) {
   const HaloPack& hp = L.halo;
   const int ppl = hp.n_phases == 4 ? hp.phases_per_launch : 1;
@@ -1169,6 +1169,7 @@ static int run_conv_halo(rcu_unet* net, const ConvLayer& L, int n_img, int cs, l
     prm.head = L.head ? L.d_head : nullptr;
     if (L.head) std::memcpy(prm.head_w, L.h_head, sizeof(prm.head_w));
     prm.logits = logits;
+    prm.head_diff = head_diff;
     prm.chunk_slices = cs; prm.slice0 = s0; prm.n_slices_total = n_slices;
     int rc;
     if (hp.n_phases == 4) {
@@ -1183,7 +1184,7 @@ static int run_conv_halo(rcu_unet* net, const ConvLayer& L, int n_img, int cs, l
   return RCU_OK;
 }
 
-static int run_conv_halo_pair(rcu_unet* net, const ConvLayer& L, int n_img, int cs, long long s0, long long n_slices, float* logits,
+static int run_conv_halo_pair(rcu_unet* net, const ConvLayer& L, int n_img, int cs, long long s0, long long n_slices, float* logits, int head_diff,
                               cudaStream_t st, long long* launches) {
   const HaloPack& hp = L.pairp;
   HaloParams prm;
@@ -1214,6 +1215,7 @@ static int run_conv_halo_pair(rcu_unet* net, const ConvLayer& L, int n_img, int 
   prm.head = L.head ? L.d_head : nullptr;
   if (L.head) std::memcpy(prm.head_w, L.h_head, sizeof(prm.head_w));
   prm.logits = logits;
+  prm.head_diff = head_diff;
   prm.chunk_slices = cs; prm.slice0 = s0; prm.n_slices_total = n_slices;
   ConvLayer view = L;
   view.map_halo = L.map_halo_pair;
@@ -1237,8 +1239,11 @@ extern "C" int rcu_unet_forward(rcu_unet* net, const float* images, int64_t n_sl
 extern "C" int rcu_unet_forward_ex(rcu_unet* net, const float* images, int64_t n_slices, int n_samples, int dropout_mode,
                                    int det_first, uint64_t seed, int64_t slice_index0, int sample0, const float* scale,
                                    const rcu_unet_outputs* outputs, void* stream) {
-  RCU_CHECK_ARG(net != nullptr && images != nullptr && outputs != nullptr && outputs->logits != nullptr, "NULL argument");
-  float* const logits = outputs->logits;
+  RCU_CHECK_ARG(net != nullptr && images != nullptr && outputs != nullptr && (outputs->logits != nullptr || outputs->logit_diff != nullptr),
+                "NULL argument");
+  RCU_CHECK_ARG(outputs->logits == nullptr || outputs->logit_diff == nullptr, "logits and logit_diff are alternatives: the head writes one of them");
+  float* const logits = outputs->logit_diff != nullptr ? outputs->logit_diff : outputs->logits;
+  const int logits_are_diff = outputs->logit_diff != nullptr ? 1 : 0;
   float* const sigma = outputs->sigma;
   float* const features = outputs->features;
   const rcu_postnet* const post = outputs->postnet;
@@ -1314,15 +1319,16 @@ extern "C" int rcu_unet_forward_ex(rcu_unet* net, const float* images, int64_t n
       } else {
         const ConvLayer& L = net->convs[op.conv];
         float* const head_out = L.out_slot ? sigma : logits;
+        const int head_diff = L.out_slot ? 0 : logits_are_diff;
         if (L.out_slot && sigma == nullptr) continue;   // nobody asked for the sigma branch
         if (net->conv_impl == 0 && L.use_pair && net->pair_enabled && ((net->halo_mask >> op.conv) & 1ull)) {
-          int rc = run_conv_halo_pair(net, L, n_img, cs, (long long)s0, (long long)n_slices, head_out, st, &launches);
+          int rc = run_conv_halo_pair(net, L, n_img, cs, (long long)s0, (long long)n_slices, head_out, head_diff, st, &launches);
           if (rc) return rc;
           pool_done = L.pool_dst.base != nullptr;
           continue;
         }
         if (net->conv_impl == 0 && L.halo.ok && ((net->halo_mask >> op.conv) & 1ull)) {
-          int rc = run_conv_halo(net, L, n_img, cs, (long long)s0, (long long)n_slices, head_out, st, &launches);
+          int rc = run_conv_halo(net, L, n_img, cs, (long long)s0, (long long)n_slices, head_out, head_diff, st, &launches);
           if (rc) return rc;
           pool_done = L.pool_dst.base != nullptr;
           continue;
@@ -1375,7 +1381,7 @@ extern "C" int rcu_unet_forward_ex(rcu_unet* net, const float* images, int64_t n
         prm.coef = net->d_coef; prm.coef_stride = net->n_cols; prm.coef_off = L.coef_off;
         prm.relu = L.relu;
         prm.accumulate = L.accumulate ? 1 : 0;
-        prm.head = nullptr; prm.logits = head_out;
+        prm.head = nullptr; prm.logits = head_out; prm.head_diff = head_diff;
         prm.chunk_slices = cs; prm.slice0 = s0; prm.n_slices_total = n_slices;
         if (net->conv_impl != 1) {
           if (L.head) prm.head = L.d_head;
@@ -1394,7 +1400,7 @@ extern "C" int rcu_unet_forward_ex(rcu_unet* net, const float* images, int64_t n
             long long hb = (px + 255) / 256;
             if (hb > (long long)sm_count() * 32) hb = (long long)sm_count() * 32;
             head_check_kernel<<<(unsigned)hb, 256, 0, st>>>(L.dst.base, L.dst.img_stride, L.d_head, head_out, n_img, H, W,
-                                                           sf, cs, (long long)s0, (long long)n_slices);
+                                                           sf, cs, (long long)s0, (long long)n_slices, head_diff);
             RCU_LAUNCH_CHECK();
             ++launches;
           }

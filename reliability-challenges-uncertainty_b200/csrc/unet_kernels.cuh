@@ -244,7 +244,8 @@ conv_check_kernel(const __nv_bfloat16* __restrict__ src, int c_in, int src_px_st
 // 1x1 head for the cross-check path: bf16 features [img][h][w][32] -> logits (the tcgen05 path fuses this).
 __global__ void __launch_bounds__(256)
 head_check_kernel(const __nv_bfloat16* __restrict__ feat, long long feat_img_stride, const float* __restrict__ head,
-                  float* __restrict__ logits, int n_img, int h, int w, int c, int chunk_slices, long long slice0, long long n_slices_total) {
+                  float* __restrict__ logits, int n_img, int h, int w, int c, int chunk_slices, long long slice0, long long n_slices_total,
+                  int head_diff) {
   const long long total = (long long)n_img * h * w;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
     const long long img = i / ((long long)h * w), px = i - img * h * w;
@@ -256,7 +257,8 @@ head_check_kernel(const __nv_bfloat16* __restrict__ feat, long long feat_img_str
     }
     const int t = (int)(img / chunk_slices), sl = (int)(img - (long long)t * chunk_slices);
     const long long gimg = (long long)t * n_slices_total + slice0 + sl;
-    reinterpret_cast<float2*>(logits)[gimg * h * w + px] = make_float2(l0, l1);
+    if (head_diff) logits[gimg * h * w + px] = l0 - l1;
+    else reinterpret_cast<float2*>(logits)[gimg * h * w + px] = make_float2(l0, l1);
   }
 }
 

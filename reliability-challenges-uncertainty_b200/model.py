@@ -282,18 +282,22 @@ class B200UNet(nn.Module):
         return 0 if self._plan is None else self._plan[3]
 
     def forward_samples(self, images, n_samples=1, dropout_mode=0, det_first=False, seed=None, slice_index0=0, sample0=0,
-                        scale=None):
+                        scale=None, diff=False):
         """All samples of all slices in one call.
 
         images: (N, C, H, W) tensor (moved to the device as float32).  Returns pixel-interleaved logits
-        float32 (n_samples, N, H, W, 2).  dropout_mode: 0 eval, 1 Philox MC dropout (sample ids sample0...),
+        float32 (n_samples, N, H, W, 2) — or, with diff=True, their differences l0 - l1, float32 (n_samples, N, H, W):
+        all a softmax over the two classes needs, at half the bytes (rcu_unet_outputs.logit_diff).
+        dropout_mode: 0 eval, 1 Philox MC dropout (sample ids sample0...),
         2 caller-supplied keep-scale table `scale` float32 (n_stochastic, N, total_dropout_channels)."""
-        return self.forward_outputs(images, n_samples, dropout_mode, det_first, seed, slice_index0, sample0, scale)['logits']
+        out = self.forward_outputs(images, n_samples, dropout_mode, det_first, seed, slice_index0, sample0, scale, logit_diff=diff)
+        return out['logit_diff' if diff else 'logits']
 
     def forward_outputs(self, images, n_samples=1, dropout_mode=0, det_first=False, seed=None, slice_index0=0, sample0=0,
-                        scale=None, sigma=False, features=False, postnet=None):
+                        scale=None, sigma=False, features=False, postnet=None, logit_diff=False):
         """forward_samples plus the optional outputs of rcu_unet_forward_ex, as a dict:
-          'logits'          (n_samples, N, H, W, 2) interleaved
+          'logits'          (n_samples, N, H, W, 2) interleaved — or, with logit_diff=True, INSTEAD of it
+          'logit_diff'      (n_samples, N, H, W) = l0 - l1 of the class head
           'sigma'           same layout, raw conv_sigma output (sigma=True, sigma_out nets)
           'features'        (n_samples, N, start_filters, H, W) float32 = UNet.features (features=True)
           'postnet_logits'  (n_samples, N, H, W, 2): `postnet` (a B200PostNet) applied to the features inside the same
@@ -303,20 +307,24 @@ class B200UNet(nn.Module):
         x = images.to(self._device, torch.float32).contiguous()
         n, _, h, w = x.shape
         self._ensure_plan(h, w, n_samples)
-        logits = torch.empty((n_samples, n, h, w, 2), dtype=torch.float32, device=self._device)
-        result = {'logits': logits}
         outputs = _lib.RcuUnetOutputs()
-        outputs.logits = logits.data_ptr()
+        if logit_diff:
+            result = {'logit_diff': torch.empty((n_samples, n, h, w), dtype=torch.float32, device=self._device)}
+            outputs.logit_diff = result['logit_diff'].data_ptr()
+        else:
+            result = {'logits': torch.empty((n_samples, n, h, w, 2), dtype=torch.float32, device=self._device)}
+            outputs.logits = result['logits'].data_ptr()
+        pair_shape = (n_samples, n, h, w, 2)
         if sigma:
             if not self.sigma_out:
                 raise ValueError('this net has no sigma head (sigma_out=False)')
-            result['sigma'] = torch.empty_like(logits)
+            result['sigma'] = torch.empty(pair_shape, dtype=torch.float32, device=self._device)
             outputs.sigma = result['sigma'].data_ptr()
         if features:
             result['features'] = torch.empty((n_samples, n, self.start_filters, h, w), dtype=torch.float32, device=self._device)
             outputs.features = result['features'].data_ptr()
         if postnet is not None:
-            result['postnet_logits'] = torch.empty_like(logits)
+            result['postnet_logits'] = torch.empty(pair_shape, dtype=torch.float32, device=self._device)
             outputs.postnet = postnet._handle
             outputs.postnet_logits = result['postnet_logits'].data_ptr()
         scale_d = None

@@ -15,6 +15,7 @@ summary consumes the logits behind it directly; anything else that touches it ge
 """
 import abc
 import itertools
+import os
 import weakref
 
 import torch
@@ -82,11 +83,17 @@ def release_engines():
     _POSTNETS.clear()
 
 
-def softmax_planar(logits_interleaved):
-    """(N, H, W, 2) interleaved logits -> (N, 2, H, W) probabilities through the aggregation kernel (1 sample)."""
-    n, h, w, _ = logits_interleaved.shape
-    out = torch.empty((n, 2, h, w), dtype=torch.float32, device=logits_interleaved.device)
-    _lib.check(_lib.lib().rcu_aggregate(_lib.ptr(logits_interleaved), 0, 1, n, h * w, _lib.ptr(out), None, None, None, None, None, None,
+# McPredictStep asks the engine for logit differences instead of logit pairs (RCU_LOGIT_DIFF=0: the pairs, for A/B and parity)
+LOGIT_DIFF = os.environ.get('RCU_LOGIT_DIFF', '1') != '0'
+
+
+def softmax_planar(logits_interleaved, diff=False):
+    """(N, H, W, 2) interleaved logits — or (N, H, W) logit differences l0 - l1 with diff=True — -> (N, 2, H, W) probabilities
+    through the aggregation kernel (1 sample)."""
+    n, h, w = logits_interleaved.shape[:3]
+    src = logits_interleaved.contiguous()
+    out = torch.empty((n, 2, h, w), dtype=torch.float32, device=src.device)
+    _lib.check(_lib.lib().rcu_aggregate(_lib.ptr(src), 3 if diff else 0, 1, n, h * w, _lib.ptr(out), None, None, None, None, None, None,
                                         _lib.current_stream()))
     return out
 
@@ -116,38 +123,41 @@ class LazyWsProbabilities(_LazyTensor):
     MultiPredictionSummary computes it in its own launch and puts the real tensor into `batch_context.output`; any other
     consumer that touches it first gets it from a stand-alone softmax pass."""
 
-    def __init__(self, logits):
-        self.logits = logits  # (N, H, W, 2) interleaved, float32
+    def __init__(self, logits, diff=False):
+        self.logits = logits  # (N, H, W, 2) interleaved, float32 — or (N, H, W) differences l0 - l1 (diff=True)
+        self.diff = diff
 
     @property
     def shape(self):
-        n, h, w, c = self.logits.shape
-        return torch.Size((n, c, h, w))
+        n, h, w = self.logits.shape[:3]
+        return torch.Size((n, 2, h, w))
 
     def materialize(self):
         if self._tensor is None:
-            self._tensor = softmax_planar(self.logits)
+            self._tensor = softmax_planar(self.logits, self.diff)
         return self._tensor
 
 
 class LazyMultiProbabilities(_LazyTensor):
     """Stands in for the stacked per-sample probabilities (T, N, 2, H, W) without materialising them."""
 
-    def __init__(self, logits):
-        self.logits = logits  # (T, N, H, W, 2) interleaved, float32
+    def __init__(self, logits, diff=False):
+        self.logits = logits  # (T, N, H, W, 2) interleaved, float32 — or (T, N, H, W) differences l0 - l1 (diff=True)
+        self.diff = diff
         self._tensor = None
 
     @property
     def shape(self):
-        t, n, h, w, c = self.logits.shape
-        return torch.Size((t, n, c, h, w))
+        t, n, h, w = self.logits.shape[:4]
+        return torch.Size((t, n, 2, h, w))
 
     def materialize(self):
         if self._tensor is None:
-            t, n, h, w, _ = self.logits.shape
-            mean = torch.empty((n, 2, h, w), dtype=torch.float32, device=self.logits.device)
-            multi = torch.empty((t, n, 2, h, w), dtype=torch.float32, device=self.logits.device)
-            _lib.check(_lib.lib().rcu_aggregate(_lib.ptr(self.logits), 0, t, n, h * w, _lib.ptr(mean), None, None, None, None,
+            t, n, h, w = self.logits.shape[:4]
+            src = self.logits.contiguous()
+            mean = torch.empty((n, 2, h, w), dtype=torch.float32, device=src.device)
+            multi = torch.empty((t, n, 2, h, w), dtype=torch.float32, device=src.device)
+            _lib.check(_lib.lib().rcu_aggregate(_lib.ptr(src), 3 if self.diff else 0, t, n, h * w, _lib.ptr(mean), None, None, None, None,
                                                 None, _lib.ptr(multi), _lib.current_stream()))
             self._tensor = multi
         return self._tensor
@@ -258,13 +268,16 @@ class McPredictStep(_BatchStepBase):
         images = batch_context.input['images']
         engine = engine_for(context.model, context.device, _context_seed(context))
         mode = 1 if engine.dropout else 0
+        # the step only ever takes softmaxes of the class logits (customsteps.py:25,33), and a two-class softmax is a function
+        # of l0 - l1 alone: the head writes that difference (4 instead of 8 bytes per voxel-sample, bit-identical probabilities)
+        diff = LOGIT_DIFF
         logits = engine.forward_samples(images, self.mc_steps + 1, dropout_mode=mode, det_first=True,
-                                        slice_index0=self.slices_seen, sample0=0)
+                                        slice_index0=self.slices_seen, sample0=0, diff=diff)
         self.slices_seen += images.shape[0]
         # the weight-scaling softmax rides in the fused summary's launch when one follows (it does in every reference
         # script, bin-dl/brats_test_default.py:46-48); anything else that touches the entry first computes it on the spot
-        batch_context.output['ws_probabilities'] = LazyWsProbabilities(logits[0]) if self.defer_ws else softmax_planar(logits[0])
-        batch_context.output['multi_probabilities'] = LazyMultiProbabilities(logits[1:])
+        batch_context.output['ws_probabilities'] = LazyWsProbabilities(logits[0], diff) if self.defer_ws else softmax_planar(logits[0], diff)
+        batch_context.output['multi_probabilities'] = LazyMultiProbabilities(logits[1:], diff)
 
 
 class EnsemblePredictionStep(_BatchStepBase):
@@ -301,7 +314,8 @@ class MultiPredictionSummary(_BatchStepBase):
         else:
             multi = batch_context.output['multi_probabilities']
         ws = batch_context.output.get('ws_probabilities')
-        ws = ws if isinstance(ws, LazyWsProbabilities) and ws._tensor is None and isinstance(multi, LazyMultiProbabilities) else None
+        ws = ws if (isinstance(ws, LazyWsProbabilities) and ws._tensor is None and isinstance(multi, LazyMultiProbabilities)
+                    and ws.diff == multi.diff) else None
         out = summarize(multi, self.do_mi, self.do_var, self.emit_prediction, self.emit_foreground, ws_logits=None if ws is None else ws.logits)
         if ws is not None:
             ws._tensor = out.pop('ws_probabilities')
@@ -321,8 +335,8 @@ def summarize(multi, do_mi=False, do_var=False, emit_prediction=False, emit_fore
     """mean / entropy / [mutual_info] / [variance] / [prediction] / [foreground = mean[:, 1], dense] of a LazyMultiProbabilities or a real
     (T, N, 2, H, W) probability tensor — one fused pass (rechun/dl/customsteps.py:57-71)."""
     if isinstance(multi, LazyMultiProbabilities):
-        src, kind = multi.logits, 0
-        t, n, h, w, c = src.shape
+        src, kind = multi.logits, (3 if multi.diff else 0)
+        t, n, h, w = src.shape[:4]
     else:
         if multi.dim() != 5 or multi.shape[2] != 2:
             raise ValueError('multi_probabilities must have shape (T, N, 2, H, W), got {}'.format(tuple(multi.shape)))
@@ -331,13 +345,15 @@ def summarize(multi, do_mi=False, do_var=False, emit_prediction=False, emit_fore
         if not src.is_cuda:
             raise _lib.RcuError('multi_probabilities must live on the GPU (there is no CPU fallback)')
     dev = src.device
-    ext = _torch_ext.ops() if kind == 0 else None
+    ws_shape = (n, h, w) if kind == 3 else (n, h, w, 2)
+    ext = _torch_ext.ops() if kind in (0, 3) else None
     if ext is not None:
         # torch-extension binding: one registered operator (outputs allocated inside, PyTorch's current stream)
-        if ws_logits is not None and tuple(ws_logits.shape) != (n, h, w, 2):
-            raise ValueError('ws_logits must be interleaved logits of shape {}'.format((n, h, w, 2)))
-        mean, entropy, mi, var, pred, fg, ws_out = ext.aggregate(src.contiguous(), None if ws_logits is None else ws_logits.contiguous(), bool(do_mi),
-                                                                  bool(do_var), bool(emit_prediction), bool(emit_foreground))
+        if ws_logits is not None and tuple(ws_logits.shape) != ws_shape:
+            raise ValueError('ws_logits must have shape {} (the layout of the samples)'.format(ws_shape))
+        op = ext.aggregate_diff if kind == 3 else ext.aggregate
+        mean, entropy, mi, var, pred, fg, ws_out = op(src.contiguous(), None if ws_logits is None else ws_logits.contiguous(), bool(do_mi),
+                                                      bool(do_var), bool(emit_prediction), bool(emit_foreground))
         out = {'probabilities': mean, 'entropy': entropy}
         if ws_logits is not None:
             out['ws_probabilities'] = ws_out
@@ -360,12 +376,12 @@ def summarize(multi, do_mi=False, do_var=False, emit_prediction=False, emit_fore
     with torch.cuda.device(dev):
         if ws_logits is not None:
             # interleaved logits (N, H, W, 2) of the deterministic weight-scaling pass: its softmax shares this launch
-            if kind != 0 or tuple(ws_logits.shape) != (n, h, w, 2):
-                raise ValueError('ws_logits must be interleaved logits of shape {}'.format((n, h, w, 2)))
+            if kind not in (0, 3) or tuple(ws_logits.shape) != ws_shape:
+                raise ValueError('ws_logits must have shape {} (the layout of the samples)'.format(ws_shape))
             ws_out = torch.empty((n, 2, h, w), dtype=torch.float32, device=dev)
-            _lib.check(_lib.lib().rcu_aggregate_ws(_lib.ptr(src), t, n, h * w, _lib.ptr(ws_logits.contiguous()), _lib.ptr(ws_out), _lib.ptr(mean),
-                                                   _lib.ptr(entropy), _lib.ptr(mi), _lib.ptr(var), _lib.ptr(pred), _lib.ptr(fg),
-                                                   _lib.current_stream()))
+            fn = _lib.lib().rcu_aggregate_ws_diff if kind == 3 else _lib.lib().rcu_aggregate_ws
+            _lib.check(fn(_lib.ptr(src.contiguous()), t, n, h * w, _lib.ptr(ws_logits.contiguous()), _lib.ptr(ws_out), _lib.ptr(mean),
+                          _lib.ptr(entropy), _lib.ptr(mi), _lib.ptr(var), _lib.ptr(pred), _lib.ptr(fg), _lib.current_stream()))
         else:
             _lib.check(_lib.lib().rcu_aggregate(_lib.ptr(src), kind, t, n, h * w, _lib.ptr(mean), _lib.ptr(entropy), _lib.ptr(mi),
                                                 _lib.ptr(var), _lib.ptr(pred), _lib.ptr(fg), None, _lib.current_stream()))

@@ -31,7 +31,7 @@ def test_header_symbols_are_exported_and_bound():
 
 def test_abi_version_and_error_channel():
     lib = _lib.lib()
-    assert lib.rcu_abi_version() == _lib.RCU_ABI_VERSION == 2
+    assert lib.rcu_abi_version() == _lib.RCU_ABI_VERSION == 3
     rc = lib.rcu_metrics_workspace_init(None, 0, None)
     assert rc == _lib.RCU_EINVAL and 'NULL' in _lib.last_error()
     with pytest.raises(ValueError):

@@ -72,3 +72,31 @@ def test_bad_shapes_raise():
         steps.summarize(torch.zeros(3, 2, 3, 4, 4).cuda())
     with pytest.raises(ValueError):
         steps.summarize(steps.LazyMultiProbabilities(torch.zeros(2, 1, 3, 5, 2).cuda()))  # odd H*W
+
+
+@pytest.mark.parametrize('t,n,h,w', [(5, 3, 6, 10), (4, 2, 5, 6), (3, 40, 240, 240), (1, 1, 2, 2), (21, 2, 240, 240)])
+def test_logit_difference_input_gives_bit_identical_outputs(t, n, h, w):
+    """input_kind 3 (l0 - l1 per pixel, what the fused head writes in logit_diff mode) against input_kind 0 (the logit pairs):
+    the two-class softmax is a function of the difference alone, so EVERY output is bit-identical — mean, entropy, MI,
+    variance, argmax, foreground, the weight-scaling softmax riding in the launch and the materialised per-sample stack;
+    small shapes (one pair per thread), hw not a multiple of four (8-byte loads) and the wide path (16-byte loads)."""
+    torch.manual_seed(t * 7 + n)
+    logits = (torch.randn(t + 1, n, h, w, 2) * 3).cuda()
+    logits[1, 0, 0, 0] = torch.tensor([40.0, -40.0])
+    logits[1, 0, 0, 1] = torch.tensor([-60.0, 60.0])
+    diff = (logits[..., 0] - logits[..., 1]).contiguous()
+    for mi_var in (False, True):
+        if mi_var and t < 2:
+            continue
+        a = steps.summarize(steps.LazyMultiProbabilities(logits[1:]), do_mi=mi_var, do_var=mi_var, emit_prediction=True, emit_foreground=True,
+                            ws_logits=logits[0])
+        b = steps.summarize(steps.LazyMultiProbabilities(diff[1:], diff=True), do_mi=mi_var, do_var=mi_var, emit_prediction=True,
+                            emit_foreground=True, ws_logits=diff[0])
+        assert sorted(a) == sorted(b)
+        for k in a:
+            assert torch.equal(a[k], b[k]), k
+        c = steps.summarize(steps.LazyMultiProbabilities(diff[1:], diff=True), do_mi=mi_var, do_var=mi_var)   # without the weight-scaling sample
+        assert torch.equal(c['probabilities'], a['probabilities']) and torch.equal(c['entropy'], a['entropy'])
+    assert torch.equal(steps.LazyMultiProbabilities(diff[1:], diff=True).materialize(), steps.LazyMultiProbabilities(logits[1:]).materialize())
+    assert torch.equal(steps.softmax_planar(diff[0], diff=True), steps.softmax_planar(logits[0]))
+    assert tuple(steps.LazyMultiProbabilities(diff[1:], diff=True).shape) == (t, n, 2, h, w)

@@ -284,3 +284,23 @@ def test_residual_net_matches_reference_golden_and_oracle():
     # a residual=False state dict of the same topology still takes the plain path
     plain = model.B200UNet(R.randomize_statistics(R.init_state_dict(R.UNetConfig(in_channels=4), 20), 7), in_channels=4, dropout=cfg.dropout)
     assert not plain.residual
+
+
+@pytest.mark.parametrize('impl', [0, 1, 2, 3])
+def test_logit_difference_output_is_the_difference_of_the_logit_pair(impl):
+    """rcu_unet_outputs.logit_diff: the head stores l0 - l1 instead of (l0, l1) — the same float32 subtraction softmax2 does on
+    the pair, so it must equal the difference of the pair output bit for bit, in every convolution implementation (pixel-pair
+    kernel, CUDA-core cross-check, per-tap kernel, pixel-row halo kernel) and with MC dropout."""
+    cfg, sd, net = _net('brats')
+    net.set_conv_impl(impl)
+    x = torch.randn(3, 4, 48, 64, generator=torch.Generator().manual_seed(5))
+    pair = net.forward_samples(x, 4, dropout_mode=1, det_first=True, seed=9, slice_index0=17)
+    diff = net.forward_samples(x, 4, dropout_mode=1, det_first=True, seed=9, slice_index0=17, diff=True)
+    assert diff.shape == pair.shape[:-1] and diff.dtype == torch.float32
+    assert torch.equal(diff, pair[..., 0] - pair[..., 1])
+    with pytest.raises(Exception):   # the two outputs are alternatives
+        out = model._lib.RcuUnetOutputs()
+        out.logits, out.logit_diff = pair.data_ptr(), diff.data_ptr()
+        import ctypes
+        model._lib.check(model._lib.lib().rcu_unet_forward_ex(net._handle, model._lib.ptr(x.cuda()), 3, 4, 1, 1, 9, 17, 0, None, ctypes.byref(out),
+                                                              model._lib.current_stream()))

@@ -46,6 +46,11 @@ print('aggregate T=20 one subject: %.4f ms (%.0f GB/s of %d B/voxel)' % (ms, (8 
 ms = timeit(lambda: steps.summarize(steps.LazyMultiProbabilities(logits[1:]), emit_prediction=True, emit_foreground=True, ws_logits=logits[0]))
 print('aggregate T=20 + weight-scaling softmax in the same launch: %.4f ms (%.0f GB/s of %d B/voxel; %.0f GB/s on the 8T+12 = 172 B/voxel accounting)'
       % (ms, (8 * T + 37) * vps / ms / 1e6, 8 * T + 37, (8 * T + 12) * vps / ms / 1e6))
+diff = (logits[..., 0] - logits[..., 1]).contiguous()
+ms = timeit(lambda: steps.summarize(steps.LazyMultiProbabilities(diff[1:], diff=True), emit_prediction=True, emit_foreground=True, ws_logits=diff[0]))
+print('aggregate T=20 + weight-scaling softmax on logit DIFFERENCES (what the head writes for McPredictStep): %.4f ms (%.0f GB/s of the %d B/voxel '
+      'it moves; %.0f GB/s on the 8T+12 = 172 B/voxel accounting)' % (ms, (4 * T + 29) * vps / ms / 1e6, 4 * T + 29, (8 * T + 12) * vps / ms / 1e6))
+del diff, logits
 for S in (1, 50):   # Beta(0.3, 0.3) maps, target ~ Bernoulli(p), 25 % mask: the data-dependent table reads see a spread
     n = S * vps
     bd = torch.distributions.Beta(torch.tensor(0.3, device=dev), torch.tensor(0.3, device=dev))
