@@ -26,6 +26,14 @@ COLS = [
     ('l1tex__m_xbar2l1tex_read_bytes.sum', 'l2_to_sm_MB', 1e-6),
     ('l1tex__m_xbar2l1tex_read_bytes.sum.pct_of_peak_sustained_elapsed', 'l2_to_sm_pct', 1),
     ('lts__throughput.avg.pct_of_peak_sustained_elapsed', 'lts_pct', 1),
+    ('smsp__inst_executed.sum', 'warp_inst_M', 1e-6),
+    ('sm__inst_executed.avg.per_cycle_elapsed', 'ipc', 1),
+    ('smsp__issue_active.avg.pct_of_peak_sustained_active', 'issue_active_pct', 1),
+    ('l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed', 'lsu_pipe_pct', 1),
+    ('l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'smem_conflicts_M', 1e-6),
+    ('smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio', 'stall_long_sb', 1),
+    ('smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio', 'stall_short_sb', 1),
+    ('smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio', 'stall_not_selected', 1),
     ('launch__registers_per_thread', 'regs', 1),
     ('sm__warps_active.avg.pct_of_peak_sustained_active', 'warps_active_pct', 1),
 ]
