@@ -51,8 +51,9 @@ int rcu_device_check(int device);
 
 /* Workspace (bytes) the metric calls below need for `n_subjects` subjects per launch. */
 size_t rcu_metrics_workspace_bytes(int n_subjects);
-/* Must be called once on a fresh workspace (zeroes the per-subject tickets); stream-ordered.  Pass the same
- * workspace_bytes to every call that uses the workspace (the tickets live at its end). */
+/* Must be called once on a fresh workspace (zeroes the per-subject tickets and accumulator tables, which every launch
+ * leaves at zero again); stream-ordered.  Pass the same workspace_bytes to every call that uses the workspace (tickets
+ * and accumulators live at its end).  Calls that share a workspace must be ordered on one stream. */
 int rcu_metrics_workspace_init(void* workspace, size_t workspace_bytes, void* stream);
 
 /* ECE reliability-bin tables.
@@ -100,7 +101,12 @@ int rcu_ue_hist(const void* values, int value_kind, const uint8_t* prediction, c
 
 /* Both of the above in one pass over (p, prediction, target, mask): 7 bytes per voxel.
  * `mask` applies to the calibration tables only (as in EceAction, bin-eval/eval_uncertainty.py:151-152 vs
- * CorrectionAction :195-202 which is unmasked). */
+ * CorrectionAction :195-202 which is unmasked).
+ * For 16-byte aligned p and 4-byte aligned byte maps (and voxels_per_subject % 4 == 0 when n_subjects > 1) this runs the
+ * shared-atomic kernel (csrc/eval_atom.cuh): integer tables bit-exact as always; conf_sum of bins 1 .. n_bins-1 is the
+ * EXACT sum (integers q = p * 2^(23+K) accumulated exactly, converted once: independent of the launch shape), bin 0 a
+ * float64 sum in a fixed order; conf_sum of the overflow slot n_bins is 0 there (a sum over NaN / out-of-range values
+ * carries no meaning; `count` and `invalid` still report them). */
 int rcu_eval_fused(const float* p, const uint8_t* prediction, const uint8_t* target, const uint8_t* mask,
                    int64_t voxels_per_subject, int n_subjects, const float* edges_f32, int n_bins,
                    const float* breaks_f32, int n_breaks, const uint8_t* seg_class, int n_classes,
