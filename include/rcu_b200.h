@@ -328,6 +328,11 @@ int rcu_unet_set_conv_impl(rcu_unet* net, int impl);
 /* Debug: bit i of `mask` lets conv i (execution order, the first conv excluded) use the halo-tile kernel when it is
  * eligible; cleared bits fall back to the per-tap kernel.  Default: all ones. */
 int rcu_unet_set_halo_mask(rcu_unet* net, uint64_t mask);
+/* First-layer dedup (default on): nn.Dropout2d sits between the first conv + bias and its BatchNorm (common/model/unet.py:13-19),
+ * so the first unit's output for a (sample, slice) is the slice's "every channel kept" image with the dropped channels
+ * replaced by constants; it is stored once per slice (two variants: deterministic pass / all kept) and the consuming
+ * convolution patches the dropped channels into its tiles.  Bit-identical results; 0 materialises it per (sample, slice). */
+int rcu_unet_set_first_layer_dedup(rcu_unet* net, int enable);
 /* Optional per-op device timing: when enabled, every kernel launch of rcu_unet_forward is bracketed by CUDA events
  * on the launch stream.  rcu_unet_read_timing synchronises those events and returns, per op of the schedule (see
  * rcu_unet_op_info), the accumulated milliseconds and launch count since the last read.  ms/launches hold n_ops

@@ -93,6 +93,7 @@ PROTOTYPES = {
     'rcu_unet_debug_activation': (c_int, [c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     'rcu_unet_set_conv_impl': (c_int, [c_void_p, c_int]),
     'rcu_unet_set_halo_mask': (c_int, [c_void_p, c_uint64]),
+    'rcu_unet_set_first_layer_dedup': (c_int, [c_void_p, c_int]),
     'rcu_unet_last_launch_count': (c_int64, [c_void_p]),
     'rcu_unet_enable_timing': (c_int, [c_void_p, c_int]),
     'rcu_unet_num_ops': (c_int, [c_void_p]),

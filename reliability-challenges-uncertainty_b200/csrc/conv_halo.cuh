@@ -46,6 +46,11 @@ enum HaloMode { HALO_CONV64 = 0, HALO_CONV32 = 1, HALO_UP64 = 2, HALO_PAIR32 = 3
 #define RCU_UP_PAIRED 1      // A/B switch: 0 runs the up-path phases one by one (and packs their weights per phase)
 #endif
 constexpr bool halo_is_pair(int mode) { return mode == HALO_PAIR32 || mode == HALO_PAIR64; }
+#ifndef RCU_HALO_PATCH_WARPS
+#define RCU_HALO_PATCH_WARPS 4
+#endif
+constexpr int kHaloPatchWarps = RCU_HALO_PATCH_WARPS;   // warps that patch dropped first-layer channels into landed tiles, stage s by warp s mod n
+constexpr int halo_patch_threads(int mode) { return mode == HALO_PAIR32 ? 32 * kHaloPatchWarps : 0; }
 constexpr int kHaloSmemBudget = 225 * 1024;
 
 struct HaloParams {
@@ -79,6 +84,13 @@ struct HaloParams {
   int head_diff;             // 1: the head stores l0 - l1 (float32 per pixel, softmax is a function of the difference alone) instead of the logit pair
   int chunk_slices;
   long long slice0, n_slices_total;
+  // HALO_PAIR32 reading the FIRST convolution's output stored once per slice instead of once per (sample, slice) (unet.cu):
+  //   0 off; 1 every image reads variant 0 (no dropout in that unit); 2 sample 0 reads variant 0 (the deterministic pass), the
+  //   others variant 1; 3 all read variant 1.  Variant 1 holds every channel as if kept; the channels Dropout2d dropped for an
+  //   image are constants (relu of the folded bias) that the patch warp writes into the landed tile before the MMAs read it.
+  int dedup_mode;
+  const float2* patch_coef;  // coefficient rows of the producing unit, [image][coef_stride] + patch_off: x == 0 marks a dropped channel, relu(y) is its value
+  int patch_off;
   // [2][32] weights + [2] bias of the fused head, in the kernel's constant bank: every FFMA of the head takes its weight
   // as a constant operand (the shared-memory copy cost three LDS per channel on the port the tensor pipe reads its operands from)
   float head_w[66];
@@ -122,7 +134,7 @@ struct HaloSmem {
   static constexpr int kOutSlot = 128 * 64;                    // one 128-pixel x 32-channel bf16 tile per epilogue group
   static constexpr int kOutBytes = G * kOutSlot;               // only reserved when the launch uses TMA stores
   static constexpr int kMaxStages = 8;
-  static constexpr int kBarBytes = (2 * kMaxStages + 2 * G + 3) * 8 + 16;
+  static constexpr int kBarBytes = (2 * kMaxStages + 2 * G + 3) * 8 + 16 + kMaxStages * 8 + 64 * kHaloPatchWarps;   // ... + landed[kMaxStages] + 32 bf16 patch values per patch warp
   static constexpr int kFixed = 1024 + kCoefBytes + kHeadBytes + kBarBytes;
   static constexpr int kAccCols = PH * N;                      // TMEM columns of one accumulator stage
   static constexpr int kTmemCols = G * kAccCols < 32 ? 32 : G * kAccCols;   // 128, 256 or 512: powers of two
@@ -132,7 +144,7 @@ struct HaloSmem {
 // G = number of TMEM accumulator stages = number of 4-warp epilogue groups (group g drains the tiles whose index in
 // the CTA's range is g mod G), so G epilogues are in flight while the MMA warp works on the next tile.
 template <int N, int G, int MODE, int PH = 1>
-__global__ void __launch_bounds__(96 + 128 * G, 1)
+__global__ void __launch_bounds__(96 + 128 * G + halo_patch_threads(MODE), 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ HaloOutMaps out_maps,
                  const __grid_constant__ HaloParams prm) {
   using S = HaloSmem<N, G, PH>;
@@ -141,6 +153,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   static_assert(N == 32 || N == 64, "halo kernel serves c_out = 32 / 64");
   static_assert(!halo_is_pair(MODE) || (N == 64 && PH == 1), "pair rows carry two 32-channel output pixels");
   constexpr bool PAIR = halo_is_pair(MODE);
+  constexpr bool PATCH = halo_patch_threads(MODE) != 0;
+  constexpr int kEpiWarp0 = 3 + (PATCH ? kHaloPatchWarps : 0);   // first epilogue warp
   extern __shared__ uint8_t smem_dyn[];
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_dyn + (base - smem_u32(smem_dyn));
@@ -158,6 +172,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const uint32_t bar_w = bar_tempty + G * 8;                        // [1]
   const uint32_t bar_turn = bar_w + 8;                              // [2] issue-turn hand-off between the two MMA warps
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_ptr + (2 * S::kMaxStages + 2 * G + 3) * 8);
+  const uint32_t bar_land = bar_turn + 16 + 16;                     // [kMaxStages] TMA landing barriers of the patch path
+  unsigned short* s_patch = reinterpret_cast<unsigned short*>(bar_ptr + (2 * S::kMaxStages + 2 * G + 3) * 8 + 16 + S::kMaxStages * 8);   // [32]
+  const bool patching = PATCH && prm.dedup_mode >= 2;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -178,6 +195,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     mbar_init(bar_w, 1);
     mbar_init(bar_turn, 1);
     mbar_init(bar_turn + 8, 1);
+    if (PATCH)
+      for (int s = 0; s < S::kMaxStages; ++s) mbar_init(bar_land + 8 * s, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -212,11 +231,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       int tx = t_begin - img * tiles_per_img - ty * prm.tiles_x;
       for (int tile = t_begin; tile < t_end; ++tile) {
         const int x0 = tx * kHaloTileW - 1, y0 = ty * kHaloTileH;
+        int src_img = img;
+        if (PATCH && prm.dedup_mode != 0) {   // the source holds [variant][slice of the chunk], not [sample][slice]
+          const int t = img / prm.chunk_slices, sl = img - t * prm.chunk_slices;
+          const int variant = prm.dedup_mode == 1 ? 0 : ((prm.dedup_mode == 2 && t == 0) ? 0 : 1);
+          src_img = variant * prm.chunk_slices + sl;
+        }
         for (int j = 0; j < prm.n_chunks; ++j) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
           const uint32_t dst = smem_a + (uint32_t)stage * prm.chunk_stride;
-          mbar_expect_tx(bar_full + 8 * stage, prm.chunk_bytes);
-          tma_load_4d(dst, &map_a, bar_full + 8 * stage, j * 64, x0, y0 - 1, img);
+          const uint32_t bar_tx = (patching ? bar_land : bar_full) + 8 * stage;   // patched tiles reach the MMA warps through the patch warp
+          mbar_expect_tx(bar_tx, prm.chunk_bytes);
+          tma_load_4d(dst, &map_a, bar_tx, j * 64, x0, y0 - 1, src_img);
           if (++stage == prm.n_stages) { stage = 0; phase ^= 1u; }
         }
         if (++tx == prm.tiles_x) { tx = 0; if (++ty == prm.tiles_y) { ty = 0; ++img; } }
@@ -386,12 +412,82 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           if (++acc == G) { acc = 0; acc_phase ^= 1u; }
       }
     }
+  } else if (PATCH && warp < kEpiWarp0) {
+    // ===================== patch warps (first-layer dedup): dropped channels of the landed tiles =====================
+    // A tile holds the "every channel kept" variant of the first convolution's output for this slice.  Dropout2d sits
+    // between conv + bias and BatchNorm (unet.py:13-19), so a dropped channel of a (sample, slice) is relu(d_c) at every
+    // pixel: its two 2-byte elements per window row (pixel 0 / 1 of the pair) are overwritten — inside the image only,
+    // the zero padding stays — then the tile is handed to the MMA warps.  One box per tile (32-channel source); tile i of
+    // the CTA's range lands in stage i mod n_stages, and a stage belongs to patch warp stage mod kHaloPatchWarps (one warp alone
+    // cannot keep up with the tensor pipe; per-stage ownership keeps the parity waits unambiguous for any n_stages).
+    if (patching) {
+      const int pw = warp - 3;
+      unsigned short* my_patch = s_patch + 32 * pw;
+      // this lane's window rows (lane, lane + 32, ...): position, byte offset and swizzle term never change
+      constexpr int kRowsPerLane = (kHaloRows * kHaloPitch + 31) / 32;
+      int wy[kRowsPerLane], wx[kRowsPerLane];
+      uint32_t roff[kRowsPerLane], rsw[kRowsPerLane];
+#pragma unroll
+      for (int k = 0; k < kRowsPerLane; ++k) {
+        const int r = lane + 32 * k;
+        wy[k] = r / kHaloPitch; wx[k] = r - wy[k] * kHaloPitch;
+        roff[k] = (uint32_t)r * 128u; rsw[k] = (uint32_t)(r & 7);
+      }
+      int cur_img = -1;
+      uint32_t mask = 0;
+      const int n_tiles = t_end - t_begin;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < n_tiles; ++i, stage = (stage + 1 == prm.n_stages ? 0 : stage + 1), phase ^= (stage == 0 ? 1u : 0u)) {
+        if (stage % kHaloPatchWarps != pw) continue;   // a stage always belongs to the same warp: it sees every phase of its barrier in order
+        const int tile = t_begin + i;
+        const int img = tile / tiles_per_img;
+        const int rem = tile - img * tiles_per_img;
+        const int ty = rem / prm.tiles_x, tx = rem - ty * prm.tiles_x;
+        if (img != cur_img) {
+          const float2 c = __ldg(prm.patch_coef + (long long)img * prm.coef_stride + prm.patch_off + lane);
+          const bool stochastic = !(prm.dedup_mode == 2 && img / prm.chunk_slices == 0);
+          mask = __ballot_sync(0xffffffffu, stochastic && c.x == 0.0f);
+          __syncwarp();
+          my_patch[lane] = __bfloat16_as_ushort(__float2bfloat16_rn(fmaxf(c.y, 0.0f)));
+          __syncwarp();
+          cur_img = img;
+        }
+        mbar_wait(bar_land + 8 * stage, phase);
+        if (mask != 0u) {
+          uint8_t* tile_ptr = base_ptr + (w_span + (uint32_t)stage * prm.chunk_stride);
+          const int yb = ty * kHaloTileH - 1, xb = tx * kHaloTileW - 1;
+          for (uint32_t m = mask; m != 0u; m &= m - 1u) {
+            const uint32_t c = (uint32_t)__ffs(m) - 1u;
+            const unsigned short v = my_patch[c];
+            const uint32_t ch = c >> 3, cl = (c & 7u) << 1;
+#pragma unroll
+            for (int k = 0; k < kRowsPerLane; ++k) {
+              const int y = yb + wy[k], xp = xb + wx[k];
+              if (lane + 32 * k < kHaloRows * kHaloPitch && y >= 0 && y < prm.in_h && xp >= 0 && xp < prm.in_w) {
+                // SWIZZLE_128B: the 16-byte piece index of an element is XORed with the row index modulo 8
+                const uint32_t o = roff[k] + (((ch ^ rsw[k]) << 4) | cl);
+#ifndef RCU_PATCH_EXP_NOSTORE
+                *reinterpret_cast<unsigned short*>(tile_ptr + o) = v;            // pixel 0 of the pair: K = c
+                *reinterpret_cast<unsigned short*>(tile_ptr + (o ^ 64u)) = v;     // pixel 1: K = 32 + c, four pieces further
+#endif
+              }
+            }
+          }
+#ifndef RCU_PATCH_EXP_NOFENCE
+          fence_proxy_async();   // generic-proxy stores -> visible to the tensor cores' async-proxy reads
+#endif
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_full + 8 * stage);
+      }
+    }
   } else {
     // ===================== epilogue: G groups of 4 warps; group g owns accumulator stage g =====================
-    const int group = (warp - 3) >> 2;
+    const int group = (warp - kEpiWarp0) >> 2;
     const int q = warp & 3;               // TMEM lane quarter this warp may access (each group holds all four)
     const int row = q * 32 + lane;
-    const int gt = threadIdx.x - 96 - group * 128;   // 0..127 inside the group
+    const int gt = threadIdx.x - 32 * kEpiWarp0 - group * 128;   // 0..127 inside the group
     float2* coef = s_coef + group * N;
     const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(group * S::kAccCols);
     uint32_t acc_phase = 0;

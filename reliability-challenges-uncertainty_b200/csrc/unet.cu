@@ -148,6 +148,10 @@ struct rcu_unet {
   int conv_impl = 0;
   unsigned long long halo_mask = ~0ull;  // debug: bit i enables the halo kernel for conv i (execution order)
   bool pair_enabled = true;              // debug: rcu_unet_set_conv_impl(net, 3) runs the pixel-row halo kernel where the pair kernel would
+  bool first_dedup = true;               // store the first convolution's output once per slice (rcu_unet_set_first_layer_dedup)
+  bool unit0_dropout = false;            // the first unit has a Dropout2d site
+  float2* d_e0coef = nullptr;            // [2][start_filters] epilogue coefficients of the first conv: deterministic / every channel kept
+  int last_dedup_mode = 0;
   long long last_launches = 0;
   int last_n_img = 0;
   // optional per-op timing
@@ -679,7 +683,7 @@ static int launch_conv_halo(const ConvLayer& L, const HaloParams& prm, const Hal
   long long grid = sm_count();
   if (grid > total_tiles) grid = total_tiles;
   if (grid < 1) return RCU_OK;
-  return launch_pdl(kern, (unsigned)grid, HS::kThreads, smem, st, L.map_halo, maps, prm);
+  return launch_pdl(kern, (unsigned)grid, HS::kThreads + halo_patch_threads(MODE), smem, st, L.map_halo, maps, prm);
 }
 
 }  // namespace rcu
@@ -774,6 +778,16 @@ extern "C" int rcu_unet_create(const rcu_unet_desc* d, int device, rcu_unet** ou
         for (int k = 0; k < 9; ++k) w[((size_t)ci * 9 + k) * sf + co] = u0.weight[((size_t)co * u0.c_in + ci) * 9 + k];
     RCU_TRY(dev_upload(net, w, &net->d_first_w));
     net->first_coef_off = unit_off[0];
+    // the two sample-independent coefficient rows of the first unit, in coef_kernel's own arithmetic (s = 1 and s = 1 / (1 - p))
+    net->unit0_dropout = u0.has_dropout != 0;
+    const float inv_keep0 = 1.0f / (1.0f - d->p_drop);
+    std::vector<float2> e0((size_t)2 * sf);
+    for (int c = 0; c < sf; ++c) {
+      const float a = fa[unit_off[0] + c], ba = fba[unit_off[0] + c], dd = fd[unit_off[0] + c];
+      e0[c] = make_float2(a * 1.0f, std::fmaf(ba, 1.0f, dd));
+      e0[sf + c] = make_float2(a * inv_keep0, std::fmaf(ba, inv_keep0, dd));
+    }
+    RCU_TRY(dev_upload(net, e0, &net->d_e0coef));
   }
   // ---- 1x1 heads ----
   std::vector<float> host_head[2];
@@ -910,6 +924,12 @@ extern "C" int rcu_unet_set_conv_impl(rcu_unet* net, int impl) {
   RCU_CHECK_ARG(impl >= 0 && impl <= 3, "conv impl must be 0 (tcgen05), 1 (cross-check), 2 (tcgen05, per-tap kernel only) or 3 (tcgen05 without the pixel-pair kernel)");
   net->pair_enabled = impl != 3;
   net->conv_impl = impl == 3 ? 0 : impl;
+  return RCU_OK;
+}
+
+extern "C" int rcu_unet_set_first_layer_dedup(rcu_unet* net, int enable) {
+  RCU_CHECK_ARG(net != nullptr, "NULL handle");
+  net->first_dedup = enable != 0;
   return RCU_OK;
 }
 
@@ -1185,7 +1205,7 @@ static int run_conv_halo(rcu_unet* net, const ConvLayer& L, int n_img, int cs, l
 }
 
 static int run_conv_halo_pair(rcu_unet* net, const ConvLayer& L, int n_img, int cs, long long s0, long long n_slices, float* logits, int head_diff,
-                              cudaStream_t st, long long* launches) {
+                              int dedup_mode, cudaStream_t st, long long* launches) {
   const HaloPack& hp = L.pairp;
   HaloParams prm;
   std::memset(&prm, 0, sizeof(prm));
@@ -1217,6 +1237,8 @@ static int run_conv_halo_pair(rcu_unet* net, const ConvLayer& L, int n_img, int 
   prm.logits = logits;
   prm.head_diff = head_diff;
   prm.chunk_slices = cs; prm.slice0 = s0; prm.n_slices_total = n_slices;
+  prm.dedup_mode = dedup_mode;
+  prm.patch_coef = net->d_coef; prm.patch_off = net->first_coef_off;
   ConvLayer view = L;
   view.map_halo = L.map_halo_pair;
   int rc = hp.pair_mode == 1 ? launch_conv_halo<64, HALO_PAIR32>(view, prm, maps, st) : launch_conv_halo<64, HALO_PAIR64>(view, prm, maps, st);
@@ -1279,6 +1301,21 @@ extern "C" int rcu_unet_forward_ex(rcu_unet* net, const float* images, int64_t n
       RCU_LAUNCH_CHECK();
       ++launches;
     }
+    // First-layer dedup: Dropout2d acts between the first conv + bias and its BatchNorm, so the unit's output for a
+    // (sample, slice) is the "every channel kept" image of the slice with the dropped channels replaced by constants.  The
+    // first conv then writes two images per slice (deterministic / all kept) instead of n_samples, and the pixel-pair kernel
+    // that reads them patches the dropped channels into its landed tiles: 21x fewer bytes written and read at 240^2, and
+    // bit-identical activations.  Needs the Philox / no-dropout modes (a caller's scale table may hold anything) and the
+    // pixel-pair kernel over a 32-channel source as the only consumer.
+    int dedup_mode = 0;
+    if (net->first_dedup && net->conv_impl == 0 && net->pair_enabled && sf == 32 && dropout_mode != 2 && !net->residual && !net->convs.empty()) {
+      const ConvLayer& L1 = net->convs[0];
+      const bool reads_first = L1.src.base == net->first_out.base && L1.use_pair && L1.pairp.pair_mode == 1 && (net->halo_mask & 1ull);
+      const int variants = (dropout_mode == 0 || !net->unit0_dropout) ? 1 : 2;
+      if (reads_first && variants * cs <= n_img)
+        dedup_mode = variants == 1 ? 1 : (det_first ? 2 : 3);
+    }
+    net->last_dedup_mode = dedup_mode;
     bool pool_done = false;   // the previous conv's epilogue already produced the pooled tensor
     for (size_t op_index = 0; op_index < net->ops.size(); ++op_index) {
       const Op& op = net->ops[op_index];
@@ -1289,13 +1326,16 @@ extern "C" int rcu_unet_forward_ex(rcu_unet* net, const float* images, int64_t n
         const int tiles = ((H + kFirstTileH - 1) / kFirstTileH) * ((W + kFirstTileW - 1) / kFirstTileW);
         const size_t smem = ((size_t)net->in_channels * 9 * sf + (size_t)net->in_channels * kFirstInPx) * sizeof(float);
         dim3 grid((unsigned)tiles, (unsigned)cs);
-        if (sf == 32)
+        if (dedup_mode != 0)   // two sample-independent variants per slice (deterministic, every channel kept) instead of n_samples images
+          first_conv_kernel<32><<<grid, 256, smem, st>>>(images, net->in_channels, H, W, (long long)s0, cs, dedup_mode == 1 ? 1 : 2, net->d_first_w,
+                                                         net->d_e0coef, sf, 0, 1, net->first_out.base, net->first_out.img_stride);
+        else if (sf == 32)
           first_conv_kernel<32><<<grid, 256, smem, st>>>(images, net->in_channels, H, W, (long long)s0, cs, n_samples, net->d_first_w,
-                                                         net->d_coef, net->n_cols, net->first_coef_off, net->first_out.base,
+                                                         net->d_coef, net->n_cols, net->first_coef_off, 0, net->first_out.base,
                                                          net->first_out.img_stride);
         else
           first_conv_kernel<64><<<grid, 256, smem, st>>>(images, net->in_channels, H, W, (long long)s0, cs, n_samples, net->d_first_w,
-                                                         net->d_coef, net->n_cols, net->first_coef_off, net->first_out.base,
+                                                         net->d_coef, net->n_cols, net->first_coef_off, 0, net->first_out.base,
                                                          net->first_out.img_stride);
         RCU_LAUNCH_CHECK();
         ++launches;
@@ -1322,7 +1362,7 @@ extern "C" int rcu_unet_forward_ex(rcu_unet* net, const float* images, int64_t n
         const int head_diff = L.out_slot ? 0 : logits_are_diff;
         if (L.out_slot && sigma == nullptr) continue;   // nobody asked for the sigma branch
         if (net->conv_impl == 0 && L.use_pair && net->pair_enabled && ((net->halo_mask >> op.conv) & 1ull)) {
-          int rc = run_conv_halo_pair(net, L, n_img, cs, (long long)s0, (long long)n_slices, head_out, head_diff, st, &launches);
+          int rc = run_conv_halo_pair(net, L, n_img, cs, (long long)s0, (long long)n_slices, head_out, head_diff, op.conv == 0 ? dedup_mode : 0, st, &launches);
           if (rc) return rc;
           pool_done = L.pool_dst.base != nullptr;
           continue;
@@ -1479,6 +1519,10 @@ extern "C" int rcu_unet_debug_activation(rcu_unet* net, int index, float* out, s
   const Op& op = net->ops[index];
   if (op.kind == OP_CONV && net->convs[op.conv].head && net->conv_impl != 1) {
     set_error("activation %d is fused away (conv_cls.0 feeds the head in registers on the tcgen05 path)", index);
+    return RCU_ENOTSUP;
+  }
+  if (op.kind == OP_FIRST && net->last_dedup_mode != 0) {
+    set_error("activation %d is stored once per slice (first-layer dedup): rcu_unet_set_first_layer_dedup(net, 0) materialises it per sample", index);
     return RCU_ENOTSUP;
   }
   const long long n = (long long)net->last_n_img * op.h * op.w * op.c;

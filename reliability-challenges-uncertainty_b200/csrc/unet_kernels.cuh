@@ -73,7 +73,7 @@ template <int C_OUT>
 __global__ void __launch_bounds__(256)
 first_conv_kernel(const float* __restrict__ images, int c_in, int h, int w, long long slice0, int chunk_slices, int n_samples,
                   const float* __restrict__ weight /* [c_in*9][C_OUT] */, const float2* __restrict__ coef, long long coef_stride,
-                  int coef_off, __nv_bfloat16* __restrict__ out, long long out_img_stride) {
+                  int coef_off, int coef_row_per_sample, __nv_bfloat16* __restrict__ out, long long out_img_stride) {
   constexpr int CG = C_OUT / 8;      // channel groups = pixels per thread
   constexpr int PG = 256 / CG;       // pixel groups
   extern __shared__ float s_first[];
@@ -114,7 +114,7 @@ first_conv_kernel(const float* __restrict__ images, int c_in, int h, int w, long
     }
   for (int t = 0; t < n_samples; ++t) {
     const int im = t * chunk_slices + sl;
-    const float2* cf = coef + (long long)im * coef_stride + coef_off + cg * 8;
+    const float2* cf = coef + (long long)(coef_row_per_sample ? t : im) * coef_stride + coef_off + cg * 8;   // dedup: one row per variant
     float2 c8[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) c8[c] = __ldg(cf + c);

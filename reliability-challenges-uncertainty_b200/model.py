@@ -249,6 +249,11 @@ class B200UNet(nn.Module):
         3 = tcgen05 without the pixel-pair kernel (A/B)."""
         _lib.check(_lib.lib().rcu_unet_set_conv_impl(self._handle, int(impl)))
 
+    def set_first_layer_dedup(self, enable):
+        """First-layer dedup (default on): the first unit's output is stored once per slice and the dropped channels of each
+        (sample, slice) are patched into the consumer's tiles; False materialises it per (sample, slice) (A/B, debug)."""
+        _lib.check(_lib.lib().rcu_unet_set_first_layer_dedup(self._handle, int(bool(enable))))
+
     def set_halo_mask(self, mask):
         """Debug: bit i lets conv i (execution order) use the halo-tile kernel; default all ones."""
         _lib.check(_lib.lib().rcu_unet_set_halo_mask(self._handle, int(mask) & 0xFFFFFFFFFFFFFFFF))

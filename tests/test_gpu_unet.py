@@ -75,6 +75,7 @@ def test_tcgen05_path_matches_cuda_core_cross_check_layer_by_layer():
     cfg, sd, net_tc = _net('brats', chunk_images=64)
     _, _, net_ck = _net('brats', chunk_images=64)
     net_ck.set_conv_impl(1)
+    net_tc.set_first_layer_dedup(False)   # activation 0 per (sample, slice), as the cross-check path stores it (the dedup has its own test)
     n, h, w = 3, 48, 64
     x = torch.randn(n, 4, h, w)
     out_tc = net_tc.forward_samples(x, 2, dropout_mode=1, det_first=True, seed=5)
@@ -304,3 +305,26 @@ def test_logit_difference_output_is_the_difference_of_the_logit_pair(impl):
         import ctypes
         model._lib.check(model._lib.lib().rcu_unet_forward_ex(net._handle, model._lib.ptr(x.cuda()), 3, 4, 1, 1, 9, 17, 0, None, ctypes.byref(out),
                                                               model._lib.current_stream()))
+
+
+@pytest.mark.parametrize('shape,n,t,det_first', [((48, 64), 3, 4, True), ((240, 240), 2, 6, True), ((64, 48), 5, 3, False), ((16, 16), 2, 2, True),
+                                                  ((240, 240), 9, 21, True)])
+def test_first_layer_dedup_is_bit_identical(shape, n, t, det_first):
+    """First-layer dedup (default): the first unit's output is stored once per slice (deterministic / every-channel-kept variant)
+    and the pixel-pair kernel patches each (sample, slice)'s dropped channels into its landed tiles.  The patched tiles hold
+    exactly the values the per-sample tensor held, so every logit must be bit-identical to the run with the dedup off — MC
+    with and without the deterministic first sample, eval mode, several chunks per call, image borders and partial tiles."""
+    cfg, sd, on = _net('brats', chunk_images=63)
+    _, _, off = _net('brats', chunk_images=63)
+    off.set_first_layer_dedup(False)
+    x = torch.randn(n, 4, *shape, generator=torch.Generator().manual_seed(n * 31 + t))
+    a = on.forward_samples(x, t, dropout_mode=1, det_first=det_first, seed=11, slice_index0=5)
+    b = off.forward_samples(x, t, dropout_mode=1, det_first=det_first, seed=11, slice_index0=5)
+    assert torch.equal(a, b)
+    assert torch.equal(on.forward_samples(x, 1, dropout_mode=0), off.forward_samples(x, 1, dropout_mode=0))
+    with pytest.raises(NotImplementedError):   # the per-sample tensor does not exist in this mode
+        on.debug_activation(0, (n * 1, shape[0], shape[1], 32))
+    # a caller-supplied scale table may hold anything: that mode keeps the per-sample tensor (and still agrees)
+    scale = metrics.philox_keep_scale_host(11, cfg.dropout, on.site_channels, 5, n, 0, t - (1 if det_first else 0))
+    c = on.forward_samples(x, t, dropout_mode=2, det_first=det_first, scale=scale)
+    assert torch.equal(c, a)

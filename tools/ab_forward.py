@@ -19,6 +19,8 @@ def worker():
     from rcu_b200 import model, synth
     torch.set_grad_enabled(False)
     net = model.B200UNet(synth.random_unet_state_dict(in_channels=4, seed=20), in_channels=4, dropout=0.05, device='cuda:0', seed=20)
+    if os.environ.get('RCU_AB_DEDUP') == '0':
+        net.set_first_layer_dedup(False)
     x = torch.randn((155, 4, 240, 240), generator=torch.Generator().manual_seed(1)).cuda()
     for i in range(3):
         net.forward_samples(x, 21, dropout_mode=1, det_first=True, slice_index0=i * 155)
@@ -35,7 +37,7 @@ def worker():
     net.read_timing()
     net.forward_samples(x, 21, dropout_mode=1, det_first=True, slice_index0=0)
     ms, _ = net.read_timing()
-    sel = {i: round(float(ms[i]), 2) for i in (1, 4, 20, 21, 23, 24, 25, 26)}
+    sel = {i: round(float(ms[i]), 2) for i in (0, 1, 4, 20, 21, 23, 24, 25, 26)}
     print('%-28s forward %.2f ms (min %.2f)  ops %s' % (os.environ.get('RCU_AB_NAME', 'default'), float(np.median(ts)), min(ts), sel), flush=True)
 
 
@@ -44,11 +46,13 @@ if __name__ == '__main__':
         worker()
     else:
         rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 2
-        libs = [('default', None)] + [(os.path.basename(p)[len('librcu_b200_'):-3], p) for p in
+        libs = [('default', None), ('default_nodedup', None)] + [(os.path.basename(p)[len('librcu_b200_'):-3], p) for p in
                                       sorted(glob.glob(os.path.join(ROOT, 'reliability-challenges-uncertainty_b200', 'build', 'variants', '*.so')))]
         for _ in range(rounds):
             for name, path in libs:
                 env = dict(os.environ, RCU_AB_NAME=name, RCU_B200_BINDING='ctypes')
+                if name.endswith('_nodedup'):
+                    env['RCU_AB_DEDUP'] = '0'
                 if path:
                     env['RCU_B200_LIB'] = path
                 subprocess.run([sys.executable, os.path.abspath(__file__), 'worker'], env=env, check=False)
