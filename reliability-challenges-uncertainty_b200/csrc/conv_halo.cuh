@@ -49,6 +49,9 @@ constexpr bool halo_is_pair(int mode) { return mode == HALO_PAIR32 || mode == HA
 #ifndef RCU_HALO_PATCH_WARPS
 #define RCU_HALO_PATCH_WARPS 4
 #endif
+#ifndef RCU_HALO_PATCH_SPLIT
+#define RCU_HALO_PATCH_SPLIT 0   // 1: every patch warp takes a share of the rows of EVERY tile (shortest hand-over); 0: whole tiles, one stage per warp
+#endif
 constexpr int kHaloPatchWarps = RCU_HALO_PATCH_WARPS;   // warps that patch dropped first-layer channels into landed tiles, stage s by warp s mod n
 constexpr int halo_patch_threads(int mode) { return mode == HALO_PAIR32 ? 32 * kHaloPatchWarps : 0; }
 constexpr int kHaloSmemBudget = 225 * 1024;
@@ -185,7 +188,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (prm.tma_store)
       for (int i = 0; i < PH; ++i) tma_prefetch_desc(&out_maps.m[i]);
     for (int s = 0; s < S::kMaxStages; ++s) {
-      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_full + 8 * s, (patching && RCU_HALO_PATCH_SPLIT) ? kHaloPatchWarps : 1);   // split patching: one arrival per patch warp
       mbar_init(bar_empty + 8 * s, 1);
     }
     for (int s = 0; s < G; ++s) {
@@ -238,7 +241,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           src_img = variant * prm.chunk_slices + sl;
         }
         for (int j = 0; j < prm.n_chunks; ++j) {
-          mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+          mbar_wait_slack(bar_empty + 8 * stage, phase ^ 1u);
           const uint32_t dst = smem_a + (uint32_t)stage * prm.chunk_stride;
           const uint32_t bar_tx = (patching ? bar_land : bar_full) + 8 * stage;   // patched tiles reach the MMA warps through the patch warp
           mbar_expect_tx(bar_tx, prm.chunk_bytes);
@@ -418,18 +421,22 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // between conv + bias and BatchNorm (unet.py:13-19), so a dropped channel of a (sample, slice) is relu(d_c) at every
     // pixel: its two 2-byte elements per window row (pixel 0 / 1 of the pair) are overwritten — inside the image only,
     // the zero padding stays — then the tile is handed to the MMA warps.  One box per tile (32-channel source); tile i of
-    // the CTA's range lands in stage i mod n_stages, and a stage belongs to patch warp stage mod kHaloPatchWarps (one warp alone
-    // cannot keep up with the tensor pipe; per-stage ownership keeps the parity waits unambiguous for any n_stages).
+    // the CTA's range lands in stage i mod n_stages.  One warp alone cannot keep up with the tensor pipe: either every patch warp
+    // takes a quarter of the rows of every tile (RCU_HALO_PATCH_SPLIT, bar_full then counts one arrival per warp), or a stage
+    // belongs to patch warp stage mod kHaloPatchWarps (per-stage ownership keeps the parity waits unambiguous for any n_stages).
     if (patching) {
       const int pw = warp - 3;
       unsigned short* my_patch = s_patch + 32 * pw;
-      // this lane's window rows (lane, lane + 32, ...): position, byte offset and swizzle term never change
-      constexpr int kRowsPerLane = (kHaloRows * kHaloPitch + 31) / 32;
+      // this lane's window rows: position, byte offset and swizzle term never change.  Split mode: the rows of a tile are dealt
+      // out over all patch warps (row = 32 * (k * warps + pw) + lane), whole-tile mode: lane, lane + 32, ... of the warp's own tiles
+      constexpr int kRowStep = RCU_HALO_PATCH_SPLIT ? 32 * kHaloPatchWarps : 32;
+      constexpr int kRowsPerLane = (kHaloRows * kHaloPitch + kRowStep - 1) / kRowStep;
+      const int row0 = RCU_HALO_PATCH_SPLIT ? 32 * pw + lane : lane;
       int wy[kRowsPerLane], wx[kRowsPerLane];
       uint32_t roff[kRowsPerLane], rsw[kRowsPerLane];
 #pragma unroll
       for (int k = 0; k < kRowsPerLane; ++k) {
-        const int r = lane + 32 * k;
+        const int r = row0 + kRowStep * k;
         wy[k] = r / kHaloPitch; wx[k] = r - wy[k] * kHaloPitch;
         roff[k] = (uint32_t)r * 128u; rsw[k] = (uint32_t)(r & 7);
       }
@@ -439,7 +446,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       for (int i = 0; i < n_tiles; ++i, stage = (stage + 1 == prm.n_stages ? 0 : stage + 1), phase ^= (stage == 0 ? 1u : 0u)) {
-        if (stage % kHaloPatchWarps != pw) continue;   // a stage always belongs to the same warp: it sees every phase of its barrier in order
+        if (!RCU_HALO_PATCH_SPLIT && stage % kHaloPatchWarps != pw) continue;   // a stage always belongs to the same warp: it sees every phase of its barrier in order
         const int tile = t_begin + i;
         const int img = tile / tiles_per_img;
         const int rem = tile - img * tiles_per_img;
@@ -453,7 +460,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           __syncwarp();
           cur_img = img;
         }
-        mbar_wait(bar_land + 8 * stage, phase);
+        mbar_wait_slack(bar_land + 8 * stage, phase);
         if (mask != 0u) {
           uint8_t* tile_ptr = base_ptr + (w_span + (uint32_t)stage * prm.chunk_stride);
           const int yb = ty * kHaloTileH - 1, xb = tx * kHaloTileW - 1;
@@ -464,7 +471,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
             for (int k = 0; k < kRowsPerLane; ++k) {
               const int y = yb + wy[k], xp = xb + wx[k];
-              if (lane + 32 * k < kHaloRows * kHaloPitch && y >= 0 && y < prm.in_h && xp >= 0 && xp < prm.in_w) {
+              if (row0 + kRowStep * k < kHaloRows * kHaloPitch && y >= 0 && y < prm.in_h && xp >= 0 && xp < prm.in_w) {
                 // SWIZZLE_128B: the 16-byte piece index of an element is XORed with the row index modulo 8
                 const uint32_t o = roff[k] + (((ch ^ rsw[k]) << 4) | cl);
 #ifndef RCU_PATCH_EXP_NOSTORE
@@ -504,7 +511,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         cur_img = img;
       }
 
-      mbar_wait(bar_tfull + 8 * group, acc_phase);
+      mbar_wait_slack(bar_tfull + 8 * group, acc_phase);
       tc_fence_after();
 
       const int y = ty * kHaloTileH + (row >> 3), x = tx * kHaloTileW + (row & 7);
@@ -512,29 +519,35 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       if constexpr (PAIR) {
         // row = pixel pair (y, x): accumulator columns [0, 32) are output pixel 2x, [32, 64) pixel 2x + 1 (prm.in_w counts pairs)
         if (prm.head != nullptr) {
-          float lg[4];
+          // 16 channels of BOTH pixels per step: a channel's coefficients are read once for the pair (the broadcast reads of the
+          // coefficients were a quarter of the kernel's shared-memory wavefronts when every pixel read them again)
+          float lg[4] = {prm.head_w[64], prm.head_w[65], prm.head_w[64], prm.head_w[65]};
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(taddr0 + (uint32_t)(half * 32), v);
+          for (int cc = 0; cc < 2; ++cc) {
+            uint32_t v0[16], v1[16];
+            tmem_ld_32x32b_x16(taddr0 + (uint32_t)(cc * 16), v0);
+            tmem_ld_32x32b_x16(taddr0 + (uint32_t)(32 + cc * 16), v1);
             tmem_ld_wait();
-            if (half == 1) {
+            if (cc == 1) {
               tc_fence_before();
               mbar_arrive_warp(bar_tempty + 8 * group);
             }
-            float l0 = prm.head_w[64], l1 = prm.head_w[65];
 #pragma unroll
-            for (int c = 0; c < 32; c += 2) {
-              const float4 cc = *reinterpret_cast<const float4*>(&coef[c]);   // two channels per 16-byte broadcast read
-              float a0 = fmaf(__uint_as_float(v[c]), cc.x, cc.y), a1 = fmaf(__uint_as_float(v[c + 1]), cc.z, cc.w);
-              if (prm.relu) { a0 = fmaxf(a0, 0.0f); a1 = fmaxf(a1, 0.0f); }
-              l0 = fmaf(a0, prm.head_w[c], l0);
-              l1 = fmaf(a0, prm.head_w[32 + c], l1);
-              l0 = fmaf(a1, prm.head_w[c + 1], l0);
-              l1 = fmaf(a1, prm.head_w[33 + c], l1);
+            for (int c = 0; c < 16; c += 2) {
+              const int ch = cc * 16 + c;
+              const float4 k = *reinterpret_cast<const float4*>(&coef[ch]);   // two channels per 16-byte broadcast read
+              float a0 = fmaf(__uint_as_float(v0[c]), k.x, k.y), a1 = fmaf(__uint_as_float(v0[c + 1]), k.z, k.w);
+              float b0 = fmaf(__uint_as_float(v1[c]), k.x, k.y), b1 = fmaf(__uint_as_float(v1[c + 1]), k.z, k.w);
+              if (prm.relu) { a0 = fmaxf(a0, 0.0f); a1 = fmaxf(a1, 0.0f); b0 = fmaxf(b0, 0.0f); b1 = fmaxf(b1, 0.0f); }
+              lg[0] = fmaf(a0, prm.head_w[ch], lg[0]);
+              lg[1] = fmaf(a0, prm.head_w[32 + ch], lg[1]);
+              lg[0] = fmaf(a1, prm.head_w[ch + 1], lg[0]);
+              lg[1] = fmaf(a1, prm.head_w[33 + ch], lg[1]);
+              lg[2] = fmaf(b0, prm.head_w[ch], lg[2]);
+              lg[3] = fmaf(b0, prm.head_w[32 + ch], lg[3]);
+              lg[2] = fmaf(b1, prm.head_w[ch + 1], lg[2]);
+              lg[3] = fmaf(b1, prm.head_w[33 + ch], lg[3]);
             }
-            lg[2 * half] = l0;
-            lg[2 * half + 1] = l1;
           }
           if (valid) {
             const int t = img / prm.chunk_slices, sl = img - t * prm.chunk_slices;
@@ -549,24 +562,30 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           }
         } else {
           uint32_t packed[2][16];
+          // 16 channels of BOTH pixels per step: a channel's coefficients are read once for the pair
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(taddr0 + (uint32_t)(half * 32), v);
+          for (int cc = 0; cc < 2; ++cc) {
+            uint32_t v0[16], v1[16];
+            tmem_ld_32x32b_x16(taddr0 + (uint32_t)(cc * 16), v0);
+            tmem_ld_32x32b_x16(taddr0 + (uint32_t)(32 + cc * 16), v1);
             tmem_ld_wait();
-            if (half == 1) {
+            if (cc == 1) {
               tc_fence_before();
               mbar_arrive_warp(bar_tempty + 8 * group);
             }
 #pragma unroll
-            for (int c = 0; c < 32; c += 2) {
-              RCU_COEF2(c);
-              float a0 = fmaf(__uint_as_float(v[c]), c0.x, c0.y);
-              float a1 = fmaf(__uint_as_float(v[c + 1]), c1.x, c1.y);
-              if (prm.relu) { a0 = fmaxf(a0, 0.0f); a1 = fmaxf(a1, 0.0f); }
-              __nv_bfloat162 b = __floats2bfloat162_rn(a0, a1);
-              packed[half][c >> 1] = *reinterpret_cast<uint32_t*>(&b);
+            for (int c = 0; c < 16; c += 2) {
+              RCU_COEF2(cc * 16 + c);
+              float a0 = fmaf(__uint_as_float(v0[c]), c0.x, c0.y), a1 = fmaf(__uint_as_float(v0[c + 1]), c1.x, c1.y);
+              float b0 = fmaf(__uint_as_float(v1[c]), c0.x, c0.y), b1 = fmaf(__uint_as_float(v1[c + 1]), c1.x, c1.y);
+              if (prm.relu) { a0 = fmaxf(a0, 0.0f); a1 = fmaxf(a1, 0.0f); b0 = fmaxf(b0, 0.0f); b1 = fmaxf(b1, 0.0f); }
+              __nv_bfloat162 pa = __floats2bfloat162_rn(a0, a1), pb = __floats2bfloat162_rn(b0, b1);
+              packed[0][cc * 8 + (c >> 1)] = *reinterpret_cast<uint32_t*>(&pa);
+              packed[1][cc * 8 + (c >> 1)] = *reinterpret_cast<uint32_t*>(&pb);
             }
+          }
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
             if (prm.tma_store) {
               // the even / odd output pixels of the tile are two strided views of the destination (out_maps.m[half])
               const uint32_t so = smem_out + (uint32_t)group * S::kOutSlot;

@@ -90,8 +90,29 @@ __device__ __forceinline__ void mbar_arrive_warp(uint32_t bar) {
   if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
 #endif
 }
+// RCU_WAIT_HINT_NS > 0 passes the suspend-time hint of mbarrier.try_wait (the thread may sleep in hardware up to that long
+// instead of returning to the polling loop); RCU_SLACK_SLEEP_NS > 0 makes the waits that have slack (epilogue groups waiting
+// for their accumulator, the producer waiting for a free stage, the patch warps) back off with nanosleep between polls.
+// ncu counts 78 polls per epilogue warp and tile (12.8 M per pixel-pair launch), yet neither switch moves the forward time
+// (A/B on B200, profiles/r02zz_ab_experiments.log: hint 1000 ns, sleep 50 / 200 / 500 ns all within 1 % of plain polling):
+// the polls do not compete with the tensor cores' operand reads.  Both default to off.
+#ifndef RCU_WAIT_HINT_NS
+#define RCU_WAIT_HINT_NS 0
+#endif
+#ifndef RCU_SLACK_SLEEP_NS
+#define RCU_SLACK_SLEEP_NS 0
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
+#if RCU_WAIT_HINT_NS > 0
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"((uint32_t)RCU_WAIT_HINT_NS)
+      : "memory");
+#else
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -99,6 +120,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "=r"(ok)
       : "r"(bar), "r"(parity)
       : "memory");
+#endif
   return ok != 0;
 }
 // Bounded wait: a protocol bug must trap, never hang the GPU.
@@ -111,6 +133,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       __trap();
     }
   }
+}
+// The same for waiters with slack: sleep between polls instead of hammering the barrier word.
+__device__ __forceinline__ void mbar_wait_slack(uint32_t bar, uint32_t parity) {
+#if RCU_SLACK_SLEEP_NS > 0
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (true) {
+    __nanosleep(RCU_SLACK_SLEEP_NS);
+    if (mbar_try_wait(bar, parity)) return;
+    if (clock64() - t0 > 4000000000LL) {
+      printf("rcu conv_tc: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+#else
+  mbar_wait(bar, parity);
+#endif
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -160,6 +199,15 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
 }
@@ -281,7 +329,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         for (int tap = 0; tap < prm.n_taps; ++tap) {
           const int xx = x0 + prm.dx[ph][tap], yy = y0 + prm.dy[ph][tap];
           for (int kc = 0; kc < k_iters_per_tap; ++kc) {
-            mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+            mbar_wait_slack(bar_empty + 8 * stage, phase ^ 1u);
             mbar_expect_tx(bar_full + 8 * stage, S::kStageBytes);
             if (kc < prm.kc0) tma_load_4d(smem_a + stage * S::kABytes, &map_a0, bar_full + 8 * stage, kc * KC, xx, yy, img);
             else tma_load_4d(smem_a + stage * S::kABytes, &map_a1, bar_full + 8 * stage, (kc - prm.kc0) * KC, xx, yy, img);
@@ -341,7 +389,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         coef[c] = __ldg(prm.coef + (long long)img * prm.coef_stride + prm.coef_off + nt * BLOCK_N + c);
       asm volatile("bar.sync 1, 128;" ::: "memory");
 
-      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      mbar_wait_slack(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
 
       const int y = ty * kTileH + (row >> 4), x = tx * kTileW + (row & 15);

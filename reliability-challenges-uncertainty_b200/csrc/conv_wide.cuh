@@ -127,14 +127,14 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int ty = r / prm.tiles_x, tx = r - ty * prm.tiles_x;
         const uint8_t* wsrc = prm.w_image + (size_t)wsel * prm.n_chunks * TAPS * kWideWTile;
         for (int c = 0; c < prm.n_chunks; ++c) {
-          mbar_wait(bar_aempty + 8 * as, aph ^ 1u);
+          mbar_wait_slack(bar_aempty + 8 * as, aph ^ 1u);
           mbar_expect_tx(bar_afull + 8 * as, kWideABytes);
           tma_load_4d(smem_a + (uint32_t)as * kWideASlot, &map_a, bar_afull + 8 * as, c * 64, tx * kWideTile - 1, ty * kWideTile - 1, img);
           if (++as == C::kAStages) { as = 0; aph ^= 1u; }
 #pragma unroll
           for (int g = 0; g < C::kWg; ++g) {
             const int taps = (g + 1) * C::kTps <= TAPS ? C::kTps : TAPS - g * C::kTps;
-            mbar_wait(bar_wempty + 8 * ws, wph ^ 1u);
+            mbar_wait_slack(bar_wempty + 8 * ws, wph ^ 1u);
             mbar_expect_tx(bar_wfull + 8 * ws, (uint32_t)taps * kWideWTile);
             for (int t = 0; t < taps; ++t)
               bulk_load(smem_w + (uint32_t)ws * C::kWSlot + (uint32_t)t * kWideWTile,
@@ -221,7 +221,7 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
         cur_key = key;
       }
-      mbar_wait(bar_tfull + 8 * group, acc_phase);
+      mbar_wait_slack(bar_tfull + 8 * group, acc_phase);
       tc_fence_after();
 #pragma unroll 1
       for (int s = 0; s < 2; ++s) {

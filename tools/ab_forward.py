@@ -37,7 +37,7 @@ def worker():
     net.read_timing()
     net.forward_samples(x, 21, dropout_mode=1, det_first=True, slice_index0=0)
     ms, _ = net.read_timing()
-    sel = {i: round(float(ms[i]), 2) for i in (0, 1, 4, 20, 21, 23, 24, 25, 26)}
+    sel = {i: round(float(ms[i]), 2) for i in (0, 1, 4, 7, 13, 15, 18, 20, 21, 23, 24, 25, 26)}
     print('%-28s forward %.2f ms (min %.2f)  ops %s' % (os.environ.get('RCU_AB_NAME', 'default'), float(np.median(ts)), min(ts), sel), flush=True)
 
 
