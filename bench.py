@@ -432,16 +432,17 @@ def run_mc_config(args, rig, isic=False):
             copy_ev['h2d'].append((a, ready))
             h2d['n'] += t.numel() * 4
             return t, extra, ready
-        nxt = fetch(0)
+        depth = 3                                   # batches in flight ahead of the compute stream, like a loader's prefetch_factor
+        queue = [fetch(k) for k in range(min(depth, len(batches)))]
         mc, fg, pred = None, [], []
         for k, (st_, b0) in enumerate(batches):
             if b0 == 0:
                 mc = steps.McPredictStep(MC_STEPS)
                 mc.slices_seen = (first_index + st_) * n_items
                 fg, pred = [], []
-            images_b, extra, ready = nxt
-            if k + 1 < len(batches):
-                nxt = fetch(k + 1)
+            images_b, extra, ready = queue.pop(0)
+            if k + depth < len(batches):
+                queue.append(fetch(k + depth))
             stream.wait_event(ready)
             images_b.record_stream(stream)
             bc = _BatchContext({'images': images_b}, b0 // BATCH)
