@@ -615,6 +615,9 @@ def run_mc_config(args, rig, isic=False):
                 'traffic': traffic, 'traffic_source': traffic_src,
                 'peak_source': '%s bf16_tflops_sustained (kernel timed inside a long step)' % peaks['source'],
                 'share_of_step': conv_ms / args.steps / ms_step_op_events,
+                # the same FLOPs over the convolutions' share of the TIMED region's step: the per-launch events of the second pass sit
+                # between the kernels and cost the programmatic-dependent-launch overlap of their prologues, so `frac` is the lower figure
+                'frac_in_timed_region': (conv_flop / args.steps) / (conv_ms / args.steps / ms_step_op_events * ms_step * 1e-3) / 1e12 / peaks['tflops_sustained'],
                 'timed_over': 'a second pass of the same %d steps with per-launch CUDA events (%.1f ms/step there)' % (args.steps, ms_step_op_events)}
     agg_alg_bytes = voxels * (8.0 * MC_STEPS + 12)                            # T logit pairs in, mean + entropy out
     agg_all_bytes = voxels * (4.0 * (MC_STEPS + 1) + 8 + 12 + 4 + 1)          # what it moves: logit DIFFERENCES in (4 B per voxel-sample incl. the weight-scaling one), its softmax, mean, entropy, foreground, prediction out
