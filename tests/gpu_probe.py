@@ -185,6 +185,7 @@ def stage_unet_tc():
     for impl in (1, 0):
         net = model.B200UNet(sd, in_channels=cfg.in_channels, dropout=cfg.dropout, chunk_images=64)
         net.set_conv_impl(impl)
+        net.set_first_layer_dedup(False)   # activation 0 per (sample, slice), so that it can be read back and compared
         nets.append(net)
     outs = [net.forward_samples(x, 2, dropout_mode=1, det_first=True, seed=5) for net in nets]
     torch.cuda.synchronize()
