@@ -58,6 +58,12 @@ constexpr bool halo_is_pair(int mode) { return mode == HALO_PAIR32 || mode == HA
 #ifndef RCU_EXP_PAIR_NOEPI
 #define RCU_EXP_PAIR_NOEPI 0    // WRONG RESULTS: the epilogue releases the accumulator and stores nothing
 #endif
+#ifndef RCU_HALO_ROLLED
+#define RCU_HALO_ROLLED 1   // pixel-row and up-path MMA sequences rolled over window rows as well (A/B)
+#endif
+#ifndef RCU_PAIR_ROLLED
+#define RCU_PAIR_ROLLED 1
+#endif
 #ifndef RCU_HALO_PATCH_SPLIT
 #define RCU_HALO_PATCH_SPLIT 0   // 1: every patch warp takes a share of the rows of EVERY tile (shortest hand-over); 0: whole tiles, one stage per warp
 #endif
@@ -325,6 +331,48 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             // weight tiles [chunk][dy]{T0: [64][64] centre, S: [32][64] side} = 768 sixteen-byte units per (chunk, dy)
             constexpr uint32_t idesc32 = make_idesc<32>();
             auto pair_taps = [&](const int jj) {
+#if RCU_PAIR_ROLLED
+              // ROLLED over the three window rows (#pragma unroll 1): with the 24 MMAs of a chunk fully unrolled ptxas hoists every
+              // descriptor computation in front of the first UTCHMMA (~130 uniform instructions, half of them uniform-register
+              // spills: 96 live descriptor registers against 63) and the tensor pipe idles through that preamble at the start of
+              // every issue turn.  A rolled row loop bounds the hoisting window to four MMAs; the next row's descriptor math then
+              // runs while the queued MMAs execute.  Centre MMAs (N = 64) of the chunk first, then its side MMAs (N = 32).
+              {
+                uint32_t a_row = lo_a + 8u, b_t0 = lo_b0 + (uint32_t)(jj * 3 * 768);
+#pragma unroll 1
+                for (int dyi = 0; dyi < 3; ++dyi, a_row += (uint32_t)(kHaloPitch * 8), b_t0 += 768u) {
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks)
+                    if (leader)
+                      umma_bf16(tmem_d, desc_from(a_row + 2 * ks, hi_a), desc_from(b_t0 + 2 * ks, hi_b), idesc, (jj > 0 || dyi > 0 || ks > 0) ? 1u : 0u);
+                }
+              }
+              {
+                uint32_t a_row = lo_a, b_s = lo_b0 + (uint32_t)(jj * 3 * 768) + 512u;
+#pragma unroll 1
+                for (int dyi = 0; dyi < 3; ++dyi, a_row += (uint32_t)(kHaloPitch * 8), b_s += 768u) {
+                  if (MODE == HALO_PAIR32) {
+                    // one chunk holds both pixels of the pair: K 32..63 is a_in = 1 (left neighbour pair -> a_o = 0),
+                    // K 0..31 is a_in = 0 (right neighbour pair -> a_o = 1)
+#pragma unroll
+                    for (int ks = 2; ks < 4; ++ks)
+                      if (leader) umma_bf16(tmem_d, desc_from(a_row + 2 * ks, hi_a), desc_from(b_s + 2 * ks, hi_b), idesc32, 1u);
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks)
+                      if (leader) umma_bf16(tmem_d + 32u, desc_from(a_row + 16u + 2 * ks, hi_a), desc_from(b_s + 2 * ks, hi_b), idesc32, 1u);
+                  } else if (jj == 0) {   // chunk 0 = pixel a_in = 0: right neighbour pair -> a_o = 1
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                      if (leader) umma_bf16(tmem_d + 32u, desc_from(a_row + 16u + 2 * ks, hi_a), desc_from(b_s + 2 * ks, hi_b), idesc32, 1u);
+                  } else {                // chunk 1 = pixel a_in = 1: left neighbour pair -> a_o = 0
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                      if (leader) umma_bf16(tmem_d, desc_from(a_row + 2 * ks, hi_a), desc_from(b_s + 2 * ks, hi_b), idesc32, 1u);
+                  }
+                }
+              }
+              return;
+#endif
 #if RCU_PAIR_CENTRE_FIRST
               // all centre MMAs of the chunk first, then all side MMAs: one shape switch per chunk instead of six (32->32: -5 %)
 #pragma unroll
@@ -384,7 +432,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             for (int pp = 0; pp < PH / 2; ++pp) {
               const uint32_t base_a = lo_a + prm.up_base16[2 * pp];                      // phase (a, 0): window row a, column 0
               const uint32_t wpp = lo_b0 + (uint32_t)((pp * prm.n_chunks + j) * 2) * (4u * kTile16);
+#if RCU_HALO_ROLLED
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
               for (int i2 = 0; i2 < 2; ++i2) {
                 const uint32_t a_row = base_a + (uint32_t)(i2 * kHaloPitch * 8);
                 const uint32_t wt = wpp + (uint32_t)i2 * (4u * kTile16);
@@ -408,6 +460,24 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const uint32_t lo_a0 = lo_a + (MODE == HALO_UP64 ? prm.up_base16[p] : 0u);
             // weight tiles are stored [phase][chunk][tap]
             const uint32_t lo_bj = lo_b0 + (uint32_t)(p * prm.n_chunks + j) * kChunkW16;
+            if constexpr (RCU_HALO_ROLLED && MODE != HALO_UP64) {
+              // rolled over the three window rows (see the pixel-pair path): three taps x kK16 MMAs per iteration
+#pragma unroll 1
+              for (int ty3 = 0; ty3 < 3; ++ty3) {
+#pragma unroll
+                for (int tx3 = 0; tx3 < 3; ++tx3) {
+                  const int tap = ty3 * 3 + tx3;
+                  const uint32_t a_off = (uint32_t)((ty3 * kHaloPitch + tx3) * 8);
+                  const uint32_t b_off = MODE == HALO_CONV32 ? (uint32_t)(tap >> 1) * kTile16 + (uint32_t)(tap & 1) * 4u : (uint32_t)tap * kTile16;
+#pragma unroll
+                  for (int ks = 0; ks < kK16; ++ks) {
+                    const uint32_t accumulate = (tap > 0 || ks > 0) ? 1u : (j > 0 ? 1u : 0u);
+                    if (leader)
+                      umma_bf16(tmem_d + (uint32_t)(p * N), desc_from(lo_a0 + a_off + 2 * ks, hi_a), desc_from(lo_bj + b_off + 2 * ks, hi_b), idesc, accumulate);
+                  }
+                }
+              }
+            } else {
 #pragma unroll
             for (int tap = 0; tap < kTaps; ++tap) {
               const uint32_t a_off = MODE == HALO_UP64 ? (uint32_t)(((tap >> 1) * kHaloPitch + (tap & 1)) * 8)
@@ -419,6 +489,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 if (leader)
                   umma_bf16(tmem_d + (uint32_t)(p * N), desc_from(lo_a0 + a_off + 2 * ks, hi_a), desc_from(lo_bj + b_off + 2 * ks, hi_b), idesc, accumulate);
               }
+            }
             }
           }
           }
