@@ -31,7 +31,7 @@ constexpr int kHaloTileW = 8;
 constexpr int kHaloPitch = kHaloTileW + 2;   // window pixels per row
 constexpr int kHaloRows = kHaloTileH + 2;    // window rows
 // 3x3 conv over 64-ch chunks / a 32-ch source / one up-path phase / pixel-pair rows over a 32-ch / a 64-ch source
-enum HaloMode { HALO_CONV64 = 0, HALO_CONV32 = 1, HALO_UP64 = 2, HALO_PAIR32 = 3, HALO_PAIR64 = 4 };
+enum HaloMode { HALO_CONV64 = 0, HALO_CONV32 = 1, HALO_UP64 = 2, HALO_PAIR32 = 3, HALO_PAIR64 = 4, HALO_PAIR32_PATCH = 5, HALO_PAIR32_HEAD = 6 };   // 5: HALO_PAIR32 + the patch warps of the first-layer dedup; 6: HALO_PAIR32 with the fused 1x1 head as its epilogue
 // Pixel-pair formulation (c_out = 32 layers).  An N = 32 tcgen05.mma reads 4 KB of A and 1 KB of B from shared memory
 // for 128 x 32 x 16 MACs: the 128 B/clk operand port, not the tensor array, bounds it (40 clk against a 16 clk floor,
 // profiles/r01_umma_probe.log).  A GEMM row that holds TWO x-adjacent pixels (the dense NHWC tensor viewed as
@@ -45,7 +45,8 @@ enum HaloMode { HALO_CONV64 = 0, HALO_CONV32 = 1, HALO_UP64 = 2, HALO_PAIR32 = 3
 #ifndef RCU_UP_PAIRED
 #define RCU_UP_PAIRED 1      // A/B switch: 0 runs the up-path phases one by one (and packs their weights per phase)
 #endif
-constexpr bool halo_is_pair(int mode) { return mode == HALO_PAIR32 || mode == HALO_PAIR64; }
+constexpr bool halo_is_pair32(int mode) { return mode == HALO_PAIR32 || mode == HALO_PAIR32_PATCH || mode == HALO_PAIR32_HEAD; }
+constexpr bool halo_is_pair(int mode) { return halo_is_pair32(mode) || mode == HALO_PAIR64; }
 #ifndef RCU_HALO_PATCH_WARPS
 #define RCU_HALO_PATCH_WARPS 4
 #endif
@@ -68,7 +69,7 @@ constexpr bool halo_is_pair(int mode) { return mode == HALO_PAIR32 || mode == HA
 #define RCU_HALO_PATCH_SPLIT 0   // 1: every patch warp takes a share of the rows of EVERY tile (shortest hand-over); 0: whole tiles, one stage per warp
 #endif
 constexpr int kHaloPatchWarps = RCU_HALO_PATCH_WARPS;   // warps that patch dropped first-layer channels into landed tiles, stage s by warp s mod n
-constexpr int halo_patch_threads(int mode) { return mode == HALO_PAIR32 ? 32 * kHaloPatchWarps : 0; }
+constexpr int halo_patch_threads(int mode) { return mode == HALO_PAIR32_PATCH ? 32 * kHaloPatchWarps : 0; }
 constexpr int kHaloSmemBudget = 225 * 1024;
 
 struct HaloParams {
@@ -331,12 +332,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             // weight tiles [chunk][dy]{T0: [64][64] centre, S: [32][64] side} = 768 sixteen-byte units per (chunk, dy)
             constexpr uint32_t idesc32 = make_idesc<32>();
             auto pair_taps = [&](const int jj) {
-#if RCU_PAIR_ROLLED
+              if constexpr (RCU_PAIR_ROLLED && MODE != HALO_PAIR32_HEAD) {
               // ROLLED over the three window rows (#pragma unroll 1): with the 24 MMAs of a chunk fully unrolled ptxas hoists every
               // descriptor computation in front of the first UTCHMMA (~130 uniform instructions, half of them uniform-register
               // spills: 96 live descriptor registers against 63) and the tensor pipe idles through that preamble at the start of
               // every issue turn.  A rolled row loop bounds the hoisting window to four MMAs; the next row's descriptor math then
               // runs while the queued MMAs execute.  Centre MMAs (N = 64) of the chunk first, then its side MMAs (N = 32).
+              // Measured: 64->32 -2.5 %, the patching kernel -7 % (its 80-register budget spilled), 32->32 unchanged and conv_cls.0 + head
+              // 7 % SLOWER (its light epilogue leaves the issue loop exposed): the head instantiation keeps the unrolled sequence.
               {
                 uint32_t a_row = lo_a + 8u, b_t0 = lo_b0 + (uint32_t)(jj * 3 * 768);
 #pragma unroll 1
@@ -351,7 +354,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 uint32_t a_row = lo_a, b_s = lo_b0 + (uint32_t)(jj * 3 * 768) + 512u;
 #pragma unroll 1
                 for (int dyi = 0; dyi < 3; ++dyi, a_row += (uint32_t)(kHaloPitch * 8), b_s += 768u) {
-                  if (MODE == HALO_PAIR32) {
+                  if (halo_is_pair32(MODE)) {
                     // one chunk holds both pixels of the pair: K 32..63 is a_in = 1 (left neighbour pair -> a_o = 0),
                     // K 0..31 is a_in = 0 (right neighbour pair -> a_o = 1)
 #pragma unroll
@@ -372,7 +375,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 }
               }
               return;
-#endif
+              }
+
 #if RCU_PAIR_CENTRE_FIRST
               // all centre MMAs of the chunk first, then all side MMAs: one shape switch per chunk instead of six (32->32: -5 %)
 #pragma unroll
@@ -399,7 +403,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                               (jj > 0 || dyi > 0 || ks > 0) ? 1u : 0u);
 #endif
 #if !RCU_EXP_PAIR_NOSIDE
-                if (MODE == HALO_PAIR32) {
+                if (halo_is_pair32(MODE)) {
                   // one chunk holds both pixels of the pair: K 32..63 is a_in = 1 (left neighbour pair -> a_o = 0),
                   // K 0..31 is a_in = 0 (right neighbour pair -> a_o = 1)
 #pragma unroll
@@ -615,7 +619,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const bool valid = (y < prm.in_h) && (x < prm.in_w);
       if constexpr (PAIR) {
         // row = pixel pair (y, x): accumulator columns [0, 32) are output pixel 2x, [32, 64) pixel 2x + 1 (prm.in_w counts pairs)
-        if (prm.head != nullptr) {
+        if constexpr (MODE == HALO_PAIR32_HEAD) {   // the head layer has its own instantiation (own register allocation, own MMA sequence)
           // 16 channels of BOTH pixels per step: a channel's coefficients are read once for the pair (the broadcast reads of the
           // coefficients were a quarter of the kernel's shared-memory wavefronts when every pixel read them again)
           float lg[4] = {prm.head_w[64], prm.head_w[65], prm.head_w[64], prm.head_w[65]};

@@ -1241,7 +1241,19 @@ static int run_conv_halo_pair(rcu_unet* net, const ConvLayer& L, int n_img, int 
   prm.patch_coef = net->d_coef; prm.patch_off = net->first_coef_off;
   ConvLayer view = L;
   view.map_halo = L.map_halo_pair;
-  int rc = hp.pair_mode == 1 ? launch_conv_halo<64, HALO_PAIR32>(view, prm, maps, st) : launch_conv_halo<64, HALO_PAIR64>(view, prm, maps, st);
+  // the first-layer consumer runs the instantiation with patch warps (736 threads, 80 registers); every other 32-channel
+  // pair layer the plain one (608 threads, 96 registers)
+  int rc;
+  if (hp.pair_mode != 1) {
+    RCU_CHECK_ARG(prm.head == nullptr, "the fused head follows a 32-channel pair layer");
+    rc = launch_conv_halo<64, HALO_PAIR64>(view, prm, maps, st);
+  } else if (prm.head != nullptr) {
+    rc = launch_conv_halo<64, HALO_PAIR32_HEAD>(view, prm, maps, st);
+  } else if (dedup_mode != 0) {
+    rc = launch_conv_halo<64, HALO_PAIR32_PATCH>(view, prm, maps, st);
+  } else {
+    rc = launch_conv_halo<64, HALO_PAIR32>(view, prm, maps, st);
+  }
   if (rc) return rc;
   ++*launches;
   return RCU_OK;
