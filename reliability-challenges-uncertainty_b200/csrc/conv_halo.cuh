@@ -53,12 +53,6 @@ constexpr bool halo_is_pair(int mode) { return halo_is_pair32(mode) || mode == H
 #ifndef RCU_PAIR_CENTRE_FIRST
 #define RCU_PAIR_CENTRE_FIRST 1  // pixel-pair MMA sequence: the 12 centre (N = 64) MMAs of a chunk first, then its 12 side (N = 32) MMAs (0: per window row)
 #endif
-#ifndef RCU_EXP_PAIR_NOSIDE
-#define RCU_EXP_PAIR_NOSIDE 0   // WRONG RESULTS: no side MMAs
-#endif
-#ifndef RCU_EXP_PAIR_NOEPI
-#define RCU_EXP_PAIR_NOEPI 0    // WRONG RESULTS: the epilogue releases the accumulator and stores nothing
-#endif
 #ifndef RCU_HALO_ROLLED
 #define RCU_HALO_ROLLED 1   // pixel-row and up-path MMA sequences rolled over window rows as well (A/B)
 #endif
@@ -402,7 +396,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     umma_bf16(tmem_d, desc_from(a_row + 8u + 2 * ks, hi_a), desc_from(b_t0 + 2 * ks, hi_b), idesc,
                               (jj > 0 || dyi > 0 || ks > 0) ? 1u : 0u);
 #endif
-#if !RCU_EXP_PAIR_NOSIDE
                 if (halo_is_pair32(MODE)) {
                   // one chunk holds both pixels of the pair: K 32..63 is a_in = 1 (left neighbour pair -> a_o = 0),
                   // K 0..31 is a_in = 0 (right neighbour pair -> a_o = 1)
@@ -421,7 +414,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                   for (int ks = 0; ks < 4; ++ks)
                     if (leader) umma_bf16(tmem_d, desc_from(a_row + 2 * ks, hi_a), desc_from(b_s + 2 * ks, hi_b), idesc32, 1u);
                 }
-#endif
               }
             };
             if (j == 0) pair_taps(0); else pair_taps(1);
@@ -661,13 +653,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               *reinterpret_cast<float4*>(dst) = make_float4(lg[0], lg[1], lg[2], lg[3]);
             }
           }
-        } else if (RCU_EXP_PAIR_NOEPI) {
-          uint32_t v0[16];
-          tmem_ld_32x32b_x16(taddr0, v0);
-          tmem_ld_wait();
-          tc_fence_before();
-          mbar_arrive_warp(bar_tempty + 8 * group);
-          if (v0[0] == 0x12345678u && valid) prm.out[0] = __float2bfloat16(1.0f);
         } else {
           uint32_t packed[2][16];
           // 16 channels of BOTH pixels per step: a channel's coefficients are read once for the pair
