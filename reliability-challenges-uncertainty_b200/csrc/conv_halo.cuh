@@ -268,7 +268,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // shallow, so a single issuer leaves the pipe idle half of the time; with two issuers one warp's bookkeeping
     // hides behind the other's MMAs.  Control flow is warp-uniform, only the tcgen05 instructions are predicated on
     // elect.sync, so descriptors live in uniform registers and MMAs issue back to back.
-    constexpr int n_issuers = 2;
+#ifndef RCU_HALO_ISSUERS
+#define RCU_HALO_ISSUERS 2
+#endif
+    constexpr int n_issuers = RCU_HALO_ISSUERS;   // 1: warp 1 alone issues every tile (A/B)
     const int mw = warp - 1;
     const bool leader = elect_one() != 0;
     constexpr uint32_t idesc = make_idesc<N>();
