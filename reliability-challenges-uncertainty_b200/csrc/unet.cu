@@ -1219,6 +1219,13 @@ static int run_conv_halo_pair(rcu_unet* net, const ConvLayer& L, int n_img, int 
   prm.n_stages = L.pair_stages;
   prm.tma_store = L.pair_tma_store ? 1 : 0;
   prm.tiles_per_turn = 1;
+  {
+    static const int tt = [] { const char* e = std::getenv("RCU_HALO_TT"); return e ? std::atoi(e) : 0; }();
+    if (tt == 2 && L.pair_stages >= 4 * hp.n_chunks) prm.tiles_per_turn = 2;   // A/B only
+  }
+  // the first-layer consumer (patch warps + fused pool) is the one pair layer that gains from two tiles per issue turn
+  // (6.75 -> 6.56 ms per step; the plain 32->32 layer and the head lose 3 - 6 %): profiles/r02zz_ab_experiments.log
+  if (dedup_mode != 0 && L.pair_stages >= 4 * hp.n_chunks) prm.tiles_per_turn = 2;
   HaloOutMaps maps;
   maps.m[0] = L.map_out_pair[0]; maps.m[1] = L.map_out_pair[1];
   prm.w_image = hp.d_wimg[0];

@@ -46,13 +46,15 @@ if __name__ == '__main__':
         worker()
     else:
         rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 2
-        libs = [('default', None), ('default_nodedup', None)] + [(os.path.basename(p)[len('librcu_b200_'):-3], p) for p in
+        libs = [('default', None), ('default_nodedup', None), ('default_tt2', None)] + [(os.path.basename(p)[len('librcu_b200_'):-3], p) for p in
                                       sorted(glob.glob(os.path.join(ROOT, 'reliability-challenges-uncertainty_b200', 'build', 'variants', '*.so')))]
         for _ in range(rounds):
             for name, path in libs:
                 env = dict(os.environ, RCU_AB_NAME=name, RCU_B200_BINDING='ctypes')
                 if name.endswith('_nodedup'):
                     env['RCU_AB_DEDUP'] = '0'
+                if name.endswith('_tt2'):
+                    env['RCU_HALO_TT'] = '2'     # two tiles per issue turn where the shared-memory ring is deep enough
                 if path:
                     env['RCU_B200_LIB'] = path
                 subprocess.run([sys.executable, os.path.abspath(__file__), 'worker'], env=env, check=False)
