@@ -15,9 +15,15 @@
 //     where SWIZZLE_64B rows would read at half rate (2-way bank conflicts, probe `rate`);
 //   * the layer's weights (<= 144 KB as pre-swizzled [c_out][64] tiles) are copied into shared memory once per CTA
 //     and stay resident while the CTA walks its tiles (persistent kernel, one CTA per SM);
-//   * the MMA warp runs warp-uniform control flow and predicates only the tcgen05.mma on elect.sync, so descriptors
-//     live in uniform registers and MMAs issue back to back (N = 32/64 tiles are 40/48-clock MMAs, bound by the
-//     128 B/clk shared-memory operand read — see the probe).
+//   * the MMA warps run warp-uniform control flow and predicate only the tcgen05.mma on elect.sync, so descriptors
+//     live in uniform registers (N = 32/64 tiles are 40/48-clock MMAs, bound by the 128 B/clk shared-memory operand
+//     read — see the probe).  The MMA sequence of a tile is ROLLED over the window rows (#pragma unroll 1): fully
+//     unrolled, ptxas hoists every descriptor computation of the tile in front of its first UTCHMMA and spills 90 - 114
+//     uniform registers into the vector registers the epilogue needs (profiles/r02zz_ab_experiments.log); the head
+//     instantiation alone keeps the unrolled form, which measured faster for it;
+//   * one kernel instantiation per role (HaloMode): pixel rows over 64- / 32-channel sources, up-path phases, and the
+//     pixel-pair rows as four instantiations — plain, with the patch warps of the first-layer dedup, with the fused head
+//     (store path compiled out), and over a 64-channel source.
 //
 // Epilogue contract is that of conv_tc.cuh (folded Dropout2d x BN coefficients + ReLU, bf16 NHWC store with a
 // channel offset / pixel stride so producers write straight into the concat buffer, or the fused 1x1 head).
