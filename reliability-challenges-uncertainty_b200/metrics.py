@@ -53,18 +53,21 @@ def _to_device(x, dtype, name, device=None):
 
 
 class _Workspace:
-    """Per-device scratch for the deterministic two-stage reductions (allocated once, reused)."""
+    """Scratch for the deterministic two-stage reductions, one per (device, stream): allocated once, reused.  The kernels keep
+    tickets and partial tables in it, so two streams of one device (a background hook next to the main loop) must not share
+    a buffer; calls on ONE stream are ordered by the stream itself."""
     _cache = {}
 
     @classmethod
     def get(cls, n_subjects):
         dev = torch.cuda.current_device()     # callers switch to the tensors' device first (torch.cuda.device(...))
+        key = (dev, int(torch.cuda.current_stream().cuda_stream))
         need = int(_lib.lib().rcu_metrics_workspace_bytes(int(n_subjects)))
-        buf = cls._cache.get(dev)
+        buf = cls._cache.get(key)
         if buf is None or buf.numel() < need:
             buf = torch.empty(need, dtype=torch.uint8, device=_device())
             _lib.check(_lib.lib().rcu_metrics_workspace_init(_lib.ptr(buf), buf.numel(), _lib.current_stream()))
-            cls._cache[dev] = buf
+            cls._cache[key] = buf
         return buf
 
 

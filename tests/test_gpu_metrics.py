@@ -274,3 +274,28 @@ np.save(sys.argv[1], np.concatenate(out))
     for name in ('atom', 'atom2'):
         assert res['lut'].shape == res[name].shape
         assert np.allclose(res['lut'], res[name], rtol=1e-12, atol=0), name
+
+
+def test_two_streams_of_one_device_do_not_share_a_workspace():
+    """The kernels keep tickets and partial tables in a workspace; the wrapper holds one per (device, stream), so a background
+    hook evaluating on a side stream next to the main loop gets the tables a lone call gets (several rounds in flight)."""
+    n = 2 * 1000003
+    p, target, mask, pred, _ = synth_metric_inputs(n, 31)
+    p2, target2, mask2, pred2, _ = synth_metric_inputs(n, 32)
+    dev = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (p, pred, target, mask.view(np.uint8), p2, pred2, target2, mask2.view(np.uint8))]
+    ref_a = [np.asarray(t) for t in metrics.eval_fused(dev[0], dev[1], dev[2], dev[3], 10, SWEEP)[:5]]
+    ref_b = [np.asarray(t) for t in metrics.eval_fused(dev[4], dev[5], dev[6], dev[7], 10, SWEEP)[:5]]
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    got_a, got_b = [], []
+    for _ in range(8):
+        got_a.append(metrics.eval_fused(dev[0], dev[1], dev[2], dev[3], 10, SWEEP, sync=False))
+        with torch.cuda.stream(side):
+            got_b.append(metrics.eval_fused(dev[4], dev[5], dev[6], dev[7], 10, SWEEP, sync=False))
+    torch.cuda.synchronize()
+    for res, ref in ((got_a, ref_a), (got_b, ref_b)):
+        for r in res:
+            for k in (0, 1, 3, 4):
+                assert np.array_equal(np.asarray(r[k].cpu() if torch.is_tensor(r[k]) else r[k]), ref[k])
+            conf = np.asarray(r[2].cpu() if torch.is_tensor(r[2]) else r[2])
+            assert np.allclose(conf, ref[2], rtol=CONF_RTOL, atol=0)
